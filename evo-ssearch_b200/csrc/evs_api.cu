@@ -1,0 +1,797 @@
+// evs_api.cu -- the C ABI of libevs.so (include/evs.h): index handles, add / search / persistence.
+// No CPU fallback anywhere: without a CUDA device every compute entry point returns EVS_ENODEV.
+#include <errno.h>
+#include <float.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "evs_internal.h"
+
+using namespace evs;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char t_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            int c__ = (e__ == cudaErrorMemoryAllocation) ? EVS_ENOMEM                                     \
+                      : (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver) ? EVS_ENODEV     \
+                                                                                         : EVS_ECUDA;    \
+            return fail(c__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                 \
+    } while (0)
+
+static ScanTuning g_tune;
+static std::mutex g_tune_mu;
+
+// ---------------------------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------------------------
+static const int kQueryChunk = 256;  // queries finalised per launch (bounds the list workspace)
+
+struct evs_index {
+    int d = 0, device = 0, storage = EVS_STORE_F32;
+    int64_t ntotal = 0, capacity = 0, id_base = 0;
+    float* xb32 = nullptr;            // fp32 rows (the master copy; what index.faiss holds)
+    void* xb16 = nullptr;             // derived bf16 rows (EVS_STORE_BF16_F32)
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;    // the handle's own stream
+    cudaEvent_t ws_free = nullptr;    // recorded after each search: the workspace may be reused after it
+    std::mutex mu;                    // serialises add/search on this handle (Flask threads)
+    // workspace (device)
+    float* q_dev = nullptr;  size_t q_cap = 0;         // staged queries [chunk][d]
+    void* lists = nullptr;   size_t lists_cap = 0;     // candidate lists
+    float* D_dev = nullptr;  int64_t* I_dev = nullptr; size_t out_cap = 0;  // [chunk][k]
+    float* margins_dev = nullptr; size_t margins_cap = 0;   // [nq of last search]
+    int64_t last_nq = 0;
+    // pinned host staging
+    float* q_pin = nullptr;  size_t q_pin_cap = 0;
+    float* D_pin = nullptr;  int64_t* I_pin = nullptr; size_t out_pin_cap = 0;
+};
+
+static int use_device(int device) {
+    CU(cudaSetDevice(device));
+    return EVS_OK;
+}
+
+template <typename T>
+static int ensure_dev(T** ptr, size_t* cap, size_t need_elems) {
+    if (*cap >= need_elems && *ptr) return EVS_OK;
+    if (*ptr) CU(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(reinterpret_cast<void**>(ptr), need_elems * sizeof(T)));
+    *cap = need_elems;
+    return EVS_OK;
+}
+
+static int pick_kp(int64_t k) { return k <= 48 ? 64 : 128; }
+
+namespace evs {
+int max_queries_per_pass(int d, int is_bf16) {
+    // keep the query registers of the vectorised kernels at <= 64 per lane
+    int per_lane = d / 32;  // query values held per lane per query
+    if (per_lane <= 0) return 1;
+    int m = 64 / per_lane;
+    if (m > 4) m = 4;
+    if (m < 1) m = 1;
+    (void)is_bf16;
+    return m;
+}
+}  // namespace evs
+
+// ---------------------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------------------
+extern "C" int evs_version(void) { return EVS_VERSION; }
+extern "C" const char* evs_last_error(void) { return t_err; }
+
+extern "C" int evs_device_count(int* count) {
+    if (!count) return fail(EVS_EINVAL, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return EVS_OK;
+}
+
+extern "C" int64_t evs_kernel_launches(void) { return (int64_t)g_kernel_launches.load(); }
+
+extern "C" int evs_set_option(const char* name, int64_t value) {
+    if (!name) return fail(EVS_EINVAL, "name is NULL");
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    if (!strcmp(name, "scan_variant")) {
+        if (value < 0 || value > 2) return fail(EVS_EINVAL, "scan_variant must be 0, 1 or 2");
+        g_tune.scan_variant = (int)value;
+    } else if (!strcmp(name, "tile_rows")) {
+        if (value < 0 || value > 1024) return fail(EVS_EINVAL, "tile_rows out of range");
+        g_tune.tile_rows = (int)value;
+    } else if (!strcmp(name, "stages")) {
+        if (value < 0 || value > 16) return fail(EVS_EINVAL, "stages out of range");
+        g_tune.stages = (int)value;
+    } else if (!strcmp(name, "ctas_per_sm")) {
+        if (value < 0 || value > 8) return fail(EVS_EINVAL, "ctas_per_sm out of range");
+        g_tune.ctas_per_sm = (int)value;
+    } else {
+        return fail(EVS_EINVAL, "unknown option '%s'", name);
+    }
+    return EVS_OK;
+}
+
+extern "C" int evs_get_option(const char* name, int64_t* value) {
+    if (!name || !value) return fail(EVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    if (!strcmp(name, "scan_variant")) *value = g_tune.scan_variant;
+    else if (!strcmp(name, "tile_rows")) *value = g_tune.tile_rows;
+    else if (!strcmp(name, "stages")) *value = g_tune.stages;
+    else if (!strcmp(name, "ctas_per_sm")) *value = g_tune.ctas_per_sm;
+    else return fail(EVS_EINVAL, "unknown option '%s'", name);
+    return EVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------------
+extern "C" int evs_index_create(int d, int device, int storage, evs_index** out) {
+    if (!out) return fail(EVS_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (d <= 0) return fail(EVS_EINVAL, "d must be > 0 (got %d)", d);
+    if (storage != EVS_STORE_F32 && storage != EVS_STORE_BF16_F32) return fail(EVS_EINVAL, "unknown storage %d", storage);
+    int ndev = 0;
+    evs_device_count(&ndev);
+    if (ndev <= 0) return fail(EVS_ENODEV, "no CUDA device: libevs has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(EVS_EINVAL, "device %d out of range (have %d)", device, ndev);
+    int rc = use_device(device);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(EVS_ENODEV, "device %d is sm_%d%d; libevs is built for sm_100a only", device, prop.major, prop.minor);
+    evs_index* idx = new (std::nothrow) evs_index();
+    if (!idx) return fail(EVS_ENOMEM, "out of host memory");
+    idx->d = d;
+    idx->device = device;
+    idx->storage = storage;
+    idx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ws_free, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete idx;
+        return fail(EVS_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+    }
+    *out = idx;
+    return EVS_OK;
+}
+
+extern "C" int evs_index_free(evs_index* idx) {
+    if (!idx) return EVS_OK;
+    cudaSetDevice(idx->device);
+    if (idx->stream) cudaStreamSynchronize(idx->stream);
+    cudaFree(idx->xb32);
+    cudaFree(idx->xb16);
+    cudaFree(idx->q_dev);
+    cudaFree(idx->lists);
+    cudaFree(idx->D_dev);
+    cudaFree(idx->I_dev);
+    cudaFree(idx->margins_dev);
+    cudaFreeHost(idx->q_pin);
+    cudaFreeHost(idx->D_pin);
+    cudaFreeHost(idx->I_pin);
+    if (idx->ws_free) cudaEventDestroy(idx->ws_free);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    delete idx;
+    return EVS_OK;
+}
+
+#define GETTER(name, type, expr)                                            \
+    extern "C" int name(const evs_index* idx, type* out) {                  \
+        if (!idx || !out) return fail(EVS_EINVAL, #name ": NULL argument"); \
+        *out = (expr);                                                      \
+        return EVS_OK;                                                      \
+    }
+GETTER(evs_index_d, int, idx->d)
+GETTER(evs_index_ntotal, int64_t, idx->ntotal)
+GETTER(evs_index_device, int, idx->device)
+GETTER(evs_index_storage, int, idx->storage)
+GETTER(evs_index_id_base, int64_t, idx->id_base)
+
+extern "C" int evs_index_set_id_base(evs_index* idx, int64_t base) {
+    if (!idx) return fail(EVS_EINVAL, "idx is NULL");
+    if (base < 0) return fail(EVS_EINVAL, "id base must be >= 0");
+    idx->id_base = base;
+    return EVS_OK;
+}
+
+// grow the row storage to hold at least `rows` rows (device-to-device copy of what is there)
+static int grow_locked(evs_index* idx, int64_t rows) {
+    if (rows <= idx->capacity) return EVS_OK;
+    if (rows >= (int64_t)0xFFFFFFFFll) return fail(EVS_ELIMIT, "a shard holds at most 2^32-2 rows");
+    const size_t d = (size_t)idx->d;
+    float* n32 = nullptr;
+    void* n16 = nullptr;
+    CU(cudaMalloc(reinterpret_cast<void**>(&n32), (size_t)rows * d * sizeof(float)));
+    if (idx->storage == EVS_STORE_BF16_F32) {
+        cudaError_t e = cudaMalloc(&n16, (size_t)rows * d * 2);
+        if (e != cudaSuccess) {
+            cudaFree(n32);
+            return fail(EVS_ENOMEM, "cudaMalloc of the bf16 copy failed: %s", cudaGetErrorString(e));
+        }
+    }
+    if (idx->ntotal > 0) {
+        CU(cudaMemcpyAsync(n32, idx->xb32, (size_t)idx->ntotal * d * sizeof(float), cudaMemcpyDeviceToDevice, idx->stream));
+        if (n16) CU(cudaMemcpyAsync(n16, idx->xb16, (size_t)idx->ntotal * d * 2, cudaMemcpyDeviceToDevice, idx->stream));
+        CU(cudaStreamSynchronize(idx->stream));
+    }
+    cudaFree(idx->xb32);
+    cudaFree(idx->xb16);
+    idx->xb32 = n32;
+    idx->xb16 = n16;
+    idx->capacity = rows;
+    return EVS_OK;
+}
+
+static int grow_for_add_locked(evs_index* idx, int64_t n) {
+    int64_t need = idx->ntotal + n;
+    if (need <= idx->capacity) return EVS_OK;
+    int64_t cap = idx->capacity + idx->capacity / 2;  // 1.5x amortised growth
+    if (cap < need) cap = need;
+    return grow_locked(idx, cap);
+}
+
+// after new fp32 rows [ntotal, ntotal+n) are in place (enqueued on idx->stream): derive bf16, publish
+static int finish_add_locked(evs_index* idx, int64_t n) {
+    const size_t d = (size_t)idx->d;
+    if (idx->storage == EVS_STORE_BF16_F32) {
+        CU(launch_f32_to_bf16(idx->xb32 + (size_t)idx->ntotal * d,
+                              reinterpret_cast<unsigned char*>(idx->xb16) + (size_t)idx->ntotal * d * 2, (long long)n * idx->d,
+                              idx->sm_count, idx->stream));
+    }
+    CU(cudaStreamSynchronize(idx->stream));
+    idx->ntotal += n;
+    return EVS_OK;
+}
+
+extern "C" int evs_index_reserve(evs_index* idx, int64_t nrows) {
+    if (!idx) return fail(EVS_EINVAL, "idx is NULL");
+    if (nrows < 0) return fail(EVS_EINVAL, "nrows must be >= 0");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    return grow_locked(idx, nrows);
+}
+
+extern "C" int evs_index_add(evs_index* idx, int64_t n, const float* x_host) {
+    if (!idx) return fail(EVS_EINVAL, "idx is NULL");
+    if (n < 0) return fail(EVS_EINVAL, "n must be >= 0");
+    if (n == 0) return EVS_OK;
+    if (!x_host) return fail(EVS_EINVAL, "x is NULL");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    if ((rc = grow_for_add_locked(idx, n))) return rc;
+    const size_t d = (size_t)idx->d;
+    CU(cudaMemcpyAsync(idx->xb32 + (size_t)idx->ntotal * d, x_host, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice,
+                       idx->stream));
+    return finish_add_locked(idx, n);
+}
+
+extern "C" int evs_index_add_dev(evs_index* idx, int64_t n, const void* x_dev, int dtype, void* stream) {
+    if (!idx) return fail(EVS_EINVAL, "idx is NULL");
+    if (n < 0) return fail(EVS_EINVAL, "n must be >= 0");
+    if (n == 0) return EVS_OK;
+    if (!x_dev) return fail(EVS_EINVAL, "x is NULL");
+    if (dtype != EVS_F32 && dtype != EVS_F16 && dtype != EVS_BF16) return fail(EVS_EINVAL, "bad dtype %d", dtype);
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    if ((rc = grow_for_add_locked(idx, n))) return rc;
+    // the producer of x_dev ran on `stream`: order our stream after it
+    if (stream && (cudaStream_t)stream != idx->stream) {
+        cudaEvent_t ev;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev, (cudaStream_t)stream));
+        CU(cudaStreamWaitEvent(idx->stream, ev, 0));
+        CU(cudaEventDestroy(ev));
+    }
+    const size_t d = (size_t)idx->d;
+    float* dst = idx->xb32 + (size_t)idx->ntotal * d;
+    if (dtype == EVS_F32)
+        CU(cudaMemcpyAsync(dst, x_dev, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToDevice, idx->stream));
+    else
+        CU(launch_to_f32(x_dev, dtype, dst, (long long)n * idx->d, idx->sm_count, idx->stream));
+    return finish_add_locked(idx, n);
+}
+
+extern "C" int evs_index_add_synth(evs_index* idx, int64_t n, uint64_t seed, int normalize) {
+    if (!idx) return fail(EVS_EINVAL, "idx is NULL");
+    if (n < 0) return fail(EVS_EINVAL, "n must be >= 0");
+    if (n == 0) return EVS_OK;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    if ((rc = grow_for_add_locked(idx, n))) return rc;
+    float* dst = idx->xb32 + (size_t)idx->ntotal * idx->d;
+    CU(launch_synth_fill(dst, n, idx->d, seed, idx->id_base + idx->ntotal, idx->sm_count, idx->stream));
+    if (normalize) CU(launch_l2_normalize(dst, n, idx->d, EVS_F32, idx->sm_count, idx->stream));
+    return finish_add_locked(idx, n);
+}
+
+extern "C" int evs_index_get_rows(const evs_index* idx, int64_t row0, int64_t n, float* out_host) {
+    if (!idx || (!out_host && n > 0)) return fail(EVS_EINVAL, "NULL argument");
+    if (row0 < 0 || n < 0 || row0 + n > idx->ntotal) return fail(EVS_EINVAL, "rows [%lld,%lld) out of range", (long long)row0, (long long)(row0 + n));
+    if (n == 0) return EVS_OK;
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    CU(cudaMemcpy(out_host, idx->xb32 + (size_t)row0 * idx->d, (size_t)n * idx->d * sizeof(float), cudaMemcpyDeviceToHost));
+    return EVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------
+struct SearchOut {
+    float* D = nullptr;        // final mode
+    int64_t* I = nullptr;
+    double* P_scores = nullptr;  // partial mode
+    int64_t* P_ids = nullptr;
+};
+
+// Enqueue the search of `nq` device-resident queries on stream `st`; outputs are device pointers.
+// idx->mu is held by the caller.
+static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out,
+                                 cudaStream_t st, bool scan_only = false) {
+    const int kp = pick_kp(k);
+    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
+    const void* scan_rows = bf16 ? idx->xb16 : (const void*)idx->xb32;
+    ScanTuning tune;
+    {
+        std::lock_guard<std::mutex> lk(g_tune_mu);
+        tune = g_tune;
+    }
+    const int qpp = max_queries_per_pass(idx->d, bf16);
+    ScanPlan plan;
+    CU(plan_scan(idx->ntotal, idx->d, bf16, kp, qpp, idx->sm_count, tune, &plan));
+    const int64_t chunk_cap = nq < kQueryChunk ? nq : kQueryChunk;
+    int rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, (size_t)chunk_cap * plan.grid * kp);
+    if (rc) return rc;
+    if ((rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
+    idx->last_nq = nq;
+
+    for (int64_t c0 = 0; c0 < nq; c0 += kQueryChunk) {
+        const int64_t cn = (nq - c0) < kQueryChunk ? (nq - c0) : kQueryChunk;
+        const float* qc = q_dev + (size_t)c0 * idx->d;
+        for (int64_t p0 = 0; p0 < cn; p0 += qpp) {
+            ScanArgs a;
+            a.xb = scan_rows;
+            a.is_bf16 = bf16;
+            a.n = idx->ntotal;
+            a.d = idx->d;
+            a.xq = qc;
+            a.q0 = (int)p0;
+            a.nq_pass = (int)((cn - p0) < qpp ? (cn - p0) : qpp);
+            a.lists = idx->lists;
+            a.kp = kp;
+            // the plan's shared-memory size was computed for qpp queries per pass: large enough for fewer
+            CU(launch_scan(a, &plan, st));
+        }
+        if (scan_only) continue;
+        FinalizeArgs f;
+        f.lists = idx->lists;
+        f.L = plan.grid;
+        f.kp = kp;
+        f.xb = idx->xb32;
+        f.xb_is_bf16 = 0;
+        f.xq = qc;
+        f.nq = cn;
+        f.d = idx->d;
+        f.k = (int)k;
+        f.id_base = idx->id_base;
+        f.D = out.D ? out.D + (size_t)c0 * k : nullptr;
+        f.I = out.I ? out.I + (size_t)c0 * k : nullptr;
+        f.P_scores = out.P_scores ? out.P_scores + (size_t)c0 * k : nullptr;
+        f.P_ids = out.P_ids ? out.P_ids + (size_t)c0 * k : nullptr;
+        f.margins = idx->margins_dev + c0;
+        CU(launch_finalize(f, st));
+    }
+    return EVS_OK;
+}
+
+// ---- fill kernels for the empty-index case (faiss returns all padding) ----
+__global__ void fill_final_kernel(float* D, long long* I, long long count) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        D[i] = -FLT_MAX;
+        I[i] = -1;
+    }
+}
+__global__ void fill_partial_kernel(double* S, long long* I, long long count) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        S[i] = -DBL_MAX;
+        I[i] = -1;
+    }
+}
+
+static int check_search_args(const evs_index* idx, int64_t nq, const void* q, int64_t k, const void* o1, const void* o2) {
+    if (!idx) return fail(EVS_EINVAL, "idx is NULL");
+    if (nq < 0) return fail(EVS_EINVAL, "nq must be >= 0");
+    if (k <= 0) return fail(EVS_EINVAL, "k must be > 0 (got %lld)", (long long)k);  // FAISS_THROW_IF_NOT(k > 0)
+    if (k > EVS_MAX_K) return fail(EVS_ELIMIT, "k = %lld exceeds EVS_MAX_K = %d", (long long)k, EVS_MAX_K);
+    if (nq > 0 && (!q || !o1 || !o2)) return fail(EVS_EINVAL, "NULL query or output buffer");
+    return EVS_OK;
+}
+
+// order stream `st` after the previous user of the handle's workspace, run, and mark the workspace busy until done
+static int search_dev_common(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st) {
+    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+    int rc;
+    if (idx->ntotal == 0) {
+        long long count = (long long)nq * k;
+        int grid = (int)((count + 255) / 256 < 1024 ? (count + 255) / 256 : 1024);
+        if (out.D) fill_final_kernel<<<grid, 256, 0, st>>>(out.D, reinterpret_cast<long long*>(out.I), count);
+        else fill_partial_kernel<<<grid, 256, 0, st>>>(out.P_scores, reinterpret_cast<long long*>(out.P_ids), count);
+        g_kernel_launches.fetch_add(1);
+        CU(cudaGetLastError());
+        idx->last_nq = 0;
+        rc = EVS_OK;
+    } else {
+        rc = search_enqueue_locked(idx, nq, q_dev, k, out, st);
+    }
+    CU(cudaEventRecord(idx->ws_free, st));
+    return rc;
+}
+
+extern "C" int evs_index_search_dev(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, float* D_dev, int64_t* I_dev,
+                                    void* stream) {
+    int rc = check_search_args(idx, nq, q_dev, k, D_dev, I_dev);
+    if (rc || nq == 0) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if ((rc = use_device(idx->device))) return rc;
+    SearchOut out;
+    out.D = D_dev;
+    out.I = I_dev;
+    return search_dev_common(idx, nq, q_dev, k, out, stream ? (cudaStream_t)stream : idx->stream);
+}
+
+extern "C" int evs_index_search_partial_dev(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, double* out_scores_dev,
+                                            int64_t* out_ids_dev, void* stream) {
+    int rc = check_search_args(idx, nq, q_dev, k, out_scores_dev, out_ids_dev);
+    if (rc || nq == 0) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if ((rc = use_device(idx->device))) return rc;
+    SearchOut out;
+    out.P_scores = out_scores_dev;
+    out.P_ids = out_ids_dev;
+    return search_dev_common(idx, nq, q_dev, k, out, stream ? (cudaStream_t)stream : idx->stream);
+}
+
+extern "C" int evs_merge_partials_dev(int device, int nparts, int64_t nq, int64_t k, const double* scores_dev,
+                                      const int64_t* ids_dev, int64_t part_stride, float* D_dev, int64_t* I_dev, void* stream) {
+    if (nparts <= 0 || nq < 0 || k <= 0) return fail(EVS_EINVAL, "bad nparts/nq/k");
+    if (nq == 0) return EVS_OK;
+    if (!scores_dev || !ids_dev || !D_dev || !I_dev) return fail(EVS_EINVAL, "NULL buffer");
+    if ((size_t)nparts * k * 16 > 200 * 1024) return fail(EVS_ELIMIT, "nparts*k too large for one merge");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (part_stride == 0) part_stride = nq * k;
+    if (part_stride < nq * k) return fail(EVS_EINVAL, "part_stride smaller than nq*k");
+    CU(launch_merge_partials(nparts, nq, (int)k, scores_dev, reinterpret_cast<const long long*>(ids_dev), part_stride, D_dev,
+                             reinterpret_cast<long long*>(I_dev), (cudaStream_t)stream));
+    return EVS_OK;
+}
+
+template <typename T>
+static int ensure_pinned(T** ptr, size_t* cap, size_t need_elems) {
+    if (*cap >= need_elems && *ptr) return EVS_OK;
+    if (*ptr) CU(cudaFreeHost(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    CU(cudaMallocHost(reinterpret_cast<void**>(ptr), need_elems * sizeof(T)));
+    *cap = need_elems;
+    return EVS_OK;
+}
+
+extern "C" int evs_index_search(evs_index* idx, int64_t nq, const float* q_host, int64_t k, float* D_host, int64_t* I_host) {
+    int rc = check_search_args(idx, nq, q_host, k, D_host, I_host);
+    if (rc || nq == 0) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if ((rc = use_device(idx->device))) return rc;
+    const size_t d = (size_t)idx->d;
+    // stage queries: caller memory -> pinned -> device (one async copy), results come back the same way
+    if ((rc = ensure_pinned(&idx->q_pin, &idx->q_pin_cap, (size_t)nq * d))) return rc;
+    if ((rc = ensure_dev(&idx->q_dev, &idx->q_cap, (size_t)nq * d))) return rc;
+    size_t out_need = (size_t)nq * k;
+    if (idx->out_cap < out_need) {
+        if (idx->D_dev) cudaFree(idx->D_dev);
+        if (idx->I_dev) cudaFree(idx->I_dev);
+        idx->D_dev = nullptr;
+        idx->I_dev = nullptr;
+        idx->out_cap = 0;
+        CU(cudaMalloc(reinterpret_cast<void**>(&idx->D_dev), out_need * sizeof(float)));
+        CU(cudaMalloc(reinterpret_cast<void**>(&idx->I_dev), out_need * sizeof(int64_t)));
+        idx->out_cap = out_need;
+    }
+    if (idx->out_pin_cap < out_need) {
+        if (idx->D_pin) cudaFreeHost(idx->D_pin);
+        if (idx->I_pin) cudaFreeHost(idx->I_pin);
+        idx->D_pin = nullptr;
+        idx->I_pin = nullptr;
+        idx->out_pin_cap = 0;
+        CU(cudaMallocHost(reinterpret_cast<void**>(&idx->D_pin), out_need * sizeof(float)));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&idx->I_pin), out_need * sizeof(int64_t)));
+        idx->out_pin_cap = out_need;
+    }
+    memcpy(idx->q_pin, q_host, (size_t)nq * d * sizeof(float));
+    cudaStream_t st = idx->stream;
+    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+    CU(cudaMemcpyAsync(idx->q_dev, idx->q_pin, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, st));
+    SearchOut out;
+    out.D = idx->D_dev;
+    out.I = idx->I_dev;
+    if ((rc = search_dev_common(idx, nq, idx->q_dev, k, out, st))) return rc;
+    CU(cudaMemcpyAsync(idx->D_pin, idx->D_dev, out_need * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(idx->I_pin, idx->I_dev, out_need * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(D_host, idx->D_pin, out_need * sizeof(float));
+    memcpy(I_host, idx->I_pin, out_need * sizeof(int64_t));
+    return EVS_OK;
+}
+
+extern "C" int evs_index_last_margins(evs_index* idx, int64_t nq, float* margins_host) {
+    if (!idx || !margins_host) return fail(EVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if (nq != idx->last_nq) return fail(EVS_EINVAL, "last search had %lld queries, not %lld", (long long)idx->last_nq, (long long)nq);
+    if (nq == 0) return EVS_OK;
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    CU(cudaEventSynchronize(idx->ws_free));
+    CU(cudaMemcpy(margins_host, idx->margins_dev, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost));
+    return EVS_OK;
+}
+
+extern "C" int evs_index_time_scan(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, int iters, float* mean_ms) {
+    int rc = check_search_args(idx, nq, q_dev, k, mean_ms, mean_ms);
+    if (rc) return rc;
+    if (nq == 0 || iters <= 0 || idx->ntotal == 0) return fail(EVS_EINVAL, "nothing to time");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if ((rc = use_device(idx->device))) return rc;
+    cudaStream_t st = idx->stream;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+    SearchOut none;
+    rc = search_enqueue_locked(idx, nq, q_dev, k, none, st, true);  // warm-up
+    if (!rc) {
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < iters && !rc; i++) rc = search_enqueue_locked(idx, nq, q_dev, k, none, st, true);
+        cudaEventRecord(e1, st);
+    }
+    cudaEventRecord(idx->ws_free, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (!rc && e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(EVS_ECUDA, "scan failed: %s", cudaGetErrorString(e));
+    *mean_ms = ms / iters;
+    return EVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone kernels
+// ---------------------------------------------------------------------------------------------
+static int device_sm_count(int device, int* sms) {
+    CU(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, device));
+    return EVS_OK;
+}
+
+extern "C" int evs_l2_normalize_dev(int device, void* x_dev, int64_t n, int d, int dtype, void* stream) {
+    if (n < 0 || d <= 0) return fail(EVS_EINVAL, "bad n/d");
+    if (dtype != EVS_F32 && dtype != EVS_F16 && dtype != EVS_BF16) return fail(EVS_EINVAL, "bad dtype %d", dtype);
+    if (n == 0) return EVS_OK;
+    if (!x_dev) return fail(EVS_EINVAL, "x is NULL");
+    int ndev = 0;
+    evs_device_count(&ndev);
+    if (ndev <= 0) return fail(EVS_ENODEV, "no CUDA device: libevs has no CPU fallback");
+    int rc = use_device(device), sms = 0;
+    if (rc || (rc = device_sm_count(device, &sms))) return rc;
+    if ((size_t)d * 4 * 8 > 200 * 1024) return fail(EVS_ELIMIT, "d = %d too large for the normalise kernel", d);
+    CU(launch_l2_normalize(x_dev, n, d, dtype, sms, (cudaStream_t)stream));
+    return EVS_OK;
+}
+
+extern "C" int evs_l2_normalize(int device, float* x_host, int64_t n, int d) {
+    if (n < 0 || d <= 0) return fail(EVS_EINVAL, "bad n/d");
+    if (n == 0) return EVS_OK;
+    if (!x_host) return fail(EVS_EINVAL, "x is NULL");
+    int ndev = 0;
+    evs_device_count(&ndev);
+    if (ndev <= 0) return fail(EVS_ENODEV, "no CUDA device: libevs has no CPU fallback");
+    int rc = use_device(device);
+    if (rc) return rc;
+    float* dev = nullptr;
+    size_t bytes = (size_t)n * d * sizeof(float);
+    CU(cudaMalloc(reinterpret_cast<void**>(&dev), bytes));
+    cudaError_t e = cudaMemcpy(dev, x_host, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = evs_l2_normalize_dev(device, dev, n, d, EVS_F32, nullptr);
+        if (!rc) e = cudaMemcpy(x_host, dev, bytes, cudaMemcpyDeviceToHost);  // default-stream copy orders after the kernel
+    }
+    cudaFree(dev);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(EVS_ECUDA, "copy failed: %s", cudaGetErrorString(e));
+    return EVS_OK;
+}
+
+extern "C" int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev, int64_t count, void* stream) {
+    if (count < 0) return fail(EVS_EINVAL, "bad count");
+    if (count == 0) return EVS_OK;
+    if (!src_dev || !dst_dev) return fail(EVS_EINVAL, "NULL buffer");
+    int rc = use_device(device), sms = 0;
+    if (rc || (rc = device_sm_count(device, &sms))) return rc;
+    CU(launch_f32_to_bf16(src_dev, dst_dev, count, sms, (cudaStream_t)stream));
+    return EVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistence: index.faiss (45-byte IndexFlat header + fp32 payload, little-endian)
+// ---------------------------------------------------------------------------------------------
+#pragma pack(push, 1)
+struct FlatHeader {
+    char fourcc[4];
+    int32_t d;
+    int64_t ntotal;
+    int64_t dummy1, dummy2;
+    uint8_t is_trained;
+    int32_t metric_type;
+    uint64_t count;  // number of float32 values
+};
+#pragma pack(pop)
+static_assert(sizeof(FlatHeader) == 45, "index.faiss flat header is 45 bytes");
+
+static const size_t kIoChunk = (size_t)64 << 20;
+
+extern "C" int evs_index_write(const evs_index* idx, const char* path) {
+    if (!idx || !path) return fail(EVS_EINVAL, "NULL argument");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(EVS_EIO, "cannot open '%s' for writing: %s", path, strerror(errno));
+    FlatHeader h;
+    memcpy(h.fourcc, "IxFI", 4);
+    h.d = idx->d;
+    h.ntotal = idx->ntotal;
+    h.dummy1 = h.dummy2 = (int64_t)1 << 20;
+    h.is_trained = 1;
+    h.metric_type = 0;
+    h.count = (uint64_t)idx->ntotal * (uint64_t)idx->d;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    size_t total = (size_t)h.count * sizeof(float);
+    void* pin = nullptr;
+    if (ok && total) {
+        size_t chunk = total < kIoChunk ? total : kIoChunk;
+        cudaError_t e = cudaMallocHost(&pin, chunk);
+        if (e != cudaSuccess) {
+            fclose(f);
+            return fail(EVS_ENOMEM, "cudaMallocHost failed: %s", cudaGetErrorString(e));
+        }
+        for (size_t off = 0; ok && off < total; off += chunk) {
+            size_t nb = total - off < chunk ? total - off : chunk;
+            e = cudaMemcpy(pin, reinterpret_cast<const unsigned char*>(idx->xb32) + off, nb, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) {
+                cudaFreeHost(pin);
+                fclose(f);
+                return fail(EVS_ECUDA, "device read failed: %s", cudaGetErrorString(e));
+            }
+            ok = fwrite(pin, 1, nb, f) == nb;
+        }
+        cudaFreeHost(pin);
+    }
+    if (fclose(f) != 0) ok = false;
+    if (!ok) return fail(EVS_EIO, "short write to '%s'", path);
+    return EVS_OK;
+}
+
+extern "C" int evs_index_read(const char* path, int device, int storage, evs_index** out) {
+    if (!path || !out) return fail(EVS_EINVAL, "NULL argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(EVS_EIO, "cannot open '%s': %s", path, strerror(errno));
+    FlatHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1) {
+        fclose(f);
+        return fail(EVS_EFORMAT, "'%s': truncated header", path);
+    }
+    const bool ip = !memcmp(h.fourcc, "IxFI", 4);
+    if (!ip && memcmp(h.fourcc, "IxF2", 4) && memcmp(h.fourcc, "IxFl", 4)) {
+        fclose(f);
+        return fail(EVS_EFORMAT, "'%s': not a flat index (fourcc %.4s)", path, h.fourcc);
+    }
+    if (h.metric_type != 0) {
+        fclose(f);
+        return fail(EVS_EFORMAT, "'%s': metric %d is not inner product", path, h.metric_type);
+    }
+    if (h.d <= 0 || h.ntotal < 0 || h.count >= ((uint64_t)1 << 40) || h.count != (uint64_t)h.ntotal * (uint64_t)h.d) {
+        fclose(f);
+        return fail(EVS_EFORMAT, "'%s': inconsistent header (d=%d ntotal=%lld count=%llu)", path, h.d, (long long)h.ntotal,
+                    (unsigned long long)h.count);
+    }
+    struct stat sb;
+    if (fstat(fileno(f), &sb) == 0 && (uint64_t)sb.st_size < sizeof(h) + h.count * 4) {
+        fclose(f);
+        return fail(EVS_EFORMAT, "'%s': truncated payload", path);
+    }
+    evs_index* idx = nullptr;
+    int rc = evs_index_create(h.d, device, storage, &idx);
+    if (rc) {
+        fclose(f);
+        return rc;
+    }
+    size_t total = (size_t)h.count * sizeof(float);
+    if (total) {
+        {
+            std::lock_guard<std::mutex> lk(idx->mu);
+            rc = grow_locked(idx, h.ntotal);
+        }
+        void* pin[2] = {nullptr, nullptr};
+        size_t chunk = total < kIoChunk ? total : kIoChunk;
+        if (!rc && (cudaMallocHost(&pin[0], chunk) != cudaSuccess || cudaMallocHost(&pin[1], chunk) != cudaSuccess))
+            rc = fail(EVS_ENOMEM, "cudaMallocHost failed");
+        // double-buffered: fread into one pinned buffer while the other is in flight to the device
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        if (!rc) {
+            cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
+        }
+        int b = 0;
+        for (size_t off = 0; !rc && off < total; off += chunk, b ^= 1) {
+            size_t nb = total - off < chunk ? total - off : chunk;
+            cudaEventSynchronize(done[b]);
+            if (fread(pin[b], 1, nb, f) != nb) {
+                rc = fail(EVS_EFORMAT, "'%s': short read", path);
+                break;
+            }
+            cudaError_t e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(idx->xb32) + off, pin[b], nb, cudaMemcpyHostToDevice,
+                                            idx->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(done[b], idx->stream);
+            if (e != cudaSuccess) rc = fail(EVS_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+        }
+        if (!rc) {
+            std::lock_guard<std::mutex> lk(idx->mu);
+            rc = finish_add_locked(idx, h.ntotal);
+        } else {
+            cudaStreamSynchronize(idx->stream);
+        }
+        if (done[0]) cudaEventDestroy(done[0]);
+        if (done[1]) cudaEventDestroy(done[1]);
+        cudaFreeHost(pin[0]);
+        cudaFreeHost(pin[1]);
+    }
+    fclose(f);
+    if (rc) {
+        evs_index_free(idx);
+        return rc;
+    }
+    *out = idx;
+    return EVS_OK;
+}

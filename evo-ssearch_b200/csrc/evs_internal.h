@@ -1,0 +1,71 @@
+// evs_internal.h -- host-side declarations shared by evs_kernels.cu and evs_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/evs.h"
+
+namespace evs {
+
+extern std::atomic<long long> g_kernel_launches;
+
+struct ScanTuning {
+    int scan_variant = 0;  // 0 auto, 1 direct loads, 2 bulk-async ring
+    int tile_rows = 0;     // ring: rows per stage (0 = ~32 KiB)
+    int stages = 0;        // ring: depth (0 = 4)
+    int ctas_per_sm = 0;   // direct: CTAs per SM (0 = 2)
+};
+
+struct ScanPlan {
+    int variant;  // 0 generic-d, 1 direct, 2 ring
+    int nv;       // 16-byte vectors per lane per row (0 for generic)
+    int grid, threads;
+    size_t smem_bytes;
+    int tile_rows, stages;
+};
+
+struct ScanArgs {
+    const void* xb;
+    int is_bf16;
+    long long n;
+    int d;
+    const float* xq;
+    int q0;
+    int nq_pass;  // 1..4 queries handled by this launch
+    void* lists;  // u64 [nq_chunk][grid][kp]
+    int kp;
+};
+
+struct FinalizeArgs {
+    const void* lists;
+    int L, kp;
+    const void* xb;
+    int xb_is_bf16;
+    const float* xq;
+    long long nq;
+    int d, k;
+    long long id_base;
+    float* D;
+    int64_t* I;
+    double* P_scores;
+    int64_t* P_ids;
+    float* margins;
+};
+
+cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int sm_count, const ScanTuning& tune,
+                      ScanPlan* plan);
+int max_queries_per_pass(int d, int is_bf16);
+cudaError_t launch_scan(const ScanArgs& a, ScanPlan* plan, cudaStream_t st);
+cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st);
+cudaError_t launch_merge_partials(int nparts, long long nq, int k, const double* scores, const long long* ids,
+                                  long long part_stride, float* D,
+                                  long long* I, cudaStream_t st);
+cudaError_t launch_l2_normalize(void* x, long long n, int d, int dtype, int sm_count, cudaStream_t st);
+cudaError_t launch_f32_to_bf16(const float* src, void* dst, long long count, int sm_count, cudaStream_t st);
+cudaError_t launch_to_f32(const void* src, int dtype, float* dst, long long count, int sm_count, cudaStream_t st);
+cudaError_t launch_synth_fill(float* out, long long n, int d, unsigned long long seed, long long row_base, int sm_count,
+                              cudaStream_t st);
+
+}  // namespace evs

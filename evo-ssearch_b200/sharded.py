@@ -1,0 +1,117 @@
+"""Row-sharded flat inner-product index: one process per GPU, one small exchange per query batch.
+
+SURVEY.md section 8(e): top-k over a union is the top-k of the per-part top-k, so database rows are
+split into contiguous blocks -- rank g owns rows ``[g*ceil(N/G), min(N, (g+1)*ceil(N/G)))`` with global
+ids = local row + block start -- queries are replicated, every rank scans its block and finalises its
+own k best in the canonical fp64 order, and ONE all-gather (NCCL over NVLink; ``nq*k*16`` bytes per
+rank) followed by a replicated G-way merge kernel gives every rank the final ``(D, I)``.  Because each
+shard's scores are produced by the same canonical arithmetic, the merged result is bit-identical to
+the single-GPU result for any G.
+
+``torch.distributed`` is plumbing only (process group, the all-gather).  The local engine and the merge
+are injectable so that the host logic can be exercised on CPU with ``gloo`` in the tests; the defaults
+are the CUDA ones and nothing here falls back to CPU on its own.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rows ``[lo, hi)`` of an ``n``-row database owned by ``rank`` of ``world`` (contiguous blocks)."""
+    per = -(-n // world) if n > 0 else 0
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi
+
+
+class ShardedIndexFlatIP:
+    """``IndexFlatIP`` over the GPUs of one box; call the same methods with the same arguments on every rank."""
+
+    def __init__(self, d: int, *, group=None, device: Optional[int] = None, storage: Optional[str] = None,
+                 local_index=None, merge: Optional[Callable] = None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.d = int(d)
+        self.is_trained = True
+        if local_index is None:
+            from .index import IndexFlatIP, merge_partials
+            local_index = IndexFlatIP(d, device=device, storage=storage)
+            merge = merge_partials if merge is None else merge
+        assert merge is not None, "an injected local_index needs an injected merge"
+        self.local = local_index
+        self._merge = merge
+        self._ntotal = 0
+
+    # -- bookkeeping --------------------------------------------------------------------------
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    def _set_layout(self, n_total: int) -> Tuple[int, int]:
+        if self._ntotal != 0:
+            raise RuntimeError("a sharded index is filled once (contiguous row blocks); reset() first")
+        lo, hi = shard_bounds(n_total, self.world, self.rank)
+        self.local.id_base = lo
+        return lo, hi
+
+    # -- add ----------------------------------------------------------------------------------
+    def add(self, x) -> None:
+        """``x`` is the FULL ``(N, d)`` array, identical on every rank; each rank keeps its block."""
+        x = np.asarray(x)
+        n, d = x.shape
+        assert d == self.d
+        lo, hi = self._set_layout(n)
+        if hi > lo:
+            self.local.add(np.ascontiguousarray(x[lo:hi], dtype="float32"))
+        self._ntotal = n
+
+    def add_local(self, x_local, n_total: int) -> None:
+        """Each rank passes only its own block (rows ``shard_bounds(n_total, world, rank)``)."""
+        lo, hi = self._set_layout(n_total)
+        assert x_local.shape[0] == hi - lo and x_local.shape[1] == self.d
+        if hi > lo:
+            self.local.add(x_local)
+        self._ntotal = n_total
+
+    def add_synthetic(self, n_total: int, seed: int, normalize: bool = True) -> None:
+        """Every rank generates its own block on its GPU (rows are a function of the global id)."""
+        lo, hi = self._set_layout(n_total)
+        if hi > lo:
+            self.local.reserve(hi - lo)
+            self.local.add_synthetic(hi - lo, seed, normalize)
+        self._ntotal = n_total
+
+    # -- search -------------------------------------------------------------------------------
+    def search_tensor(self, xq, k: int):
+        """``xq``: ``(nq, d)`` tensor on this rank's device, identical on every rank -> tensors ``(D, I)``."""
+        import torch
+        assert k > 0
+        nq = xq.shape[0]
+        S, I = self.local.search_partial(xq, k)  # float64 [nq,k], int64 [nq,k] with global ids
+        if self.world == 1:
+            return self._merge(S.unsqueeze(0), I.unsqueeze(0), k)
+        mine = torch.stack((S.view(torch.int64), I))  # [2,nq,k] -- one payload, one collective
+        allp = torch.empty((self.world,) + tuple(mine.shape), dtype=torch.int64, device=mine.device)
+        self._dist.all_gather_into_tensor(allp, mine, group=self.group)
+        # strided views of the gathered buffer: part stride 2*nq*k, each [nq,k] block dense
+        return self._merge(allp.view(torch.float64)[:, 0], allp[:, 1], k)
+
+    def search(self, x, k: int):
+        """numpy in, numpy out, like ``IndexFlatIP.search``; every rank returns the same ``(D, I)``."""
+        import torch
+        x = np.ascontiguousarray(np.asarray(x), dtype="float32")
+        n, d = x.shape
+        assert d == self.d
+        assert k > 0
+        dev = getattr(self.local, "torch_device", None)
+        if dev is None:
+            dev = torch.device("cuda", self.local.device)
+        xq = torch.from_numpy(x).to(dev, non_blocking=False)
+        D, I = self.search_tensor(xq, k)
+        return D.cpu().numpy(), I.cpu().numpy()

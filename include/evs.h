@@ -1,0 +1,175 @@
+/*
+ * evs.h -- C ABI of libevs.so, the B200 (sm_100a) flat inner-product top-k engine that replaces the
+ * faiss-cpu calls on evo-ssearch's similarity-search hot path.
+ *
+ * The reference has no FFI layer of its own: its hot path is five calls into the third-party faiss
+ * Python module.  Each entry point below names the reference call site it
+ * stands in for (file:line into the reference tree) and the de-facto faiss C++ signature underneath.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative EVS_E* code otherwise; it never aborts or
+ *     exits.  evs_last_error() returns a thread-local message for the last failure on this thread.
+ *   - plain pointers and sizes only.  "host" pointers are ordinary process memory owned by the
+ *     caller; "dev" pointers are CUDA device pointers on the index's device (e.g. torch tensors'
+ *     data_ptr()); `stream` is a cudaStream_t passed as void* (NULL = the index's own stream).
+ *   - the index handle owns all device memory it allocates; the caller owns every buffer it passes.
+ *     add() copies, so the caller may free its array immediately (oldapp.py:86-88 does).
+ *   - search on one handle may be entered from several threads (the Flask dev server is threaded,
+ *     oldapp.py:2258); calls on the same handle are serialised internally.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     EVS_ENODEV.
+ *
+ * Result contract (faiss IndexFlat::search with METRIC_INNER_PRODUCT, k-entry heap handler):
+ *   D[nq*k] float32 scores in descending order, I[nq*k] int64 row ids, unfilled slots
+ *   (-FLT_MAX, -1).  Ranking is by the inner product of the fp32 inputs accumulated in fp64 in the
+ *   fixed CANON-32 order, ties by ascending id -- independent of tile shape, batch
+ *   size, storage precision of the scan and GPU count.
+ */
+#ifndef EVS_H_
+#define EVS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(EVS_BUILDING) && defined(__GNUC__)
+#define EVS_API __attribute__((visibility("default")))
+#else
+#define EVS_API
+#endif
+
+#define EVS_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define EVS_OK 0
+#define EVS_EINVAL (-1)   /* bad argument (faiss: assert / FAISS_THROW_IF_NOT)         */
+#define EVS_ENODEV (-2)   /* no usable CUDA device                                      */
+#define EVS_ECUDA (-3)    /* a CUDA runtime call or kernel failed                       */
+#define EVS_ENOMEM (-4)   /* host or device allocation failed                           */
+#define EVS_EIO (-5)      /* file could not be opened / read / written                  */
+#define EVS_EFORMAT (-6)  /* not a flat index.faiss file, or corrupt                    */
+#define EVS_ELIMIT (-7)   /* outside the limits of this build (k > EVS_MAX_K, ...)      */
+
+/* element types of device buffers */
+#define EVS_F32 0
+#define EVS_F16 1
+#define EVS_BF16 2
+
+/* storage / scan modes of an index */
+#define EVS_STORE_F32 0        /* fp32 rows; fp32 scan                                             */
+#define EVS_STORE_BF16_F32 1   /* fp32 master + derived bf16 copy; bf16 scan, fp32 canonical rerank */
+
+#define EVS_MAX_K 112          /* app limit is 48 (config.py:29); candidates kept per list: 64 or 128 */
+
+typedef struct evs_index evs_index; /* opaque */
+
+/* ---- library ------------------------------------------------------------------------------- */
+EVS_API int evs_version(void);
+EVS_API const char* evs_last_error(void);
+/* number of visible CUDA devices (0 and EVS_OK when there is none) */
+EVS_API int evs_device_count(int* count);
+
+/* ---- index lifecycle ------------------------------------------------------------------------
+ * evs_index_create   <- faiss.IndexFlatIP(d)                         oldapp.py:87
+ *                       (faiss::IndexFlatIP::IndexFlatIP(idx_t d)); ntotal = 0, is_trained = 1.
+ *                       `device` = CUDA ordinal, `storage` = EVS_STORE_*.
+ * evs_index_free     <- Python GC of the faiss index object.
+ */
+EVS_API int evs_index_create(int d, int device, int storage, evs_index** out);
+EVS_API int evs_index_free(evs_index* idx);
+EVS_API int evs_index_d(const evs_index* idx, int* d);
+EVS_API int evs_index_ntotal(const evs_index* idx, int64_t* ntotal);
+EVS_API int evs_index_device(const evs_index* idx, int* device);
+EVS_API int evs_index_storage(const evs_index* idx, int* storage);
+/* global id of local row 0 (row sharding: this handle owns rows [base, base+ntotal)) */
+EVS_API int evs_index_set_id_base(evs_index* idx, int64_t base);
+EVS_API int evs_index_id_base(const evs_index* idx, int64_t* base);
+
+/* ---- add ------------------------------------------------------------------------------------
+ * evs_index_add         <- index.add(embeddings_array)              oldapp.py:88
+ *                          (void faiss::IndexFlatCodes::add(idx_t n, const float* x)); host fp32,
+ *                          C-contiguous n x d; ids continue from ntotal.
+ * evs_index_add_dev     same from a device buffer of dtype EVS_F32/F16/BF16 (keeps CLIP output on
+ *                          the GPU instead of the .cpu().numpy() bounce at oldapp.py:36/44/52).
+ * evs_index_reserve     optional capacity hint (rows) to avoid regrowth copies.
+ * evs_index_add_synth   appends n synthetic rows generated on the device: counter-based function of
+ *                          (seed, id_base + local row, column), optionally L2-normalised
+ *                          (bench/tests only; 100M rows cannot come from the host).
+ */
+EVS_API int evs_index_reserve(evs_index* idx, int64_t nrows);
+EVS_API int evs_index_add(evs_index* idx, int64_t n, const float* x_host);
+EVS_API int evs_index_add_dev(evs_index* idx, int64_t n, const void* x_dev, int dtype, void* stream);
+EVS_API int evs_index_add_synth(evs_index* idx, int64_t n, uint64_t seed, int normalize);
+/* copy rows [row0, row0+n) back to host fp32 (faiss reconstruct_n; used by write and tests) */
+EVS_API int evs_index_get_rows(const evs_index* idx, int64_t row0, int64_t n, float* out_host);
+
+/* ---- search ---------------------------------------------------------------------------------
+ * evs_index_search      <- index.search(q.reshape(1,-1), k)         oldapp.py:2005, :2112
+ *                          (void faiss::IndexFlat::search(idx_t n, const float* x, idx_t k,
+ *                           float* distances, idx_t* labels, ...) const).  Host pointers.
+ *                          k <= 0 -> EVS_EINVAL (FAISS_THROW_IF_NOT(k > 0)); nq == 0 is a no-op.
+ * evs_index_search_dev  same with device pointers for queries and results, enqueued on `stream`
+ *                          without a host synchronisation.
+ * evs_index_search_partial_dev
+ *                       row-sharded search, stage 1: this shard's k best as (fp64 canonical score,
+ *                          int64 global id) pairs, sorted best first, padded with
+ *                          (-DBL_MAX, -1): out_scores[nq*k], out_ids[nq*k] device buffers.  The
+ *                          caller all-gathers these across ranks (NCCL) and calls evs_merge_partials_dev.
+ * evs_merge_partials_dev
+ *                       stage 2: merge `nparts` partial lists laid out [part][nq][k] into the
+ *                          final D float32[nq*k], I int64[nq*k] on `device`.  `part_stride` is the
+ *                          distance between consecutive parts in 8-byte elements, for both arrays
+ *                          (0 = dense, nq*k), so one all-gathered buffer can hold scores and ids.
+ */
+EVS_API int evs_index_search(evs_index* idx, int64_t nq, const float* q_host, int64_t k, float* D_host, int64_t* I_host);
+EVS_API int evs_index_search_dev(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, float* D_dev, int64_t* I_dev,
+                         void* stream);
+EVS_API int evs_index_search_partial_dev(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, double* out_scores_dev,
+                                 int64_t* out_ids_dev, void* stream);
+EVS_API int evs_merge_partials_dev(int device, int nparts, int64_t nq, int64_t k, const double* scores_dev,
+                           const int64_t* ids_dev, int64_t part_stride, float* D_dev, int64_t* I_dev, void* stream);
+/* per-query safety margin of the last search on this handle: canonical score of the k-th result
+ * minus the scan score of the worst retained candidate (+inf when every row was a candidate).
+ * A positive margin larger than the scan's error bound certifies the result exact. */
+EVS_API int evs_index_last_margins(evs_index* idx, int64_t nq, float* margins_host);
+
+/* ---- persistence: <folder>/.clip_index/index.faiss -------------------------------------------
+ * evs_index_write       <- faiss.write_index(index, path)           oldapp.py:98
+ * evs_index_read        <- faiss.read_index(path)                   oldapp.py:117
+ *                          45-byte IndexFlat header + fp32 row-major payload;
+ *                          accepts fourcc IxFI / IxF2 / IxFl like faiss's reader, keeps the
+ *                          inner-product metric only (EVS_EFORMAT for L2 files).
+ */
+EVS_API int evs_index_write(const evs_index* idx, const char* path);
+EVS_API int evs_index_read(const char* path, int device, int storage, evs_index** out);
+
+/* ---- stand-alone kernels ---------------------------------------------------------------------
+ * evs_l2_normalize_dev  <- x /= x.norm(dim=-1, keepdim=True)        oldapp.py:35, :43, :51
+ *                          in place on an n x d device buffer of dtype EVS_F32/F16/BF16; no epsilon
+ *                          (a zero row becomes NaN, as in the reference).
+ * evs_l2_normalize      same for a host fp32 buffer (staged through the device).
+ * evs_f32_to_bf16_dev   the one-time fp32 -> bf16 database layout kernel (round to nearest even).
+ */
+EVS_API int evs_l2_normalize_dev(int device, void* x_dev, int64_t n, int d, int dtype, void* stream);
+EVS_API int evs_l2_normalize(int device, float* x_host, int64_t n, int d);
+EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev, int64_t count, void* stream);
+
+/* ---- tuning / introspection (bench and tests) -------------------------------------------------
+ * evs_set_option: "scan_variant" (0 = auto, 1 = direct-load kernel, 2 = bulk-async ring kernel),
+ *                 "tile_rows", "stages", "ctas_per_sm".  Unknown names -> EVS_EINVAL.
+ * evs_kernel_launches: number of kernels this library has launched in this process.
+ * evs_index_time_scan: runs the scan stage alone `iters` times on the index's stream for queries
+ *                 already on the device and returns the mean kernel time in ms measured with CUDA
+ *                 events on that stream (roofline measurement; results are discarded).
+ */
+EVS_API int evs_set_option(const char* name, int64_t value);
+EVS_API int evs_get_option(const char* name, int64_t* value);
+EVS_API int64_t evs_kernel_launches(void);
+EVS_API int evs_index_time_scan(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, int iters, float* mean_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVS_H_ */
