@@ -49,6 +49,7 @@ SIGNATURES = {
     "evs_get_option": (_i, [_c.c_char_p, _pi64]),
     "evs_kernel_launches": (_i64, []),
     "evs_index_time_scan": (_i, [_vp, _i64, _vp, _i64, _i, _pf]),
+    "evs_index_scan_profile": (_i, [_vp, _pi64, _c.POINTER(_c.c_double)]),
 }
 
 _lib = None

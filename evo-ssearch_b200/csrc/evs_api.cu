@@ -11,6 +11,8 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "evs_internal.h"
 
@@ -41,6 +43,7 @@ static int fail(int code, const char* fmt, ...) {
 
 static ScanTuning g_tune;
 static std::mutex g_tune_mu;
+static int g_profile_scans = 0;  // record CUDA events around every search's scan launches
 
 // ---------------------------------------------------------------------------------------------
 // the handle
@@ -62,6 +65,9 @@ struct evs_index {
     float* D_dev = nullptr;  int64_t* I_dev = nullptr; size_t out_cap = 0;  // [chunk][k]
     float* margins_dev = nullptr; size_t margins_cap = 0;   // [nq of last search]
     int64_t last_nq = 0;
+    // optional per-search timing of the scan stage (option "profile_scans")
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
     // pinned host staging
     float* q_pin = nullptr;  size_t q_pin_cap = 0;
     float* D_pin = nullptr;  int64_t* I_pin = nullptr; size_t out_pin_cap = 0;
@@ -133,6 +139,8 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "ctas_per_sm")) {
         if (value < 0 || value > 8) return fail(EVS_EINVAL, "ctas_per_sm out of range");
         g_tune.ctas_per_sm = (int)value;
+    } else if (!strcmp(name, "profile_scans")) {
+        g_profile_scans = value ? 1 : 0;
     } else {
         return fail(EVS_EINVAL, "unknown option '%s'", name);
     }
@@ -146,6 +154,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tile_rows")) *value = g_tune.tile_rows;
     else if (!strcmp(name, "stages")) *value = g_tune.stages;
     else if (!strcmp(name, "ctas_per_sm")) *value = g_tune.ctas_per_sm;
+    else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
     else return fail(EVS_EINVAL, "unknown option '%s'", name);
     return EVS_OK;
 }
@@ -197,6 +206,10 @@ extern "C" int evs_index_free(evs_index* idx) {
     cudaFreeHost(idx->q_pin);
     cudaFreeHost(idx->D_pin);
     cudaFreeHost(idx->I_pin);
+    for (auto& pe : idx->prof_events) {
+        cudaEventDestroy(pe.first);
+        cudaEventDestroy(pe.second);
+    }
     if (idx->ws_free) cudaEventDestroy(idx->ws_free);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
@@ -364,9 +377,11 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
     const void* scan_rows = bf16 ? idx->xb16 : (const void*)idx->xb32;
     ScanTuning tune;
+    int profile;
     {
         std::lock_guard<std::mutex> lk(g_tune_mu);
         tune = g_tune;
+        profile = g_profile_scans && !scan_only;
     }
     const int qpp = max_queries_per_pass(idx->d, bf16);
     ScanPlan plan;
@@ -380,6 +395,17 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
     for (int64_t c0 = 0; c0 < nq; c0 += kQueryChunk) {
         const int64_t cn = (nq - c0) < kQueryChunk ? (nq - c0) : kQueryChunk;
         const float* qc = q_dev + (size_t)c0 * idx->d;
+        std::pair<cudaEvent_t, cudaEvent_t>* pe = nullptr;
+        if (profile && idx->prof_used < 65536) {
+            if (idx->prof_used == idx->prof_events.size()) {
+                cudaEvent_t a = nullptr, b = nullptr;
+                CU(cudaEventCreate(&a));
+                CU(cudaEventCreate(&b));
+                idx->prof_events.emplace_back(a, b);
+            }
+            pe = &idx->prof_events[idx->prof_used++];
+            CU(cudaEventRecord(pe->first, st));
+        }
         for (int64_t p0 = 0; p0 < cn; p0 += qpp) {
             ScanArgs a;
             a.xb = scan_rows;
@@ -394,6 +420,7 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
             // the plan's shared-memory size was computed for qpp queries per pass: large enough for fewer
             CU(launch_scan(a, &plan, st));
         }
+        if (pe) CU(cudaEventRecord(pe->second, st));
         if (scan_only) continue;
         FinalizeArgs f;
         f.lists = idx->lists;
@@ -594,6 +621,24 @@ extern "C" int evs_index_time_scan(evs_index* idx, int64_t nq, const float* q_de
     if (rc) return rc;
     if (e != cudaSuccess) return fail(EVS_ECUDA, "scan failed: %s", cudaGetErrorString(e));
     *mean_ms = ms / iters;
+    return EVS_OK;
+}
+
+extern "C" int evs_index_scan_profile(evs_index* idx, int64_t* count, double* total_ms) {
+    if (!idx || !count || !total_ms) return fail(EVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    double sum = 0.0;
+    for (size_t i = 0; i < idx->prof_used; i++) {
+        CU(cudaEventSynchronize(idx->prof_events[i].second));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, idx->prof_events[i].first, idx->prof_events[i].second));
+        sum += ms;
+    }
+    *count = (int64_t)idx->prof_used;
+    *total_ms = sum;
+    idx->prof_used = 0;
     return EVS_OK;
 }
 

@@ -216,6 +216,12 @@ class IndexFlatIP:
                                         int(iters), ctypes.byref(ms)))
         return ms.value
 
+    def scan_profile(self):
+        """(searches recorded, summed scan ms) since the last call; needs ``set_option("profile_scans", 1)``."""
+        n, ms = ctypes.c_int64(0), ctypes.c_double(0)
+        check(lib().evs_index_scan_profile(self._h, ctypes.byref(n), ctypes.byref(ms)))
+        return n.value, ms.value
+
     # -- reconstruct ----------------------------------------------------------------------------
     def reconstruct_n(self, n0: int = 0, ni: int = -1) -> np.ndarray:
         if ni == -1:

@@ -93,12 +93,15 @@ class ShardedIndexFlatIP:
         import torch
         assert k > 0
         nq = xq.shape[0]
+        if self.world == 1 and hasattr(self.local, "_search_torch"):
+            return self.local.search(xq, k)  # one shard: the finalise kernel emits (D, I) directly
         S, I = self.local.search_partial(xq, k)  # float64 [nq,k], int64 [nq,k] with global ids
         if self.world == 1:
             return self._merge(S.unsqueeze(0), I.unsqueeze(0), k)
         mine = torch.stack((S.view(torch.int64), I))  # [2,nq,k] -- one payload, one collective
-        allp = torch.empty((self.world,) + tuple(mine.shape), dtype=torch.int64, device=mine.device)
-        self._dist.all_gather_into_tensor(allp, mine, group=self.group)
+        flat = torch.empty((self.world * 2, nq, k), dtype=torch.int64, device=mine.device)
+        self._dist.all_gather_into_tensor(flat, mine, group=self.group)  # concatenation along dim 0
+        allp = flat.view(self.world, 2, nq, k)
         # strided views of the gathered buffer: part stride 2*nq*k, each [nq,k] block dense
         return self._merge(allp.view(torch.float64)[:, 0], allp[:, 1], k)
 
@@ -109,6 +112,8 @@ class ShardedIndexFlatIP:
         n, d = x.shape
         assert d == self.d
         assert k > 0
+        if self.world == 1 and hasattr(self.local, "_search_torch"):
+            return self.local.search(x, k)  # one shard: the C ABI host entry point (evs_index_search)
         dev = getattr(self.local, "torch_device", None)
         if dev is None:
             dev = torch.device("cuda", self.local.device)

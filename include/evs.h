@@ -158,7 +158,7 @@ EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev,
 
 /* ---- tuning / introspection (bench and tests) -------------------------------------------------
  * evs_set_option: "scan_variant" (0 = auto, 1 = direct-load kernel, 2 = bulk-async ring kernel),
- *                 "tile_rows", "stages", "ctas_per_sm".  Unknown names -> EVS_EINVAL.
+ *                 "tile_rows", "stages", "ctas_per_sm", "profile_scans".  Unknown names -> EVS_EINVAL.
  * evs_kernel_launches: number of kernels this library has launched in this process.
  * evs_index_time_scan: runs the scan stage alone `iters` times on the index's stream for queries
  *                 already on the device and returns the mean kernel time in ms measured with CUDA
@@ -168,6 +168,10 @@ EVS_API int evs_set_option(const char* name, int64_t value);
 EVS_API int evs_get_option(const char* name, int64_t* value);
 EVS_API int64_t evs_kernel_launches(void);
 EVS_API int evs_index_time_scan(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, int iters, float* mean_ms);
+/* With option "profile_scans" = 1 every search records a CUDA event pair around its scan launches on
+ * the stream it runs on.  This call waits for them, returns how many searches were recorded since the
+ * last call and the sum of their scan durations in ms, and resets the record. */
+EVS_API int evs_index_scan_profile(evs_index* idx, int64_t* count, double* total_ms);
 
 #ifdef __cplusplus
 }

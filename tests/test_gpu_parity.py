@@ -1,0 +1,451 @@
+"""GPU (B200) parity tests proper: the CUDA path, called through the C ABI of libevs.so, against the
+CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * ids and fp32 scores BIT-EXACT against the oracle's canonical ranking (CANON-32 fp64 scores,
+    (score desc, id asc)) -- for every scan variant, storage precision, query batch and shard count;
+  * against the faiss restatement: ids identical except exact ties and near-ties closer than the fp32
+    accumulation error, scores within 1e-5 relative (tolerance written below as RTOL);
+  * normalise / layout / generator kernels bit-exact against their oracle definitions, and within
+    1 ulp-level tolerance of torch's own ops.
+"""
+import ctypes
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import evo_ssearch_b200 as evs
+import oracle
+from oracle import faiss_io
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star: "scores within 1e-5 relative"
+NEG = np.float32(-np.finfo(np.float32).max)
+
+
+@pytest.fixture(autouse=True)
+def _reset_options():
+    yield
+    for name in ("scan_variant", "tile_rows", "stages", "ctas_per_sm"):
+        evs.set_option(name, 0)
+
+
+def _index(xb, storage="f32", variant=0):
+    evs.set_option("scan_variant", variant)
+    idx = evs.IndexFlatIP(xb.shape[1], storage=storage)
+    idx.add(xb)
+    return idx
+
+
+def _assert_canon(idx, xq, xb, k):
+    D, I = idx.search(xq, k)
+    Dr, Ir = oracle.canon_search(xq, xb, k)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (xq.shape[0], k)
+    assert np.array_equal(I, Ir), f"ids differ: {np.argwhere(I != Ir)[:5]}"
+    assert np.array_equal(D, Dr), "scores differ from the canonical fp32-rounded fp64 scores"
+    return D, I
+
+
+def _assert_faiss_near_tie_aware(D, I, xq, xb, k):
+    """ids equal to the faiss restatement except (near-)ties; scores within RTOL."""
+    Df, If = oracle.faiss_seq_search(xq, xb, k)
+    valid = If >= 0
+    assert np.array_equal(valid, I >= 0)
+    assert np.allclose(D[valid], Df[valid], rtol=RTOL, atol=1e-7)
+    eps = xb.shape[1] * 2.0 ** -24  # fp32 accumulation bound for unit-norm inputs
+    for q in range(xq.shape[0]):
+        for r in np.nonzero(I[q] != If[q])[0]:
+            a, b = I[q, r], If[q, r]
+            sa = oracle.dot_canon32(xb[a], xq[q])
+            sb = oracle.dot_canon32(xb[b], xq[q])
+            assert abs(sa - sb) <= eps, f"query {q} rank {r}: ids {a} vs {b} differ by {abs(sa - sb)}"
+
+
+# ------------------------------------------------------------------------------------------------
+def test_hand_cases(golden_dir):
+    with open(os.path.join(golden_dir, "hand_cases.json")) as f:
+        cases = json.load(f)
+    for variant in (1, 2):
+        for c in cases:
+            xb = np.array(c["xb"], np.float32)
+            xq = np.array(c["xq"], np.float32)
+            idx = _index(xb, variant=variant)
+            D, I = idx.search(xq, c["k"])
+            assert I.tolist() == c["canon_I"], (c["name"], variant)
+            assert np.array_equal(D, np.array(c["canon_D"], np.float32)), (c["name"], variant)
+
+
+def test_c1_golden_config(golden_dir):
+    """BASELINE config 1: 10k x 512, 1 query, k = 12, against the committed golden vectors."""
+    with open(os.path.join(golden_dir, "c1_10k_512.json")) as f:
+        g = json.load(f)
+    xb = oracle.synth_fill(g["n"], g["d"], g["seed_xb"])
+    xq = oracle.synth_fill(1, g["d"], g["seed_xq"])
+    for variant in (1, 2):
+        for storage in ("f32", "bf16"):
+            idx = _index(xb, storage, variant)
+            D, I = idx.search(xq, g["k"])
+            assert I.tolist() == g["canon_I"], (variant, storage)
+            assert [float(v).hex() for v in D[0]] == g["canon_D_f32_hex"], (variant, storage)
+            assert I.tolist() == g["faiss_I"]
+            Df = np.array([float.fromhex(h) for h in g["faiss_D_f32_hex"]], np.float32)
+            assert np.allclose(D[0], Df, rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+@pytest.mark.parametrize("d", [512, 768])
+def test_sweep_app_dims(variant, storage, d):
+    n = 20011  # not a multiple of any tile
+    xb = oracle.synth_fill(n, d, 100 + d)
+    xq = oracle.synth_fill(17, d, 200 + d)
+    idx = _index(xb, storage, variant)
+    for nq, k in ((1, 48), (2, 12), (3, 3), (4, 48), (5, 1), (16, 48), (17, 30)):
+        D, I = _assert_canon(idx, xq[:nq], xb, k)
+        if storage == "f32" and nq <= 4:
+            _assert_faiss_near_tie_aware(D, I, xq[:nq], xb, k)
+    m = idx.last_margins(17)
+    assert (m > (1e-5 if storage == "f32" else 1e-3)).all(), m.min()  # candidates cover the scan's error band
+
+
+@pytest.mark.parametrize("d", [1, 45, 100, 128, 256, 384, 1024])
+def test_other_dims(d):
+    rng = np.random.default_rng(d)
+    xb = rng.standard_normal((3001, d)).astype(np.float32)
+    xq = rng.standard_normal((5, d)).astype(np.float32)
+    for variant in (1, 2):
+        for storage in ("f32", "bf16") if d >= 128 else ("f32",):
+            idx = _index(xb, storage, variant)
+            _assert_canon(idx, xq, xb, 48)
+            _assert_canon(idx, xq[:1], xb, 100)
+
+
+def test_small_and_edge_sizes():
+    d = 512
+    xq = oracle.synth_fill(3, d, 7)
+    for n in (1, 2, 15, 16, 17, 47, 48, 49, 63, 64, 65, 129, 1000):
+        xb = oracle.synth_fill(n, d, 1000 + n)
+        for variant in (1, 2):
+            idx = _index(xb, "f32", variant)
+            for k in (1, 12, 48, 112):
+                D, I = _assert_canon(idx, xq, xb, k)
+                if k > n:
+                    assert (I[:, n:] == -1).all() and (D[:, n:] == NEG).all()
+
+
+def test_empty_index_and_argument_errors():
+    idx = evs.IndexFlatIP(512)
+    assert idx.ntotal == 0 and idx.is_trained and idx.d == 512
+    D, I = idx.search(np.zeros((2, 512), np.float32), 5)
+    assert (I == -1).all() and (D == NEG).all()  # faiss: all padding on an empty index
+    D0, I0 = idx.search(np.zeros((0, 512), np.float32), 5)
+    assert D0.shape == (0, 5) and I0.shape == (0, 5)
+    with pytest.raises(AssertionError):
+        idx.search(np.zeros((1, 256), np.float32), 5)  # faiss wrapper: assert d == self.d
+    with pytest.raises(AssertionError):
+        idx.search(np.zeros((1, 512), np.float32), 0)  # assert k > 0
+    with pytest.raises(AssertionError):
+        idx.add(np.zeros((3, 100), np.float32))
+    with pytest.raises(evs.EvsError) as e:
+        idx.search(np.zeros((1, 512), np.float32), 113)
+    assert e.value.code == -7  # EVS_ELIMIT
+    idx.add(np.zeros((0, 512), np.float32))
+    assert idx.ntotal == 0
+
+
+def test_exact_ties_and_duplicates():
+    d = 512
+    base = oracle.synth_fill(300, d, 5)
+    xb = np.concatenate([base, base[:100], base[50:150], base])  # every row occurs 2-3 times
+    xq = oracle.synth_fill(4, d, 6)
+    for variant in (1, 2):
+        for storage in ("f32", "bf16"):
+            idx = _index(xb, storage, variant)
+            for k in (1, 7, 48, 100):
+                _assert_canon(idx, xq, xb, k)
+    # all rows identical: canonical order is the k lowest ids
+    same = np.repeat(base[:1], 5000, axis=0)
+    D, I = _index(same).search(xq[:1], 48)
+    assert I[0].tolist() == list(range(48)) and (D[0] == D[0, 0]).all()
+
+
+def test_zero_and_nan_rows():
+    d = 512
+    xb = oracle.synth_fill(500, d, 8)
+    xb[3] = 0.0
+    xb[10] = np.nan  # what a normalised zero embedding looks like (oldapp.py:35 has no epsilon)
+    xq = oracle.synth_fill(1, d, 9)
+    D, I = _index(xb).search(xq, 48)
+    assert 10 not in I[0]  # a NaN score never enters (faiss: heap_top < NaN is false)
+    ok = np.ones(500, bool)
+    ok[10] = False
+    Dr, Ir = oracle.canon_search(xq, xb[ok], 48)
+    remap = np.nonzero(ok)[0]
+    assert np.array_equal(I[0], remap[Ir[0]]) and np.array_equal(D, Dr)
+
+
+def test_incremental_add_and_reconstruct():
+    d = 768
+    xb = oracle.synth_fill(5000, d, 31)
+    idx = evs.IndexFlatIP(d, storage="bf16")
+    for lo, hi in ((0, 1), (1, 1000), (1000, 1003), (1003, 5000)):  # forces regrowth copies
+        idx.add(xb[lo:hi])
+    assert idx.ntotal == 5000
+    assert np.array_equal(idx.reconstruct_n(0, 5000), xb)
+    assert np.array_equal(idx.reconstruct(1234), xb[1234])
+    _assert_canon(idx, oracle.synth_fill(2, d, 32), xb, 48)
+    idx.reset()
+    assert idx.ntotal == 0
+
+
+def test_fp16_query_view_like_the_app():
+    """oldapp.py:52/2005: on CUDA the query is an fp16 vector reshaped to (1, d); faiss casts to fp32."""
+    d = 512
+    xb = oracle.synth_fill(4000, d, 41)
+    q16 = oracle.synth_fill(1, d, 42).astype(np.float16).reshape(-1)
+    idx = _index(xb)
+    D, I = idx.search(q16.reshape(1, -1), 12)
+    Dr, Ir = oracle.canon_search(q16.astype(np.float32).reshape(1, -1), xb, 12)
+    assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
+
+
+def test_device_tensor_api_matches_host_api():
+    import torch
+    d = 512
+    xb = oracle.synth_fill(30000, d, 51)
+    xq = oracle.synth_fill(6, d, 52)
+    host = _index(xb)
+    dev = evs.IndexFlatIP(d)
+    dev.add(torch.from_numpy(xb).cuda())
+    Dh, Ih = host.search(xq, 48)
+    Dt, It = dev.search(torch.from_numpy(xq).cuda(), 48)
+    assert Dt.is_cuda and It.dtype == torch.int64
+    assert np.array_equal(Dt.cpu().numpy(), Dh) and np.array_equal(It.cpu().numpy(), Ih)
+    # half-precision encoder output is widened exactly (oldapp.py:86 astype('float32'))
+    xh = torch.from_numpy(xb[:1000]).cuda().half()
+    h = evs.IndexFlatIP(d)
+    h.add(xh)
+    assert np.array_equal(h.reconstruct_n(0, 1000), xh.float().cpu().numpy())
+
+
+def test_partials_and_merge_equal_single_index():
+    """Row sharding emulated on one GPU: G shards -> partials -> merge kernel == one index, bit for bit."""
+    import torch
+    d, n, k = 512, 9001, 48
+    xb = oracle.synth_fill(n, d, 61)
+    xb[n - 1] = xb[0]  # exact tie across shards
+    xq = oracle.synth_fill(5, d, 62)
+    single = _index(xb)
+    Ds, Is = single.search(xq, k)
+    xq_t = torch.from_numpy(xq).cuda()
+    for G in (1, 2, 3, 8):
+        S, I = [], []
+        for g in range(G):
+            lo, hi = evs.shard_bounds(n, G, g)
+            sh = evs.IndexFlatIP(d)
+            sh.id_base = lo
+            sh.add(xb[lo:hi])
+            s, i = sh.search_partial(xq_t, k)
+            S.append(s)
+            I.append(i)
+        D, Ifin = evs.merge_partials(torch.stack(S), torch.stack(I), k)
+        assert np.array_equal(Ifin.cpu().numpy(), Is) and np.array_equal(D.cpu().numpy(), Ds), G
+    # shards with fewer than k rows, and empty shards (more ranks than rows)
+    tiny = xb[:5]
+    Dt, It = _index(tiny).search(xq, 12)
+    S, I = [], []
+    for g in range(8):
+        lo, hi = evs.shard_bounds(5, 8, g)
+        sh = evs.IndexFlatIP(d)
+        sh.id_base = lo
+        if hi > lo:
+            sh.add(tiny[lo:hi])
+        s, i = sh.search_partial(xq_t, 12)
+        S.append(s)
+        I.append(i)
+    D, Ifin = evs.merge_partials(torch.stack(S), torch.stack(I), 12)
+    assert np.array_equal(Ifin.cpu().numpy(), It) and np.array_equal(D.cpu().numpy(), Dt)
+
+
+def test_concurrent_search_threads():
+    """The Flask dev server is threaded (oldapp.py:2258): concurrent searches on one handle."""
+    d = 512
+    xb = oracle.synth_fill(50000, d, 71)
+    idx = _index(xb)
+    qs = [oracle.synth_fill(1, d, 100 + t) for t in range(8)]
+    want = [oracle.canon_search(q, xb, 48) for q in qs]
+    errs = []
+
+    def work(t):
+        for _ in range(20):
+            D, I = idx.search(qs[t], 48)
+            if not (np.array_equal(I, want[t][1]) and np.array_equal(D, want[t][0])):
+                errs.append(t)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels (1) of north_star: normalise and the bf16 layout kernel; the synthetic generator
+# ------------------------------------------------------------------------------------------------
+def test_normalize_bitexact_vs_oracle_and_close_to_torch():
+    import torch
+    rng = np.random.default_rng(81)
+    for d in (512, 768, 45, 1):
+        x = (rng.standard_normal((1000, d)) * rng.uniform(0.01, 50.0, (1000, 1))).astype(np.float32)
+        want = oracle.l2_normalize(x)
+        got = x.copy()
+        evs.normalize_L2(got)  # host entry point (faiss.normalize_L2 signature)
+        assert np.array_equal(got, want), d
+        t = torch.from_numpy(x).cuda()
+        ref = t / t.norm(dim=-1, keepdim=True)  # the reference's expression (oldapp.py:35)
+        evs.normalize_L2(t)
+        assert np.array_equal(t.cpu().numpy(), want)
+        assert torch.allclose(t, ref, rtol=3e-7, atol=0)  # fp32: within 2 ulp of torch's own reduction order
+    # encoder dtypes on CUDA (clip.load gives fp16): same expression evaluated in that dtype
+    for dt, tol in ((torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)):
+        t = torch.from_numpy(rng.standard_normal((257, 512)).astype(np.float32)).cuda().to(dt)
+        ref = t / t.norm(dim=-1, keepdim=True)
+        evs.normalize_L2(t)
+        assert torch.allclose(t.float(), ref.float(), rtol=tol, atol=tol * 1e-2)
+        assert torch.allclose(t.float().norm(dim=-1), torch.ones(257, device="cuda"), atol=tol)
+    z = np.zeros((2, 8), np.float32)
+    evs.normalize_L2(z)
+    assert np.isnan(z).all()  # no epsilon
+
+
+def test_bf16_layout_kernel_is_rne():
+    import torch
+    from evo_ssearch_b200 import _lib
+    rng = np.random.default_rng(82)
+    for count in (8 * 1000, 8 * 1000 + 5, 3):
+        x = torch.from_numpy(rng.standard_normal(count).astype(np.float32)).cuda()
+        out = torch.empty(count, dtype=torch.bfloat16, device="cuda")
+        _lib.check(_lib.lib().evs_f32_to_bf16_dev(0, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                  count, None))
+        torch.cuda.synchronize()
+        assert torch.equal(out, x.to(torch.bfloat16))
+
+
+def test_synthetic_generator_bitexact():
+    for d, n in ((512, 3000), (768, 100), (45, 77)):
+        idx = evs.IndexFlatIP(d)
+        idx.id_base = 12345
+        idx.add_synthetic(n, seed=3)
+        assert np.array_equal(idx.reconstruct_n(0, n), oracle.synth_fill(n, d, 3, row_base=12345))
+        idx.add_synthetic(10, seed=3, normalize=False)  # continues the global row counter
+        assert np.array_equal(idx.reconstruct_n(n, 10), oracle.synth_fill(10, d, 3, row_base=12345 + n, normalize=False))
+
+
+# ------------------------------------------------------------------------------------------------
+# .clip_index/index.faiss
+# ------------------------------------------------------------------------------------------------
+def test_index_file_bytes_and_roundtrip(golden_dir, tmp_path):
+    fixture = os.path.join(golden_dir, "index_flat_3x4.faiss")
+    idx = evs.read_index(fixture)
+    assert (idx.d, idx.ntotal) == (4, 3)
+    out = tmp_path / "index.faiss"
+    evs.write_index(idx, str(out))
+    assert out.read_bytes() == open(fixture, "rb").read()  # byte-exact
+    xb = oracle.synth_fill(70001, 512, 91)  # payload larger than one 64 MiB staging chunk
+    a = _index(xb)
+    evs.write_index(a, str(out))
+    assert out.stat().st_size == 45 + 4 * xb.size
+    assert out.read_bytes() == faiss_io.pack_index_flat(xb)
+    b = evs.read_index(str(out), storage="bf16")
+    assert b.ntotal == 70001 and np.array_equal(b.reconstruct_n(0, 10), xb[:10])
+    xq = oracle.synth_fill(2, 512, 92)
+    _assert_canon(b, xq, xb, 48)
+    with pytest.raises(evs.EvsError):
+        evs.read_index(str(tmp_path / "nope.faiss"))
+
+
+# ------------------------------------------------------------------------------------------------
+# full BASELINE sizes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_config2_1m_x_512_exact(storage):
+    """BASELINE config 2: 1M x 512, k = 48, query batches 1 and 16 -- bit-exact against the oracle."""
+    n, d, k = 1_000_000, 512, 48
+    idx = evs.IndexFlatIP(d, storage=storage)
+    idx.add_synthetic(n, seed=0)
+    xb = oracle.synth_fill(n, d, 0)
+    assert np.array_equal(idx.reconstruct_n(n - 1000, 1000), xb[-1000:])
+    xq = oracle.synth_fill(16, d, 1)
+    for variant in (1, 2):
+        evs.set_option("scan_variant", variant)
+        D1, I1 = _assert_canon(idx, xq[:1], xb, k)
+        D16, I16 = _assert_canon(idx, xq, xb, k)
+        assert np.array_equal(I16[0], I1[0])  # batch-size invariance
+    if storage == "f32":
+        _assert_faiss_near_tie_aware(D16, I16, xq, xb, k)
+        assert (idx.last_margins(16) > 1e-5).all()
+
+
+def test_metric_size_10m_x_512_properties():
+    """10M x 512 (the metric's size): planted neighbours must come back exactly, in order, and the
+    result must not depend on scan variant, storage precision or sharding."""
+    import torch
+    n_blocks, block, d, k = 10, 1_000_000, 512, 48
+    q = oracle.synth_fill(1, d, 1)
+    # 48 planted rows r_j = a_j q + sqrt(1 - a_j^2) u_j (u_j orthogonal to q): score ~ a_j >> any random score
+    rng = np.random.default_rng(7)
+    u = rng.standard_normal((k, d))
+    u -= (u @ q[0].astype(np.float64))[:, None] * q[0]
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    a = 0.95 - 0.01 * np.arange(k)
+    planted = (a[:, None] * q[0] + np.sqrt(1 - a[:, None] ** 2) * u).astype(np.float32)
+    results = {}
+    for storage in ("f32", "bf16"):
+        idx = evs.IndexFlatIP(d, storage=storage)
+        idx.reserve(n_blocks * block + k)
+        want_ids = []
+        for b in range(n_blocks):
+            idx.add_synthetic(block, seed=0)
+            sl = slice(b * 5, min(k, b * 5 + 5))
+            if planted[sl].shape[0]:
+                want_ids += list(range(idx.ntotal, idx.ntotal + planted[sl].shape[0]))
+                idx.add(planted[sl])
+        assert idx.ntotal == n_blocks * block + k
+        for variant in (1, 2):
+            evs.set_option("scan_variant", variant)
+            D, I = idx.search(q, k)
+            assert I[0].tolist() == want_ids
+            want_scores = np.array([oracle.dot_canon32(planted[j], q[0]) for j in range(k)]).astype(np.float32)
+            assert np.array_equal(D[0], want_scores)
+            results[(storage, variant)] = (D, I)
+        # below the planted rows: top-96 minus the planted = true top-48 of the random rows; check invariance
+        D2, I2 = idx.search(q, 96)
+        results[(storage, "k96")] = (D2, I2)
+        assert (np.diff(D2[0].astype(np.float64)) <= 0).all()
+        if storage == "f32":
+            # sharded: 4 shards on this one GPU -> partials -> merge == unsharded
+            xq_t = torch.from_numpy(q).cuda()
+            rows = idx.ntotal
+            S, Is = [], []
+            for g in range(4):
+                lo, hi = evs.shard_bounds(rows, 4, g)
+                sh = evs.IndexFlatIP(d)
+                sh.id_base = lo
+                t = torch.empty((hi - lo, d), dtype=torch.float32, device="cuda")
+                for c0 in range(lo, hi, 500_000):
+                    c1 = min(hi, c0 + 500_000)
+                    t[c0 - lo:c1 - lo] = torch.from_numpy(idx.reconstruct_n(c0, c1 - c0)).cuda()
+                sh.add(t)
+                del t
+                s, i = sh.search_partial(xq_t, 96)
+                S.append(s)
+                Is.append(i)
+                del sh
+            Dm, Im = evs.merge_partials(torch.stack(S), torch.stack(Is), 96)
+            assert np.array_equal(Im.cpu().numpy(), I2) and np.array_equal(Dm.cpu().numpy(), D2)
+        del idx
+    assert np.array_equal(results[("f32", "k96")][1], results[("bf16", "k96")][1])
+    assert np.array_equal(results[("f32", "k96")][0], results[("bf16", "k96")][0])

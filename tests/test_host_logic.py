@@ -1,0 +1,78 @@
+"""CPU: host-side logic that needs no device -- shard layout, limit clamp, handler post-processing,
+load_index failure contract, pickle compatibility of the .clip_index side files."""
+import os
+import pickle
+
+import numpy as np
+
+import evo_ssearch_b200 as evs
+from evo_ssearch_b200 import lifecycle
+
+
+def test_shard_bounds_cover_and_partition():
+    for n in (0, 1, 7, 8, 9, 1000, 10_000_000):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [evs.shard_bounds(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            for (lo, hi), (lo2, _) in zip(blocks, blocks[1:]):
+                assert lo <= hi == lo2
+            per = -(-n // world) if n else 0
+            assert all(hi - lo <= per for lo, hi in blocks)
+    assert evs.shard_bounds(10, 4, 3) == (9, 10)
+    assert evs.shard_bounds(3, 8, 5) == (3, 3)  # more ranks than rows: empty shards
+
+
+def test_clamp_limit_matches_reference_rule():
+    # oldapp.py:1985-1990: int in [MIN_RESULTS, MAX_RESULTS] else DEFAULT_RESULTS
+    assert evs.clamp_limit(12) == 12 and evs.clamp_limit("24") == 24
+    assert evs.clamp_limit(3) == 3 and evs.clamp_limit(48) == 48
+    assert evs.clamp_limit(2) == 12 and evs.clamp_limit(49) == 12
+    assert evs.clamp_limit(None) == 12 and evs.clamp_limit("abc") == 12
+
+
+class _FakeIndex:
+    def __init__(self, D, I):
+        self.D, self.I, self.calls = D, I, []
+
+    def search(self, x, k):
+        self.calls.append((x.shape, k))
+        return self.D[:, :k], self.I[:, :k]
+
+
+def test_collect_filters_and_sorts_like_the_handlers():
+    paths = [f"/p/{i}.jpg" for i in range(4)]
+    meta = [{"path": p, "mtime": float(m), "size": 10 + i} for i, (p, m) in enumerate(zip(paths, (5, 9, 1, 7)))]
+    D = np.array([[0.9, 0.8, 0.7, -3.4e38, 0.1]], np.float32)
+    I = np.array([[2, 0, 3, -1, 99]], np.int64)  # -1 padding and an out-of-range id are dropped (oldapp.py:2009)
+    idx = _FakeIndex(D, I)
+    res = lifecycle._collect(idx, paths, meta, np.zeros(8, np.float32), 48, "similarity")
+    assert idx.calls == [((1, 8), 4)]  # k = min(limit, len(paths)) (oldapp.py:2002), query reshaped to (1, d)
+    assert [r["path"] for r in res] == ["/p/2.jpg", "/p/0.jpg", "/p/3.jpg"]
+    assert res[0]["filename"] == "2.jpg" and abs(res[0]["similarity"] - 0.9) < 1e-6
+    assert res[0]["metadata"] == {"mtime": 1.0, "size": 12}
+    res_t = lifecycle._collect(_FakeIndex(D, I), paths, meta, np.zeros(8, np.float32), 48, "time")
+    assert [r["path"] for r in res_t] == ["/p/3.jpg", "/p/0.jpg", "/p/2.jpg"]  # mtime desc (oldapp.py:2043-2045)
+    assert lifecycle._collect(_FakeIndex(D, I), [], None, np.zeros(8, np.float32), 12, "similarity") == []
+
+
+def test_load_index_failure_contract(tmp_path):
+    assert evs.load_index(tmp_path) == (None, None, None)  # no .clip_index
+    ci = tmp_path / ".clip_index"
+    ci.mkdir()
+    assert evs.load_index(tmp_path) == (None, None, None)  # no index.faiss
+    (ci / "index.faiss").write_bytes(b"garbage")
+    with open(ci / "paths.pkl", "wb") as f:
+        pickle.dump(["a.jpg"], f)
+    assert evs.load_index(tmp_path) == (None, None, None)  # corrupt file is "not indexed" (oldapp.py:134-135)
+
+
+def test_side_files_are_plain_pickles(tmp_path):
+    paths = ["/x/a.jpg", "/x/b.png"]
+    meta = [{"path": p, "mtime": 1.5, "size": 3} for p in paths]
+    with open(tmp_path / "paths.pkl", "wb") as f:
+        pickle.dump(paths, f)
+    with open(tmp_path / "metadata.pkl", "wb") as f:
+        pickle.dump(meta, f)
+    assert pickle.load(open(tmp_path / "paths.pkl", "rb")) == paths
+    assert pickle.load(open(tmp_path / "metadata.pkl", "rb"))[1]["size"] == 3
+    assert evs.config.INDEX_FOLDER_NAME == os.getenv("EVOSSEARCH_INDEX_FOLDER", ".clip_index")
