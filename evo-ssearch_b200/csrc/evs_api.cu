@@ -319,7 +319,7 @@ extern "C" int evs_index_add_dev(evs_index* idx, int64_t n, const void* x_dev, i
     if (rc) return rc;
     if ((rc = grow_for_add_locked(idx, n))) return rc;
     // the producer of x_dev ran on `stream`: order our stream after it
-    if (stream && (cudaStream_t)stream != idx->stream) {
+    if ((cudaStream_t)stream != idx->stream) {
         cudaEvent_t ev;
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU(cudaEventRecord(ev, (cudaStream_t)stream));
@@ -495,7 +495,7 @@ extern "C" int evs_index_search_dev(evs_index* idx, int64_t nq, const float* q_d
     SearchOut out;
     out.D = D_dev;
     out.I = I_dev;
-    return search_dev_common(idx, nq, q_dev, k, out, stream ? (cudaStream_t)stream : idx->stream);
+    return search_dev_common(idx, nq, q_dev, k, out, (cudaStream_t)stream);
 }
 
 extern "C" int evs_index_search_partial_dev(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, double* out_scores_dev,
@@ -507,7 +507,7 @@ extern "C" int evs_index_search_partial_dev(evs_index* idx, int64_t nq, const fl
     SearchOut out;
     out.P_scores = out_scores_dev;
     out.P_ids = out_ids_dev;
-    return search_dev_common(idx, nq, q_dev, k, out, stream ? (cudaStream_t)stream : idx->stream);
+    return search_dev_common(idx, nq, q_dev, k, out, (cudaStream_t)stream);
 }
 
 extern "C" int evs_merge_partials_dev(int device, int nparts, int64_t nq, int64_t k, const double* scores_dev,

@@ -523,7 +523,9 @@ cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int 
     plan->threads = 256;
     plan->tile_rows = plan->stages = 0;
     plan->smem_bytes = (size_t)(plan->threads / 32) * nq_pass * 2 * kp * 8;
-    int per_sm = tune.ctas_per_sm > 0 ? tune.ctas_per_sm : 2;
+    // measured on B200 at 10M x 512 (profiles/r01_tune_scan_*): fp32 rows peak at 2 CTAs/SM, bf16 rows
+    // (half the bytes in flight per row) need 4
+    int per_sm = tune.ctas_per_sm > 0 ? tune.ctas_per_sm : (is_bf16 ? 4 : 2);
     long long groups = (n + 3) / 4;
     plan->grid = clamp_grid((groups + 7) / 8, sm_count * per_sm);
     return cudaSuccess;

@@ -11,7 +11,8 @@
  *     exits.  evs_last_error() returns a thread-local message for the last failure on this thread.
  *   - plain pointers and sizes only.  "host" pointers are ordinary process memory owned by the
  *     caller; "dev" pointers are CUDA device pointers on the index's device (e.g. torch tensors'
- *     data_ptr()); `stream` is a cudaStream_t passed as void* (NULL = the index's own stream).
+ *     data_ptr()); `stream` is a cudaStream_t passed as void*, used as CUDA itself would use it
+ *     (NULL = the legacy default stream, which is what torch's default stream is).
  *   - the index handle owns all device memory it allocates; the caller owns every buffer it passes.
  *     add() copies, so the caller may free its array immediately (oldapp.py:86-88 does).
  *   - search on one handle may be entered from several threads (the Flask dev server is threaded,

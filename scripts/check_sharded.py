@@ -1,0 +1,45 @@
+"""torchrun --nproc-per-node G scripts/check_sharded.py : row-sharded search over G GPUs (NCCL all-gather +
+merge kernel) must equal the CPU oracle's canonical ranking bit for bit, for f32 and bf16 storage."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import evo_ssearch_b200 as evs  # noqa: E402
+import oracle  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for n, d, k, nqs in ((1_000_003, 512, 48, (1, 16)), (200_001, 768, 12, (1, 5)), (5, 512, 12, (3,))):
+    xb = oracle.synth_fill(n, d, 0)
+    if n > 10:
+        xb[n - 1] = xb[0]  # exact tie across the first and last shard
+    xq = oracle.synth_fill(max(nqs), d, 1)
+    for storage in ("f32", "bf16"):
+        sh = evs.ShardedIndexFlatIP(d, device=local, storage=storage)
+        sh.add(xb)
+        for nq in nqs:
+            D, I = sh.search(xq[:nq], k)
+            Dr, Ir = oracle.canon_search(xq[:nq], xb, k)
+            good = bool(np.array_equal(I, Ir) and np.array_equal(D, Dr))
+            ok = ok and good
+            if rank == 0:
+                print(f"n={n} d={d} k={k} nq={nq} storage={storage} world={world}: {'OK' if good else 'MISMATCH'}", flush=True)
+        # generated-in-place shards equal host-fed shards
+        sh2 = evs.ShardedIndexFlatIP(d, device=local, storage=storage)
+        sh2.add_synthetic(n, seed=0)
+        lo, hi = evs.shard_bounds(n, world, rank)
+        if hi > lo:
+            ref = oracle.synth_fill(n, d, 0)
+            ok = ok and bool(np.array_equal(sh2.local.reconstruct_n(0, hi - lo), ref[lo:hi]))
+t = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+if rank == 0:
+    print("SHARDED_PARITY_OK" if int(t.item()) == 1 else "SHARDED_PARITY_FAILED", flush=True)
+sys.exit(0 if int(t.item()) == 1 else 1)
