@@ -50,6 +50,8 @@ SIGNATURES = {
     "evs_kernel_launches": (_i64, []),
     "evs_index_time_scan": (_i, [_vp, _i64, _vp, _i64, _i, _pf]),
     "evs_index_scan_profile": (_i, [_vp, _pi64, _c.POINTER(_c.c_double)]),
+    "evs_index_tc_max_queries": (_i, [_vp, _pi]),
+    "evs_index_tc_scores_dev": (_i, [_vp, _i64, _vp, _vp, _pi, _vp]),
 }
 
 _lib = None

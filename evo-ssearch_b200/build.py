@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libevs.so")
-SOURCES = ["evs_kernels.cu", "evs_api.cu"]
+SOURCES = ["evs_kernels.cu", "evs_api.cu", "evs_tc.cu"]
 HEADERS = ["evs_common.cuh", "evs_scan.cuh", "evs_internal.h", os.path.join("..", "..", "include", "evs.h")]
 
 NVCC_FLAGS = [

@@ -64,6 +64,9 @@ struct evs_index {
     void* lists = nullptr;   size_t lists_cap = 0;     // candidate lists
     float* D_dev = nullptr;  int64_t* I_dev = nullptr; size_t out_cap = 0;  // [chunk][k]
     float* margins_dev = nullptr; size_t margins_cap = 0;   // [nq of last search]
+    unsigned char* tc_ws = nullptr; size_t tc_ws_cap = 0;   // tensor-core scan workspace
+    int* tc_overflow = nullptr; size_t tc_overflow_cap = 0; // [nq] overflow flags of the tensor-core scan
+    int* tc_overflow_pin = nullptr; size_t tc_overflow_pin_cap = 0;
     int64_t last_nq = 0;
     // optional per-search timing of the scan stage (option "profile_scans")
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -139,6 +142,9 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "ctas_per_sm")) {
         if (value < 0 || value > 8) return fail(EVS_EINVAL, "ctas_per_sm out of range");
         g_tune.ctas_per_sm = (int)value;
+    } else if (!strcmp(name, "tc_min_nq")) {
+        if (value < 0) return fail(EVS_EINVAL, "tc_min_nq must be >= 0");
+        g_tune.tc_min_nq = (int)value;
     } else if (!strcmp(name, "profile_scans")) {
         g_profile_scans = value ? 1 : 0;
     } else {
@@ -154,6 +160,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tile_rows")) *value = g_tune.tile_rows;
     else if (!strcmp(name, "stages")) *value = g_tune.stages;
     else if (!strcmp(name, "ctas_per_sm")) *value = g_tune.ctas_per_sm;
+    else if (!strcmp(name, "tc_min_nq")) *value = g_tune.tc_min_nq;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
     else return fail(EVS_EINVAL, "unknown option '%s'", name);
     return EVS_OK;
@@ -203,6 +210,9 @@ extern "C" int evs_index_free(evs_index* idx) {
     cudaFree(idx->D_dev);
     cudaFree(idx->I_dev);
     cudaFree(idx->margins_dev);
+    cudaFree(idx->tc_ws);
+    cudaFree(idx->tc_overflow);
+    cudaFreeHost(idx->tc_overflow_pin);
     cudaFreeHost(idx->q_pin);
     cudaFreeHost(idx->D_pin);
     cudaFreeHost(idx->I_pin);
@@ -371,8 +381,101 @@ struct SearchOut {
 
 // Enqueue the search of `nq` device-resident queries on stream `st`; outputs are device pointers.
 // idx->mu is held by the caller.
+template <typename T>
+static int ensure_pinned(T** ptr, size_t* cap, size_t need_elems);
+
 static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out,
-                                 cudaStream_t st, bool scan_only = false) {
+                                 cudaStream_t st, bool scan_only = false, bool allow_tc = true);
+
+// Tensor-core path for a batch: one database pass per block of up to tc_max_queries queries.
+// Queries whose candidate buffers overflowed are re-run through the GEMV path (needs one host sync).
+static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st,
+                            bool scan_only, int profile) {
+    const int kp = pick_kp(k);
+    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
+    const void* scan_rows = bf16 ? idx->xb16 : (const void*)idx->xb32;
+    const int nb_max = tc_max_queries(idx->d, bf16);
+    TcPlan pl;
+    CU(tc_plan(idx->ntotal, idx->d, bf16, (int)(nq < nb_max ? nq : nb_max), kp, idx->sm_count, &pl));
+    int rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc_workspace_bytes(pl));
+    if (rc) return rc;
+    if ((rc = ensure_dev(&idx->tc_overflow, &idx->tc_overflow_cap, (size_t)nq))) return rc;
+    const int64_t chunk_cap = nq < kQueryChunk ? nq : kQueryChunk;
+    if ((rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, (size_t)chunk_cap * kp))) return rc;
+    if ((rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
+    idx->last_nq = nq;
+    for (int64_t c0 = 0; c0 < nq; c0 += kQueryChunk) {
+        const int64_t cn = (nq - c0) < kQueryChunk ? (nq - c0) : kQueryChunk;
+        std::pair<cudaEvent_t, cudaEvent_t>* pe = nullptr;
+        if (profile && idx->prof_used < 65536) {
+            if (idx->prof_used == idx->prof_events.size()) {
+                cudaEvent_t a = nullptr, b = nullptr;
+                CU(cudaEventCreate(&a));
+                CU(cudaEventCreate(&b));
+                idx->prof_events.emplace_back(a, b);
+            }
+            pe = &idx->prof_events[idx->prof_used++];
+            CU(cudaEventRecord(pe->first, st));
+        }
+        for (int64_t b0 = 0; b0 < cn; b0 += nb_max) {
+            const int nb = (int)((cn - b0) < nb_max ? (cn - b0) : nb_max);
+            TcPlan plb;
+            CU(tc_plan(idx->ntotal, idx->d, bf16, nb, kp, idx->sm_count, &plb));
+            TcArgs a;
+            a.xb = scan_rows;
+            a.is_bf16 = bf16;
+            a.n = idx->ntotal;
+            a.d = idx->d;
+            a.xq = q_dev + (size_t)(c0 + b0) * idx->d;
+            a.nq = nb;
+            a.lists = reinterpret_cast<unsigned long long*>(idx->lists) + (size_t)b0 * kp;
+            a.overflow_out = idx->tc_overflow + c0 + b0;
+            CU(tc_scan_block(a, plb, idx->tc_ws, st));
+        }
+        if (pe) CU(cudaEventRecord(pe->second, st));
+        if (scan_only) continue;
+        FinalizeArgs f;
+        f.lists = idx->lists;
+        f.L = 1;
+        f.kp = kp;
+        f.xb = idx->xb32;
+        f.xb_is_bf16 = 0;
+        f.xq = q_dev + (size_t)c0 * idx->d;
+        f.nq = cn;
+        f.d = idx->d;
+        f.k = (int)k;
+        f.id_base = idx->id_base;
+        f.D = out.D ? out.D + (size_t)c0 * k : nullptr;
+        f.I = out.I ? out.I + (size_t)c0 * k : nullptr;
+        f.P_scores = out.P_scores ? out.P_scores + (size_t)c0 * k : nullptr;
+        f.P_ids = out.P_ids ? out.P_ids + (size_t)c0 * k : nullptr;
+        f.margins = idx->margins_dev + c0;
+        CU(launch_finalize(f, st));
+    }
+    if (scan_only) return EVS_OK;
+    // exactness guard: re-run overflowed queries with the GEMV scan
+    if ((rc = ensure_pinned(&idx->tc_overflow_pin, &idx->tc_overflow_pin_cap, (size_t)nq))) return rc;
+    CU(cudaMemcpyAsync(idx->tc_overflow_pin, idx->tc_overflow, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int64_t q = 0; q < nq; q++) {
+        if (!idx->tc_overflow_pin[q]) continue;
+        SearchOut o1;
+        o1.D = out.D ? out.D + (size_t)q * k : nullptr;
+        o1.I = out.I ? out.I + (size_t)q * k : nullptr;
+        o1.P_scores = out.P_scores ? out.P_scores + (size_t)q * k : nullptr;
+        o1.P_ids = out.P_ids ? out.P_ids + (size_t)q * k : nullptr;
+        float* keep = idx->margins_dev;
+        idx->margins_dev = keep + q;  // the re-run writes this query's margin in place
+        rc = search_enqueue_locked(idx, 1, q_dev + (size_t)q * idx->d, k, o1, st, false, false);
+        idx->margins_dev = keep;
+        idx->last_nq = nq;
+        if (rc) return rc;
+    }
+    return EVS_OK;
+}
+
+static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out,
+                                 cudaStream_t st, bool scan_only, bool allow_tc) {
     const int kp = pick_kp(k);
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
     const void* scan_rows = bf16 ? idx->xb16 : (const void*)idx->xb32;
@@ -383,13 +486,15 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
         tune = g_tune;
         profile = g_profile_scans && !scan_only;
     }
+    if (allow_tc && tune.tc_min_nq > 0 && nq >= tune.tc_min_nq && idx->ntotal >= 65536 && tc_max_queries(idx->d, bf16) > 0)
+        return search_tc_locked(idx, nq, q_dev, k, out, st, scan_only, profile);
     const int qpp = max_queries_per_pass(idx->d, bf16);
     ScanPlan plan;
     CU(plan_scan(idx->ntotal, idx->d, bf16, kp, qpp, idx->sm_count, tune, &plan));
     const int64_t chunk_cap = nq < kQueryChunk ? nq : kQueryChunk;
     int rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, (size_t)chunk_cap * plan.grid * kp);
     if (rc) return rc;
-    if ((rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
+    if (allow_tc && (rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
     idx->last_nq = nq;
 
     for (int64_t c0 = 0; c0 < nq; c0 += kQueryChunk) {
@@ -639,6 +744,42 @@ extern "C" int evs_index_scan_profile(evs_index* idx, int64_t* count, double* to
     *count = (int64_t)idx->prof_used;
     *total_ms = sum;
     idx->prof_used = 0;
+    return EVS_OK;
+}
+
+extern "C" int evs_index_tc_max_queries(const evs_index* idx, int* max_queries) {
+    if (!idx || !max_queries) return fail(EVS_EINVAL, "NULL argument");
+    *max_queries = tc_max_queries(idx->d, idx->storage == EVS_STORE_BF16_F32);
+    return EVS_OK;
+}
+
+extern "C" int evs_index_tc_scores_dev(evs_index* idx, int64_t nq, const float* q_dev, float* out_dev, int* npad, void* stream) {
+    if (!idx || !q_dev || !out_dev || !npad) return fail(EVS_EINVAL, "NULL argument");
+    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
+    const int nb_max = tc_max_queries(idx->d, bf16);
+    if (nb_max == 0) return fail(EVS_ELIMIT, "d = %d is not supported by the tensor-core scan", idx->d);
+    if (nq <= 0 || nq > nb_max) return fail(EVS_EINVAL, "nq must be in [1, %d]", nb_max);
+    if (idx->ntotal == 0) return fail(EVS_EINVAL, "empty index");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    TcPlan pl;
+    CU(tc_plan(idx->ntotal, idx->d, bf16, (int)nq, 64, idx->sm_count, &pl));
+    if ((rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc_workspace_bytes(pl)))) return rc;
+    TcArgs a;
+    a.xb = bf16 ? idx->xb16 : (const void*)idx->xb32;
+    a.is_bf16 = bf16;
+    a.n = idx->ntotal;
+    a.d = idx->d;
+    a.xq = q_dev;
+    a.nq = (int)nq;
+    a.lists = nullptr;
+    a.overflow_out = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+    CU(tc_dump_scores(a, pl, idx->tc_ws, out_dev, st));
+    CU(cudaEventRecord(idx->ws_free, st));
+    *npad = pl.npad;
     return EVS_OK;
 }
 

@@ -15,7 +15,8 @@ struct ScanTuning {
     int scan_variant = 0;  // 0 auto, 1 direct loads, 2 bulk-async ring
     int tile_rows = 0;     // ring: rows per stage (0 = ~32 KiB)
     int stages = 0;        // ring: depth (0 = 4)
-    int ctas_per_sm = 0;   // direct: CTAs per SM (0 = 2)
+    int ctas_per_sm = 0;   // direct: CTAs per SM (0 = 2 fp32 / 4 bf16)
+    int tc_min_nq = 4;     // query batches of at least this many use the tensor-core scan (0 = never)
 };
 
 struct ScanPlan {
@@ -53,6 +54,29 @@ struct FinalizeArgs {
     int64_t* P_ids;
     float* margins;
 };
+
+// tensor-core scan (evs_tc.cu)
+struct TcPlan {
+    int npad, nk, stages, grid, pre_grid, groups, gpow2, cap, cap_total, kp;
+    size_t smem;
+    long long ntiles, pre_tiles, pre_stride;
+    size_t off_gmax, off_tau0, off_counts, off_overflow, off_cand, off_qbf16, off_end;
+};
+struct TcArgs {
+    const void* xb;   // database rows (fp32 or bf16)
+    int is_bf16;
+    long long n;
+    int d;
+    const float* xq;  // this block's queries, fp32 [nq][d]
+    int nq;
+    void* lists;      // out: u64 [nq][kp]
+    int* overflow_out;  // out (optional): int [nq]
+};
+int tc_max_queries(int d, int is_bf16);
+cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, TcPlan* pl);
+size_t tc_workspace_bytes(const TcPlan& pl);
+cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, cudaStream_t st);
+cudaError_t tc_dump_scores(const TcArgs& a, const TcPlan& pl, unsigned char* ws, float* out, cudaStream_t st);
 
 cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int sm_count, const ScanTuning& tune,
                       ScanPlan* plan);

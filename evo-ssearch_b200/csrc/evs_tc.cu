@@ -1,0 +1,595 @@
+// evs_tc.cu -- tensor-core scan for query batches: tcgen05.mma + TMEM accumulators + TMA-staged tiles.
+//
+// Same job as evs_scan.cuh (the inner loop of index.search(), /root/reference/oldapp.py:2005, :2112)
+// for batches of more than a few queries, where scoring really is a dense contraction
+//     S[row][query] = sum_i xb[row][i] * xq[query][i]
+// One database pass serves up to NQ_MAX queries (instead of 4 with the CUDA-core GEMV):
+//   A operand = database tile, M = 128 rows x 128-byte K chunks, streamed from HBM by TMA
+//               (cp.async.bulk.tensor.2d, 128B swizzle) through a shared-memory ring;
+//   B operand = the query block, N = 16..128 queries, loaded once and kept resident in shared memory;
+//   D         = 128 rows (TMEM lanes) x N queries (TMEM columns) fp32, double-buffered in TMEM so the
+//               MMA of tile i+1 overlaps the epilogue of tile i.
+// bf16 rows use kind::f16 (bf16 x bf16 -> fp32); fp32 rows use kind::tf32 directly on the fp32 bits.
+// Scan precision only has to find the k' candidates: the final ranking is the canonical fp64
+// re-score, so results are identical to the other scan paths.
+//
+// Warp roles (256 threads, 1 CTA per SM, persistent over row tiles dealt round-robin):
+//   warp 0  TMA producer (one lane)      warp 1  MMA issuer (one lane)      warp 2  TMEM alloc/dealloc
+//   warps 4-7  epilogue: warp e owns TMEM lanes 32e..32e+31 = rows 32e..32e+31 of the tile.
+// Epilogue modes:
+//   MODE_MAX     per (32-row group, query) maximum -> gmax      (threshold pre-pass over sampled tiles)
+//   MODE_SELECT  every score >= tau0[query] is appended to the (CTA, query) candidate buffer
+//   MODE_DUMP    raw scores to global memory (tests)
+// tau0[query] = k'-th largest group maximum of the pre-pass: at least k' distinct rows score >= tau0,
+// so it is a valid lower bound of the k'-th best score and the SELECT pass keeps a superset of the
+// top k'.  A (CTA, query) buffer that overflows raises overflow[query]; the host re-runs those queries
+// through the GEMV path (exactness never depends on the data).
+#include <cuda.h>
+#include <float.h>
+
+#include "evs_internal.h"
+#include "evs_common.cuh"
+
+namespace evs {
+
+enum { MODE_MAX = 0, MODE_SELECT = 1, MODE_DUMP = 2 };
+
+struct TcParams {
+    long long n;          // rows in the shard
+    int d;                // dimension
+    int nq;               // valid queries in this block (<= npad)
+    int npad;             // N of the MMA: nq rounded up to 16
+    int nk;               // 128-byte K chunks per row
+    int stages;           // ring depth
+    long long ntiles;     // tiles this launch walks: tile = (blockIdx.x + i*gridDim.x) * tile_stride
+    long long tile_stride;
+    // MODE_MAX
+    uint32_t* gmax;       // [ntiles*4][npad] ordered-uint maxima per 32-row group
+    // MODE_SELECT
+    const float* tau0;    // [npad]
+    u64* cand;            // [gridDim.x][npad][cap]
+    int cap;
+    int* counts;          // [gridDim.x][npad]
+    int* overflow;        // [npad] set to 1 when a buffer overflowed
+    // MODE_DUMP
+    float* dump;          // [n][npad]
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: TMA tensor loads, tcgen05 alloc / mma / commit / ld
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// arrive on an mbarrier when all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (what TMA SWIZZLE_128B writes):
+// rows are 128 bytes apart, 8-row groups 1024 bytes apart (SBO), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: fp32 accumulate, A and B K-major, M x N tile
+__host__ __device__ constexpr uint32_t make_idesc(bool tf32, int M, int N) {
+    return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel.  dynamic shared memory (1024-byte aligned base):
+//   [0, nk*npad*128)                  resident query block, chunk-major: chunk c at c*npad*128
+//   [.., + stages*16384)              ring of database tiles (128 rows x 128 B)
+//   then barriers, TMEM base address, tau0[npad], cnt[npad]
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;           // rows per tile = MMA M
+constexpr int TC_STAGE_BYTES = TC_BM * 128;
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256, 1)
+tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant__ CUtensorMap tm_q, TcParams p) {
+    constexpr bool TF32 = sizeof(T) == 4;
+    constexpr int EC = 128 / sizeof(T);        // elements per 128-byte chunk
+    constexpr int KSTEP_BYTES = 32;            // one MMA consumes 32 bytes of K per row (16 bf16 / 8 tf32)
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages, NK = p.nk, NP = p.npad;
+
+    // 128B-swizzled operands need 1024-byte aligned bases: align by hand (1 KiB of slack is allocated)
+    unsigned char* q_smem = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    unsigned char* ring = q_smem + (size_t)NK * NP * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * TC_STAGE_BYTES);
+    uint64_t* q_full = bars;             // 1
+    uint64_t* full = bars + 1;           // S
+    uint64_t* empty = full + S;          // S
+    uint64_t* acc_full = empty + S;      // 2
+    uint64_t* acc_empty = acc_full + 2;  // 2
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* tau_s = reinterpret_cast<float*>(tmem_base_smem + 4);
+    int* cnt_s = reinterpret_cast<int*>(tau_s + NP);
+
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(2 * NP)) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tm_db);
+        prefetch_tmap(&tm_q);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_smem, tmem_cols);
+    if (MODE == MODE_SELECT) {
+        for (int c = threadIdx.x; c < NP; c += blockDim.x) {
+            tau_s[c] = (c < p.nq) ? p.tau0[c] : INFINITY;
+            cnt_s[c] = 0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    // tiles of this CTA
+    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, (uint32_t)(NK * NP * 128));
+            for (int c = 0; c < NK; c++) tma_load_2d(q_smem + (size_t)c * NP * 128, &tm_q, c * EC, 0, q_full);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long i = 0; i < my_tiles; i++) {
+                const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
+                const int row0 = (int)(tile * TC_BM);
+                for (int c = 0; c < NK; c++) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+                    tma_load_2d(ring + (size_t)stage * TC_STAGE_BYTES, &tm_db, c * EC, row0, &full[stage]);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TF32, TC_BM, NP);
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long i = 0; i < my_tiles; i++) {
+                const int a = (int)(i & 1);
+                const uint32_t aphase = (uint32_t)((i >> 1) & 1);
+                mbar_wait(&acc_empty[a], aphase ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * NP);
+                for (int c = 0; c < NK; c++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + (size_t)stage * TC_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(q_smem + (size_t)c * NP * 128);
+#pragma unroll
+                    for (int k = 0; k < 128 / KSTEP_BYTES; k++) {
+                        umma<TF32>(d_tmem, smem_desc_sw128(a_addr + k * KSTEP_BYTES), smem_desc_sw128(b_addr + k * KSTEP_BYTES),
+                                   idesc, (uint32_t)((c | k) != 0));
+                    }
+                    umma_commit(&empty[stage]);  // frees the ring slot when these MMAs have read it
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(&acc_full[a]);  // accumulator complete -> epilogue
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int e = warp & 3;                 // TMEM lane quarter
+        const int row_in_tile = e * 32 + lane;  // this thread's row
+        for (long long i = 0; i < my_tiles; i++) {
+            const int a = (int)(i & 1);
+            const uint32_t aphase = (uint32_t)((i >> 1) & 1);
+            const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
+            const long long row = tile * TC_BM + row_in_tile;
+            const bool row_ok = row < p.n;
+            mbar_wait(&acc_full[a], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(a * NP);
+            for (int c0 = 0; c0 < NP; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                if (MODE == MODE_DUMP) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) p.dump[(size_t)row * NP + c0 + j] = __uint_as_float(v[j]);
+                    }
+                } else if (MODE == MODE_MAX) {
+                    const long long g = ((blockIdx.x + i * gridDim.x) * 4 + e);  // 32-row group index of this launch
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        uint32_t o = row_ok ? score_to_ordered(__uint_as_float(v[j])) : 0u;
+                        o = __reduce_max_sync(0xffffffffu, o);
+                        if (lane == j) p.gmax[(size_t)g * NP + c0 + j] = o;
+                    }
+                } else {
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float s = __uint_as_float(v[j]);
+                            const int c = c0 + j;
+                            if (s >= tau_s[c]) {
+                                int slot = atomicAdd(&cnt_s[c], 1);
+                                if (slot < p.cap)
+                                    p.cand[((size_t)blockIdx.x * NP + c) * p.cap + slot] = make_key(s, (uint32_t)row);
+                                else
+                                    p.overflow[c] = 1;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (MODE == MODE_SELECT) {
+        for (int c = threadIdx.x; c < NP; c += blockDim.x) {
+            int n = cnt_s[c];
+            p.counts[(size_t)blockIdx.x * NP + c] = n < p.cap ? n : p.cap;
+        }
+    }
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tau0[query] = kp-th largest of the pre-pass group maxima (descending bitonic sort in shared memory)
+// grid = npad queries, block = 256; dynamic smem = gpow2 * 4 bytes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict__ gmax, int groups, int gpow2, int npad, int nq,
+                                                      int kp, float* __restrict__ tau0) {
+    extern __shared__ uint32_t sv[];
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < gpow2; i += blockDim.x) sv[i] = (i < groups) ? gmax[(size_t)i * npad + c] : 0u;
+    for (int size = 2; size <= gpow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (gpow2 >> 1); t += blockDim.x) {
+                int i = ((t / stride) * (stride << 1)) + (t % stride), j = i + stride;
+                bool desc = ((i & size) == 0);
+                uint32_t x = sv[i], y = sv[j];
+                if (desc ? (x < y) : (x > y)) {
+                    sv[i] = y;
+                    sv[j] = x;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // fewer than kp groups (or NaN-only groups): no usable bound -> admit everything
+        uint32_t o = (groups >= kp) ? sv[kp - 1] : 0u;
+        tau0[c] = (c < nq && o != 0u) ? ordered_to_score(o) : ((c < nq) ? -INFINITY : INFINITY);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather the (CTA, query) candidate buffers of one query into a sorted top-kp list
+// (same list format the GEMV scan writes: [query][1][kp], sorted descending, 0 = empty)
+// grid = nq, block = 1024; dynamic smem = cap_total * 8
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) tc_gather_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int nctas,
+                                                         int npad, int cap, int kp, int cap_total, u64* __restrict__ lists,
+                                                         int* __restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char sraw[];
+    u64* keys = reinterpret_cast<u64*>(sraw);
+    __shared__ int s_total;
+    const int c = blockIdx.x;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    // one warp per CTA buffer: copy its keys into the shared array
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = warp; b < nctas; b += 32) {
+        const int n = counts[(size_t)b * npad + c];
+        int base = 0;
+        if (lane == 0 && n > 0) base = atomicAdd(&s_total, n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const u64* src = cand + ((size_t)b * npad + c) * cap;
+        for (int i = lane; i < n; i += 32)
+            if (base + i < cap_total) keys[base + i] = src[i];
+    }
+    __syncthreads();
+    int total = s_total;
+    if (total > cap_total) {
+        if (threadIdx.x == 0) overflow[c] = 1;
+        total = cap_total;
+    }
+    int pow2 = kp;
+    while (pow2 < total) pow2 <<= 1;
+    for (int i = total + threadIdx.x; i < pow2; i += blockDim.x) keys[i] = 0ull;
+    for (int size = 2; size <= pow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (pow2 >> 1); t += blockDim.x) {
+                int i = ((t / stride) * (stride << 1)) + (t % stride);
+                cmpx_desc(keys, i, i + stride, (i & size) == 0);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kp; i += blockDim.x) lists[(size_t)c * kp + i] = keys[i];
+}
+
+__global__ void f32_to_bf16_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long count) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D row-major [rows][d] tensor, box = 128 bytes of K x box_rows rows, 128-byte swizzle
+static cudaError_t make_tmap(CUtensorMap* map, const void* base, long long rows, int d, bool is_f32, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return cudaErrorNotSupported;
+    const size_t esz = is_f32 ? 4 : 2;
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)d * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                     gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// largest query block (multiple of 16, <= 128) whose resident copy leaves room for a useful ring
+int tc_max_queries(int d, int is_bf16) {
+    const size_t esz = is_bf16 ? 2 : 4;
+    if (((size_t)d * esz) % 128) return 0;  // K must be whole 128-byte chunks
+    size_t per_query = (size_t)d * esz;
+    int n = (int)((128 * 1024) / per_query) / 16 * 16;
+    if (n > 128) n = 128;
+    return n < 16 ? 0 : n;
+}
+
+static size_t tc_smem_bytes(int nk, int npad, int stages) {
+    return (size_t)nk * npad * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(1 + 2 * stages + 4) * 8 + 16 + (size_t)npad * 8 + 1024;
+}
+
+template <typename T, int MODE>
+static cudaError_t launch_tc_mode(const CUtensorMap& tdb, const CUtensorMap& tq, const TcParams& p, int grid, size_t smem,
+                                  cudaStream_t st) {
+    auto kern = tc_scan_kernel<T, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 256, smem, st>>>(tdb, tq, p);
+    g_kernel_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_tc(bool is_bf16, const CUtensorMap& tdb, const CUtensorMap& tq, const TcParams& p, int grid,
+                             size_t smem, cudaStream_t st) {
+    return is_bf16 ? launch_tc_mode<__nv_bfloat16, MODE>(tdb, tq, p, grid, smem, st)
+                   : launch_tc_mode<float, MODE>(tdb, tq, p, grid, smem, st);
+}
+
+static int pick_stages(int nk, int npad) {
+    int stages = 8;
+    while (stages > 2 && tc_smem_bytes(nk, npad, stages) > 226 * 1024) stages--;
+    return stages;
+}
+
+size_t tc_workspace_bytes(const TcPlan& pl) {
+    return pl.off_end;
+}
+
+// Plan one query block of `nq` (<= tc_max_queries) queries over `n` rows.
+cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, TcPlan* pl) {
+    const size_t esz = is_bf16 ? 2 : 4;
+    pl->npad = (nq + 15) / 16 * 16;
+    pl->nk = (int)((size_t)d * esz / 128);
+    pl->stages = pick_stages(pl->nk, pl->npad);
+    pl->smem = tc_smem_bytes(pl->nk, pl->npad, pl->stages);
+    if (pl->smem > 227 * 1024) return cudaErrorInvalidValue;
+    pl->ntiles = (n + TC_BM - 1) / TC_BM;
+    pl->grid = (int)(pl->ntiles < sm_count ? pl->ntiles : sm_count);
+    // pre-pass sample: every `stride`-th tile, at least 512 tiles (or all of them)
+    long long want = pl->ntiles / 128;
+    if (want < 512) want = 512;
+    if (want > pl->ntiles) want = pl->ntiles;
+    pl->pre_stride = pl->ntiles / want;
+    pl->pre_tiles = (pl->ntiles + pl->pre_stride - 1) / pl->pre_stride;
+    pl->pre_grid = (int)(pl->pre_tiles < sm_count ? pl->pre_tiles : sm_count);
+    pl->groups = (int)(pl->pre_tiles * 4);
+    int g2 = 1;
+    while (g2 < pl->groups) g2 <<= 1;
+    pl->gpow2 = g2;
+    pl->cap = 256;
+    pl->cap_total = 16384;
+    pl->kp = kp;
+    // workspace layout
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = (off + bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    pl->off_gmax = take((size_t)pl->groups * pl->npad * 4);
+    pl->off_tau0 = take((size_t)pl->npad * 4);
+    pl->off_counts = take((size_t)pl->grid * pl->npad * 4);
+    pl->off_overflow = take((size_t)pl->npad * 4);
+    pl->off_cand = take((size_t)pl->grid * pl->npad * pl->cap * 8);
+    pl->off_qbf16 = take((size_t)pl->npad * d * 2);
+    pl->off_end = off;
+    return cudaSuccess;
+}
+
+// Scan one query block with the tensor-core path; writes one sorted kp-list per query into `lists`
+// ([nq][kp], the format finalize_kernel takes with L = 1) and sets overflow[q] = 1 where the result
+// must not be trusted.  `ws` is a device workspace of tc_workspace_bytes(pl).
+cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, cudaStream_t st) {
+    CUtensorMap tdb, tq;
+    cudaError_t e = make_tmap(&tdb, a.xb, a.n, a.d, !a.is_bf16, TC_BM);
+    if (e != cudaSuccess) return e;
+    const void* qsrc = a.xq;
+    if (a.is_bf16) {
+        __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qbf16);
+        long long cnt = (long long)a.nq * a.d;
+        f32_to_bf16_rows_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(a.xq, qb, cnt);
+        g_kernel_launches.fetch_add(1);
+        qsrc = qb;
+    }
+    e = make_tmap(&tq, qsrc, a.nq, a.d, !a.is_bf16, pl.npad);
+    if (e != cudaSuccess) return e;
+
+    TcParams p;
+    p.n = a.n;
+    p.d = a.d;
+    p.nq = a.nq;
+    p.npad = pl.npad;
+    p.nk = pl.nk;
+    p.stages = pl.stages;
+    p.gmax = reinterpret_cast<uint32_t*>(ws + pl.off_gmax);
+    p.tau0 = reinterpret_cast<const float*>(ws + pl.off_tau0);
+    p.cand = reinterpret_cast<u64*>(ws + pl.off_cand);
+    p.cap = pl.cap;
+    p.counts = reinterpret_cast<int*>(ws + pl.off_counts);
+    p.overflow = reinterpret_cast<int*>(ws + pl.off_overflow);
+    p.dump = nullptr;
+
+    // 1. threshold pre-pass over the sampled tiles
+    p.ntiles = pl.pre_tiles;
+    p.tile_stride = pl.pre_stride;
+    e = launch_tc<MODE_MAX>(a.is_bf16, tdb, tq, p, pl.pre_grid, pl.smem, st);
+    if (e != cudaSuccess) return e;
+    tc_tau0_kernel<<<pl.npad, 256, (size_t)pl.gpow2 * 4, st>>>(p.gmax, pl.groups, pl.gpow2, pl.npad, a.nq, pl.kp,
+                                                             reinterpret_cast<float*>(ws + pl.off_tau0));
+    g_kernel_launches.fetch_add(1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ws + pl.off_overflow, 0, (size_t)pl.npad * 4, st)) != cudaSuccess) return e;
+    // 2. selection pass over every tile
+    p.ntiles = pl.ntiles;
+    p.tile_stride = 1;
+    e = launch_tc<MODE_SELECT>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st);
+    if (e != cudaSuccess) return e;
+    // 3. per query: gather + sort -> top-kp list
+    size_t gs = (size_t)pl.cap_total * 8;
+    cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
+    tc_gather_kernel<<<a.nq, 1024, gs, st>>>(p.cand, p.counts, pl.grid, pl.npad, pl.cap, pl.kp, pl.cap_total,
+                                            reinterpret_cast<u64*>(a.lists), p.overflow);
+    g_kernel_launches.fetch_add(1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (a.overflow_out)
+        e = cudaMemcpyAsync(a.overflow_out, ws + pl.off_overflow, (size_t)a.nq * 4, cudaMemcpyDeviceToDevice, st);
+    return e;
+}
+
+// tests: raw tensor-core scores of every row against a query block, [n][npad] fp32
+cudaError_t tc_dump_scores(const TcArgs& a, const TcPlan& pl, unsigned char* ws, float* out, cudaStream_t st) {
+    CUtensorMap tdb, tq;
+    cudaError_t e = make_tmap(&tdb, a.xb, a.n, a.d, !a.is_bf16, TC_BM);
+    if (e != cudaSuccess) return e;
+    const void* qsrc = a.xq;
+    if (a.is_bf16) {
+        __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qbf16);
+        long long cnt = (long long)a.nq * a.d;
+        f32_to_bf16_rows_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(a.xq, qb, cnt);
+        g_kernel_launches.fetch_add(1);
+        qsrc = qb;
+    }
+    if ((e = make_tmap(&tq, qsrc, a.nq, a.d, !a.is_bf16, pl.npad)) != cudaSuccess) return e;
+    TcParams p = {};
+    p.n = a.n;
+    p.d = a.d;
+    p.nq = a.nq;
+    p.npad = pl.npad;
+    p.nk = pl.nk;
+    p.stages = pl.stages;
+    p.ntiles = pl.ntiles;
+    p.tile_stride = 1;
+    p.dump = out;
+    return launch_tc<MODE_DUMP>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st);
+}
+
+}  // namespace evs

@@ -216,6 +216,26 @@ class IndexFlatIP:
                                         int(iters), ctypes.byref(ms)))
         return ms.value
 
+    def tc_max_queries(self) -> int:
+        """Queries one tensor-core pass serves for this index (0 = dimension not supported)."""
+        v = ctypes.c_int(0)
+        check(lib().evs_index_tc_max_queries(self._h, ctypes.byref(v)))
+        return v.value
+
+    def tc_scores(self, xq_cuda):
+        """Diagnostics: raw tensor-core scan scores, ``float32[ntotal, nq]`` CUDA tensor."""
+        import torch
+        assert _is_torch_cuda(xq_cuda) and xq_cuda.dtype == torch.float32 and xq_cuda.is_contiguous()
+        nq = xq_cuda.shape[0]
+        npad = (nq + 15) // 16 * 16
+        out = torch.empty((self.ntotal, npad), dtype=torch.float32, device=xq_cuda.device)
+        got = ctypes.c_int(0)
+        st = torch.cuda.current_stream(xq_cuda.device).cuda_stream
+        check(lib().evs_index_tc_scores_dev(self._h, nq, ctypes.c_void_p(xq_cuda.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                            ctypes.byref(got), ctypes.c_void_p(st)))
+        assert got.value == npad
+        return out[:, :nq]
+
     def scan_profile(self):
         """(searches recorded, summed scan ms) since the last call; needs ``set_option("profile_scans", 1)``."""
         n, ms = ctypes.c_int64(0), ctypes.c_double(0)

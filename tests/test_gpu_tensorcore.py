@@ -1,0 +1,100 @@
+"""GPU: the tcgen05/TMEM tensor-core scan (query batches) -- raw scores against torch, and the full
+search against the oracle's canonical ranking (must be bit-identical to every other scan path)."""
+import numpy as np
+import pytest
+
+import evo_ssearch_b200 as evs
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _reset_options():
+    yield
+    evs.set_option("tc_min_nq", 4)
+    evs.set_option("scan_variant", 0)
+
+
+@pytest.mark.parametrize("storage,d", [("bf16", 512), ("f32", 512), ("bf16", 768), ("f32", 768), ("bf16", 1024), ("bf16", 64)])
+def test_tc_raw_scores_match_torch(storage, d):
+    import torch
+    n = 70_001  # tail tile, more tiles than SMs
+    idx = evs.IndexFlatIP(d, storage=storage)
+    idx.add_synthetic(n, seed=3)
+    xb = torch.from_numpy(idx.reconstruct_n(0, n)).cuda()
+    nmax = idx.tc_max_queries()
+    assert nmax >= 16
+    for nq in sorted({1, 16, 17, nmax}):
+        xq = torch.from_numpy(oracle.synth_fill(nq, d, 4)).cuda()
+        got = idx.tc_scores(xq)
+        torch.cuda.synchronize()
+        if storage == "bf16":
+            ref = (xb.bfloat16().double() @ xq.bfloat16().double().T).float()  # exact products of the rounded inputs
+            tol = 2e-6  # only fp32 accumulation order differs
+        else:
+            ref = (xb.double() @ xq.double().T).float()
+            tol = 5e-4  # tf32 truncates each operand to 10 mantissa bits: ~4e-5 rms on unit vectors, ~4 sigma max
+        err = (got - ref).abs().max().item()
+        assert err <= tol, (storage, d, nq, err)
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+@pytest.mark.parametrize("d", [512, 768])
+def test_tc_search_equals_oracle(storage, d):
+    n = 200_003
+    xb = oracle.synth_fill(n, d, 11)
+    xb[n - 1] = xb[5]
+    idx = evs.IndexFlatIP(d, storage=storage)
+    idx.add(xb)
+    nmax = idx.tc_max_queries()
+    xq_all = oracle.synth_fill(2 * nmax + 3, d, 12)
+    evs.set_option("tc_min_nq", 1)  # force the tensor-core scan even for one query
+    for nq, k in ((1, 48), (5, 12), (16, 48), (17, 1), (nmax, 48), (nmax + 1, 48), (2 * nmax + 3, 100)):
+        xq = xq_all[:nq]
+        D, I = idx.search(xq, k)
+        Dr, Ir = oracle.canon_search(xq, xb, k)
+        assert np.array_equal(I, Ir), (storage, d, nq, k, np.argwhere(I != Ir)[:4])
+        assert np.array_equal(D, Dr), (storage, d, nq, k)
+    m = idx.last_margins(2 * nmax + 3)
+    assert (m > (2e-4 if storage == "f32" else 5e-4)).all(), m.min()
+    # identical to the GEMV path
+    evs.set_option("tc_min_nq", 0)
+    D2, I2 = idx.search(xq_all[:20], 48)
+    evs.set_option("tc_min_nq", 1)
+    D3, I3 = idx.search(xq_all[:20], 48)
+    assert np.array_equal(I2, I3) and np.array_equal(D2, D3)
+
+
+def test_tc_overflow_falls_back_exactly():
+    """Adversarial data: thousands of identical rows all beat the pre-pass threshold -> candidate
+    buffers overflow -> those queries are re-run through the GEMV scan; the answer stays exact."""
+    d, n = 512, 150_000
+    xb = oracle.synth_fill(n, d, 21)
+    q = oracle.synth_fill(8, d, 22)
+    xb[1000:61000] = q[0]  # 60000 duplicates of query 0 itself
+    idx = evs.IndexFlatIP(d)
+    idx.add(xb)
+    evs.set_option("tc_min_nq", 1)
+    D, I = idx.search(q, 48)
+    Dr, Ir = oracle.canon_search(q, xb, 48)
+    assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
+    assert I[0].tolist() == list(range(1000, 1048))
+
+
+def test_config3_1m_x_512_bf16_nq4096_recall():
+    """BASELINE config 3: 1M x 512 bf16, 4096 queries, k = 48: recall@k against the fp32 ground truth
+    (bar: >= 0.999; the canonical re-rank makes it exact) checked on a sample of the batch."""
+    n, d, k, nq = 1_000_000, 512, 48, 4096
+    idx = evs.IndexFlatIP(d, storage="bf16")
+    idx.add_synthetic(n, seed=0)
+    xq = oracle.synth_fill(nq, d, 1)
+    D, I = idx.search(xq, k)
+    xb = oracle.synth_fill(n, d, 0)
+    sample = np.arange(0, nq, 64)
+    Dr, Ir = oracle.canon_search(xq[sample], xb, k)
+    hits = sum(len(set(I[s].tolist()) & set(Ir[j].tolist())) for j, s in enumerate(sample))
+    recall = hits / (len(sample) * k)
+    assert recall >= 0.999, recall
+    assert np.array_equal(I[sample], Ir) and np.array_equal(D[sample], Dr)  # in fact exact
+    assert (np.diff(D.astype(np.float64), axis=1) <= 0).all()
