@@ -48,7 +48,8 @@ static int g_profile_scans = 0;  // record CUDA events around every search's sca
 // ---------------------------------------------------------------------------------------------
 // the handle
 // ---------------------------------------------------------------------------------------------
-static const int kQueryChunk = 256;  // queries finalised per launch (bounds the list workspace)
+static const int kQueryChunk = 256;     // GEMV path: queries finalised per launch (bounds the list workspace)
+static const int kTcQueryChunk = 2048;  // tensor-core path: queries per launch set
 
 struct evs_index {
     int d = 0, device = 0, storage = EVS_STORE_F32;
@@ -145,6 +146,9 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "tc_min_nq")) {
         if (value < 0) return fail(EVS_EINVAL, "tc_min_nq must be >= 0");
         g_tune.tc_min_nq = (int)value;
+    } else if (!strcmp(name, "tc_stages")) {
+        if (value < 2 || value > 14) return fail(EVS_EINVAL, "tc_stages must be in [2, 14]");
+        g_tc_max_stages = (int)value;
     } else if (!strcmp(name, "profile_scans")) {
         g_profile_scans = value ? 1 : 0;
     } else {
@@ -161,6 +165,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "stages")) *value = g_tune.stages;
     else if (!strcmp(name, "ctas_per_sm")) *value = g_tune.ctas_per_sm;
     else if (!strcmp(name, "tc_min_nq")) *value = g_tune.tc_min_nq;
+    else if (!strcmp(name, "tc_stages")) *value = g_tc_max_stages;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
     else return fail(EVS_EINVAL, "unknown option '%s'", name);
     return EVS_OK;
@@ -394,18 +399,17 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
     const int kp = pick_kp(k);
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
     const void* scan_rows = bf16 ? idx->xb16 : (const void*)idx->xb32;
-    const int nb_max = tc_max_queries(idx->d, bf16);
     TcPlan pl;
-    CU(tc_plan(idx->ntotal, idx->d, bf16, (int)(nq < nb_max ? nq : nb_max), kp, idx->sm_count, &pl));
+    CU(tc_plan(idx->ntotal, idx->d, bf16, (int)(nq < kTcQueryChunk ? nq : kTcQueryChunk), kp, idx->sm_count, &pl));
     int rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc_workspace_bytes(pl));
     if (rc) return rc;
     if ((rc = ensure_dev(&idx->tc_overflow, &idx->tc_overflow_cap, (size_t)nq))) return rc;
-    const int64_t chunk_cap = nq < kQueryChunk ? nq : kQueryChunk;
+    const int64_t chunk_cap = nq < kTcQueryChunk ? nq : kTcQueryChunk;
     if ((rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, (size_t)chunk_cap * kp))) return rc;
     if ((rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
     idx->last_nq = nq;
-    for (int64_t c0 = 0; c0 < nq; c0 += kQueryChunk) {
-        const int64_t cn = (nq - c0) < kQueryChunk ? (nq - c0) : kQueryChunk;
+    for (int64_t c0 = 0; c0 < nq; c0 += kTcQueryChunk) {
+        const int64_t cn = (nq - c0) < kTcQueryChunk ? (nq - c0) : kTcQueryChunk;
         std::pair<cudaEvent_t, cudaEvent_t>* pe = nullptr;
         if (profile && idx->prof_used < 65536) {
             if (idx->prof_used == idx->prof_events.size()) {
@@ -417,19 +421,19 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
             pe = &idx->prof_events[idx->prof_used++];
             CU(cudaEventRecord(pe->first, st));
         }
-        for (int64_t b0 = 0; b0 < cn; b0 += nb_max) {
-            const int nb = (int)((cn - b0) < nb_max ? (cn - b0) : nb_max);
-            TcPlan plb;
-            CU(tc_plan(idx->ntotal, idx->d, bf16, nb, kp, idx->sm_count, &plb));
+        {
+            TcPlan plb;  // same workspace bound: cn <= the chunk the workspace was sized for
+            CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, &plb));
+            if (tc_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
             TcArgs a;
             a.xb = scan_rows;
             a.is_bf16 = bf16;
             a.n = idx->ntotal;
             a.d = idx->d;
-            a.xq = q_dev + (size_t)(c0 + b0) * idx->d;
-            a.nq = nb;
-            a.lists = reinterpret_cast<unsigned long long*>(idx->lists) + (size_t)b0 * kp;
-            a.overflow_out = idx->tc_overflow + c0 + b0;
+            a.xq = q_dev + (size_t)c0 * idx->d;
+            a.nq = (int)cn;
+            a.lists = idx->lists;
+            a.overflow_out = idx->tc_overflow + c0;
             CU(tc_scan_block(a, plb, idx->tc_ws, st));
         }
         if (pe) CU(cudaEventRecord(pe->second, st));

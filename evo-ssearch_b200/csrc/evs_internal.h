@@ -57,7 +57,7 @@ struct FinalizeArgs {
 
 // tensor-core scan (evs_tc.cu)
 struct TcPlan {
-    int npad, nk, stages, grid, pre_grid, groups, gpow2, cap, cap_total, kp;
+    int npad, nblocks, nqp, nk, stages, grid, pre_grid, groups, gpow2, cap, cap_total, kp;
     size_t smem;
     long long ntiles, pre_tiles, pre_stride;
     size_t off_gmax, off_tau0, off_counts, off_overflow, off_cand, off_qbf16, off_end;
@@ -67,11 +67,12 @@ struct TcArgs {
     int is_bf16;
     long long n;
     int d;
-    const float* xq;  // this block's queries, fp32 [nq][d]
+    const float* xq;  // the queries of this launch set, fp32 [nq][d]
     int nq;
     void* lists;      // out: u64 [nq][kp]
     int* overflow_out;  // out (optional): int [nq]
 };
+extern int g_tc_max_stages;
 int tc_max_queries(int d, int is_bf16);
 cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, TcPlan* pl);
 size_t tc_workspace_bytes(const TcPlan& pl);

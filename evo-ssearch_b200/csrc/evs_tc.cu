@@ -37,22 +37,24 @@ enum { MODE_MAX = 0, MODE_SELECT = 1, MODE_DUMP = 2 };
 struct TcParams {
     long long n;          // rows in the shard
     int d;                // dimension
-    int nq;               // valid queries in this block (<= npad)
-    int npad;             // N of the MMA: nq rounded up to 16
+    int nq;               // valid queries of this launch (all blocks)
+    int npad;             // N of the MMA = queries per block (multiple of 16)
+    int nblocks;          // query blocks walked inside the launch: block b = queries [b*npad, (b+1)*npad)
+    int nqp;              // nblocks * npad (padded query count; row pitch of the per-query arrays)
     int nk;               // 128-byte K chunks per row
     int stages;           // ring depth
     long long ntiles;     // tiles this launch walks: tile = (blockIdx.x + i*gridDim.x) * tile_stride
     long long tile_stride;
     // MODE_MAX
-    uint32_t* gmax;       // [ntiles*4][npad] ordered-uint maxima per 32-row group
+    uint32_t* gmax;       // [ntiles*4][nqp] ordered-uint maxima per 32-row group
     // MODE_SELECT
-    const float* tau0;    // [npad]
-    u64* cand;            // [gridDim.x][npad][cap]
+    const float* tau0;    // [nqp]
+    u64* cand;            // [gridDim.x][nqp][cap]
     int cap;
-    int* counts;          // [gridDim.x][npad]
-    int* overflow;        // [npad] set to 1 when a buffer overflowed
+    int* counts;          // [gridDim.x][nqp]
+    int* overflow;        // [nqp] set to 1 when a buffer overflowed
     // MODE_DUMP
-    float* dump;          // [n][npad]
+    float* dump;          // [n][nqp]
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -143,8 +145,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
     unsigned char* q_smem = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     unsigned char* ring = q_smem + (size_t)NK * NP * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * TC_STAGE_BYTES);
-    uint64_t* q_full = bars;             // 1
-    uint64_t* full = bars + 1;           // S
+    uint64_t* q_full = bars;             // 1: the query block has landed
+    uint64_t* q_empty = bars + 1;        // 1: every MMA that reads the query block has completed
+    uint64_t* full = bars + 2;           // S
     uint64_t* empty = full + S;          // S
     uint64_t* acc_full = empty + S;      // 2
     uint64_t* acc_empty = acc_full + 2;  // 2
@@ -159,6 +162,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         prefetch_tmap(&tm_db);
         prefetch_tmap(&tm_q);
         mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -170,37 +174,34 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_base_smem, tmem_cols);
-    if (MODE == MODE_SELECT) {
-        for (int c = threadIdx.x; c < NP; c += blockDim.x) {
-            tau_s[c] = (c < p.nq) ? p.tau0[c] : INFINITY;
-            cnt_s[c] = 0;
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
-    // tiles of this CTA
+    // tiles of this CTA (the same list for every query block)
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, (uint32_t)(NK * NP * 128));
-            for (int c = 0; c < NK; c++) tma_load_2d(q_smem + (size_t)c * NP * 128, &tm_q, c * EC, 0, q_full);
+        if (lane == 0 && my_tiles > 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long i = 0; i < my_tiles; i++) {
-                const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
-                const int row0 = (int)(tile * TC_BM);
-                for (int c = 0; c < NK; c++) {
-                    mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
-                    tma_load_2d(ring + (size_t)stage * TC_STAGE_BYTES, &tm_db, c * EC, row0, &full[stage]);
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1u;
+            for (int b = 0; b < p.nblocks; b++) {
+                if (b > 0) mbar_wait(q_empty, (uint32_t)((b - 1) & 1));  // previous block's MMAs are done with it
+                mbar_arrive_expect_tx(q_full, (uint32_t)(NK * NP * 128));
+                for (int c = 0; c < NK; c++) tma_load_2d(q_smem + (size_t)c * NP * 128, &tm_q, c * EC, b * NP, q_full);
+                for (long long i = 0; i < my_tiles; i++) {
+                    const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
+                    const int row0 = (int)(tile * TC_BM);
+                    for (int c = 0; c < NK; c++) {
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+                        tma_load_2d(ring + (size_t)stage * TC_STAGE_BYTES, &tm_db, c * EC, row0, &full[stage]);
+                        if (++stage == S) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
                     }
                 }
             }
@@ -208,35 +209,39 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (lane == 0 && my_tiles > 0) {
             const uint32_t idesc = make_idesc(TF32, TC_BM, NP);
-            mbar_wait(q_full, 0);
-            tc_fence_after();
             int stage = 0;
             uint32_t phase = 0;
-            for (long long i = 0; i < my_tiles; i++) {
-                const int a = (int)(i & 1);
-                const uint32_t aphase = (uint32_t)((i >> 1) & 1);
-                mbar_wait(&acc_empty[a], aphase ^ 1u);  // epilogue has drained this accumulator
+            long long it = 0;  // tile counter across blocks: accumulator buffer and its phase
+            for (int b = 0; b < p.nblocks; b++) {
+                mbar_wait(q_full, (uint32_t)(b & 1));
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(a * NP);
-                for (int c = 0; c < NK; c++) {
-                    mbar_wait(&full[stage], phase);
+                for (long long i = 0; i < my_tiles; i++, it++) {
+                    const int a = (int)(it & 1);
+                    const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+                    mbar_wait(&acc_empty[a], aphase ^ 1u);  // epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(ring + (size_t)stage * TC_STAGE_BYTES);
-                    const uint32_t b_addr = smem_u32(q_smem + (size_t)c * NP * 128);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * NP);
+                    for (int c = 0; c < NK; c++) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(ring + (size_t)stage * TC_STAGE_BYTES);
+                        const uint32_t b_addr = smem_u32(q_smem + (size_t)c * NP * 128);
 #pragma unroll
-                    for (int k = 0; k < 128 / KSTEP_BYTES; k++) {
-                        umma<TF32>(d_tmem, smem_desc_sw128(a_addr + k * KSTEP_BYTES), smem_desc_sw128(b_addr + k * KSTEP_BYTES),
-                                   idesc, (uint32_t)((c | k) != 0));
+                        for (int k = 0; k < 128 / KSTEP_BYTES; k++) {
+                            umma<TF32>(d_tmem, smem_desc_sw128(a_addr + k * KSTEP_BYTES),
+                                       smem_desc_sw128(b_addr + k * KSTEP_BYTES), idesc, (uint32_t)((c | k) != 0));
+                        }
+                        umma_commit(&empty[stage]);  // frees the ring slot when these MMAs have read it
+                        if (++stage == S) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
                     }
-                    umma_commit(&empty[stage]);  // frees the ring slot when these MMAs have read it
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    umma_commit(&acc_full[a]);  // accumulator complete -> epilogue
                 }
-                umma_commit(&acc_full[a]);  // accumulator complete -> epilogue
+                umma_commit(q_empty);  // the query block may be overwritten once all of the above completed
             }
         }
         __syncwarp();
@@ -244,75 +249,89 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         // ================= epilogue =================
         const int e = warp & 3;                 // TMEM lane quarter
         const int row_in_tile = e * 32 + lane;  // this thread's row
-        for (long long i = 0; i < my_tiles; i++) {
-            const int a = (int)(i & 1);
-            const uint32_t aphase = (uint32_t)((i >> 1) & 1);
-            const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
-            const long long row = tile * TC_BM + row_in_tile;
-            const bool row_ok = row < p.n;
-            mbar_wait(&acc_full[a], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(a * NP);
-            for (int c0 = 0; c0 < NP; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
-                if (MODE == MODE_DUMP) {
-                    if (row_ok) {
+        const int et = threadIdx.x - 128;       // 0..127 among the epilogue threads
+        long long it = 0;
+        for (int b = 0; b < p.nblocks; b++) {
+            const int qb = b * NP;  // first query of the block
+            if (MODE == MODE_SELECT) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // all epilogue warps have left the previous block
+                for (int c = et; c < NP; c += 128) {
+                    tau_s[c] = (qb + c < p.nq) ? p.tau0[qb + c] : INFINITY;
+                    cnt_s[c] = 0;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            for (long long i = 0; i < my_tiles; i++, it++) {
+                const int a = (int)(it & 1);
+                const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+                const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
+                const long long row = tile * TC_BM + row_in_tile;
+                const bool row_ok = row < p.n;
+                mbar_wait(&acc_full[a], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(a * NP);
+                for (int c0 = 0; c0 < NP; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c0, v);
+                    if (MODE == MODE_DUMP) {
+                        if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 16; j++) p.dump[(size_t)row * NP + c0 + j] = __uint_as_float(v[j]);
-                    }
-                } else if (MODE == MODE_MAX) {
-                    const long long g = ((blockIdx.x + i * gridDim.x) * 4 + e);  // 32-row group index of this launch
+                            for (int j = 0; j < 16; j++) p.dump[(size_t)row * p.nqp + qb + c0 + j] = __uint_as_float(v[j]);
+                        }
+                    } else if (MODE == MODE_MAX) {
+                        const long long g = ((blockIdx.x + i * gridDim.x) * 4 + e);  // 32-row group index of this launch
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        uint32_t o = row_ok ? score_to_ordered(__uint_as_float(v[j])) : 0u;
-                        o = __reduce_max_sync(0xffffffffu, o);
-                        if (lane == j) p.gmax[(size_t)g * NP + c0 + j] = o;
-                    }
-                } else {
-                    // branch-free filter: 16 compares into a bit mask, one warp-uniform test per group;
-                    // admissions are ~1e-3 of the scores, so the insert path below is rare
-                    uint32_t mask = 0;
+                        for (int j = 0; j < 16; j++) {
+                            uint32_t o = row_ok ? score_to_ordered(__uint_as_float(v[j])) : 0u;
+                            o = __reduce_max_sync(0xffffffffu, o);
+                            if (lane == j) p.gmax[(size_t)g * p.nqp + qb + c0 + j] = o;
+                        }
+                    } else {
+                        // branch-free filter: 16 compares into a bit mask, one warp-uniform test per group;
+                        // admissions are ~1e-3 of the scores, so the insert path below is rare
+                        uint32_t mask = 0;
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; j4++) {
-                        const float4 t = *reinterpret_cast<const float4*>(&tau_s[c0 + 4 * j4]);
-                        mask |= (__uint_as_float(v[4 * j4 + 0]) >= t.x ? 1u : 0u) << (4 * j4 + 0);
-                        mask |= (__uint_as_float(v[4 * j4 + 1]) >= t.y ? 1u : 0u) << (4 * j4 + 1);
-                        mask |= (__uint_as_float(v[4 * j4 + 2]) >= t.z ? 1u : 0u) << (4 * j4 + 2);
-                        mask |= (__uint_as_float(v[4 * j4 + 3]) >= t.w ? 1u : 0u) << (4 * j4 + 3);
-                    }
-                    if (!row_ok) mask = 0;
-                    if (__any_sync(0xffffffffu, mask != 0)) {
-                        while (mask) {
-                            const int j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const int c = c0 + j;
-                            float s = 0.f;
+                        for (int j4 = 0; j4 < 4; j4++) {
+                            const float4 t = *reinterpret_cast<const float4*>(&tau_s[c0 + 4 * j4]);
+                            mask |= (__uint_as_float(v[4 * j4 + 0]) >= t.x ? 1u : 0u) << (4 * j4 + 0);
+                            mask |= (__uint_as_float(v[4 * j4 + 1]) >= t.y ? 1u : 0u) << (4 * j4 + 1);
+                            mask |= (__uint_as_float(v[4 * j4 + 2]) >= t.z ? 1u : 0u) << (4 * j4 + 2);
+                            mask |= (__uint_as_float(v[4 * j4 + 3]) >= t.w ? 1u : 0u) << (4 * j4 + 3);
+                        }
+                        if (!row_ok) mask = 0;
+                        if (__any_sync(0xffffffffu, mask != 0)) {
+                            while (mask) {
+                                const int j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const int c = c0 + j;
+                                float s = 0.f;
 #pragma unroll
-                            for (int jj = 0; jj < 16; jj++)
-                                if (jj == j) s = __uint_as_float(v[jj]);
-                            int slot = atomicAdd(&cnt_s[c], 1);
-                            if (slot < p.cap)
-                                p.cand[((size_t)blockIdx.x * NP + c) * p.cap + slot] = make_key(s, (uint32_t)row);
-                            else
-                                p.overflow[c] = 1;
+                                for (int jj = 0; jj < 16; jj++)
+                                    if (jj == j) s = __uint_as_float(v[jj]);
+                                int slot = atomicAdd(&cnt_s[c], 1);
+                                if (slot < p.cap)
+                                    p.cand[((size_t)blockIdx.x * p.nqp + qb + c) * p.cap + slot] = make_key(s, (uint32_t)row);
+                                else
+                                    p.overflow[qb + c] = 1;
+                            }
                         }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[a]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
+            if (MODE == MODE_SELECT) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // every epilogue warp has finished the block
+                for (int c = et; c < NP; c += 128) {
+                    int n = cnt_s[c];
+                    p.counts[(size_t)blockIdx.x * p.nqp + qb + c] = n < p.cap ? n : p.cap;
+                }
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (MODE == MODE_SELECT) {
-        for (int c = threadIdx.x; c < NP; c += blockDim.x) {
-            int n = cnt_s[c];
-            p.counts[(size_t)blockIdx.x * NP + c] = n < p.cap ? n : p.cap;
-        }
-    }
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
@@ -447,7 +466,7 @@ int tc_max_queries(int d, int is_bf16) {
 }
 
 static size_t tc_smem_bytes(int nk, int npad, int stages) {
-    return (size_t)nk * npad * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(1 + 2 * stages + 4) * 8 + 32 + (size_t)npad * 8 + 1024;
+    return (size_t)nk * npad * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4) * 8 + 32 + (size_t)npad * 8 + 1024;
 }
 
 template <typename T, int MODE>
@@ -468,20 +487,24 @@ static cudaError_t launch_tc(bool is_bf16, const CUtensorMap& tdb, const CUtenso
                    : launch_tc_mode<float, MODE>(tdb, tq, p, grid, smem, st);
 }
 
+int g_tc_max_stages = 8;  // option "tc_stages"
 static int pick_stages(int nk, int npad) {
-    int stages = 8;
+    int stages = g_tc_max_stages;
     while (stages > 2 && tc_smem_bytes(nk, npad, stages) > 226 * 1024) stages--;
     return stages;
 }
 
-size_t tc_workspace_bytes(const TcPlan& pl) {
-    return pl.off_end;
-}
+size_t tc_workspace_bytes(const TcPlan& pl) { return pl.off_end; }
 
-// Plan one query block of `nq` (<= tc_max_queries) queries over `n` rows.
+// Plan a launch set for `nq` queries over `n` rows: blocks of npad <= tc_max_queries queries are walked
+// inside one persistent launch, so the fixed costs (launches, prologues, pre-pass) are paid once.
 cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, TcPlan* pl) {
     const size_t esz = is_bf16 ? 2 : 4;
-    pl->npad = (nq + 15) / 16 * 16;
+    const int nbmax = tc_max_queries(d, is_bf16);
+    if (nbmax == 0 || nq <= 0) return cudaErrorInvalidValue;
+    pl->npad = nq >= nbmax ? nbmax : (nq + 15) / 16 * 16;
+    pl->nblocks = (nq + pl->npad - 1) / pl->npad;
+    pl->nqp = pl->nblocks * pl->npad;
     pl->nk = (int)((size_t)d * esz / 128);
     pl->stages = pick_stages(pl->nk, pl->npad);
     pl->smem = tc_smem_bytes(pl->nk, pl->npad, pl->stages);
@@ -499,9 +522,14 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     int g2 = 1;
     while (g2 < pl->groups) g2 <<= 1;
     pl->gpow2 = g2;
-    pl->cap = 256;
-    pl->cap_total = 16384;
     pl->kp = kp;
+    // candidate capacity per (CTA, query): the pre-pass threshold admits about 1.1 * kp * n / sampled_rows
+    // rows per query; give every CTA 4x its share plus slack (an overflow only costs a re-run)
+    double expect = 1.1 * kp * (double)n / ((double)pl->groups * 32.0) / pl->grid;
+    int cap = 32;
+    while (cap < 4.0 * expect + 24.0 && cap < 1024) cap <<= 1;
+    pl->cap = cap;
+    pl->cap_total = 16384;
     // workspace layout
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -509,60 +537,67 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
         off = (off + bytes + 255) & ~(size_t)255;
         return o;
     };
-    pl->off_gmax = take((size_t)pl->groups * pl->npad * 4);
-    pl->off_tau0 = take((size_t)pl->npad * 4);
-    pl->off_counts = take((size_t)pl->grid * pl->npad * 4);
-    pl->off_overflow = take((size_t)pl->npad * 4);
-    pl->off_cand = take((size_t)pl->grid * pl->npad * pl->cap * 8);
-    pl->off_qbf16 = take((size_t)pl->npad * d * 2);
+    pl->off_gmax = take((size_t)pl->groups * pl->nqp * 4);
+    pl->off_tau0 = take((size_t)pl->nqp * 4);
+    pl->off_counts = take((size_t)pl->grid * pl->nqp * 4);
+    pl->off_overflow = take((size_t)pl->nqp * 4);
+    pl->off_cand = take((size_t)pl->grid * pl->nqp * pl->cap * 8);
+    pl->off_qbf16 = take((size_t)pl->nqp * d * 2);
     pl->off_end = off;
     return cudaSuccess;
 }
 
-// Scan one query block with the tensor-core path; writes one sorted kp-list per query into `lists`
-// ([nq][kp], the format finalize_kernel takes with L = 1) and sets overflow[q] = 1 where the result
-// must not be trusted.  `ws` is a device workspace of tc_workspace_bytes(pl).
-cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, cudaStream_t st) {
-    CUtensorMap tdb, tq;
-    cudaError_t e = make_tmap(&tdb, a.xb, a.n, a.d, !a.is_bf16, TC_BM);
+static cudaError_t tc_prepare(const TcArgs& a, const TcPlan& pl, unsigned char* ws, CUtensorMap* tdb, CUtensorMap* tq,
+                              TcParams* p, cudaStream_t st) {
+    cudaError_t e = make_tmap(tdb, a.xb, a.n, a.d, !a.is_bf16, TC_BM);
     if (e != cudaSuccess) return e;
     const void* qsrc = a.xq;
     if (a.is_bf16) {
         __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qbf16);
         long long cnt = (long long)a.nq * a.d;
-        f32_to_bf16_rows_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(a.xq, qb, cnt);
+        long long blocks = (cnt + 255) / 256;
+        f32_to_bf16_rows_kernel<<<(int)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(a.xq, qb, cnt);
         g_kernel_launches.fetch_add(1);
         qsrc = qb;
     }
-    e = make_tmap(&tq, qsrc, a.nq, a.d, !a.is_bf16, pl.npad);
-    if (e != cudaSuccess) return e;
+    if ((e = make_tmap(tq, qsrc, a.nq, a.d, !a.is_bf16, pl.npad)) != cudaSuccess) return e;
+    *p = TcParams{};
+    p->n = a.n;
+    p->d = a.d;
+    p->nq = a.nq;
+    p->npad = pl.npad;
+    p->nblocks = pl.nblocks;
+    p->nqp = pl.nqp;
+    p->nk = pl.nk;
+    p->stages = pl.stages;
+    p->gmax = reinterpret_cast<uint32_t*>(ws + pl.off_gmax);
+    p->tau0 = reinterpret_cast<const float*>(ws + pl.off_tau0);
+    p->cand = reinterpret_cast<u64*>(ws + pl.off_cand);
+    p->cap = pl.cap;
+    p->counts = reinterpret_cast<int*>(ws + pl.off_counts);
+    p->overflow = reinterpret_cast<int*>(ws + pl.off_overflow);
+    return cudaSuccess;
+}
 
+// Scan `a.nq` queries with the tensor-core path; writes one sorted kp-list per query into `lists`
+// ([nq][kp], the format finalize_kernel takes with L = 1) and sets overflow[q] = 1 where the result
+// must not be trusted.  `ws` is a device workspace of tc_workspace_bytes(pl).
+cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, cudaStream_t st) {
+    CUtensorMap tdb, tq;
     TcParams p;
-    p.n = a.n;
-    p.d = a.d;
-    p.nq = a.nq;
-    p.npad = pl.npad;
-    p.nk = pl.nk;
-    p.stages = pl.stages;
-    p.gmax = reinterpret_cast<uint32_t*>(ws + pl.off_gmax);
-    p.tau0 = reinterpret_cast<const float*>(ws + pl.off_tau0);
-    p.cand = reinterpret_cast<u64*>(ws + pl.off_cand);
-    p.cap = pl.cap;
-    p.counts = reinterpret_cast<int*>(ws + pl.off_counts);
-    p.overflow = reinterpret_cast<int*>(ws + pl.off_overflow);
-    p.dump = nullptr;
-
+    cudaError_t e = tc_prepare(a, pl, ws, &tdb, &tq, &p, st);
+    if (e != cudaSuccess) return e;
     // 1. threshold pre-pass over the sampled tiles
     p.ntiles = pl.pre_tiles;
     p.tile_stride = pl.pre_stride;
     e = launch_tc<MODE_MAX>(a.is_bf16, tdb, tq, p, pl.pre_grid, pl.smem, st);
     if (e != cudaSuccess) return e;
-    tc_tau0_kernel<<<pl.npad, 256, (size_t)pl.gpow2 * 4, st>>>(p.gmax, pl.groups, pl.gpow2, pl.npad, a.nq, pl.kp,
-                                                             reinterpret_cast<float*>(ws + pl.off_tau0));
+    tc_tau0_kernel<<<pl.nqp, 256, (size_t)pl.gpow2 * 4, st>>>(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp,
+                                                            reinterpret_cast<float*>(ws + pl.off_tau0));
     g_kernel_launches.fetch_add(1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(ws + pl.off_overflow, 0, (size_t)pl.npad * 4, st)) != cudaSuccess) return e;
-    // 2. selection pass over every tile
+    if ((e = cudaMemsetAsync(ws + pl.off_overflow, 0, (size_t)pl.nqp * 4, st)) != cudaSuccess) return e;
+    // 2. selection pass over every tile, all query blocks in one persistent launch
     p.ntiles = pl.ntiles;
     p.tile_stride = 1;
     e = launch_tc<MODE_SELECT>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st);
@@ -570,7 +605,7 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     // 3. per query: gather + sort -> top-kp list
     size_t gs = (size_t)pl.cap_total * 8;
     cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
-    tc_gather_kernel<<<a.nq, 1024, gs, st>>>(p.cand, p.counts, pl.grid, pl.npad, pl.cap, pl.kp, pl.cap_total,
+    tc_gather_kernel<<<a.nq, 1024, gs, st>>>(p.cand, p.counts, pl.grid, pl.nqp, pl.cap, pl.kp, pl.cap_total,
                                             reinterpret_cast<u64*>(a.lists), p.overflow);
     g_kernel_launches.fetch_add(1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -579,27 +614,12 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     return e;
 }
 
-// tests: raw tensor-core scores of every row against a query block, [n][npad] fp32
+// tests: raw tensor-core scores of every row against the queries, [n][nqp] fp32
 cudaError_t tc_dump_scores(const TcArgs& a, const TcPlan& pl, unsigned char* ws, float* out, cudaStream_t st) {
     CUtensorMap tdb, tq;
-    cudaError_t e = make_tmap(&tdb, a.xb, a.n, a.d, !a.is_bf16, TC_BM);
+    TcParams p;
+    cudaError_t e = tc_prepare(a, pl, ws, &tdb, &tq, &p, st);
     if (e != cudaSuccess) return e;
-    const void* qsrc = a.xq;
-    if (a.is_bf16) {
-        __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qbf16);
-        long long cnt = (long long)a.nq * a.d;
-        f32_to_bf16_rows_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(a.xq, qb, cnt);
-        g_kernel_launches.fetch_add(1);
-        qsrc = qb;
-    }
-    if ((e = make_tmap(&tq, qsrc, a.nq, a.d, !a.is_bf16, pl.npad)) != cudaSuccess) return e;
-    TcParams p = {};
-    p.n = a.n;
-    p.d = a.d;
-    p.nq = a.nq;
-    p.npad = pl.npad;
-    p.nk = pl.nk;
-    p.stages = pl.stages;
     p.ntiles = pl.ntiles;
     p.tile_stride = 1;
     p.dump = out;
