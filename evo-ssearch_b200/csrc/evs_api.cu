@@ -624,7 +624,7 @@ extern "C" int evs_merge_partials_dev(int device, int nparts, int64_t nq, int64_
     if (nparts <= 0 || nq < 0 || k <= 0) return fail(EVS_EINVAL, "bad nparts/nq/k");
     if (nq == 0) return EVS_OK;
     if (!scores_dev || !ids_dev || !D_dev || !I_dev) return fail(EVS_EINVAL, "NULL buffer");
-    if ((size_t)nparts * k * 16 > 200 * 1024) return fail(EVS_ELIMIT, "nparts*k too large for one merge");
+    if ((size_t)nparts * k * 24 > 200 * 1024) return fail(EVS_ELIMIT, "nparts*k too large for one merge");
     int rc = use_device(device);
     if (rc) return rc;
     if (part_stride == 0) part_stride = nq * k;

@@ -43,69 +43,222 @@ struct FinalizeParams {
 __device__ __forceinline__ bool cand_better(double sa, long long ia, double sb, long long ib) {
     return (sa > sb) || (sa == sb && ia < ib);
 }
+// The same order on integers (DSETP is quarter-rate on B200, and short-circuit logic branches):
+// map the score to an order-preserving u64 (-0.0 folded onto +0.0 so that equal doubles stay equal).
+__device__ __forceinline__ u64 score_rank_key(double s) { return f64_to_ordered(s == 0.0 ? 0.0 : s); }
+__device__ __forceinline__ int better_i(u64 oa, long long ia, u64 ob, long long ib) {
+    return (int)(oa > ob) | ((int)(oa == ob) & (int)(ia < ib));
+}
+// exact fp32 -> fp64 widening with integer ops for normal numbers (F2F.F64.F32 issues at 1/8 rate)
+__device__ __forceinline__ double widen_f32(float f) {
+    const uint32_t u = __float_as_uint(f);
+    const uint32_t e = (u >> 23) & 0xFFu;
+    if (e == 0u || e == 255u) return (double)f;  // zero, subnormal, inf, nan: the slow exact path
+    const uint32_t hi = (u & 0x80000000u) | ((e + 896u) << 20) | ((u & 0x007FFFFFu) >> 3);
+    const uint32_t lo = u << 29;
+    return __hiloint2double((int)hi, (int)lo);
+}
 
-__device__ __forceinline__ double canon32_dot_bf16(const __nv_bfloat16* __restrict__ x, const float* __restrict__ q,
+__device__ __forceinline__ double canon32_dot_bf16(const __nv_bfloat16* __restrict__ x, const double* __restrict__ q,
                                                    int d, int lane) {
     double acc = 0.0;
     const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
-    for (int i = lane; i < d; i += 32) acc = fma((double)__uint_as_float(((uint32_t)xs[i]) << 16), (double)q[i], acc);
+    for (int i = lane; i < d; i += 32) acc = fma((double)__uint_as_float(((uint32_t)xs[i]) << 16), q[i], acc);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
     return acc;
 }
 
-// grid = nq, block = 1024.  dynamic smem: 32*kp*8 (warp lists) + kp*8 (scores) + kp*8 (ids)
+// CANON-32 of TWO rows at once with the row loads batched (same accumulation order per row; the two
+// rows' load latencies and fp64 chains overlap).  A null row pointer yields -DBL_MAX.
+__device__ __forceinline__ void canon32_dot_pair(const float* __restrict__ xa, const float* __restrict__ xb,
+                                                 const double* __restrict__ qs, int d, int lane, double& ra, double& rb) {
+    double acca = 0.0, accb = 0.0;
+    for (int base = 0; base < d; base += 512) {
+        float va[16], vb[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            int i = base + lane + 32 * u;
+            va[u] = (xa && i < d) ? __ldg(xa + i) : 0.f;
+            vb[u] = (xb && i < d) ? __ldg(xb + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            int i = base + lane + 32 * u;
+            if (i < d) {
+                const double qv = qs[i];
+                acca = fma(widen_f32(va[u]), qv, acca);
+                accb = fma(widen_f32(vb[u]), qv, accb);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        acca = acca + __shfl_xor_sync(0xffffffffu, acca, off);
+        accb = accb + __shfl_xor_sync(0xffffffffu, accb, off);
+    }
+    ra = xa ? acca : -DBL_MAX;
+    rb = xb ? accb : -DBL_MAX;
+}
+
+// grid = nq, block = 1024.
+// The L per-CTA lists are sorted, so the global top-kp is found without merging them all:
+//   T0 = kp-th largest list HEAD is a lower bound of the kp-th best key (kp heads are >= it), only the
+//   <= kp lists whose head is >= T0 can hold survivors, and only their prefix >= T0 does.  The
+//   survivors (about kp + a few for unordered data, kp*kp at most) are sorted in shared memory.
+// dynamic smem: surv[kp*kp] u64 | heads[L] u64 | sc[kp] f64 | id[kp] i64 | ok[kp] u64 | qs[d] f64
 __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kp = p.kp;
-    u64* A = reinterpret_cast<u64*>(smem_raw);            // [32][kp]
-    double* sc = reinterpret_cast<double*>(A + 32 * kp);  // [kp]
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int warp = t >> 5, lane = t & 31, nwarps = nt >> 5;
+    const int kp = p.kp, L = p.L;
+    u64* surv = reinterpret_cast<u64*>(smem_raw);           // [kp*kp]
+    u64* heads = surv + (size_t)kp * kp;                    // [L]
+    double* sc = reinterpret_cast<double*>(heads + L);      // [kp]
     long long* id = reinterpret_cast<long long*>(sc + kp);  // [kp]
-    __shared__ int s_nvalid;
+    u64* ok = reinterpret_cast<u64*>(id + kp);              // [kp] integer rank keys of the scores
+    double* qs = reinterpret_cast<double*>(ok + kp);        // [d] the query widened once
+    __shared__ int s_nsurv, s_nvalid;
+    __shared__ u64 s_T0;
     const int qi = blockIdx.x;
-    const u64* lists = p.lists + (size_t)qi * p.L * kp;
+    const u64* lists = p.lists + (size_t)qi * L * kp;
+    const float* q = p.xq + (size_t)qi * p.d;
 
-    // 1. every warp folds its share of the L sorted lists into its own sorted top-kp
-    u64* Aw = A + (size_t)warp * kp;
-    for (int i = lane; i < kp; i += 32) Aw[i] = (warp < p.L) ? lists[(size_t)warp * kp + i] : 0ull;
-    for (int l = warp + 32; l < p.L; l += 32) warp_merge_top(Aw, lists + (size_t)l * kp, kp, lane);
-    // 2. tree over the 32 warps
-    for (int step = 1; step < 32; step <<= 1) {
-        __syncthreads();
-        if ((warp % (2 * step)) == 0) warp_merge_top(Aw, A + (size_t)(warp + step) * kp, kp, lane);
+    for (int i = t; i < p.d; i += nt) qs[i] = (double)q[i];
+    for (int l = t; l < L; l += nt) heads[l] = lists[(size_t)l * kp];
+    if (t == 0) {
+        s_nsurv = 0;
+        s_nvalid = 0;
+        s_T0 = 0ull;
     }
     __syncthreads();
+    // 1. T0 = kp-th largest head (non-empty keys are unique, so exactly one head has rank kp-1).
+    //    `nper` adjacent lanes share one head and split the comparison range.
+    //    Only every `hs`-th head is ranked (about 2.3*kp of them): still a valid bound (kp keys are >= it),
+    //    a quarter of the comparisons, a few more survivors.  If the survivors then overflow their
+    //    buffer the bound is recomputed from every head (then at most kp lists qualify: <= kp*kp keys).
+    int hs = 1;
+    while ((L / (hs * 2)) * 10 >= kp * 23) hs <<= 1;
+    for (int attempt = 0; attempt < 2; attempt++) {
+    if (attempt == 1) {
+        if (s_nsurv <= kp * kp || hs == 1) break;  // uniform: read after the barrier below
+        __syncthreads();
+        if (t == 0) {
+            s_nsurv = 0;
+            s_T0 = 0ull;
+        }
+        hs = 1;
+        __syncthreads();
+    }
+    const int Ls = (L + hs - 1) / hs;  // sampled heads: lists 0, hs, 2hs, ...
+    if (Ls >= kp) {
+        int nper = 1;
+        while (nper < 32 && nper * 2 * Ls <= nt) nper <<= 1;
+        const int part = t & (nper - 1);
+        for (int l0 = 0; l0 < Ls; l0 += nt / nper) {
+            const int l = l0 + t / nper;
+            const u64 h = l < Ls ? heads[l * hs] : 0ull;
+            int r = 0;
+            if (h != 0ull)
+                for (int j = part; j < Ls; j += nper) r += heads[j * hs] > h ? 1 : 0;
+            for (int off = 1; off < nper; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+            if (h != 0ull && part == 0 && r == kp - 1) s_T0 = h;
+        }
+    }
+    __syncthreads();
+    const u64 T0 = s_T0;  // 0: fewer than kp non-empty lists -> every key survives (at most kp*kp)
+    // 2. survivors: one warp per qualifying list, prefix >= T0
+    for (int l = warp; l < L; l += nwarps) {
+        const u64 h = heads[l];
+        if (h == 0ull || h < T0) continue;  // warp-uniform
+        const u64* src = lists + (size_t)l * kp;
+        u64 keys[4];  // kp <= 128: all loads of the list issued before the first use
+#pragma unroll
+        for (int u = 0; u < 4; u++) keys[u] = (32 * u + lane < kp) ? src[32 * u + lane] : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool keep = keys[u] != 0ull && keys[u] >= T0;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m == 0u) break;
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&s_nsurv, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            const int dst = pos + __popc(m & ((1u << lane) - 1u));
+            if (keep && dst < kp * kp) surv[dst] = keys[u];
+        }
+    }
+    __syncthreads();
+    }  // attempt
+    // 3. the kp best survivors in descending order -> A[0..kp)
+    const int nsurv = s_nsurv;
+    const u64* A;
+    if (nsurv <= nt && nsurv + kp <= kp * kp) {
+        // usual case (a few more than kp survivors): rank by counting, one barrier instead of a sort
+        u64* top = surv + nsurv;  // kp slots behind the survivors
+        for (int i = t; i < kp; i += nt) top[i] = 0ull;
+        __syncthreads();
+        if (t < nsurv) {
+            const u64 key = surv[t];
+            int r = 0;
+            for (int j = 0; j < nsurv; j++) r += surv[j] > key ? 1 : 0;
+            if (r < kp) top[r] = key;
+        }
+        __syncthreads();
+        A = top;
+    } else {
+        int pow2 = kp;
+        while (pow2 < nsurv) pow2 <<= 1;
+        for (int i = nsurv + t; i < pow2; i += nt) surv[i] = 0ull;
+        for (int size = 2; size <= pow2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int e = t; e < (pow2 >> 1); e += nt) {
+                    int i = ((e / stride) * (stride << 1)) + (e % stride);
+                    cmpx_desc(surv, i, i + stride, (i & size) == 0);
+                }
+            }
+        }
+        __syncthreads();
+        A = surv;  // A[0..kp) = the kp best scan keys
+    }
 
-    // 3. canonical re-score of the kp candidates (one warp per candidate)
-    const float* q = p.xq + (size_t)qi * p.d;
-    for (int c = warp; c < kp; c += 32) {
-        u64 key = A[c];
-        double s = -DBL_MAX;
-        long long row = -1;
-        if (key != 0ull) {
-            row = (long long)key_row(key);
-            if (p.xb_is_bf16)
-                s = canon32_dot_bf16(reinterpret_cast<const __nv_bfloat16*>(p.xb) + (size_t)row * p.d, q, p.d, lane);
-            else
-                s = canon32_dot(reinterpret_cast<const float*>(p.xb) + (size_t)row * p.d, q, p.d, lane);
+    // 4. canonical re-score of the kp candidates (a warp takes two candidates at a time)
+    for (int c = 2 * warp; c < kp; c += 2 * nwarps) {
+        const u64 ka = A[c], kb = (c + 1 < kp) ? A[c + 1] : 0ull;
+        const long long rowa = ka ? (long long)key_row(ka) : -1, rowb = kb ? (long long)key_row(kb) : -1;
+        double sa = -DBL_MAX, sb = -DBL_MAX;
+        if (p.xb_is_bf16) {
+            const __nv_bfloat16* xb16 = reinterpret_cast<const __nv_bfloat16*>(p.xb);
+            if (ka) sa = canon32_dot_bf16(xb16 + (size_t)rowa * p.d, qs, p.d, lane);
+            if (kb) sb = canon32_dot_bf16(xb16 + (size_t)rowb * p.d, qs, p.d, lane);
+        } else {
+            const float* xb32 = reinterpret_cast<const float*>(p.xb);
+            canon32_dot_pair(ka ? xb32 + (size_t)rowa * p.d : nullptr, kb ? xb32 + (size_t)rowb * p.d : nullptr, qs, p.d, lane,
+                             sa, sb);
         }
         if (lane == 0) {
-            sc[c] = s;
-            id[c] = row;
+            sc[c] = sa;
+            id[c] = rowa;
+            ok[c] = rowa >= 0 ? score_rank_key(sa) : 0ull;
+            if (c + 1 < kp) {
+                sc[c + 1] = sb;
+                id[c + 1] = rowb;
+                ok[c + 1] = rowb >= 0 ? score_rank_key(sb) : 0ull;
+            }
         }
     }
-    if (threadIdx.x == 0) s_nvalid = 0;
     __syncthreads();
 
-    // 4. rank by counting under (score desc, id asc); ids are unique so ranks are a permutation
-    const int t = threadIdx.x;
+    // 5. rank by counting under (score desc, id asc); ids are unique so ranks are a permutation
     if (t < kp && id[t] >= 0) {
         atomicAdd(&s_nvalid, 1);
         const double st = sc[t];
         const long long it = id[t];
+        const u64 ot = ok[t];
         int rank = 0;
-        for (int j = 0; j < kp; j++) rank += (id[j] >= 0 && cand_better(sc[j], id[j], st, it)) ? 1 : 0;
+        // empty slots have id -1 and key 0: a real candidate never loses to them (its key is > 0 or, for
+        // -DBL_MAX-like scores, ties are broken by id < -1 being impossible) -> mask by id >= 0 arithmetically
+        for (int j = 0; j < kp; j++) rank += better_i(ok[j], id[j], ot, it) & (int)(id[j] >= 0);
         if (rank < p.k) {
             if (p.D) {
                 p.D[(size_t)qi * p.k + rank] = (float)st;
@@ -122,9 +275,9 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
         }
     }
     __syncthreads();
-    // 5. padding (-FLT_MAX,-1) / (-DBL_MAX,-1) for the slots no candidate ranked into
+    // 6. padding (-FLT_MAX,-1) / (-DBL_MAX,-1) for the slots no candidate ranked into
     const int nvalid = s_nvalid;
-    for (int r = nvalid + t; r < p.k; r += blockDim.x) {
+    for (int r = nvalid + t; r < p.k; r += nt) {
         if (p.D) {
             p.D[(size_t)qi * p.k + r] = -FLT_MAX;
             p.I[(size_t)qi * p.k + r] = -1;
@@ -147,14 +300,18 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(int nparts, long lo
     const int m = nparts * k;
     double* sc = reinterpret_cast<double*>(smem_raw);
     long long* id = reinterpret_cast<long long*>(sc + m);
+    u64* ok = reinterpret_cast<u64*>(id + m);  // integer rank keys (see score_rank_key)
     __shared__ int s_nvalid;
     const long long qi = blockIdx.x;
     if (threadIdx.x == 0) s_nvalid = 0;
     for (int e = threadIdx.x; e < m; e += blockDim.x) {
         int part = e / k, r = e % k;
         size_t src = (size_t)part * part_stride + (size_t)qi * k + r;
-        sc[e] = scores[src];
-        id[e] = ids[src];
+        const double sv = scores[src];
+        const long long iv = ids[src];
+        sc[e] = sv;
+        id[e] = iv;
+        ok[e] = iv >= 0 ? score_rank_key(sv) : 0ull;
     }
     __syncthreads();
     for (int e = threadIdx.x; e < m; e += blockDim.x) {
@@ -162,8 +319,9 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(int nparts, long lo
         atomicAdd(&s_nvalid, 1);
         const double st = sc[e];
         const long long it = id[e];
+        const u64 ot = ok[e];
         int rank = 0;
-        for (int j = 0; j < m; j++) rank += (id[j] >= 0 && cand_better(sc[j], id[j], st, it)) ? 1 : 0;
+        for (int j = 0; j < m; j++) rank += better_i(ok[j], id[j], ot, it) & (int)(id[j] >= 0);
         if (rank < k) {
             D[(size_t)qi * k + rank] = (float)st;
             I[(size_t)qi * k + rank] = it;
@@ -377,7 +535,7 @@ cudaError_t launch_synth_fill(float* out, long long n, int d, unsigned long long
 cudaError_t launch_merge_partials(int nparts, long long nq, int k, const double* scores, const long long* ids,
                                   long long part_stride, float* D, long long* I, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    size_t smem = (size_t)nparts * k * 16;
+    size_t smem = (size_t)nparts * k * 24;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -403,10 +561,14 @@ cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
     p.P_scores = a.P_scores;
     p.P_ids = reinterpret_cast<long long*>(a.P_ids);
     p.margins = a.margins;
-    size_t smem = (size_t)32 * a.kp * 8 + (size_t)a.kp * 16;
+    size_t smem = (size_t)a.kp * a.kp * 8 + (size_t)a.L * 8 + (size_t)a.kp * 24 + (size_t)a.d * 8 + 16;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    finalize_kernel<<<(unsigned)a.nq, 1024, smem, st>>>(p);
+    // small batches: 1024 threads shorten the single CTA's critical path; large batches: 256 threads
+    // so that several queries share an SM
+    const int threads = a.nq <= 296 ? 1024 : 256;
+    finalize_kernel<<<(unsigned)a.nq, threads, smem, st>>>(p);
     EVS_LAUNCH_CHECK();
     return cudaSuccess;
 }
