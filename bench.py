@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="scan kernel: 0 auto, 1 direct loads, 2 bulk-async ring")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="row sample for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how shard partials meet -- peer-store exchange kernels over NVLink, or NCCL all-gather + merge")
     ap.add_argument("--extra", action="store_true", help="also time query batches 1/4/16/64 (reported under 'extra')")
     return ap.parse_args()
 
@@ -254,7 +256,8 @@ def run_evs(a) -> int:
         return float(t.item())
 
     evs.set_option("scan_variant", a.variant)
-    index = evs.ShardedIndexFlatIP(a.dim, device=local_rank, storage=a.storage)
+    index = evs.ShardedIndexFlatIP(a.dim, device=local_rank, storage=a.storage, exchange=a.exchange,
+                                   exchange_max_nq=max(64, a.nq), exchange_max_k=a.k)
     t_build = time.perf_counter()
     index.add_synthetic(a.rows, seed=0)
     barrier()
@@ -313,7 +316,8 @@ def run_evs(a) -> int:
     e2e = {"value": a.steps * a.nq / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / a.steps * 1e3,
            "h2d_bytes_per_step": a.nq * a.dim * 4, "d2h_bytes_per_step": a.nq * a.k * 12,
            "api": "IndexFlatIP.search(numpy) -> numpy via evs_index_search" if world == 1
-                  else "ShardedIndexFlatIP.search(numpy) -> numpy (H2D, scan, NCCL all-gather, merge, D2H)"}
+                  else ("ShardedIndexFlatIP.search(numpy) -> numpy (H2D, scan, NCCL all-gather, merge, D2H)" if a.exchange == "nccl"
+                        else "ShardedIndexFlatIP.search(numpy) -> numpy (H2D, scan, peer-store exchange + merge kernels, D2H)")}
     # host API and device API must agree on the last step's query
     same = bool(np.array_equal(Ih, I_last.cpu().numpy()) and np.array_equal(Dh, D_last.cpu().numpy()))
 
@@ -353,6 +357,7 @@ def run_evs(a) -> int:
             "dtype": a.storage, "data": "synthetic",
             "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "nq": a.nq, "k": a.k,
                        "storage": a.storage, "sharding": f"rows/{world}", "rows_per_gpu": rows_local,
+                       "exchange": None if world == 1 else a.exchange,
                        "scan_variant": evs.get_option("scan_variant"),
                        "l2": "inputs larger than L2 (database >> 126 MB); a different query every step",
                        "build_s": round(t_build, 3)},

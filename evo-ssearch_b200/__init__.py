@@ -10,14 +10,14 @@ Importable as ``evo_ssearch_b200`` (shim at the repo root) or, faiss-style, ``im
 """
 from ._lib import EvsError, device_count, get_option, kernel_launches, set_option  # noqa: F401
 from .config import Config, config  # noqa: F401
-from .index import (METRIC_INNER_PRODUCT, METRIC_L2, IndexFlatIP, merge_partials, normalize_L2,  # noqa: F401
-                    read_index, write_index)
+from .index import (METRIC_INNER_PRODUCT, METRIC_L2, IndexFlatIP, PeerExchange, merge_partials,  # noqa: F401
+                    normalize_L2, read_index, write_index)
 from .lifecycle import (clamp_limit, create_index, evict_index, load_index, save_index, search_image,  # noqa: F401
                         search_text)
 from .sharded import ShardedIndexFlatIP, shard_bounds  # noqa: F401
 
 __all__ = [
-    "IndexFlatIP", "read_index", "write_index", "normalize_L2", "merge_partials", "METRIC_INNER_PRODUCT", "METRIC_L2",
+    "IndexFlatIP", "PeerExchange", "read_index", "write_index", "normalize_L2", "merge_partials", "METRIC_INNER_PRODUCT", "METRIC_L2",
     "create_index", "save_index", "load_index", "evict_index", "search_text", "search_image", "clamp_limit",
     "ShardedIndexFlatIP", "shard_bounds", "config", "Config", "EvsError", "device_count", "set_option",
     "get_option", "kernel_launches",

@@ -12,6 +12,7 @@ EVS_OK, EVS_EINVAL, EVS_ENODEV, EVS_ECUDA, EVS_ENOMEM, EVS_EIO, EVS_EFORMAT, EVS
 EVS_F32, EVS_F16, EVS_BF16 = 0, 1, 2
 EVS_STORE_F32, EVS_STORE_BF16_F32 = 0, 1
 EVS_MAX_K = 112
+EVS_IPC_HANDLE_BYTES = 64
 
 _c = ctypes
 _vp, _i, _i64, _u64 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64
@@ -52,6 +53,12 @@ SIGNATURES = {
     "evs_index_scan_profile": (_i, [_vp, _pi64, _c.POINTER(_c.c_double)]),
     "evs_index_tc_max_queries": (_i, [_vp, _pi]),
     "evs_index_tc_scores_dev": (_i, [_vp, _i64, _vp, _vp, _pi, _vp]),
+    "evs_exchange_create": (_i, [_i, _i, _i, _i64, _i64, _c.POINTER(_vp)]),
+    "evs_exchange_handle": (_i, [_vp, _vp, _i64]),
+    "evs_exchange_connect": (_i, [_vp, _vp, _i64]),
+    "evs_exchange_status": (_i, [_vp, _pi, _pi64]),
+    "evs_exchange_free": (_i, [_vp]),
+    "evs_index_search_exchange_dev": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None

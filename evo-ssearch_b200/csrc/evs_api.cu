@@ -382,6 +382,7 @@ struct SearchOut {
     int64_t* I = nullptr;
     double* P_scores = nullptr;  // partial mode
     int64_t* P_ids = nullptr;
+    const Exchange* x = nullptr;  // exchange mode: the finalise kernel stores the partial into every rank's slot
 };
 
 // Enqueue the search of `nq` device-resident queries on stream `st`; outputs are device pointers.
@@ -478,6 +479,11 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
     return EVS_OK;
 }
 
+static bool takes_tc_path(const evs_index* idx, int64_t nq, const ScanTuning& tune) {
+    return tune.tc_min_nq > 0 && nq >= tune.tc_min_nq && idx->ntotal >= 65536 &&
+           tc_max_queries(idx->d, idx->storage == EVS_STORE_BF16_F32) > 0;
+}
+
 static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out,
                                  cudaStream_t st, bool scan_only, bool allow_tc) {
     const int kp = pick_kp(k);
@@ -490,7 +496,7 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
         tune = g_tune;
         profile = g_profile_scans && !scan_only;
     }
-    if (allow_tc && tune.tc_min_nq > 0 && nq >= tune.tc_min_nq && idx->ntotal >= 65536 && tc_max_queries(idx->d, bf16) > 0)
+    if (allow_tc && takes_tc_path(idx, nq, tune))
         return search_tc_locked(idx, nq, q_dev, k, out, st, scan_only, profile);
     const int qpp = max_queries_per_pass(idx->d, bf16);
     ScanPlan plan;
@@ -547,6 +553,11 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
         f.P_scores = out.P_scores ? out.P_scores + (size_t)c0 * k : nullptr;
         f.P_ids = out.P_ids ? out.P_ids + (size_t)c0 * k : nullptr;
         f.margins = idx->margins_dev + c0;
+        if (out.x) {
+            f.x = *out.x;
+            f.x.nq_total = nq;
+            f.x.q_off = c0;
+        }
         CU(launch_finalize(f, st));
     }
     return EVS_OK;
@@ -688,6 +699,163 @@ extern "C" int evs_index_search(evs_index* idx, int64_t nq, const float* q_host,
     CU(cudaStreamSynchronize(st));
     memcpy(D_host, idx->D_pin, out_need * sizeof(float));
     memcpy(I_host, idx->I_pin, out_need * sizeof(int64_t));
+    return EVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer-store exchange of shard partials (row sharding, one process per GPU)
+// ---------------------------------------------------------------------------------------------
+struct evs_exchange {
+    int device = 0, rank = 0, world = 0;
+    int64_t max_nq = 0, max_k = 0;
+    size_t slot_bytes = 0, total_bytes = 0;
+    unsigned char* local = nullptr;     // [2][world][slot_bytes] slots, [2][world] u64 flags, done counter, timeout flag
+    unsigned char* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool opened[8] = {false, false, false, false, false, false, false, false};
+    bool connected = false;
+    unsigned long long seq = 0;
+    double* stage_scores = nullptr;     // local partial staging for the paths that cannot write the slots themselves
+    int64_t* stage_ids = nullptr;
+    std::mutex mu;
+    size_t flags_off() const { return 2 * (size_t)world * slot_bytes; }
+    unsigned* done() const { return reinterpret_cast<unsigned*>(local + flags_off() + 2 * (size_t)world * 8); }
+    int* timed_out() const { return reinterpret_cast<int*>(local + flags_off() + 2 * (size_t)world * 8 + 8); }
+};
+
+extern "C" int evs_exchange_create(int device, int rank, int world, int64_t max_nq, int64_t max_k, evs_exchange** out) {
+    if (!out) return fail(EVS_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > 8) return fail(EVS_ELIMIT, "world must be in [1, 8] (one NVSwitch box), got %d", world);
+    if (rank < 0 || rank >= world) return fail(EVS_EINVAL, "rank %d out of range for world %d", rank, world);
+    if (max_nq <= 0 || max_k <= 0 || max_k > EVS_MAX_K) return fail(EVS_EINVAL, "bad max_nq/max_k");
+    int ndev = 0;
+    evs_device_count(&ndev);
+    if (ndev <= 0) return fail(EVS_ENODEV, "no CUDA device: libevs has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(EVS_EINVAL, "device %d out of range (have %d)", device, ndev);
+    int rc = use_device(device);
+    if (rc) return rc;
+    evs_exchange* ex = new (std::nothrow) evs_exchange();
+    if (!ex) return fail(EVS_ENOMEM, "out of host memory");
+    ex->device = device;
+    ex->rank = rank;
+    ex->world = world;
+    ex->max_nq = max_nq;
+    ex->max_k = max_k;
+    ex->slot_bytes = ((size_t)max_nq * max_k * 16 + 255) & ~(size_t)255;
+    ex->total_bytes = ex->flags_off() + 2 * (size_t)world * 8 + 16;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ex->local), ex->total_bytes);
+    if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->total_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ex->stage_scores), (size_t)max_nq * max_k * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ex->stage_ids), (size_t)max_nq * max_k * 8);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(ex->local);
+        cudaFree(ex->stage_scores);
+        cudaFree(ex->stage_ids);
+        delete ex;
+        return fail(e == cudaErrorMemoryAllocation ? EVS_ENOMEM : EVS_ECUDA, "exchange allocation failed: %s", cudaGetErrorString(e));
+    }
+    ex->peer[rank] = ex->local;
+    ex->connected = (world == 1);
+    *out = ex;
+    return EVS_OK;
+}
+
+extern "C" int evs_exchange_handle(evs_exchange* ex, void* handle_out, int64_t handle_bytes) {
+    if (!ex || !handle_out) return fail(EVS_EINVAL, "NULL argument");
+    if (handle_bytes != EVS_IPC_HANDLE_BYTES) return fail(EVS_EINVAL, "handle buffer must be %d bytes", EVS_IPC_HANDLE_BYTES);
+    static_assert(sizeof(cudaIpcMemHandle_t) == EVS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    int rc = use_device(ex->device);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ex->local));
+    memcpy(handle_out, &h, sizeof(h));
+    return EVS_OK;
+}
+
+extern "C" int evs_exchange_connect(evs_exchange* ex, const void* handles, int64_t handles_bytes) {
+    if (!ex || !handles) return fail(EVS_EINVAL, "NULL argument");
+    if (handles_bytes != (int64_t)ex->world * EVS_IPC_HANDLE_BYTES)
+        return fail(EVS_EINVAL, "expected %d handles of %d bytes", ex->world, EVS_IPC_HANDLE_BYTES);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    int rc = use_device(ex->device);
+    if (rc) return rc;
+    for (int g = 0; g < ex->world; g++) {
+        if (g == ex->rank || ex->opened[g]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const unsigned char*>(handles) + (size_t)g * EVS_IPC_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));  // maps the peer's buffer over NVLink
+        ex->peer[g] = reinterpret_cast<unsigned char*>(p);
+        ex->opened[g] = true;
+    }
+    ex->connected = true;
+    return EVS_OK;
+}
+
+extern "C" int evs_exchange_status(evs_exchange* ex, int* timed_out, int64_t* searches) {
+    if (!ex) return fail(EVS_EINVAL, "ex is NULL");
+    std::lock_guard<std::mutex> lk(ex->mu);
+    int rc = use_device(ex->device);
+    if (rc) return rc;
+    if (timed_out) CU(cudaMemcpy(timed_out, ex->timed_out(), sizeof(int), cudaMemcpyDeviceToHost));
+    if (searches) *searches = (int64_t)ex->seq;
+    return EVS_OK;
+}
+
+extern "C" int evs_exchange_free(evs_exchange* ex) {
+    if (!ex) return EVS_OK;
+    cudaSetDevice(ex->device);
+    cudaDeviceSynchronize();
+    for (int g = 0; g < ex->world; g++)
+        if (ex->opened[g]) cudaIpcCloseMemHandle(ex->peer[g]);
+    cudaFree(ex->local);
+    cudaFree(ex->stage_scores);
+    cudaFree(ex->stage_ids);
+    delete ex;
+    return EVS_OK;
+}
+
+extern "C" int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_dev, int64_t k,
+                                             float* D_dev, int64_t* I_dev, void* stream) {
+    int rc = check_search_args(idx, nq, q_dev, k, D_dev, I_dev);
+    if (rc || nq == 0) return rc;
+    if (!ex) return fail(EVS_EINVAL, "ex is NULL");
+    if (!ex->connected) return fail(EVS_EINVAL, "exchange is not connected (evs_exchange_connect)");
+    if (ex->device != idx->device) return fail(EVS_EINVAL, "exchange lives on device %d, index on %d", ex->device, idx->device);
+    if (nq > ex->max_nq || k > ex->max_k)
+        return fail(EVS_ELIMIT, "nq=%lld k=%lld exceed the exchange's capacity (%lld, %lld)", (long long)nq, (long long)k,
+                    (long long)ex->max_nq, (long long)ex->max_k);
+    std::lock_guard<std::mutex> lk(idx->mu);
+    std::lock_guard<std::mutex> lkx(ex->mu);
+    if ((rc = use_device(idx->device))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    Exchange x;
+    for (int g = 0; g < ex->world; g++) x.peer[g] = ex->peer[g];
+    x.rank = ex->rank;
+    x.world = ex->world;
+    x.seq = ++ex->seq;              // every rank calls in the same order: the sequence numbers agree
+    x.parity = (int)(x.seq & 1ull);  // two generations of slots: a fast rank may start search s+1 while a slow one merges s
+    x.slot_bytes = ex->slot_bytes;
+    x.done = ex->done();
+    x.nq_total = nq;
+    ScanTuning tune;
+    {
+        std::lock_guard<std::mutex> lkt(g_tune_mu);
+        tune = g_tune;
+    }
+    SearchOut out;
+    if (idx->ntotal == 0 || takes_tc_path(idx, nq, tune)) {
+        // empty shard / tensor-core scan (host-side overflow repair): partial into local staging, then publish
+        out.P_scores = ex->stage_scores;
+        out.P_ids = ex->stage_ids;
+        if ((rc = search_dev_common(idx, nq, q_dev, k, out, st))) return rc;
+        CU(launch_publish_partials(x, nq, (int)k, ex->stage_scores, reinterpret_cast<const long long*>(ex->stage_ids), st));
+    } else {
+        out.x = &x;  // the finalise kernel stores this shard's k best straight into every rank's slot
+        if ((rc = search_dev_common(idx, nq, q_dev, k, out, st))) return rc;
+    }
+    CU(launch_merge_exchange(x, nq, (int)k, D_dev, reinterpret_cast<long long*>(I_dev), ex->timed_out(), st));
     return EVS_OK;
 }
 

@@ -39,6 +39,20 @@ struct ScanArgs {
     int kp;
 };
 
+// Peer-store exchange of shard partials (row sharding): every rank owns a symmetric buffer
+//   [2 parities][world shards][slot_bytes]  gather slots (float64 scores [nq*k] then int64 ids [nq*k])
+//   [2 parities][world shards] uint64       arrival flags holding the search sequence number
+// and sees all ranks' buffers through peer-mapped pointers.
+struct Exchange {
+    unsigned char* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int rank = 0, world = 0, parity = 0;
+    unsigned long long seq = 0;
+    size_t slot_bytes = 0;
+    unsigned* done = nullptr;  // local counter of finished finalize CTAs
+    long long nq_total = 0;    // queries of the whole search (a search may be finalised in several launches)
+    long long q_off = 0;       // first query of this launch
+};
+
 struct FinalizeArgs {
     const void* lists;
     int L, kp;
@@ -53,6 +67,7 @@ struct FinalizeArgs {
     double* P_scores;
     int64_t* P_ids;
     float* margins;
+    Exchange x;
 };
 
 // tensor-core scan (evs_tc.cu)
@@ -84,6 +99,10 @@ cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int 
 int max_queries_per_pass(int d, int is_bf16);
 cudaError_t launch_scan(const ScanArgs& a, ScanPlan* plan, cudaStream_t st);
 cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st);
+cudaError_t launch_publish_partials(const Exchange& x, long long nq, int k, const double* scores, const long long* ids,
+                                    cudaStream_t st);
+cudaError_t launch_merge_exchange(const Exchange& x, long long nq, int k, float* D, long long* I, int* timed_out,
+                                  cudaStream_t st);
 cudaError_t launch_merge_partials(int nparts, long long nq, int k, const double* scores, const long long* ids,
                                   long long part_stride, float* D,
                                   long long* I, cudaStream_t st);

@@ -38,7 +38,18 @@ struct FinalizeParams {
     double* P_scores;  // [nq][k]
     long long* P_ids;  // [nq][k]
     float* margins;    // [nq] (may be null)
+    // mode 2: shard partial written straight into every rank's gather buffer over NVLink (peer stores)
+    Exchange x;
 };
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ bool cand_better(double sa, long long ia, double sb, long long ib) {
     return (sa > sb) || (sa == sb && ia < ib);
@@ -263,6 +274,13 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
             if (p.D) {
                 p.D[(size_t)qi * p.k + rank] = (float)st;
                 p.I[(size_t)qi * p.k + rank] = it + p.id_base;
+            } else if (p.x.world > 0) {
+                const size_t e = (size_t)(p.x.q_off + qi) * p.k + rank;
+                for (int g = 0; g < p.x.world; g++) {  // the same 16 bytes to every rank's slot for this shard
+                    unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
+                    reinterpret_cast<double*>(slot)[e] = st;
+                    reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = it + p.id_base;
+                }
             } else {
                 p.P_scores[(size_t)qi * p.k + rank] = st;
                 p.P_ids[(size_t)qi * p.k + rank] = it + p.id_base;
@@ -281,12 +299,126 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
         if (p.D) {
             p.D[(size_t)qi * p.k + r] = -FLT_MAX;
             p.I[(size_t)qi * p.k + r] = -1;
+        } else if (p.x.world > 0) {
+            const size_t e = (size_t)(p.x.q_off + qi) * p.k + r;
+            for (int g = 0; g < p.x.world; g++) {
+                unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
+                reinterpret_cast<double*>(slot)[e] = -DBL_MAX;
+                reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = -1;
+            }
         } else {
             p.P_scores[(size_t)qi * p.k + r] = -DBL_MAX;
             p.P_ids[(size_t)qi * p.k + r] = -1;
         }
     }
     if (t == 0 && p.margins && nvalid < p.k) p.margins[qi] = INFINITY;
+    if (p.x.world > 0) {
+        // publish: when the last query's CTA has written its part, raise this shard's flag on every rank
+        __syncthreads();
+        if (t == 0) {
+            __threadfence_system();
+            const unsigned prev = atomicAdd(p.x.done, 1u);
+            if (prev == (unsigned)p.x.nq_total - 1u) {  // counts across the launches of one search
+                *p.x.done = 0u;
+                __threadfence_system();
+                for (int g = 0; g < p.x.world; g++) {
+                    unsigned long long* flags = reinterpret_cast<unsigned long long*>(p.x.peer[g] + 2 * (size_t)p.x.world * p.x.slot_bytes);
+                    st_release_sys_u64(flags + (size_t)p.x.parity * p.x.world + p.x.rank, p.x.seq);
+                }
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// publish: copy this shard's partial (scores[nq*k], ids[nq*k]) into its slot on EVERY rank over NVLink
+// (peer stores), then raise the arrival flag on every rank.  Used when the partial was produced by a
+// path that cannot write the slots itself (tensor-core scan with its host-side overflow repair, empty
+// shard).  grid = any, block = 256.
+// =============================================================================================
+__global__ void __launch_bounds__(256) publish_partials_kernel(Exchange x, long long count, const double* __restrict__ scores,
+                                                              const long long* __restrict__ ids) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
+        const double sv = scores[e];
+        const long long iv = ids[e];
+        for (int g = 0; g < x.world; g++) {
+            unsigned char* slot = x.peer[g] + ((size_t)x.parity * x.world + x.rank) * x.slot_bytes;
+            reinterpret_cast<double*>(slot)[e] = sv;
+            reinterpret_cast<long long*>(slot + (size_t)count * 8)[e] = iv;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned prev = atomicAdd(x.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *x.done = 0u;
+            __threadfence_system();
+            for (int g = 0; g < x.world; g++) {
+                unsigned long long* flags = reinterpret_cast<unsigned long long*>(x.peer[g] + 2 * (size_t)x.world * x.slot_bytes);
+                st_release_sys_u64(flags + (size_t)x.parity * x.world + x.rank, x.seq);
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// merge after the peer-store exchange: wait until every shard's flag for this search has arrived in the
+// LOCAL gather buffer, then rank the world*k partials of each query.  grid = nq, block = 256.
+// Every rank runs this kernel on its own GPU; the flags are written by the other GPUs' finalize kernels.
+// =============================================================================================
+__global__ void __launch_bounds__(256) merge_exchange_kernel(Exchange x, long long nq, int k, float* __restrict__ D,
+                                                            long long* __restrict__ I, int* __restrict__ timed_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = x.world * k;
+    double* sc = reinterpret_cast<double*>(smem_raw);
+    long long* id = reinterpret_cast<long long*>(sc + m);
+    u64* ok = reinterpret_cast<u64*>(id + m);
+    __shared__ int s_nvalid;
+    const long long qi = blockIdx.x;
+    unsigned char* local = x.peer[x.rank];
+    if (threadIdx.x < x.world) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(local + 2 * (size_t)x.world * x.slot_bytes) +
+                                         (size_t)x.parity * x.world + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(flag) < x.seq) {
+            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a rank never arrived; report instead of hanging
+                *timed_out = 1;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    if (threadIdx.x == 0) s_nvalid = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < m; e += blockDim.x) {
+        const int part = e / k, r = e % k;
+        const unsigned char* slot = local + ((size_t)x.parity * x.world + part) * x.slot_bytes;
+        const double sv = __ldcv(reinterpret_cast<const double*>(slot) + (size_t)qi * k + r);
+        const long long iv = __ldcv(reinterpret_cast<const long long*>(slot + (size_t)nq * k * 8) + (size_t)qi * k + r);
+        sc[e] = sv;
+        id[e] = iv;
+        ok[e] = iv >= 0 ? score_rank_key(sv) : 0ull;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < m; e += blockDim.x) {
+        if (id[e] < 0) continue;
+        atomicAdd(&s_nvalid, 1);
+        const double st = sc[e];
+        const long long it = id[e];
+        const u64 ot = ok[e];
+        int rank = 0;
+        for (int j = 0; j < m; j++) rank += better_i(ok[j], id[j], ot, it) & (int)(id[j] >= 0);
+        if (rank < k) {
+            D[(size_t)qi * k + rank] = (float)st;
+            I[(size_t)qi * k + rank] = it;
+        }
+    }
+    __syncthreads();
+    for (int r = s_nvalid + threadIdx.x; r < k; r += blockDim.x) {
+        D[(size_t)qi * k + r] = -FLT_MAX;
+        I[(size_t)qi * k + r] = -1;
+    }
 }
 
 // =============================================================================================
@@ -544,6 +676,28 @@ cudaError_t launch_merge_partials(int nparts, long long nq, int k, const double*
     return cudaSuccess;
 }
 
+cudaError_t launch_publish_partials(const Exchange& x, long long nq, int k, const double* scores, const long long* ids,
+                                    cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    const long long count = nq * k;
+    int grid = (int)((count + 255) / 256 < 64 ? (count + 255) / 256 : 64);
+    publish_partials_kernel<<<grid, 256, 0, st>>>(x, count, scores, ids);
+    EVS_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_merge_exchange(const Exchange& x, long long nq, int k, float* D, long long* I, int* timed_out,
+                                  cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    size_t smem = (size_t)x.world * k * 24;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(merge_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    merge_exchange_kernel<<<(unsigned)nq, 256, smem, st>>>(x, nq, k, D, I, timed_out);
+    EVS_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
 cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
     if (a.nq <= 0) return cudaSuccess;
     FinalizeParams p;
@@ -561,6 +715,7 @@ cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
     p.P_scores = a.P_scores;
     p.P_ids = reinterpret_cast<long long*>(a.P_ids);
     p.margins = a.margins;
+    p.x = a.x;
     size_t smem = (size_t)a.kp * a.kp * 8 + (size_t)a.L * 8 + (size_t)a.kp * 24 + (size_t)a.d * 8 + 16;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)

@@ -200,6 +200,22 @@ class IndexFlatIP:
                                                  ctypes.c_void_p(st)))
         return S, I
 
+    def search_exchange(self, exchange: "PeerExchange", x, k: int):
+        """Row-sharded search in one call (CUDA tensors only): scan this shard, store its k best into every
+        rank's exchange slot over NVLink, wait for all shards' partials and merge -> final ``(D, I)``.
+        Collective: every rank calls it in the same order with the same ``nq`` and ``k``."""
+        import torch
+        assert _is_torch_cuda(x) and x.dim() == 2 and x.shape[1] == self.d and k > 0
+        x = x.to(torch.float32).contiguous()
+        n = x.shape[0]
+        D = torch.empty((n, k), dtype=torch.float32, device=x.device)
+        I = torch.empty((n, k), dtype=torch.int64, device=x.device)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        check(lib().evs_index_search_exchange_dev(self._h, exchange._h, n, ctypes.c_void_p(x.data_ptr()), int(k),
+                                                  ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                                  ctypes.c_void_p(st)))
+        return D, I
+
     def last_margins(self, nq: int) -> np.ndarray:
         """Safety margin per query of the last search (see ``evs_index_last_margins``)."""
         out = np.empty(nq, np.float32)
@@ -252,6 +268,43 @@ class IndexFlatIP:
 
     def reconstruct(self, key: int) -> np.ndarray:
         return self.reconstruct_n(int(key), 1)[0]
+
+
+class PeerExchange:
+    """Symmetric peer-mapped buffer for the shard-partial exchange (``evs_exchange_*``): replaces the
+    all-gather + merge of a row-sharded search by NVLink stores issued from the finalise kernel and a
+    flag-waiting merge kernel.  One per rank; ``connect`` takes the 64-byte handles of all ranks in
+    rank order (exchanged by the caller, e.g. ``torch.distributed.all_gather``)."""
+
+    def __init__(self, device: int, rank: int, world: int, max_nq: int = 1024, max_k: int = 48):
+        self._h = ctypes.c_void_p()
+        self.rank, self.world, self.max_nq, self.max_k = int(rank), int(world), int(max_nq), int(max_k)
+        check(lib().evs_exchange_create(int(device), self.rank, self.world, self.max_nq, self.max_k, ctypes.byref(self._h)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().evs_exchange_free(h)
+            except Exception:
+                pass
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(_lib.EVS_IPC_HANDLE_BYTES)
+        check(lib().evs_exchange_handle(self._h, buf, _lib.EVS_IPC_HANDLE_BYTES))
+        return buf.raw
+
+    def connect(self, handles) -> None:
+        """``handles``: the ``world`` handles in rank order (bytes objects or one concatenated bytes)."""
+        blob = handles if isinstance(handles, (bytes, bytearray)) else b"".join(bytes(h) for h in handles)
+        assert len(blob) == self.world * _lib.EVS_IPC_HANDLE_BYTES
+        check(lib().evs_exchange_connect(self._h, ctypes.c_char_p(bytes(blob)), len(blob)))
+
+    def status(self):
+        """``(timed_out, searches)``: whether any merge gave up waiting for a rank, and the search count."""
+        t, n = ctypes.c_int(0), ctypes.c_int64(0)
+        check(lib().evs_exchange_status(self._h, ctypes.byref(t), ctypes.byref(n)))
+        return bool(t.value), n.value
 
 
 def write_index(index: IndexFlatIP, fname: str) -> None:

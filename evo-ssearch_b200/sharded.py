@@ -8,6 +8,11 @@ rank) followed by a replicated G-way merge kernel gives every rank the final ``(
 shard's scores are produced by the same canonical arithmetic, the merged result is bit-identical to
 the single-GPU result for any G.
 
+``exchange="peer"`` replaces the NCCL call and the separate merge by the library's peer-store exchange
+(``evs_exchange_*``): the finalise kernel writes the shard's partial into every rank's mapped buffer over
+NVLink and a flag-waiting merge kernel produces ``(D, I)`` -- two kernels fewer on the single-query
+latency path, no host-launched collective.  The default ``"nccl"`` path is the portable one.
+
 ``torch.distributed`` is plumbing only (process group, the all-gather).  The local engine and the merge
 are injectable so that the host logic can be exercised on CPU with ``gloo`` in the tests; the defaults
 are the CUDA ones and nothing here falls back to CPU on its own.
@@ -31,7 +36,8 @@ class ShardedIndexFlatIP:
     """``IndexFlatIP`` over the GPUs of one box; call the same methods with the same arguments on every rank."""
 
     def __init__(self, d: int, *, group=None, device: Optional[int] = None, storage: Optional[str] = None,
-                 local_index=None, merge: Optional[Callable] = None):
+                 local_index=None, merge: Optional[Callable] = None, exchange: str = "nccl",
+                 exchange_max_nq: int = 1024, exchange_max_k: int = 48):
         import torch.distributed as dist
         self._dist = dist
         self.group = group
@@ -47,6 +53,24 @@ class ShardedIndexFlatIP:
         self.local = local_index
         self._merge = merge
         self._ntotal = 0
+        assert exchange in ("nccl", "peer")
+        self.exchange = exchange
+        self._px = None
+        if exchange == "peer" and self.world > 1:
+            self._px = self._make_peer_exchange(exchange_max_nq, exchange_max_k)
+
+    def _make_peer_exchange(self, max_nq: int, max_k: int):
+        """Create this rank's buffer and swap the 64-byte IPC handles with one small all-gather."""
+        import torch
+        from .index import PeerExchange
+        px = PeerExchange(self.local.device, self.rank, self.world, max_nq, max_k)
+        dev = torch.device("cuda", self.local.device)
+        mine = torch.frombuffer(bytearray(px.handle()), dtype=torch.uint8).to(dev)
+        allh = torch.empty((self.world, mine.numel()), dtype=torch.uint8, device=dev)
+        self._dist.all_gather_into_tensor(allh, mine, group=self.group)
+        px.connect(allh.cpu().numpy().tobytes())
+        self._dist.barrier(group=self.group)  # every rank has mapped every buffer before the first search
+        return px
 
     # -- bookkeeping --------------------------------------------------------------------------
     @property
@@ -95,6 +119,8 @@ class ShardedIndexFlatIP:
         nq = xq.shape[0]
         if self.world == 1 and hasattr(self.local, "_search_torch"):
             return self.local.search(xq, k)  # one shard: the finalise kernel emits (D, I) directly
+        if self._px is not None and nq <= self._px.max_nq and k <= self._px.max_k:
+            return self.local.search_exchange(self._px, xq, k)  # partial -> peers' slots -> merge, no NCCL call
         S, I = self.local.search_partial(xq, k)  # float64 [nq,k], int64 [nq,k] with global ids
         if self.world == 1:
             return self._merge(S.unsqueeze(0), I.unsqueeze(0), k)

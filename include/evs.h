@@ -131,6 +131,29 @@ EVS_API int evs_index_search_partial_dev(evs_index* idx, int64_t nq, const float
                                  int64_t* out_ids_dev, void* stream);
 EVS_API int evs_merge_partials_dev(int device, int nparts, int64_t nq, int64_t k, const double* scores_dev,
                            const int64_t* ids_dev, int64_t part_stride, float* D_dev, int64_t* I_dev, void* stream);
+/* ---- peer-store exchange (row sharding without a host-launched collective) ---------------------
+ * Replaces the all-gather + merge of SURVEY.md section 8(e) -- (fp64 score, id)[nq][k] per rank -- by
+ * stores over NVLink: every rank owns one symmetric buffer of `world` slots (two generations) that all
+ * ranks map (CUDA IPC).  evs_index_search_exchange_dev scans the local shard, and its finalise kernel
+ * writes the shard's k best into slot `rank` of EVERY rank's buffer, then raises a flag there
+ * (st.release.sys); a merge kernel on each rank waits for the `world` flags of this search
+ * (ld.acquire.sys) and ranks the world*k partials into the final (D, I).  No NCCL call, no host
+ * synchronisation; all ranks must call it in the same order with the same nq and k.
+ *   evs_exchange_create   allocate the local buffer for at most max_nq queries x max_k results.
+ *   evs_exchange_handle   64-byte IPC handle of the local buffer (all-gather these out of band).
+ *   evs_exchange_connect  map the peers' buffers from `world` handles laid out by rank.
+ *   evs_exchange_status   *timed_out = 1 if some merge waited ~10 s for a rank that never arrived.
+ * world == 1 needs no connect.  One process per GPU (two ranks of one exchange must not share a GPU).
+ */
+#define EVS_IPC_HANDLE_BYTES 64
+typedef struct evs_exchange evs_exchange; /* opaque */
+EVS_API int evs_exchange_create(int device, int rank, int world, int64_t max_nq, int64_t max_k, evs_exchange** out);
+EVS_API int evs_exchange_handle(evs_exchange* ex, void* handle_out, int64_t handle_bytes);
+EVS_API int evs_exchange_connect(evs_exchange* ex, const void* handles, int64_t handles_bytes);
+EVS_API int evs_exchange_status(evs_exchange* ex, int* timed_out, int64_t* searches);
+EVS_API int evs_exchange_free(evs_exchange* ex);
+EVS_API int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_dev, int64_t k,
+                                  float* D_dev, int64_t* I_dev, void* stream);
 /* per-query safety margin of the last search on this handle: canonical score of the k-th result
  * minus the scan score of the worst retained candidate (+inf when every row was a candidate).
  * A positive margin larger than the scan's error bound certifies the result exact. */

@@ -1,5 +1,7 @@
-"""torchrun --nproc-per-node G scripts/check_sharded.py : row-sharded search over G GPUs (NCCL all-gather +
-merge kernel) must equal the CPU oracle's canonical ranking bit for bit, for f32 and bf16 storage."""
+"""torchrun --nproc-per-node G scripts/check_sharded.py : row-sharded search over G GPUs must equal the CPU
+oracle's canonical ranking bit for bit, for f32 and bf16 storage, through both exchanges: the NCCL
+all-gather + merge kernel, and the peer-store exchange (finalise kernel writes every rank's slot over
+NVLink, flag-waiting merge kernel)."""
 import os
 import sys
 
@@ -20,16 +22,21 @@ for n, d, k, nqs in ((1_000_003, 512, 48, (1, 16)), (200_001, 768, 12, (1, 5)), 
     if n > 10:
         xb[n - 1] = xb[0]  # exact tie across the first and last shard
     xq = oracle.synth_fill(max(nqs), d, 1)
-    for storage in ("f32", "bf16"):
-        sh = evs.ShardedIndexFlatIP(d, device=local, storage=storage)
+    for storage, exchange in (("f32", "nccl"), ("bf16", "nccl"), ("f32", "peer"), ("bf16", "peer")):
+        sh = evs.ShardedIndexFlatIP(d, device=local, storage=storage, exchange=exchange, exchange_max_nq=64)
         sh.add(xb)
         for nq in nqs:
-            D, I = sh.search(xq[:nq], k)
-            Dr, Ir = oracle.canon_search(xq[:nq], xb, k)
-            good = bool(np.array_equal(I, Ir) and np.array_equal(D, Dr))
-            ok = ok and good
+            for rep in range(3 if exchange == "peer" else 1):  # both slot generations and their reuse
+                D, I = sh.search(xq[:nq], k)
+                Dr, Ir = oracle.canon_search(xq[:nq], xb, k)
+                good = bool(np.array_equal(I, Ir) and np.array_equal(D, Dr))
+                ok = ok and good
             if rank == 0:
-                print(f"n={n} d={d} k={k} nq={nq} storage={storage} world={world}: {'OK' if good else 'MISMATCH'}", flush=True)
+                print(f"n={n} d={d} k={k} nq={nq} storage={storage} exchange={exchange} world={world}: "
+                      f"{'OK' if good else 'MISMATCH'}", flush=True)
+        if sh._px is not None:
+            timed_out, searches = sh._px.status()
+            ok = ok and not timed_out and searches > 0
         # generated-in-place shards equal host-fed shards
         sh2 = evs.ShardedIndexFlatIP(d, device=local, storage=storage)
         sh2.add_synthetic(n, seed=0)

@@ -90,3 +90,10 @@ def test_null_and_range_arguments():
     assert L.evs_index_ntotal(None, ctypes.byref(n)) == _lib.EVS_EINVAL
     assert L.evs_index_search(None, 1, None, 1, None, None) == _lib.EVS_EINVAL
     assert L.evs_merge_partials_dev(0, 0, 1, 1, None, None, 0, None, None, None) == _lib.EVS_EINVAL
+    ex = ctypes.c_void_p()
+    assert L.evs_exchange_create(0, 0, 9, 16, 48, ctypes.byref(ex)) == _lib.EVS_ELIMIT  # one box: world <= 8
+    assert L.evs_exchange_create(0, 2, 2, 16, 48, ctypes.byref(ex)) == _lib.EVS_EINVAL
+    assert L.evs_exchange_create(0, 0, 1, 16, 4096, ctypes.byref(ex)) == _lib.EVS_EINVAL
+    assert L.evs_exchange_free(None) == 0
+    assert L.evs_index_search_exchange_dev(None, None, 1, None, 1, None, None, None) == _lib.EVS_EINVAL
+    assert not ex.value

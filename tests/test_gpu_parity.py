@@ -271,6 +271,43 @@ def test_partials_and_merge_equal_single_index():
     assert np.array_equal(Ifin.cpu().numpy(), It) and np.array_equal(D.cpu().numpy(), Dt)
 
 
+def test_peer_exchange_single_rank_equals_search():
+    """evs_exchange_* with world = 1 (the slots live on this GPU): the fused finalise -> slot -> flag ->
+    merge path, the publish path (tensor-core scan, empty shard), slot-generation reuse and the limits.
+    The cross-GPU case runs under torchrun in scripts/check_sharded.py (tests/test_gpu_sharded.py)."""
+    import torch
+    d, n, k = 512, 70_001, 48
+    xb = oracle.synth_fill(n, d, 71)
+    xq = oracle.synth_fill(300, d, 72)
+    idx = _index(xb)
+    idx.id_base = 1000
+    px = evs.PeerExchange(0, 0, 1, max_nq=300, max_k=48)
+    assert len(px.handle()) == 64
+    xq_t = torch.from_numpy(xq).cuda()
+    evs.set_option("tc_min_nq", 0)  # GEMV scan: the finalise kernel writes the slots itself
+    try:
+        for nq, kk in ((1, 48), (3, 12), (1, 48), (300, 48), (2, 1)):  # 300 > one finalise launch (256 queries)
+            Dr, Ir = idx.search(xq[:nq], kk)
+            D, I = idx.search_exchange(px, xq_t[:nq], kk)
+            assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr), (nq, kk)
+        evs.set_option("tc_min_nq", 4)  # tensor-core scan: partial staged locally, then published
+        Dr, Ir = idx.search(xq[:40], 48)
+        D, I = idx.search_exchange(px, xq_t[:40], 48)
+        assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
+    finally:
+        evs.set_option("tc_min_nq", 4)
+    empty = evs.IndexFlatIP(d)
+    D, I = empty.search_exchange(px, xq_t[:2], 5)
+    assert (I.cpu().numpy() == -1).all() and (D.cpu().numpy() == np.finfo(np.float32).min).all()
+    timed_out, searches = px.status()
+    assert not timed_out and searches == 7
+    with pytest.raises(evs.EvsError):
+        idx.search_exchange(px, torch.from_numpy(oracle.synth_fill(301, d, 1)).cuda(), 48)  # beyond max_nq
+    px2 = evs.PeerExchange(0, 0, 2, max_nq=4, max_k=48)  # world 2, never connected
+    with pytest.raises(evs.EvsError):
+        idx.search_exchange(px2, xq_t[:1], 48)
+
+
 def test_concurrent_search_threads():
     """The Flask dev server is threaded (oldapp.py:2258): concurrent searches on one handle."""
     d = 512
