@@ -49,7 +49,7 @@ static int g_profile_scans = 0;  // record CUDA events around every search's sca
 // the handle
 // ---------------------------------------------------------------------------------------------
 static const int kQueryChunk = 256;     // GEMV path: queries finalised per launch (bounds the list workspace)
-static const int kTcQueryChunk = 2048;  // tensor-core path: queries per launch set
+static const int kTcQueryChunk = 4096;  // tensor-core path: queries per launch set
 
 struct evs_index {
     int d = 0, device = 0, storage = EVS_STORE_F32;
@@ -146,6 +146,12 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "tc_min_nq")) {
         if (value < 0) return fail(EVS_EINVAL, "tc_min_nq must be >= 0");
         g_tune.tc_min_nq = (int)value;
+    } else if (!strcmp(name, "tc_pair_min_nq")) {
+        if (value < 0) return fail(EVS_EINVAL, "tc_pair_min_nq must be >= 0");
+        g_tune.tc_pair_min_nq = (int)value;
+    } else if (!strcmp(name, "tc2_slice_tiles")) {
+        if (value < 0 || value > 4096) return fail(EVS_EINVAL, "tc2_slice_tiles must be in [0, 4096]");
+        g_tc2_slice_tiles = (int)value;
     } else if (!strcmp(name, "tc_stages")) {
         if (value < 2 || value > 14) return fail(EVS_EINVAL, "tc_stages must be in [2, 14]");
         g_tc_max_stages = (int)value;
@@ -165,6 +171,8 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "stages")) *value = g_tune.stages;
     else if (!strcmp(name, "ctas_per_sm")) *value = g_tune.ctas_per_sm;
     else if (!strcmp(name, "tc_min_nq")) *value = g_tune.tc_min_nq;
+    else if (!strcmp(name, "tc_pair_min_nq")) *value = g_tune.tc_pair_min_nq;
+    else if (!strcmp(name, "tc2_slice_tiles")) *value = g_tc2_slice_tiles;
     else if (!strcmp(name, "tc_stages")) *value = g_tc_max_stages;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
     else return fail(EVS_EINVAL, "unknown option '%s'", name);
@@ -396,13 +404,27 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
 // Tensor-core path for a batch: one database pass per block of up to tc_max_queries queries.
 // Queries whose candidate buffers overflowed are re-run through the GEMV path (needs one host sync).
 static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st,
-                            bool scan_only, int profile) {
+                            bool scan_only, int profile, int pair_min_nq) {
     const int kp = pick_kp(k);
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
     const void* scan_rows = bf16 ? idx->xb16 : (const void*)idx->xb32;
-    TcPlan pl;
-    CU(tc_plan(idx->ntotal, idx->d, bf16, (int)(nq < kTcQueryChunk ? nq : kTcQueryChunk), kp, idx->sm_count, &pl));
-    int rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc_workspace_bytes(pl));
+    // batches of pair_min_nq or more queries go through the CTA-pair kernel (N up to 256 per MMA, L2-shared slices)
+    const bool can_pair = pair_min_nq > 0 && tc2_max_half(idx->d, bf16) > 0 && idx->sm_count >= 2;
+    auto use_pair = [&](int64_t cn) { return can_pair && cn >= pair_min_nq; };
+    const int64_t first = nq < kTcQueryChunk ? nq : kTcQueryChunk;
+    size_t ws_need = 0;
+    if (use_pair(first)) {
+        Tc2Plan p2;
+        CU(tc2_plan(idx->ntotal, idx->d, bf16, (int)first, kp, idx->sm_count, &p2));
+        ws_need = tc2_workspace_bytes(p2);
+    }
+    const int64_t last = nq % kTcQueryChunk;  // a shorter final chunk may take the other kernel
+    if (!use_pair(first) || (last && !use_pair(last))) {
+        TcPlan pl;
+        CU(tc_plan(idx->ntotal, idx->d, bf16, (int)(use_pair(first) ? last : first), kp, idx->sm_count, &pl));
+        if (tc_workspace_bytes(pl) > ws_need) ws_need = tc_workspace_bytes(pl);
+    }
+    int rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, ws_need);
     if (rc) return rc;
     if ((rc = ensure_dev(&idx->tc_overflow, &idx->tc_overflow_cap, (size_t)nq))) return rc;
     const int64_t chunk_cap = nq < kTcQueryChunk ? nq : kTcQueryChunk;
@@ -423,9 +445,6 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
             CU(cudaEventRecord(pe->first, st));
         }
         {
-            TcPlan plb;  // same workspace bound: cn <= the chunk the workspace was sized for
-            CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, &plb));
-            if (tc_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
             TcArgs a;
             a.xb = scan_rows;
             a.is_bf16 = bf16;
@@ -435,7 +454,17 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
             a.nq = (int)cn;
             a.lists = idx->lists;
             a.overflow_out = idx->tc_overflow + c0;
-            CU(tc_scan_block(a, plb, idx->tc_ws, st));
+            if (use_pair(cn)) {
+                Tc2Plan plb;
+                CU(tc2_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, &plb));
+                if (tc2_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
+                CU(tc2_scan(a, plb, idx->tc_ws, st));
+            } else {
+                TcPlan plb;  // same workspace bound: cn <= the chunk the workspace was sized for
+                CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, &plb));
+                if (tc_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
+                CU(tc_scan_block(a, plb, idx->tc_ws, st));
+            }
         }
         if (pe) CU(cudaEventRecord(pe->second, st));
         if (scan_only) continue;
@@ -497,7 +526,7 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
         profile = g_profile_scans && !scan_only;
     }
     if (allow_tc && takes_tc_path(idx, nq, tune))
-        return search_tc_locked(idx, nq, q_dev, k, out, st, scan_only, profile);
+        return search_tc_locked(idx, nq, q_dev, k, out, st, scan_only, profile, tune.tc_pair_min_nq);
     const int qpp = max_queries_per_pass(idx->d, bf16);
     ScanPlan plan;
     CU(plan_scan(idx->ntotal, idx->d, bf16, kp, qpp, idx->sm_count, tune, &plan));
@@ -926,18 +955,21 @@ extern "C" int evs_index_tc_max_queries(const evs_index* idx, int* max_queries) 
 }
 
 extern "C" int evs_index_tc_scores_dev(evs_index* idx, int64_t nq, const float* q_dev, float* out_dev, int* npad, void* stream) {
-    if (!idx || !q_dev || !out_dev || !npad) return fail(EVS_EINVAL, "NULL argument");
+    if (!idx || !q_dev || !npad) return fail(EVS_EINVAL, "NULL argument");
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
     const int nb_max = tc_max_queries(idx->d, bf16);
     if (nb_max == 0) return fail(EVS_ELIMIT, "d = %d is not supported by the tensor-core scan", idx->d);
-    if (nq <= 0 || nq > nb_max) return fail(EVS_EINVAL, "nq must be in [1, %d]", nb_max);
+    int pair_min;
+    {
+        std::lock_guard<std::mutex> lk(g_tune_mu);
+        pair_min = g_tune.tc_pair_min_nq;
+    }
+    const bool pair = pair_min > 0 && nq >= pair_min && tc2_max_half(idx->d, bf16) > 0;
+    if (nq <= 0 || (!pair && nq > nb_max) || nq > 4096) return fail(EVS_EINVAL, "nq must be in [1, %d]", pair ? 4096 : nb_max);
     if (idx->ntotal == 0) return fail(EVS_EINVAL, "empty index");
     std::lock_guard<std::mutex> lk(idx->mu);
     int rc = use_device(idx->device);
     if (rc) return rc;
-    TcPlan pl;
-    CU(tc_plan(idx->ntotal, idx->d, bf16, (int)nq, 64, idx->sm_count, &pl));
-    if ((rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc_workspace_bytes(pl)))) return rc;
     TcArgs a;
     a.xb = bf16 ? idx->xb16 : (const void*)idx->xb32;
     a.is_bf16 = bf16;
@@ -948,10 +980,25 @@ extern "C" int evs_index_tc_scores_dev(evs_index* idx, int64_t nq, const float* 
     a.lists = nullptr;
     a.overflow_out = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
-    CU(tc_dump_scores(a, pl, idx->tc_ws, out_dev, st));
+    if (pair) {
+        Tc2Plan pl;
+        CU(tc2_plan(idx->ntotal, idx->d, bf16, (int)nq, 64, idx->sm_count, &pl));
+        *npad = pl.nqp;
+        if (!out_dev) return EVS_OK;  // pitch query
+        if ((rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc2_workspace_bytes(pl)))) return rc;
+        CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+        CU(tc2_dump_scores(a, pl, idx->tc_ws, out_dev, st));
+        *npad = pl.nqp;
+    } else {
+        TcPlan pl;
+        CU(tc_plan(idx->ntotal, idx->d, bf16, (int)nq, 64, idx->sm_count, &pl));
+        *npad = pl.npad;
+        if (!out_dev) return EVS_OK;  // pitch query
+        if ((rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc_workspace_bytes(pl)))) return rc;
+        CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+        CU(tc_dump_scores(a, pl, idx->tc_ws, out_dev, st));
+    }
     CU(cudaEventRecord(idx->ws_free, st));
-    *npad = pl.npad;
     return EVS_OK;
 }
 

@@ -17,6 +17,7 @@ struct ScanTuning {
     int stages = 0;        // ring: depth (0 = 4)
     int ctas_per_sm = 0;   // direct: CTAs per SM (0 = 2 fp32 / 4 bf16)
     int tc_min_nq = 4;     // query batches of at least this many use the tensor-core scan (0 = never)
+    int tc_pair_min_nq = 129;  // ... and of at least this many the CTA-pair kernel (evs_tc2.cu); 0 = never
 };
 
 struct ScanPlan {
@@ -87,6 +88,20 @@ struct TcArgs {
     void* lists;      // out: u64 [nq][kp]
     int* overflow_out;  // out (optional): int [nq]
 };
+// CTA-pair tensor-core scan for large batches (evs_tc2.cu)
+struct Tc2Plan {
+    int npad, half, nqb, nqp, nk, stages, grid, pre_grid, groups, gpow2, cap, cap_total, kp;
+    int slice_tiles, pre_slice_tiles;
+    size_t smem;
+    long long ntiles, nslices, pre_tiles, pre_stride, pre_nslices;
+    size_t off_gmax, off_tau0, off_counts, off_overflow, off_cand, off_qbf16, off_end;
+};
+extern int g_tc2_slice_tiles;
+int tc2_max_half(int d, int is_bf16);
+cudaError_t tc2_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, Tc2Plan* pl);
+size_t tc2_workspace_bytes(const Tc2Plan& pl);
+cudaError_t tc2_scan(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, cudaStream_t st);
+cudaError_t tc2_dump_scores(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, float* out, cudaStream_t st);
 extern int g_tc_max_stages;
 int tc_max_queries(int d, int is_bf16);
 cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, TcPlan* pl);

@@ -29,10 +29,9 @@
 
 #include "evs_internal.h"
 #include "evs_common.cuh"
+#include "evs_tc_common.cuh"
 
 namespace evs {
-
-enum { MODE_MAX = 0, MODE_SELECT = 1, MODE_DUMP = 2 };
 
 struct TcParams {
     long long n;          // rows in the shard
@@ -58,78 +57,11 @@ struct TcParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-// PTX wrappers: TMA tensor loads, tcgen05 alloc / mma / commit / ld
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <bool TF32>
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (TF32) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
-}
-// arrive on an mbarrier when all MMAs issued so far by this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory operand descriptor (what TMA SWIZZLE_128B writes):
-// rows are 128 bytes apart, 8-row groups 1024 bytes apart (SBO), descriptor version 1 (sm_100).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: fp32 accumulate, A and B K-major, M x N tile
-__host__ __device__ constexpr uint32_t make_idesc(bool tf32, int M, int N) {
-    return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// ---------------------------------------------------------------------------------------------
 // the kernel.  dynamic shared memory (1024-byte aligned base):
 //   [0, nk*npad*128)                  resident query block, chunk-major: chunk c at c*npad*128
 //   [.., + stages*16384)              ring of database tiles (128 rows x 128 B)
 //   then barriers, TMEM base address, tau0[npad], cnt[npad]
 // ---------------------------------------------------------------------------------------------
-constexpr int TC_BM = 128;           // rows per tile = MMA M
-constexpr int TC_STAGE_BYTES = TC_BM * 128;
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256, 1)
@@ -441,7 +373,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2-D row-major [rows][d] tensor, box = 128 bytes of K x box_rows rows, 128-byte swizzle
-static cudaError_t make_tmap(CUtensorMap* map, const void* base, long long rows, int d, bool is_f32, int box_rows) {
+cudaError_t tc_make_tmap(CUtensorMap* map, const void* base, long long rows, int d, bool is_f32, int box_rows) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return cudaErrorNotSupported;
     const size_t esz = is_f32 ? 4 : 2;
@@ -453,6 +385,30 @@ static cudaError_t make_tmap(CUtensorMap* map, const void* base, long long rows,
                      gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t tc_queries_to_bf16(const float* xq, void* dst, long long count, cudaStream_t st) {
+    long long blocks = (count + 255) / 256;
+    f32_to_bf16_rows_kernel<<<(int)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(xq, reinterpret_cast<__nv_bfloat16*>(dst), count);
+    g_kernel_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+cudaError_t tc_launch_tau0(const uint32_t* gmax, int groups, int gpow2, int nqp, int nq, int kp, float* tau0, cudaStream_t st) {
+    if ((size_t)gpow2 * 4 > 48 * 1024)
+        cudaFuncSetAttribute(tc_tau0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)gpow2 * 4));
+    tc_tau0_kernel<<<nqp, 256, (size_t)gpow2 * 4, st>>>(gmax, groups, gpow2, nqp, nq, kp, tau0);
+    g_kernel_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+cudaError_t tc_launch_gather(const u64* cand, const int* counts, int nctas, int nqp, int cap, int kp, int cap_total, int nq,
+                             u64* lists, int* overflow, cudaStream_t st) {
+    size_t gs = (size_t)cap_total * 8;
+    cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
+    tc_gather_kernel<<<nq, 1024, gs, st>>>(cand, counts, nctas, nqp, cap, kp, cap_total, lists, overflow);
+    g_kernel_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 // largest query block (multiple of 16, <= 128) whose resident copy leaves room for a useful ring
@@ -549,18 +505,15 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
 
 static cudaError_t tc_prepare(const TcArgs& a, const TcPlan& pl, unsigned char* ws, CUtensorMap* tdb, CUtensorMap* tq,
                               TcParams* p, cudaStream_t st) {
-    cudaError_t e = make_tmap(tdb, a.xb, a.n, a.d, !a.is_bf16, TC_BM);
+    cudaError_t e = tc_make_tmap(tdb, a.xb, a.n, a.d, !a.is_bf16, TC_BM);
     if (e != cudaSuccess) return e;
     const void* qsrc = a.xq;
     if (a.is_bf16) {
-        __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qbf16);
-        long long cnt = (long long)a.nq * a.d;
-        long long blocks = (cnt + 255) / 256;
-        f32_to_bf16_rows_kernel<<<(int)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(a.xq, qb, cnt);
-        g_kernel_launches.fetch_add(1);
+        void* qb = ws + pl.off_qbf16;
+        if ((e = tc_queries_to_bf16(a.xq, qb, (long long)a.nq * a.d, st)) != cudaSuccess) return e;
         qsrc = qb;
     }
-    if ((e = make_tmap(tq, qsrc, a.nq, a.d, !a.is_bf16, pl.npad)) != cudaSuccess) return e;
+    if ((e = tc_make_tmap(tq, qsrc, a.nq, a.d, !a.is_bf16, pl.npad)) != cudaSuccess) return e;
     *p = TcParams{};
     p->n = a.n;
     p->d = a.d;
@@ -592,10 +545,9 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     p.tile_stride = pl.pre_stride;
     e = launch_tc<MODE_MAX>(a.is_bf16, tdb, tq, p, pl.pre_grid, pl.smem, st);
     if (e != cudaSuccess) return e;
-    tc_tau0_kernel<<<pl.nqp, 256, (size_t)pl.gpow2 * 4, st>>>(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp,
-                                                            reinterpret_cast<float*>(ws + pl.off_tau0));
-    g_kernel_launches.fetch_add(1);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = tc_launch_tau0(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp, reinterpret_cast<float*>(ws + pl.off_tau0), st)) !=
+        cudaSuccess)
+        return e;
     if ((e = cudaMemsetAsync(ws + pl.off_overflow, 0, (size_t)pl.nqp * 4, st)) != cudaSuccess) return e;
     // 2. selection pass over every tile, all query blocks in one persistent launch
     p.ntiles = pl.ntiles;
@@ -603,12 +555,9 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     e = launch_tc<MODE_SELECT>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st);
     if (e != cudaSuccess) return e;
     // 3. per query: gather + sort -> top-kp list
-    size_t gs = (size_t)pl.cap_total * 8;
-    cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
-    tc_gather_kernel<<<a.nq, 1024, gs, st>>>(p.cand, p.counts, pl.grid, pl.nqp, pl.cap, pl.kp, pl.cap_total,
-                                            reinterpret_cast<u64*>(a.lists), p.overflow);
-    g_kernel_launches.fetch_add(1);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = tc_launch_gather(p.cand, p.counts, pl.grid, pl.nqp, pl.cap, pl.kp, pl.cap_total, a.nq,
+                              reinterpret_cast<u64*>(a.lists), p.overflow, st)) != cudaSuccess)
+        return e;
     if (a.overflow_out)
         e = cudaMemcpyAsync(a.overflow_out, ws + pl.off_overflow, (size_t)a.nq * 4, cudaMemcpyDeviceToDevice, st);
     return e;

@@ -243,13 +243,15 @@ class IndexFlatIP:
         import torch
         assert _is_torch_cuda(xq_cuda) and xq_cuda.dtype == torch.float32 and xq_cuda.is_contiguous()
         nq = xq_cuda.shape[0]
-        npad = (nq + 15) // 16 * 16
-        out = torch.empty((self.ntotal, npad), dtype=torch.float32, device=xq_cuda.device)
         got = ctypes.c_int(0)
         st = torch.cuda.current_stream(xq_cuda.device).cuda_stream
+        check(lib().evs_index_tc_scores_dev(self._h, nq, ctypes.c_void_p(xq_cuda.data_ptr()), None, ctypes.byref(got),
+                                            ctypes.c_void_p(st)))  # pitch query
+        pitch = got.value
+        out = torch.empty((self.ntotal, pitch), dtype=torch.float32, device=xq_cuda.device)
         check(lib().evs_index_tc_scores_dev(self._h, nq, ctypes.c_void_p(xq_cuda.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                             ctypes.byref(got), ctypes.c_void_p(st)))
-        assert got.value == npad
+        assert got.value == pitch
         return out[:, :nq]
 
     def scan_profile(self):

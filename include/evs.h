@@ -183,7 +183,9 @@ EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev,
 /* ---- tuning / introspection (bench and tests) -------------------------------------------------
  * evs_set_option: "scan_variant" (0 = auto, 1 = direct-load kernel, 2 = bulk-async ring kernel),
  *                 "tile_rows", "stages", "ctas_per_sm", "profile_scans", "tc_min_nq" (query batches of at
- *                 least this many use the tensor-core scan; 0 = never).  Unknown names -> EVS_EINVAL.
+ *                 least this many use the tensor-core scan; 0 = never), "tc_pair_min_nq" (... and of at
+ *                 least this many the CTA-pair kernel; 0 = never), "tc_stages", "tc2_slice_tiles".
+ *                 Unknown names -> EVS_EINVAL.
  * evs_kernel_launches: number of kernels this library has launched in this process.
  * evs_index_time_scan: runs the scan stage alone `iters` times on the index's stream for queries
  *                 already on the device and returns the mean kernel time in ms measured with CUDA
@@ -197,10 +199,11 @@ EVS_API int evs_index_time_scan(evs_index* idx, int64_t nq, const float* q_dev, 
  * the stream it runs on.  This call waits for them, returns how many searches were recorded since the
  * last call and the sum of their scan durations in ms, and resets the record. */
 EVS_API int evs_index_scan_profile(evs_index* idx, int64_t* count, double* total_ms);
-/* Diagnostics for the tensor-core scan (tcgen05): raw scan scores of every row against a block of
- * nq <= evs_index_tc_max_queries() queries, out_dev = float32 [ntotal][npad], npad = nq rounded up to
- * 16 (returned in *npad).  bf16 storage scores bf16 rows x bf16-rounded queries, fp32 storage scores
- * in tf32; both accumulate in fp32. */
+/* Diagnostics for the tensor-core scans (tcgen05): raw scan scores of every row against nq queries,
+ * out_dev = float32 [ntotal][pitch]; the pitch (queries padded per block) is returned in *npad, and a call
+ * with out_dev = NULL only returns it.  nq <= evs_index_tc_max_queries() uses the one-CTA kernel; batches of
+ * at least option "tc_pair_min_nq" queries (<= 4096) the CTA-pair kernel (cta_group::2).  bf16 storage scores
+ * bf16 rows x bf16-rounded queries, fp32 storage scores in tf32; both accumulate in fp32. */
 EVS_API int evs_index_tc_max_queries(const evs_index* idx, int* max_queries);
 EVS_API int evs_index_tc_scores_dev(evs_index* idx, int64_t nq, const float* q_dev, float* out_dev, int* npad, void* stream);
 

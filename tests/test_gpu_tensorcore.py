@@ -13,6 +13,8 @@ pytestmark = pytest.mark.gpu
 def _reset_options():
     yield
     evs.set_option("tc_min_nq", 4)
+    evs.set_option("tc_pair_min_nq", 129)
+    evs.set_option("tc2_slice_tiles", 0)
     evs.set_option("scan_variant", 0)
 
 
@@ -37,6 +39,57 @@ def test_tc_raw_scores_match_torch(storage, d):
             tol = 5e-4  # tf32 truncates each operand to 10 mantissa bits: ~4e-5 rms on unit vectors, ~4 sigma max
         err = (got - ref).abs().max().item()
         assert err <= tol, (storage, d, nq, err)
+
+
+@pytest.mark.parametrize("storage,d", [("bf16", 512), ("f32", 512), ("bf16", 768), ("bf16", 64)])
+def test_tc_pair_raw_scores_match_torch(storage, d):
+    """The CTA-pair kernel (cta_group::2, M = 256 rows per MMA, query block split over two CTAs): every score of
+    every (row, query), including the second CTA's half of the queries, a tail pair-tile whose second CTA is
+    empty, several query blocks and several slices per pair."""
+    import torch
+    n = 70_001 + 128  # last pair-tile: rows only in the first CTA
+    idx = evs.IndexFlatIP(d, storage=storage)
+    idx.add_synthetic(n, seed=3)
+    xb = torch.from_numpy(idx.reconstruct_n(0, n)).cuda()
+    evs.set_option("tc_pair_min_nq", 1)
+    for nq, slice_tiles in ((1, 0), (33, 0), (256, 3), (600, 0)):
+        evs.set_option("tc2_slice_tiles", slice_tiles)
+        xq = torch.from_numpy(oracle.synth_fill(nq, d, 4)).cuda()
+        got = idx.tc_scores(xq)
+        torch.cuda.synchronize()
+        if storage == "bf16":
+            ref = (xb.bfloat16().double() @ xq.bfloat16().double().T).float()
+            tol = 2e-6
+        else:
+            ref = (xb.double() @ xq.double().T).float()
+            tol = 5e-4
+        err = (got - ref).abs().max().item()
+        assert err <= tol, (storage, d, nq, err)
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_tc_pair_search_equals_oracle(storage):
+    d, n = 512, 200_003
+    xb = oracle.synth_fill(n, d, 11)
+    xb[n - 1] = xb[5]
+    idx = evs.IndexFlatIP(d, storage=storage)
+    idx.add(xb)
+    xq_all = oracle.synth_fill(700, d, 12)
+    evs.set_option("tc_min_nq", 1)
+    evs.set_option("tc_pair_min_nq", 1)
+    for nq, k in ((1, 48), (40, 12), (257, 48), (700, 100)):
+        xq = xq_all[:nq]
+        D, I = idx.search(xq, k)
+        sample = np.unique(np.linspace(0, nq - 1, 24).astype(int))
+        Dr, Ir = oracle.canon_search(xq[sample], xb, k)
+        assert np.array_equal(I[sample], Ir), (storage, nq, k)
+        assert np.array_equal(D[sample], Dr), (storage, nq, k)
+    m = idx.last_margins(700)
+    assert (m > (2e-4 if storage == "f32" else 5e-4)).all(), m.min()
+    # identical to the one-CTA tensor-core kernel on the whole batch
+    evs.set_option("tc_pair_min_nq", 0)
+    D1, I1 = idx.search(xq_all, 100)
+    assert np.array_equal(I1, I) and np.array_equal(D1, D)
 
 
 @pytest.mark.parametrize("storage", ["f32", "bf16"])
