@@ -271,81 +271,170 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// tau0[query] = kp-th largest of the pre-pass group maxima (descending bitonic sort in shared memory)
-// grid = npad queries, block = 256; dynamic smem = gpow2 * 4 bytes
+// tau0[query] = kp-th largest of the pre-pass group maxima, by a warp-level radix select (4 passes of 8 bits
+// over the ordered-uint maxima, a 256-bin histogram per warp in shared memory).  A warp per query, 8 queries
+// per CTA: the 8 warps read the same 32-byte sectors of gmax ([group][query] layout).
+// grid = nqp / 8, block = 256.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict__ gmax, int groups, int gpow2, int npad, int nq,
-                                                      int kp, float* __restrict__ tau0) {
-    extern __shared__ uint32_t sv[];
-    const int c = blockIdx.x;
-    for (int i = threadIdx.x; i < gpow2; i += blockDim.x) sv[i] = (i < groups) ? gmax[(size_t)i * npad + c] : 0u;
-    for (int size = 2; size <= gpow2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < (gpow2 >> 1); t += blockDim.x) {
-                int i = ((t / stride) * (stride << 1)) + (t % stride), j = i + stride;
-                bool desc = ((i & size) == 0);
-                uint32_t x = sv[i], y = sv[j];
-                if (desc ? (x < y) : (x > y)) {
-                    sv[i] = y;
-                    sv[j] = x;
+__global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict__ gmax, int groups, int npad, int nq, int kp,
+                                                      float* __restrict__ tau0) {
+    __shared__ int hist_all[8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + warp;
+    int* hist = hist_all[warp];
+    uint32_t prefix = 0;  // the high bits of the answer found so far
+    int krem = kp;        // rank of the answer among the values that share `prefix`
+    bool found = groups >= kp;
+    for (int pass = 0; pass < 4 && found; pass++) {
+        const int shift = 24 - 8 * pass;
+#pragma unroll
+        for (int b = 0; b < 8; b++) hist[lane * 8 + b] = 0;
+        __syncwarp();
+        for (int i = lane; i < groups; i += 32) {
+            const uint32_t v = __ldg(gmax + (size_t)i * npad + c);
+            const bool in = pass == 0 || (v >> (shift + 8)) == prefix;
+            if (in) atomicAdd(&hist[(v >> shift) & 255u], 1);
+        }
+        __syncwarp();
+        // lane l owns bins [8l, 8l+8); walk from the top bin down until krem values are covered
+        int mine[8], lsum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            mine[b] = hist[lane * 8 + b];
+            lsum += mine[b];
+        }
+        int above = lsum;  // inclusive suffix sum over lanes >= this one
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_down_sync(0xffffffffu, above, off);
+            if (lane + off < 32) above += o;
+        }
+        above -= lsum;  // values in bins of higher lanes
+        const bool here = above < krem && krem <= above + lsum;
+        const uint32_t bal = __ballot_sync(0xffffffffu, here);
+        if (bal == 0u) {  // fewer than krem values share the prefix: cannot happen for groups >= kp, be safe
+            found = false;
+            break;
+        }
+        const int src = __ffs(bal) - 1;
+        int bin = 0, newk = 0;
+        if (lane == src) {
+            int acc = above;
+#pragma unroll
+            for (int b = 7; b >= 0; b--) {
+                if (acc < krem && krem <= acc + mine[b]) {
+                    bin = lane * 8 + b;
+                    newk = krem - acc;
                 }
+                acc += mine[b];
             }
         }
+        bin = __shfl_sync(0xffffffffu, bin, src);
+        krem = __shfl_sync(0xffffffffu, newk, src);
+        prefix = (prefix << 8) | (uint32_t)bin;
+        __syncwarp();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // fewer than kp groups (or NaN-only groups): no usable bound -> admit everything
-        uint32_t o = (groups >= kp) ? sv[kp - 1] : 0u;
+    if (lane == 0) {
+        // fewer than kp groups (or NaN-only groups, ordered value 0): no usable bound -> admit everything
+        const uint32_t o = found ? prefix : 0u;
         tau0[c] = (c < nq && o != 0u) ? ordered_to_score(o) : ((c < nq) ? -INFINITY : INFINITY);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // gather the (CTA, query) candidate buffers of one query into a sorted top-kp list
-// (same list format the GEMV scan writes: [query][1][kp], sorted descending, 0 = empty)
-// grid = nq, block = 1024; dynamic smem = cap_total * 8
+// (same list format the GEMV scan writes: [query][1][kp], sorted descending, 0 = empty).
+// The union holds ~k' * n / sampled_rows keys (about a thousand) of which kp are wanted, so instead of sorting
+// it: (1) head = maximum of each buffer, (2) T = kp-th largest head -- at least kp keys are >= T, so the top kp
+// are among the keys >= T, typically ~2 kp of them, (3) those survivors are ranked by counting (or a bitonic sort
+// when there are many).  grid = nq, block = 256; dynamic smem = nctas * 8 bytes (heads) + GATHER_SURV * 8.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tc_gather_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int nctas,
-                                                         int npad, int cap, int kp, int cap_total, u64* __restrict__ lists,
-                                                         int* __restrict__ overflow) {
+constexpr int GATHER_SURV = 4096;
+
+__global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int nctas,
+                                                        int npad, int cap, int kp, u64* __restrict__ lists, int* __restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char sraw[];
-    u64* keys = reinterpret_cast<u64*>(sraw);
-    __shared__ int s_total;
+    u64* surv = reinterpret_cast<u64*>(sraw);
+    u64* heads = surv + GATHER_SURV;
+    __shared__ int s_n;
+    __shared__ u64 s_T;
     const int c = blockIdx.x;
-    if (threadIdx.x == 0) s_total = 0;
-    __syncthreads();
-    // one warp per CTA buffer: copy its keys into the shared array
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int b = warp; b < nctas; b += 32) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nt = blockDim.x, nwarps = nt >> 5;
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        s_T = 0ull;
+    }
+    // 1. heads
+    for (int b = warp; b < nctas; b += nwarps) {
         const int n = counts[(size_t)b * npad + c];
-        int base = 0;
-        if (lane == 0 && n > 0) base = atomicAdd(&s_total, n);
-        base = __shfl_sync(0xffffffffu, base, 0);
         const u64* src = cand + ((size_t)b * npad + c) * cap;
-        for (int i = lane; i < n; i += 32)
-            if (base + i < cap_total) keys[base + i] = src[i];
+        u64 m = 0ull;
+        for (int i = lane; i < n; i += 32) m = umax64(m, src[i]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) m = umax64(m, __shfl_xor_sync(0xffffffffu, m, off));
+        if (lane == 0) heads[b] = m;
     }
     __syncthreads();
-    int total = s_total;
-    if (total > cap_total) {
-        if (threadIdx.x == 0) overflow[c] = 1;
-        total = cap_total;
+    // 2. T = kp-th largest head (keys are unique, so ranks are); 0 when fewer than kp buffers hold anything
+    for (int b = threadIdx.x; b < nctas; b += nt) {
+        const u64 hb = heads[b];
+        if (hb == 0ull) continue;
+        int r = 0;
+        for (int j = 0; j < nctas; j++) r += heads[j] > hb ? 1 : 0;
+        if (r == kp - 1) s_T = hb;
     }
-    int pow2 = kp;
-    while (pow2 < total) pow2 <<= 1;
-    for (int i = total + threadIdx.x; i < pow2; i += blockDim.x) keys[i] = 0ull;
-    for (int size = 2; size <= pow2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < (pow2 >> 1); t += blockDim.x) {
-                int i = ((t / stride) * (stride << 1)) + (t % stride);
-                cmpx_desc(keys, i, i + stride, (i & size) == 0);
-            }
+    __syncthreads();
+    const u64 T = s_T;
+    // 3. survivors
+    for (int b = warp; b < nctas; b += nwarps) {
+        if (heads[b] < T || heads[b] == 0ull) continue;  // warp-uniform
+        const int n = counts[(size_t)b * npad + c];
+        const u64* src = cand + ((size_t)b * npad + c) * cap;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const u64 key = (i0 + lane < n) ? src[i0 + lane] : 0ull;
+            const bool keep = key != 0ull && key >= T;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m == 0u) continue;
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&s_n, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            const int dst = pos + __popc(m & ((1u << lane) - 1u));
+            if (keep && dst < GATHER_SURV) surv[dst] = key;
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kp; i += blockDim.x) lists[(size_t)c * kp + i] = keys[i];
+    int nsurv = s_n;
+    if (nsurv > GATHER_SURV) {
+        if (threadIdx.x == 0) overflow[c] = 1;  // the caller re-runs this query through the GEMV scan
+        nsurv = GATHER_SURV;
+    }
+    u64* out = lists + (size_t)c * kp;
+    if (nsurv <= 512) {
+        // 4a. rank by counting
+        for (int i = nsurv + threadIdx.x; i < kp; i += nt) out[i] = 0ull;  // slots no survivor ranks into
+        for (int i = threadIdx.x; i < nsurv; i += nt) {
+            const u64 key = surv[i];
+            int r = 0;
+            for (int j = 0; j < nsurv; j++) r += surv[j] > key ? 1 : 0;
+            if (r < kp) out[r] = key;
+        }
+    } else {
+        // 4b. many survivors (clustered candidates): bitonic sort, descending
+        int pow2 = 1024;
+        while (pow2 < nsurv) pow2 <<= 1;
+        for (int i = nsurv + threadIdx.x; i < pow2; i += nt) surv[i] = 0ull;
+        for (int size = 2; size <= pow2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int t = threadIdx.x; t < (pow2 >> 1); t += nt) {
+                    int i = ((t / stride) * (stride << 1)) + (t % stride);
+                    cmpx_desc(surv, i, i + stride, (i & size) == 0);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kp; i += nt) out[i] = surv[i];
+    }
 }
 
 __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long count) {
@@ -395,18 +484,20 @@ cudaError_t tc_queries_to_bf16(const float* xq, void* dst, long long count, cuda
 }
 
 cudaError_t tc_launch_tau0(const uint32_t* gmax, int groups, int gpow2, int nqp, int nq, int kp, float* tau0, cudaStream_t st) {
-    if ((size_t)gpow2 * 4 > 48 * 1024)
-        cudaFuncSetAttribute(tc_tau0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)gpow2 * 4));
-    tc_tau0_kernel<<<nqp, 256, (size_t)gpow2 * 4, st>>>(gmax, groups, gpow2, nqp, nq, kp, tau0);
+    (void)gpow2;
+    if (nqp % 8) return cudaErrorInvalidValue;  // npad is a multiple of 16
+    tc_tau0_kernel<<<nqp / 8, 256, 0, st>>>(gmax, groups, nqp, nq, kp, tau0);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
 
 cudaError_t tc_launch_gather(const u64* cand, const int* counts, int nctas, int nqp, int cap, int kp, int cap_total, int nq,
                              u64* lists, int* overflow, cudaStream_t st) {
-    size_t gs = (size_t)cap_total * 8;
-    cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
-    tc_gather_kernel<<<nq, 1024, gs, st>>>(cand, counts, nctas, nqp, cap, kp, cap_total, lists, overflow);
+    (void)cap_total;
+    const size_t gs = (size_t)GATHER_SURV * 8 + (size_t)nctas * 8;
+    if (gs > 48 * 1024 && gs <= 200 * 1024)
+        cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
+    tc_gather_kernel<<<nq, 256, gs, st>>>(cand, counts, nctas, nqp, cap, kp, lists, overflow);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }

@@ -14,12 +14,21 @@
 //     74 pairs, so the pairs that run at the same time share a handful of slices (a few MB each): the database
 //     streams from HBM once per launch and is re-read from the 126 MB L2 by the other query blocks.
 //   * the query block of the next item is re-loaded (128 KB per CTA, from L2) only when it changes.
-// Warp roles per CTA (256 threads): warp 0 TMA producer (one lane), warp 1 MMA issuer (one lane, leader CTA
-// only), warp 2 TMEM alloc/dealloc, warps 4-7 epilogue (TMEM lane quarter e = warp & 3).
+// Warp roles per CTA (384 threads): warp 0 TMA producer (one lane), warp 1 MMA issuer (one lane, leader CTA
+// only), warp 2 TMEM alloc/dealloc, warps 4-11 epilogue: two warps per TMEM lane quarter (e = warp & 3), which
+// take alternate 32-column groups, so that every SM sub-partition has two epilogue warps to overlap the
+// tcgen05.ld latency of one with the filter arithmetic of the other (one warp per quarter left the MMA issuer
+// waiting on acc_empty 40 % of the time: ncu, profiles/r01_ncu_tc2_select_v1.txt).
 // Barriers: full[s] and q_full collect the TMA bytes of BOTH CTAs on the leader's barrier (cp.async.bulk.tensor
 // .cta_group::2 with the leader's barrier address); empty[s], q_empty and acc_full[a] are signalled in both CTAs
-// by tcgen05.commit ... multicast::cluster; acc_empty[a] lives in the leader and counts the 8 epilogue warps of
-// the pair (the peer's arrive remotely through mapa + mbarrier.arrive.shared::cluster).
+// by tcgen05.commit ... multicast::cluster; acc_empty[a] lives in the leader and counts the 16 epilogue warps of
+// the pair (the peer's arrive remotely through mapa + mbarrier.arrive.shared::cluster), each as soon as its last
+// tcgen05.ld of the tile has completed -- before it filters that last group.
+// SELECT epilogue: scores are packed to bf16x2 (cvt.rn.bf16x2.f32) and compared two at a time with the
+// bf16-rounded thresholds (set.ge.u32.bf16x2; rounding is monotonic, so score >= tau implies bf16(score) >=
+// bf16(tau): no false negatives); the 16 compare results are folded into a 32-bit column mask with one LOP3
+// each.  Columns flagged by any lane are then visited warp-uniformly: exact fp32 test, one shared-memory
+// atomic per (warp, column) for the slots, 8-byte key stores.
 // Epilogue modes and the threshold scheme (pre-pass maxima -> tau0 -> branch-free filter -> candidate buffers ->
 // gather) are those of evs_tc.cu; exactness never depends on the data (overflow -> GEMV re-run by the caller).
 #include <cuda.h>
@@ -57,8 +66,46 @@ struct Tc2Params {
     float* dump;           // [n][nqp]
 };
 
+constexpr int TC2_THREADS = 384;      // 4 control warps + 8 epilogue warps
+constexpr int TC2_EPI_THREADS = 256;
+
+// 32 scores of one row (32 consecutive queries) against the bf16-rounded thresholds of those queries (64 bytes in
+// shared memory): bit b < 16 of the result <-> column 2b, bit 16 + b <-> column 2b + 1
+__device__ __forceinline__ uint32_t prefilter_mask_bf16(const uint32_t (&v)[32], const uint4* tau_b) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i4 = 0; i4 < 4; i4++) {
+        const uint4 t4 = tau_b[i4];
+        const uint32_t tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i4 * 4 + u;  // column pair (2i, 2i + 1)
+            uint32_t pk, r;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(__uint_as_float(v[2 * i + 1])), "f"(__uint_as_float(v[2 * i])));
+            asm("set.ge.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(pk), "r"(tt[u]));
+            mask |= r & ((1u << i) | (1u << (16 + i)));
+        }
+    }
+    return mask;
+}
+
+// v[j] for a warp-uniform j: a jump table instead of 32 predicated moves
+__device__ __forceinline__ float pick_uniform(const uint32_t (&v)[32], int j) {
+    uint32_t r;
+    switch (j) {
+#define EVS_PICK(J) case J: r = v[J]; break;
+        EVS_PICK(0) EVS_PICK(1) EVS_PICK(2) EVS_PICK(3) EVS_PICK(4) EVS_PICK(5) EVS_PICK(6) EVS_PICK(7)
+        EVS_PICK(8) EVS_PICK(9) EVS_PICK(10) EVS_PICK(11) EVS_PICK(12) EVS_PICK(13) EVS_PICK(14) EVS_PICK(15)
+        EVS_PICK(16) EVS_PICK(17) EVS_PICK(18) EVS_PICK(19) EVS_PICK(20) EVS_PICK(21) EVS_PICK(22) EVS_PICK(23)
+        EVS_PICK(24) EVS_PICK(25) EVS_PICK(26) EVS_PICK(27) EVS_PICK(28) EVS_PICK(29) EVS_PICK(30)
+#undef EVS_PICK
+        default: r = v[31]; break;
+    }
+    return __uint_as_float(r);
+}
+
 template <typename T, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant__ CUtensorMap tm_q, Tc2Params p) {
     constexpr bool TF32 = sizeof(T) == 4;
     constexpr int EC = 128 / sizeof(T);  // elements per 128-byte chunk
@@ -85,6 +132,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* tau_s = reinterpret_cast<float*>(tmem_base_smem + 4);
     int* cnt_s = reinterpret_cast<int*>(tau_s + NP);
+    __nv_bfloat16* tau_b = reinterpret_cast<__nv_bfloat16*>(cnt_s + NP);  // 16-byte aligned: NP is a multiple of 32
 
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(2 * NP)) tmem_cols <<= 1;
@@ -100,7 +148,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 8);
+            mbar_init(&acc_empty[a], 16);
         }
         mbar_fence_init();
     }
@@ -196,12 +244,15 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ================= epilogue (both CTAs) =================
-        const int e = warp & 3;                 // TMEM lane quarter
+        // ================= epilogue (both CTAs), 8 warps =================
+        const int e = warp & 3;                 // TMEM lane quarter of this warp
+        const int h = (warp - 4) >> 2;          // which of the quarter's two warps: takes 32-column groups h, h+2, ...
         const int row_in_tile = (int)cta_rank * TC_BM + e * 32 + lane;
-        const int et = threadIdx.x - 128;       // 0..127 among the epilogue threads
+        const int et = threadIdx.x - 128;       // 0..255 among the epilogue threads
+        const int ngroups = NP / 32;
         const uint32_t acc_empty_leader0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
         const uint32_t acc_empty_leader1 = mapa_u32(smem_u32(&acc_empty[1]), 0);
+        const uint32_t lt_mask = (1u << lane) - 1u;
         long long tcount = 0;
         int cur_b = -1;
         for (long long it = pair; it < nitems; it += npairs) {
@@ -209,18 +260,20 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
             const int b = (int)(it % p.nqb);
             const int qb = b * NP;
             if (MODE == MODE_SELECT && b != cur_b) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // all epilogue warps have left the previous block
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // all epilogue warps have left the previous block
                 if (cur_b >= 0) {
-                    for (int c = et; c < NP; c += 128) {
+                    for (int c = et; c < NP; c += TC2_EPI_THREADS) {
                         const int n = cnt_s[c];
                         p.counts[(size_t)blockIdx.x * p.nqp + cur_b * NP + c] = n < p.cap ? n : p.cap;
                     }
                 }
-                for (int c = et; c < NP; c += 128) {
-                    tau_s[c] = (qb + c < p.nq) ? p.tau0[qb + c] : INFINITY;
+                for (int c = et; c < NP; c += TC2_EPI_THREADS) {
+                    const float tq = (qb + c < p.nq) ? p.tau0[qb + c] : INFINITY;
+                    tau_s[c] = tq;
+                    tau_b[c] = __float2bfloat16_rn(tq);
                     cnt_s[c] = p.counts[(size_t)blockIdx.x * p.nqp + qb + c];
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             cur_b = b;
             const long long t0 = s * p.slice_tiles;
@@ -232,61 +285,74 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                 mbar_wait(&acc_full[a], (uint32_t)((tcount >> 1) & 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(a * NP);
-                for (int c0 = 0; c0 < NP; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32_nowait(taddr + c0, v);
-                    tmem_ld_wait();
-                    if (MODE == MODE_DUMP) {
-                        if (row_ok) {
+                uint32_t v[2][32];
+                if (h < ngroups) tmem_ld32_nowait(taddr + h * 32, v[0]);
+                else if (lane == 0) {  // fewer groups than warps in this quarter: nothing to read
+                    tc_fence_before();
+                    mbar_arrive_cluster_relaxed(a ? acc_empty_leader1 : acc_empty_leader0);
+                }
 #pragma unroll
-                            for (int j = 0; j < 32; j++) p.dump[(size_t)row * p.nqp + qb + c0 + j] = __uint_as_float(v[j]);
+                for (int gi = 0; gi < 4; gi++) {  // at most 8 groups per tile, 4 per warp
+                    const int g = h + 2 * gi;
+                    if (g < ngroups) {
+                        tmem_ld_wait();
+                        if (g + 2 < ngroups) {
+                            tmem_ld32_nowait(taddr + (g + 2) * 32, v[(gi + 1) & 1]);  // in flight while this group is filtered
+                        } else {
+                            // this warp's last read of the accumulator is complete: hand it back before filtering
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster_relaxed(a ? acc_empty_leader1 : acc_empty_leader0);
                         }
-                    } else if (MODE == MODE_MAX) {
-                        const long long g = (t * 2 + cta_rank) * 4 + e;  // 32-row group index in the walked list
+                        const uint32_t(&vc)[32] = v[gi & 1];
+                        const int c0 = g * 32;
+                        if (MODE == MODE_DUMP) {
+                            if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            uint32_t o = row_ok ? score_to_ordered(__uint_as_float(v[j])) : 0u;
-                            o = __reduce_max_sync(0xffffffffu, o);
-                            if (lane == j) p.gmax[(size_t)g * p.nqp + qb + c0 + j] = o;
-                        }
-                    } else {
-                        // branch-free filter: 32 compares into a bit mask, one warp-uniform test per group
-                        uint32_t mask = 0;
+                                for (int j = 0; j < 32; j++) p.dump[(size_t)row * p.nqp + qb + c0 + j] = __uint_as_float(vc[j]);
+                            }
+                        } else if (MODE == MODE_MAX) {
+                            const long long gr = (t * 2 + cta_rank) * 4 + e;  // 32-row group index in the walked list
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; j4++) {
-                            const float4 tq = *reinterpret_cast<const float4*>(&tau_s[c0 + 4 * j4]);
-                            mask |= (__uint_as_float(v[4 * j4 + 0]) >= tq.x ? 1u : 0u) << (4 * j4 + 0);
-                            mask |= (__uint_as_float(v[4 * j4 + 1]) >= tq.y ? 1u : 0u) << (4 * j4 + 1);
-                            mask |= (__uint_as_float(v[4 * j4 + 2]) >= tq.z ? 1u : 0u) << (4 * j4 + 2);
-                            mask |= (__uint_as_float(v[4 * j4 + 3]) >= tq.w ? 1u : 0u) << (4 * j4 + 3);
-                        }
-                        if (!row_ok) mask = 0;
-                        if (__any_sync(0xffffffffu, mask != 0)) {
-                            while (mask) {
-                                const int j = __ffs(mask) - 1;
-                                mask &= mask - 1;
+                            for (int j = 0; j < 32; j++) {
+                                uint32_t o = row_ok ? score_to_ordered(__uint_as_float(vc[j])) : 0u;
+                                o = __reduce_max_sync(0xffffffffu, o);
+                                if (lane == j) p.gmax[(size_t)gr * p.nqp + qb + c0 + j] = o;
+                            }
+                        } else {
+                            uint32_t mask = prefilter_mask_bf16(vc, reinterpret_cast<const uint4*>(tau_b + c0));
+                            if (!row_ok) mask = 0;
+                            uint32_t cols = __reduce_or_sync(0xffffffffu, mask);  // columns flagged by any row of this warp
+                            while (cols) {
+                                const int bit = __ffs(cols) - 1;
+                                cols &= cols - 1;
+                                const int j = bit < 16 ? 2 * bit : 2 * (bit - 16) + 1;
                                 const int c = c0 + j;
-                                float sc = 0.f;
-#pragma unroll
-                                for (int jj = 0; jj < 32; jj++)
-                                    if (jj == j) sc = __uint_as_float(v[jj]);
-                                const int slot = atomicAdd(&cnt_s[c], 1);
-                                if (slot < p.cap)
-                                    p.cand[((size_t)blockIdx.x * p.nqp + qb + c) * p.cap + slot] = make_key(sc, (uint32_t)row);
-                                else
-                                    p.overflow[qb + c] = 1;
+                                const float sc = pick_uniform(vc, j);
+                                const bool hit = ((mask >> bit) & 1u) && sc >= tau_s[c];  // exact test
+                                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                                if (bal) {
+                                    const int src = __ffs(bal) - 1;
+                                    int base = 0;
+                                    if (lane == src) base = atomicAdd(&cnt_s[c], __popc(bal));
+                                    base = __shfl_sync(0xffffffffu, base, src);
+                                    if (hit) {
+                                        const int slot = base + __popc(bal & lt_mask);
+                                        if (slot < p.cap)
+                                            p.cand[((size_t)blockIdx.x * p.nqp + qb + c) * p.cap + slot] = make_key(sc, (uint32_t)row);
+                                        else
+                                            p.overflow[qb + c] = 1;
+                                    }
+                                }
                             }
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(a ? acc_empty_leader1 : acc_empty_leader0);
             }
         }
         if (MODE == MODE_SELECT && cur_b >= 0) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int c = et; c < NP; c += 128) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int c = et; c < NP; c += TC2_EPI_THREADS) {
                 const int n = cnt_s[c];
                 p.counts[(size_t)blockIdx.x * p.nqp + cur_b * NP + c] = n < p.cap ? n : p.cap;
             }
@@ -304,7 +370,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
 // host side
 // =============================================================================================
 static size_t tc2_smem_bytes(int nk, int half, int stages) {
-    return (size_t)nk * half * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4) * 8 + 16 + (size_t)half * 16;
+    return (size_t)nk * half * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4) * 8 + 16 + (size_t)half * 20;
 }
 
 // query rows resident per CTA: the largest multiple of 16 (<= 128) that leaves room for >= 4 ring stages
@@ -396,7 +462,7 @@ static cudaError_t launch_tc2_mode(const CUtensorMap& tdb, const CUtensorMap& tq
     auto kern = tc2_scan_kernel<T, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 256, smem, st>>>(tdb, tq, p);  // __cluster_dims__(2,1,1): grid is even
+    kern<<<grid, TC2_THREADS, smem, st>>>(tdb, tq, p);  // __cluster_dims__(2,1,1): grid is even
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }

@@ -97,6 +97,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// the same without memory ordering: enough after tcgen05.wait::ld + tcgen05.fence::before_thread_sync when the
+// only thing handed over is a TMEM accumulator (a release arrive costs MEMBAR.ALL.CTA + ERRBAR per call)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA tile load issued by either CTA of a pair; completion bytes are counted on the mbarrier at
 // `bar_cluster_addr`, which may live in the peer CTA (the leader's barrier collects both halves)
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
