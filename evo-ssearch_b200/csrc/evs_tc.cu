@@ -48,9 +48,9 @@ struct TcParams {
     uint32_t* gmax;       // [ntiles*4][nqp] ordered-uint maxima per 32-row group
     // MODE_SELECT
     const float* tau0;    // [nqp]
-    u64* cand;            // [gridDim.x][nqp][cap]
+    u64* cand;            // [nqp][gridDim.x][cap]: the buffers of one query are contiguous for the gather
     int cap;
-    int* counts;          // [gridDim.x][nqp]
+    int* counts;          // [nqp][gridDim.x]
     int* overflow;        // [nqp] set to 1 when a buffer overflowed
     // MODE_DUMP
     float* dump;          // [n][nqp]
@@ -242,7 +242,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                                     if (jj == j) s = __uint_as_float(v[jj]);
                                 int slot = atomicAdd(&cnt_s[c], 1);
                                 if (slot < p.cap)
-                                    p.cand[((size_t)blockIdx.x * p.nqp + qb + c) * p.cap + slot] = make_key(s, (uint32_t)row);
+                                    p.cand[((size_t)(qb + c) * gridDim.x + blockIdx.x) * p.cap + slot] = make_key(s, (uint32_t)row);
                                 else
                                     p.overflow[qb + c] = 1;
                             }
@@ -257,7 +257,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // every epilogue warp has finished the block
                 for (int c = et; c < NP; c += 128) {
                     int n = cnt_s[c];
-                    p.counts[(size_t)blockIdx.x * p.nqp + qb + c] = n < p.cap ? n : p.cap;
+                    p.counts[(size_t)(qb + c) * gridDim.x + blockIdx.x] = n < p.cap ? n : p.cap;
                 }
             }
         }
@@ -277,11 +277,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
 // grid = nqp / 8, block = 256.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict__ gmax, int groups, int npad, int nq, int kp,
-                                                      float* __restrict__ tau0) {
+                                                      float* __restrict__ tau0, int staged) {
     __shared__ int hist_all[8][256];
+    extern __shared__ uint32_t tile[];  // staged: [8 queries][groups + 1], filled with whole 32-byte sectors of gmax
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * 8 + warp;
     int* hist = hist_all[warp];
+    const int pitch = groups + 1;
+    if (staged) {
+        const int q = threadIdx.x & 7;
+        for (int i = threadIdx.x >> 3; i < groups; i += 32) tile[q * pitch + i] = __ldg(gmax + (size_t)i * npad + blockIdx.x * 8 + q);
+        __syncthreads();
+    }
+    const uint32_t* mine_vals = tile + warp * pitch;
     uint32_t prefix = 0;  // the high bits of the answer found so far
     int krem = kp;        // rank of the answer among the values that share `prefix`
     bool found = groups >= kp;
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
         for (int b = 0; b < 8; b++) hist[lane * 8 + b] = 0;
         __syncwarp();
         for (int i = lane; i < groups; i += 32) {
-            const uint32_t v = __ldg(gmax + (size_t)i * npad + c);
+            const uint32_t v = staged ? mine_vals[i] : __ldg(gmax + (size_t)i * npad + c);
             const bool in = pass == 0 || (v >> (shift + 8)) == prefix;
             if (in) atomicAdd(&hist[(v >> shift) & 255u], 1);
         }
@@ -345,95 +353,125 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
 // gather the (CTA, query) candidate buffers of one query into a sorted top-kp list
 // (same list format the GEMV scan writes: [query][1][kp], sorted descending, 0 = empty).
 // The union holds ~k' * n / sampled_rows keys (about a thousand) of which kp are wanted, so instead of sorting
-// it: (1) head = maximum of each buffer, (2) T = kp-th largest head -- at least kp keys are >= T, so the top kp
-// are among the keys >= T, typically ~2 kp of them, (3) those survivors are ranked by counting (or a bitonic sort
-// when there are many).  grid = nq, block = 256; dynamic smem = nctas * 8 bytes (heads) + GATHER_SURV * 8.
+// it: (1) compact the valid keys into shared memory (the buffers of a query are contiguous: [query][cta][cap]),
+// (2) cut them into 2 kp strided chunks, T = kp-th largest chunk maximum -- at least kp keys are >= T, so the top
+// kp are among the keys >= T, typically ~1.5 kp of them -- (3) rank those survivors by counting.  Many survivors
+// (clustered candidates) fall back to a bitonic sort.  grid = nq, block = 256.
 // ---------------------------------------------------------------------------------------------
-constexpr int GATHER_SURV = 4096;
+constexpr int GATHER_ALL = 4096;   // keys of one query held in shared memory; more -> overflow (GEMV re-run)
+constexpr int GATHER_SURV = 1024;
 
 __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int nctas,
-                                                        int npad, int cap, int kp, u64* __restrict__ lists, int* __restrict__ overflow) {
+                                                        int cap, int kp, u64* __restrict__ lists, int* __restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char sraw[];
-    u64* surv = reinterpret_cast<u64*>(sraw);
-    u64* heads = surv + GATHER_SURV;
-    __shared__ int s_n;
+    u64* all = reinterpret_cast<u64*>(sraw);       // GATHER_ALL
+    u64* surv = all + GATHER_ALL;                  // GATHER_SURV
+    u64* cmax = surv + GATHER_SURV;                // 2 * kp
+    int* cnt = reinterpret_cast<int*>(cmax + 2 * kp);  // nctas
+    __shared__ int s_n, s_m;
     __shared__ u64 s_T;
     const int c = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nt = blockDim.x, nwarps = nt >> 5;
+    const u64* base = cand + (size_t)c * nctas * cap;
+    for (int b = threadIdx.x; b < nctas; b += nt) cnt[b] = counts[(size_t)c * nctas + b];
     if (threadIdx.x == 0) {
         s_n = 0;
+        s_m = 0;
         s_T = 0ull;
     }
-    // 1. heads
-    for (int b = warp; b < nctas; b += nwarps) {
-        const int n = counts[(size_t)b * npad + c];
-        const u64* src = cand + ((size_t)b * npad + c) * cap;
-        u64 m = 0ull;
-        for (int i = lane; i < n; i += 32) m = umax64(m, src[i]);
+    __syncthreads();
+    // 1. compaction: a warp takes 4 buffers at a time so that their loads are in flight together
+    for (int b0 = warp * 4; b0 < nctas; b0 += nwarps * 4) {
+        u64 key[4];
+        int nb[4];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) m = umax64(m, __shfl_xor_sync(0xffffffffu, m, off));
-        if (lane == 0) heads[b] = m;
+        for (int u = 0; u < 4; u++) {
+            nb[u] = (b0 + u < nctas) ? cnt[b0 + u] : 0;
+            key[u] = (lane < nb[u]) ? base[(size_t)(b0 + u) * cap + lane] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            for (int i0 = 0; i0 < nb[u]; i0 += 32) {  // warp-uniform; more than one round only for counts > 32
+                const u64 k = i0 == 0 ? key[u] : ((i0 + lane < nb[u]) ? base[(size_t)(b0 + u) * cap + i0 + lane] : 0ull);
+                const bool valid = k != 0ull;
+                const unsigned m = __ballot_sync(0xffffffffu, valid);
+                if (m == 0u) continue;
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_n, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const int dst = pos + __popc(m & ((1u << lane) - 1u));
+                if (valid && dst < GATHER_ALL) all[dst] = k;
+            }
+        }
     }
     __syncthreads();
-    // 2. T = kp-th largest head (keys are unique, so ranks are); 0 when fewer than kp buffers hold anything
-    for (int b = threadIdx.x; b < nctas; b += nt) {
-        const u64 hb = heads[b];
-        if (hb == 0ull) continue;
-        int r = 0;
-        for (int j = 0; j < nctas; j++) r += heads[j] > hb ? 1 : 0;
-        if (r == kp - 1) s_T = hb;
+    int total = s_n;
+    if (total > GATHER_ALL) {
+        if (threadIdx.x == 0) overflow[c] = 1;  // the caller re-runs this query through the GEMV scan
+        total = GATHER_ALL;
     }
-    __syncthreads();
-    const u64 T = s_T;
-    // 3. survivors
-    for (int b = warp; b < nctas; b += nwarps) {
-        if (heads[b] < T || heads[b] == 0ull) continue;  // warp-uniform
-        const int n = counts[(size_t)b * npad + c];
-        const u64* src = cand + ((size_t)b * npad + c) * cap;
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const u64 key = (i0 + lane < n) ? src[i0 + lane] : 0ull;
-            const bool keep = key != 0ull && key >= T;
+    u64* out = lists + (size_t)c * kp;
+    // 2. threshold from strided chunk maxima (only worth it when there are clearly more than kp keys)
+    const int nch = 2 * kp;
+    const u64* src = all;
+    int nsrc = total;
+    if (total > 4 * kp) {
+        for (int j = threadIdx.x; j < nch; j += nt) {
+            u64 m = 0ull;
+            for (int i = j; i < total; i += nch) m = umax64(m, all[i]);
+            cmax[j] = m;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < nch; j += nt) {
+            const u64 mj = cmax[j];
+            int r = 0;
+            for (int i = 0; i < nch; i++) r += cmax[i] > mj ? 1 : 0;
+            if (r == kp - 1) s_T = mj;  // keys are unique and every chunk is non-empty, so exactly one chunk has this rank
+        }
+        __syncthreads();
+        const u64 T = s_T;
+        for (int i0 = warp * 32; i0 < total; i0 += nt) {
+            const u64 k = (i0 + lane < total) ? all[i0 + lane] : 0ull;
+            const bool keep = k != 0ull && k >= T;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (m == 0u) continue;
             int pos = 0;
-            if (lane == 0) pos = atomicAdd(&s_n, __popc(m));
+            if (lane == 0) pos = atomicAdd(&s_m, __popc(m));
             pos = __shfl_sync(0xffffffffu, pos, 0);
             const int dst = pos + __popc(m & ((1u << lane) - 1u));
-            if (keep && dst < GATHER_SURV) surv[dst] = key;
+            if (keep && dst < GATHER_SURV) surv[dst] = k;
         }
+        __syncthreads();
+        if (s_m <= GATHER_SURV) {
+            src = surv;
+            nsrc = s_m;
+        }  // else: too many survivors for the side array -> sort everything below
     }
-    __syncthreads();
-    int nsurv = s_n;
-    if (nsurv > GATHER_SURV) {
-        if (threadIdx.x == 0) overflow[c] = 1;  // the caller re-runs this query through the GEMV scan
-        nsurv = GATHER_SURV;
-    }
-    u64* out = lists + (size_t)c * kp;
-    if (nsurv <= 512) {
-        // 4a. rank by counting
-        for (int i = nsurv + threadIdx.x; i < kp; i += nt) out[i] = 0ull;  // slots no survivor ranks into
-        for (int i = threadIdx.x; i < nsurv; i += nt) {
-            const u64 key = surv[i];
+    if (nsrc <= GATHER_SURV) {
+        // 3a. rank by counting
+        for (int i = nsrc + threadIdx.x; i < kp; i += nt) out[i] = 0ull;  // slots no key ranks into
+        for (int i = threadIdx.x; i < nsrc; i += nt) {
+            const u64 key = src[i];
             int r = 0;
-            for (int j = 0; j < nsurv; j++) r += surv[j] > key ? 1 : 0;
+            for (int j = 0; j < nsrc; j++) r += src[j] > key ? 1 : 0;
             if (r < kp) out[r] = key;
         }
     } else {
-        // 4b. many survivors (clustered candidates): bitonic sort, descending
-        int pow2 = 1024;
-        while (pow2 < nsurv) pow2 <<= 1;
-        for (int i = nsurv + threadIdx.x; i < pow2; i += nt) surv[i] = 0ull;
+        // 3b. bitonic sort of everything, descending
+        int pow2 = 2048;
+        while (pow2 < total) pow2 <<= 1;
+        for (int i = total + threadIdx.x; i < pow2; i += nt) all[i] = 0ull;
         for (int size = 2; size <= pow2; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 __syncthreads();
                 for (int t = threadIdx.x; t < (pow2 >> 1); t += nt) {
                     int i = ((t / stride) * (stride << 1)) + (t % stride);
-                    cmpx_desc(surv, i, i + stride, (i & size) == 0);
+                    cmpx_desc(all, i, i + stride, (i & size) == 0);
                 }
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < kp; i += nt) out[i] = surv[i];
+        for (int i = threadIdx.x; i < kp; i += nt) out[i] = all[i];
     }
 }
 
@@ -486,7 +524,11 @@ cudaError_t tc_queries_to_bf16(const float* xq, void* dst, long long count, cuda
 cudaError_t tc_launch_tau0(const uint32_t* gmax, int groups, int gpow2, int nqp, int nq, int kp, float* tau0, cudaStream_t st) {
     (void)gpow2;
     if (nqp % 8) return cudaErrorInvalidValue;  // npad is a multiple of 16
-    tc_tau0_kernel<<<nqp / 8, 256, 0, st>>>(gmax, groups, nqp, nq, kp, tau0);
+    const size_t tile_bytes = (size_t)8 * (groups + 1) * 4;
+    const int staged = tile_bytes <= 160 * 1024;
+    if (staged && tile_bytes > 40 * 1024)
+        cudaFuncSetAttribute(tc_tau0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes);
+    tc_tau0_kernel<<<nqp / 8, 256, staged ? tile_bytes : 0, st>>>(gmax, groups, nqp, nq, kp, tau0, staged);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -494,10 +536,11 @@ cudaError_t tc_launch_tau0(const uint32_t* gmax, int groups, int gpow2, int nqp,
 cudaError_t tc_launch_gather(const u64* cand, const int* counts, int nctas, int nqp, int cap, int kp, int cap_total, int nq,
                              u64* lists, int* overflow, cudaStream_t st) {
     (void)cap_total;
-    const size_t gs = (size_t)GATHER_SURV * 8 + (size_t)nctas * 8;
-    if (gs > 48 * 1024 && gs <= 200 * 1024)
-        cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
-    tc_gather_kernel<<<nq, 256, gs, st>>>(cand, counts, nctas, nqp, cap, kp, lists, overflow);
+    (void)nqp;
+    const size_t gs = (size_t)(GATHER_ALL + GATHER_SURV + 2 * kp) * 8 + (size_t)nctas * 4;
+    if (gs > 200 * 1024) return cudaErrorInvalidValue;
+    if (gs > 40 * 1024) cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
+    tc_gather_kernel<<<nq, 256, gs, st>>>(cand, counts, nctas, cap, kp, lists, overflow);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }

@@ -58,9 +58,9 @@ struct Tc2Params {
     uint32_t* gmax;        // [ntiles * 8][nqp] ordered-uint maxima per 32-row group
     // MODE_SELECT
     const float* tau0;     // [nqp]
-    u64* cand;             // [gridDim.x][nqp][cap]
+    u64* cand;             // [nqp][gridDim.x][cap]: the buffers of one query are contiguous for the gather
     int cap;
-    int* counts;           // [gridDim.x][nqp], zeroed before the launch; persists across the items of a CTA
+    int* counts;           // [nqp][gridDim.x], zeroed before the launch; persists across the items of a CTA
     int* overflow;         // [nqp]
     // MODE_DUMP
     float* dump;           // [n][nqp]
@@ -264,14 +264,14 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                 if (cur_b >= 0) {
                     for (int c = et; c < NP; c += TC2_EPI_THREADS) {
                         const int n = cnt_s[c];
-                        p.counts[(size_t)blockIdx.x * p.nqp + cur_b * NP + c] = n < p.cap ? n : p.cap;
+                        p.counts[(size_t)(cur_b * NP + c) * gridDim.x + blockIdx.x] = n < p.cap ? n : p.cap;
                     }
                 }
                 for (int c = et; c < NP; c += TC2_EPI_THREADS) {
                     const float tq = (qb + c < p.nq) ? p.tau0[qb + c] : INFINITY;
                     tau_s[c] = tq;
                     tau_b[c] = __float2bfloat16_rn(tq);
-                    cnt_s[c] = p.counts[(size_t)blockIdx.x * p.nqp + qb + c];
+                    cnt_s[c] = p.counts[(size_t)(qb + c) * gridDim.x + blockIdx.x];
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
@@ -339,7 +339,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                                     if (hit) {
                                         const int slot = base + __popc(bal & lt_mask);
                                         if (slot < p.cap)
-                                            p.cand[((size_t)blockIdx.x * p.nqp + qb + c) * p.cap + slot] = make_key(sc, (uint32_t)row);
+                                            p.cand[((size_t)(qb + c) * gridDim.x + blockIdx.x) * p.cap + slot] = make_key(sc, (uint32_t)row);
                                         else
                                             p.overflow[qb + c] = 1;
                                     }
@@ -354,7 +354,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
             asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int c = et; c < NP; c += TC2_EPI_THREADS) {
                 const int n = cnt_s[c];
-                p.counts[(size_t)blockIdx.x * p.nqp + cur_b * NP + c] = n < p.cap ? n : p.cap;
+                p.counts[(size_t)(cur_b * NP + c) * gridDim.x + blockIdx.x] = n < p.cap ? n : p.cap;
             }
         }
     }
