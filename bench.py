@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how shard partials meet -- peer-store exchange kernels over NVLink, or NCCL all-gather + merge")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the short BASELINE config 2 / 3 legs (1M x 512: fp32 nq 1 and 16; bf16 nq 4096) reported under 'configs'")
     ap.add_argument("--extra", action="store_true", help="also time query batches 1/4/16/64 (reported under 'extra')")
     return ap.parse_args()
 
@@ -124,6 +126,70 @@ def measured_peak_gbs():
         except Exception:  # noqa: BLE001
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_peak_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["bf16_tflops"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def config_legs(evs, torch, dev, k):
+    """BASELINE configs 2 and 3 on this GPU, device-timed (CUDA events on torch's stream around back-to-back
+    IndexFlatIP.search calls with device-resident queries).  Each leg carries its own roofline: HBM for the
+    streaming cases, dense bf16 tensor throughput for the 4096-query batch."""
+    hbm_peak, _ = measured_peak_gbs()
+    tf_burst, tf_sust, tf_src = measured_peak_tflops()
+    out = []
+
+    def queries(d, nq):
+        qi = evs.IndexFlatIP(d, device=dev.index)
+        qi.add_synthetic(nq, seed=1)
+        return torch.from_numpy(qi.reconstruct_n(0, nq)).to(dev)
+
+    def timed(idx, xq, reps):
+        for _ in range(3):
+            idx.search(xq, k)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            idx.search(xq, k)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    for tag, rows, d, storage, nqs in (("C2", 1_000_000, 512, "f32", (1, 16)), ("C3", 1_000_000, 512, "bf16", (4096,))):
+        idx = evs.IndexFlatIP(d, device=dev.index, storage=storage)
+        idx.reserve(rows)
+        idx.add_synthetic(rows, seed=0)
+        esz = 2 if storage == "bf16" else 4
+        for nq in nqs:
+            xq = queries(d, nq)
+            ms = timed(idx, xq, 50 if nq <= 64 else 5)
+            scan_ms = idx.time_scan(xq, k, iters=20 if nq <= 64 else 3)
+            rec = {"config": f"{tag}: {rows}x{d} {storage}, nq={nq}, k={k}", "ms_per_search": ms, "queries_per_s": nq / ms * 1e3,
+                   "scan_ms": scan_ms}
+            if nq <= 64:
+                alg = rows * d * esz + nq * d * 4 + nq * k * 12
+                ach = alg / (scan_ms * 1e-3) / 1e9
+                rec["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                   "frac_whole_search": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+            else:
+                flops = 2.0 * nq * rows * d
+                ach = flops / (scan_ms * 1e-3) / 1e12
+                rec["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst,
+                                   "frac_of_sustained": ach / tf_sust, "peak_source": tf_src,
+                                   "frac_whole_search": flops / (ms * 1e-3) / 1e12 / tf_burst,
+                                   "kernel": "evs::tc2_scan_kernel (tcgen05.mma cta_group::2) incl. threshold pre-pass, tau0, gather"}
+            out.append(rec)
+        del idx
+    return out
 
 
 def ncu_traffic_per_launch(a, world):
@@ -346,6 +412,12 @@ def run_evs(a) -> int:
             ms, _, _ = timed_device(qd, max(10, a.steps // 4), 3)
             extra[f"nq{nq}"] = {"queries_per_s": max(10, a.steps // 4) * nq / (ms * 1e-3)}
 
+    configs = None
+    if world == 1 and not a.no_configs:
+        del index
+        torch.cuda.empty_cache()
+        configs = config_legs(evs, torch, dev, a.k)
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline(a)
@@ -366,6 +438,8 @@ def run_evs(a) -> int:
         }
         if extra:
             line["extra"] = extra
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

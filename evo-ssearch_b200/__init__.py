@@ -13,12 +13,12 @@ from .config import Config, config  # noqa: F401
 from .index import (METRIC_INNER_PRODUCT, METRIC_L2, IndexFlatIP, PeerExchange, merge_partials,  # noqa: F401
                     normalize_L2, read_index, write_index)
 from .lifecycle import (clamp_limit, create_index, evict_index, load_index, save_index, search_image,  # noqa: F401
-                        search_text)
+                        search_text, update_index)
 from .sharded import ShardedIndexFlatIP, shard_bounds  # noqa: F401
 
 __all__ = [
     "IndexFlatIP", "PeerExchange", "read_index", "write_index", "normalize_L2", "merge_partials", "METRIC_INNER_PRODUCT", "METRIC_L2",
-    "create_index", "save_index", "load_index", "evict_index", "search_text", "search_image", "clamp_limit",
+    "create_index", "update_index", "save_index", "load_index", "evict_index", "search_text", "search_image", "clamp_limit",
     "ShardedIndexFlatIP", "shard_bounds", "config", "Config", "EvsError", "device_count", "set_option",
     "get_option", "kernel_launches",
 ]

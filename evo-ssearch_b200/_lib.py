@@ -35,6 +35,7 @@ SIGNATURES = {
     "evs_index_add": (_i, [_vp, _i64, _vp]),
     "evs_index_add_dev": (_i, [_vp, _i64, _vp, _i, _vp]),
     "evs_index_add_synth": (_i, [_vp, _i64, _u64, _i]),
+    "evs_index_add_rows_from": (_i, [_vp, _vp, _i64, _vp]),
     "evs_index_get_rows": (_i, [_vp, _i64, _i64, _vp]),
     "evs_index_search": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "evs_index_search_dev": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),

@@ -372,6 +372,33 @@ extern "C" int evs_index_add_synth(evs_index* idx, int64_t n, uint64_t seed, int
     return finish_add_locked(idx, n);
 }
 
+extern "C" int evs_index_add_rows_from(evs_index* dst, const evs_index* src, int64_t n, const int64_t* rows_host) {
+    if (!dst || !src) return fail(EVS_EINVAL, "NULL index");
+    if (dst == src) return fail(EVS_EINVAL, "source and destination must be different indexes");
+    if (n < 0) return fail(EVS_EINVAL, "n must be >= 0");
+    if (n == 0) return EVS_OK;
+    if (!rows_host) return fail(EVS_EINVAL, "rows is NULL");
+    if (dst->d != src->d) return fail(EVS_EINVAL, "dimension mismatch: %d vs %d", dst->d, src->d);
+    if (dst->device != src->device) return fail(EVS_EINVAL, "indexes live on different devices (%d, %d)", dst->device, src->device);
+    for (int64_t i = 0; i < n; i++)
+        if (rows_host[i] < 0 || rows_host[i] >= src->ntotal)
+            return fail(EVS_EINVAL, "row %lld out of range [0, %lld)", (long long)rows_host[i], (long long)src->ntotal);
+    std::lock_guard<std::mutex> lk(dst->mu);
+    int rc = use_device(dst->device);
+    if (rc) return rc;
+    if ((rc = grow_for_add_locked(dst, n))) return rc;
+    long long* ids_dev = nullptr;
+    CU(cudaMalloc(reinterpret_cast<void**>(&ids_dev), (size_t)n * sizeof(long long)));
+    cudaError_t e = cudaMemcpyAsync(ids_dev, rows_host, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, dst->stream);
+    if (e == cudaSuccess)
+        e = launch_gather_rows(src->xb32, ids_dev, dst->xb32 + (size_t)dst->ntotal * dst->d, n, dst->d, dst->sm_count, dst->stream);
+    if (e == cudaSuccess) rc = finish_add_locked(dst, n);  // synchronises the stream
+    else cudaStreamSynchronize(dst->stream);
+    cudaFree(ids_dev);
+    if (e != cudaSuccess) return fail(EVS_ECUDA, "row gather failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
 extern "C" int evs_index_get_rows(const evs_index* idx, int64_t row0, int64_t n, float* out_host) {
     if (!idx || (!out_host && n > 0)) return fail(EVS_EINVAL, "NULL argument");
     if (row0 < 0 || n < 0 || row0 + n > idx->ntotal) return fail(EVS_EINVAL, "rows [%lld,%lld) out of range", (long long)row0, (long long)(row0 + n));

@@ -557,6 +557,25 @@ __global__ void __launch_bounds__(256) to_f32_kernel(const T* __restrict__ src, 
 }
 
 // =============================================================================================
+// row gather: dst[i][:] = src[ids[i]][:] (incremental re-index keeps the rows of unchanged files on the device).
+// One warp per row, 128-bit copies when d % 4 == 0.
+// =============================================================================================
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ ids,
+                                                         float* __restrict__ dst, long long n, int d) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        const float* s = src + (size_t)ids[r] * d;
+        float* o = dst + (size_t)r * d;
+        if ((d & 3) == 0) {
+            for (int i = lane; i < (d >> 2); i += 32) reinterpret_cast<float4*>(o)[i] = reinterpret_cast<const float4*>(s)[i];
+        } else {
+            for (int i = lane; i < d; i += 32) o[i] = s[i];
+        }
+    }
+}
+
+// =============================================================================================
 // synthetic rows: value(seed, global row, col) -- same integer function as oracle/orc_synth_fill
 // =============================================================================================
 __device__ __forceinline__ u64 splitmix64(u64 z) {
@@ -650,6 +669,15 @@ cudaError_t launch_to_f32(const void* src, int dtype, float* dst, long long coun
     else if (dtype == EVS_BF16)
         to_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, count);
     else return cudaErrorInvalidValue;
+    EVS_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_gather_rows(const float* src, const long long* ids_dev, float* dst, long long n, int d, int sm_count,
+                               cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    int grid = clamp_grid((n * 32 + 255) / 256, sm_count * 16);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(src, ids_dev, dst, n, d);
     EVS_LAUNCH_CHECK();
     return cudaSuccess;
 }

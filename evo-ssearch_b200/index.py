@@ -139,6 +139,12 @@ class IndexFlatIP:
         x = np.ascontiguousarray(x, dtype="float32")
         check(lib().evs_index_add(self._h, n, x.ctypes.data_as(ctypes.c_void_p)))
 
+    def add_rows_from(self, src: "IndexFlatIP", rows) -> None:
+        """Append rows ``rows`` (ids into ``src``) of another index on the same device, device to device."""
+        rows = np.ascontiguousarray(np.asarray(rows, dtype=np.int64))
+        assert rows.ndim == 1 and src.d == self.d
+        check(lib().evs_index_add_rows_from(self._h, src._h, rows.shape[0], rows.ctypes.data_as(ctypes.c_void_p)))
+
     def add_synthetic(self, n: int, seed: int, normalize: bool = True) -> None:
         """Append ``n`` counter-based synthetic rows generated on the device (bench / tests)."""
         check(lib().evs_index_add_synth(self._h, int(n), int(seed), int(bool(normalize))))

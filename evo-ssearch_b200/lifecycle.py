@@ -2,7 +2,8 @@
 
 Mirrors ``oldapp.py``::
 
-    create_index(folder)                         oldapp.py:54-90
+    create_index(folder)                         oldapp.py:54-90   (+ batched indexing, config.BATCH_SIZE)
+    update_index(folder)                         -- incremental re-index from metadata.pkl
     save_index(index, paths, metadata, folder)   oldapp.py:92-106
     load_index(folder)                           oldapp.py:108-135
     search (text) handler body                   oldapp.py:1985-2045  -> search_text
@@ -34,33 +35,161 @@ _cache_lock = threading.Lock()
 _cache: Dict[str, Tuple[Tuple[int, int], IndexFlatIP, list, Optional[list]]] = {}
 
 
-def create_index(folder_path, encoder) -> Tuple[Optional[IndexFlatIP], Optional[List[str]], Optional[List[dict]]]:
+def _walk(folder_path: Path) -> List[Path]:
+    """The reference's walk: one non-recursive glob per supported extension (oldapp.py:64-65)."""
+    out: List[Path] = []
+    for ext in config.SUPPORTED_EXTENSIONS:
+        out.extend(folder_path.glob(f"*{ext}"))
+    return out
+
+
+def _is_cuda_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
+
+
+def _embed_files(files: List[Path], encoder, batch_size: int, index: Optional[IndexFlatIP]):
+    """Embed ``files`` and append the embeddings to ``index`` (created on first use) in order.
+
+    Two encoder protocols:
+      * the reference's ``get_image_embedding(path) -> (d,)`` (already normalised, oldapp.py:30-37), called
+        per image and stacked ``BATCH_SIZE`` at a time before one ``add`` -- ``np.array(...).astype('float32')``
+        as oldapp.py:86;
+      * optional ``encode_images(paths) -> (m, d)`` raw (un-normalised) features as a numpy array or a CUDA
+        tensor of dtype float32/float16/bfloat16, i.e. one batched CLIP forward (the
+        reference's ``config.BATCH_SIZE`` is dead code).  The batch is L2-normalised by the library's kernel
+        where it lies (oldapp.py:35 done for ``m`` rows at once) and appended without leaving the device.  A
+        batch that fails is retried image by image so that one unreadable file only drops itself.
+    Returns ``(index, ok_files)``; files whose embedding failed are printed and skipped like the reference.
+    """
+    from .index import normalize_L2
+    ok: List[Path] = []
+    batched = getattr(encoder, "encode_images", None)
+    for b0 in range(0, len(files), batch_size):
+        chunk = files[b0:b0 + batch_size]
+        feats = None
+        if batched is not None:
+            try:
+                feats = batched([str(p) for p in chunk])
+                if feats.shape[0] != len(chunk):
+                    raise ValueError("encode_images returned a different number of rows")
+            except Exception as e:  # noqa: BLE001
+                print(f"Error processing batch of {len(chunk)} images ({e}); retrying one by one")
+                feats = None
+        if feats is not None:
+            if _is_cuda_tensor(feats):
+                feats = feats.contiguous()
+            else:
+                feats = np.ascontiguousarray(np.asarray(feats), dtype="float32")
+            normalize_L2(feats)
+            good = chunk
+        else:
+            rows, good = [], []
+            for img_path in chunk:
+                try:
+                    rows.append(encoder.get_image_embedding(img_path))
+                    good.append(img_path)
+                except Exception as e:  # noqa: BLE001 - the reference prints and continues
+                    print(f"Error processing {img_path}: {e}")
+            if not rows:
+                continue
+            feats = np.array(rows).astype("float32")
+        if index is None:
+            index = IndexFlatIP(int(feats.shape[1]))
+        index.add(feats)
+        ok.extend(good)
+    return index, ok
+
+
+def _file_meta(img_path: Path) -> dict:
+    stat = img_path.stat()
+    return {"path": str(img_path), "mtime": stat.st_mtime, "size": stat.st_size}
+
+
+def create_index(folder_path, encoder, batch_size: Optional[int] = None
+                 ) -> Tuple[Optional[IndexFlatIP], Optional[List[str]], Optional[List[dict]]]:
     """Embed every supported image directly inside ``folder_path`` and build the index (oldapp.py:54-90).
 
     Same walk as the reference: one non-recursive glob per extension, per-image failures are printed
-    and skipped, ``(None, None, None)`` when nothing could be embedded.  Embeddings are stacked and
-    cast to float32 exactly as ``np.array(embeddings).astype('float32')`` (oldapp.py:86).
+    and skipped, ``(None, None, None)`` when nothing could be embedded.  Embeddings are appended
+    ``batch_size`` (default ``config.BATCH_SIZE``) rows at a time; see ``_embed_files`` for the two encoder
+    protocols.  With the reference's per-image protocol the index rows are exactly
+    ``np.array(embeddings).astype('float32')`` (oldapp.py:86).
     """
     folder_path = Path(folder_path)
-    image_paths: List[str] = []
-    embeddings: List[np.ndarray] = []
-    image_metadata: List[dict] = []
-    for ext in config.SUPPORTED_EXTENSIONS:
-        for img_path in folder_path.glob(f"*{ext}"):
-            try:
-                embedding = encoder.get_image_embedding(img_path)
-                embeddings.append(embedding)
-                image_paths.append(str(img_path))
-                stat = img_path.stat()
-                image_metadata.append({"path": str(img_path), "mtime": stat.st_mtime, "size": stat.st_size})
-            except Exception as e:  # noqa: BLE001 - the reference prints and continues
-                print(f"Error processing {img_path}: {e}")
-    if not embeddings:
+    batch_size = max(1, int(batch_size or config.BATCH_SIZE))
+    index, ok = _embed_files(_walk(folder_path), encoder, batch_size, None)
+    if index is None or not ok:
         return None, None, None
-    embeddings_array = np.array(embeddings).astype("float32")
-    index = IndexFlatIP(embeddings_array.shape[1])
-    index.add(embeddings_array)
-    return index, image_paths, image_metadata
+    return index, [str(p) for p in ok], [_file_meta(p) for p in ok]
+
+
+def update_index(folder_path, encoder, batch_size: Optional[int] = None):
+    """Incremental re-index: re-use the stored embedding of every file whose
+    ``(path, mtime, size)`` still matches ``metadata.pkl`` (oldapp.py:71-78 writes exactly these), embed only
+    new or changed files, drop deleted ones.  Kept rows never leave the GPU (``evs_index_add_rows_from``).
+
+    Returns ``(index, image_paths, image_metadata, stats)`` in the order a fresh ``create_index`` would
+    produce, so the two are interchangeable; the caller saves with ``save_index`` as after ``create_index``.
+    Falls back to ``create_index`` when the folder has no usable index or no metadata.
+    """
+    folder_path = Path(folder_path)
+    batch_size = max(1, int(batch_size or config.BATCH_SIZE))
+    old_index, old_paths, old_meta = load_index(folder_path)
+    files = _walk(folder_path)
+    stats = {"kept": 0, "embedded": 0, "removed": 0, "failed": 0}
+    if old_index is None or not old_meta or len(old_meta) != len(old_paths) or old_index.ntotal != len(old_paths):
+        index, paths, meta = create_index(folder_path, encoder, batch_size)
+        stats["embedded"] = 0 if paths is None else len(paths)
+        stats["failed"] = len(files) - stats["embedded"]
+        return index, paths, meta, stats
+    known = {m["path"]: (row, m.get("mtime"), m.get("size")) for row, m in enumerate(old_meta)}
+    plan = []   # per file in walk order: ("keep", old row, meta) or ("new", position among the files to embed, None)
+    todo: List[Path] = []
+    for img_path in files:
+        hit = known.get(str(img_path))
+        try:
+            meta = _file_meta(img_path)
+        except OSError as e:
+            print(f"Error processing {img_path}: {e}")
+            stats["failed"] += 1
+            continue
+        if hit is not None and hit[1] == meta["mtime"] and hit[2] == meta["size"]:
+            plan.append(("keep", hit[0], meta))
+        else:
+            plan.append(("new", len(todo), meta))
+            todo.append(img_path)
+    fresh, ok = _embed_files(todo, encoder, batch_size, None)
+    ok_pos = {str(p): i for i, p in enumerate(ok)}  # row of each successfully embedded file in `fresh`
+    stats["failed"] += len(todo) - len(ok)
+    # pool = [kept rows of the old index][fresh rows]; the final index is one gather of the pool in walk order
+    kept_rows = [row for kind, row, _ in plan if kind == "keep"]
+    d = old_index.d
+    pool = IndexFlatIP(d, device=old_index.device, storage="f32")
+    if kept_rows:
+        pool.add_rows_from(old_index, kept_rows)
+    if fresh is not None and fresh.ntotal:
+        pool.add_rows_from(fresh, np.arange(fresh.ntotal))
+    perm, paths, metas = [], [], []
+    nkept = 0
+    for kind, ref, meta in plan:
+        if kind == "keep":
+            perm.append(nkept)
+            nkept += 1
+        else:
+            pos = ok_pos.get(str(todo[ref]))
+            if pos is None:
+                continue  # embedding failed: skipped like create_index does
+            perm.append(len(kept_rows) + pos)
+        paths.append(meta["path"])
+        metas.append(meta)
+    stats["kept"] = len(kept_rows)
+    stats["embedded"] = len(ok)
+    stats["removed"] = len(old_paths) - len(kept_rows) - sum(1 for p in todo if str(p) in known)
+    if not perm:
+        return None, None, None, stats
+    index = IndexFlatIP(d, device=old_index.device, storage=old_index.storage)
+    index.add_rows_from(pool, perm)
+    return index, paths, metas, stats
 
 
 def save_index(index: IndexFlatIP, image_paths, image_metadata, folder_path) -> None:

@@ -103,6 +103,9 @@ EVS_API int evs_index_reserve(evs_index* idx, int64_t nrows);
 EVS_API int evs_index_add(evs_index* idx, int64_t n, const float* x_host);
 EVS_API int evs_index_add_dev(evs_index* idx, int64_t n, const void* x_dev, int dtype, void* stream);
 EVS_API int evs_index_add_synth(evs_index* idx, int64_t n, uint64_t seed, int normalize);
+/* append rows `rows_host[0..n)` of `src` (same d, same device) to `dst`, device to device: the incremental
+ * re-index of SURVEY.md section 8(f) rank 4 keeps the embeddings of unchanged files without a host round trip */
+EVS_API int evs_index_add_rows_from(evs_index* dst, const evs_index* src, int64_t n, const int64_t* rows_host);
 /* copy rows [row0, row0+n) back to host fp32 (faiss reconstruct_n; used by write and tests) */
 EVS_API int evs_index_get_rows(const evs_index* idx, int64_t row0, int64_t n, float* out_host);
 

@@ -107,3 +107,99 @@ def test_empty_folder_and_missing_metadata(tmp_path):
     assert i2.ntotal == 1 and p2 == paths and m2 is None
     res = evs.search_text(tmp_path, "anything", enc, limit=12)
     assert len(res) == 1 and res[0]["metadata"] == {}
+
+
+class BatchEncoder(StubEncoder):
+    """Adds the optional batched protocol: ``encode_images(paths)`` -> raw (un-normalised) features on the GPU,
+    like one ``model.encode_image`` call on a stacked batch."""
+
+    def __init__(self, as_tensor=True):
+        self.as_tensor = as_tensor
+        self.batches = []
+        self.single_calls = 0
+
+    def raw(self, name):
+        return oracle.synth_fill(1, self.d, seed=zlib.crc32(("raw:" + name).encode()), normalize=False)[0] * 3.5
+
+    def get_image_embedding(self, image_path):
+        self.single_calls += 1
+        name = os.path.basename(str(image_path))
+        if name.startswith("broken"):
+            raise OSError("cannot identify image file")
+        return oracle.l2_normalize(self.raw(name)[None, :])[0]
+
+    def encode_images(self, paths):
+        names = [os.path.basename(p) for p in paths]
+        self.batches.append(len(names))
+        if any(n.startswith("broken") for n in names):
+            raise OSError("cannot identify image file")  # the whole batch fails, like a stacked forward would
+        raw = np.stack([self.raw(n) for n in names])
+        if self.as_tensor:
+            import torch
+            return torch.from_numpy(raw).cuda()
+        return raw
+
+
+@pytest.mark.parametrize("as_tensor", [True, False])
+def test_batched_indexing_equals_per_image(tmp_path, as_tensor):
+    _make_folder(tmp_path)
+    enc = BatchEncoder(as_tensor)
+    index, paths, meta = evs.create_index(tmp_path, enc, batch_size=7)
+    assert index.ntotal == len(paths) == len(meta) == 42
+    assert max(enc.batches) == 7 and sum(enc.batches) >= 42
+    assert 0 < enc.single_calls <= 7  # only the batch holding the unreadable file was retried one by one
+    # rows = our normalise kernel applied to the raw batch = the oracle's normaliser, bit for bit
+    want = np.stack([oracle.l2_normalize(enc.raw(os.path.basename(p))[None, :])[0] for p in paths])
+    assert np.array_equal(index.reconstruct_n(0, 42), want)
+    # and the same index as the reference's one-image-at-a-time protocol builds
+    ref_index, ref_paths, _ = evs.create_index(tmp_path, StubNoBatch(enc), batch_size=1)
+    assert ref_paths == paths and np.array_equal(ref_index.reconstruct_n(0, 42), want)
+
+
+class StubNoBatch:
+    def __init__(self, inner):
+        self.inner = inner
+
+    def get_image_embedding(self, p):
+        return self.inner.get_image_embedding(p)
+
+
+def test_incremental_reindex_equals_fresh_index(tmp_path):
+    enc = BatchEncoder()
+    _make_folder(tmp_path)
+    index, paths, meta = evs.create_index(tmp_path, enc)
+    evs.save_index(index, paths, meta, tmp_path)
+    # nothing changed: every row is kept, nothing is embedded
+    enc.batches.clear()
+    enc.single_calls = 0
+    i1, p1, m1, st = evs.update_index(tmp_path, enc)
+    assert st == {"kept": 42, "embedded": 0, "removed": 0, "failed": 1} and enc.batches == [1]  # broken_1.jpg is re-tried
+    assert p1 == paths and m1 == meta and np.array_equal(i1.reconstruct_n(0, 42), index.reconstruct_n(0, 42))
+    # delete two, add three, change one (size differs -> re-embedded)
+    os.remove(tmp_path / "img_003.jpg")
+    os.remove(tmp_path / "a.png")
+    for nm in ("new_1.jpg", "new_2.png", "new_3.webp"):
+        (tmp_path / nm).write_bytes(b"n" * 7)
+    (tmp_path / "img_010.jpg").write_bytes(b"changed-content")
+    enc.batches.clear()
+    enc.single_calls = 0
+    i2, p2, m2, st = evs.update_index(tmp_path, enc, batch_size=16)
+    assert st["kept"] == 39 and st["embedded"] == 4 and st["removed"] == 2 and st["failed"] == 1
+    assert sum(enc.batches) + enc.single_calls <= 5 + 5  # 5 files to embed (one unreadable), nothing else touched
+    fresh, pf, mf = evs.create_index(tmp_path, BatchEncoder())
+    assert p2 == pf and m2 == mf
+    assert np.array_equal(i2.reconstruct_n(0, i2.ntotal), fresh.reconstruct_n(0, fresh.ntotal))
+    evs.save_index(i2, p2, m2, tmp_path)
+    res = evs.search_text(tmp_path, "x", enc, limit=48)
+    assert len(res) == 43
+    # no index yet -> behaves like create_index
+    other = tmp_path / "other"
+    other.mkdir()
+    (other / "one.jpg").write_bytes(b"1")
+    i3, p3, m3, st3 = evs.update_index(other, enc)
+    assert i3.ntotal == 1 and st3["embedded"] == 1 and st3["kept"] == 0
+    # row gather argument checks
+    with pytest.raises(evs.EvsError):
+        i3.add_rows_from(i2, [i2.ntotal])
+    with pytest.raises(evs.EvsError):
+        i3.add_rows_from(i3, [0])
