@@ -8,6 +8,7 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <string>
@@ -43,7 +44,8 @@ static int fail(int code, const char* fmt, ...) {
 
 static ScanTuning g_tune;
 static std::mutex g_tune_mu;
-static int g_profile_scans = 0;  // record CUDA events around every search's scan launches
+static int g_profile_scans = 0;
+static std::atomic<long long> g_tc_fallbacks{0};  // queries re-run through the GEMV scan after a tensor-core overflow  // record CUDA events around every search's scan launches
 
 // ---------------------------------------------------------------------------------------------
 // the handle
@@ -175,6 +177,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tc2_slice_tiles")) *value = g_tc2_slice_tiles;
     else if (!strcmp(name, "tc_stages")) *value = g_tc_max_stages;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
+    else if (!strcmp(name, "tc_fallbacks")) *value = g_tc_fallbacks.load();  // read-only counter
     else return fail(EVS_EINVAL, "unknown option '%s'", name);
     return EVS_OK;
 }
@@ -520,6 +523,7 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
     CU(cudaStreamSynchronize(st));
     for (int64_t q = 0; q < nq; q++) {
         if (!idx->tc_overflow_pin[q]) continue;
+        g_tc_fallbacks.fetch_add(1);
         SearchOut o1;
         o1.D = out.D ? out.D + (size_t)q * k : nullptr;
         o1.I = out.I ? out.I + (size_t)q * k : nullptr;

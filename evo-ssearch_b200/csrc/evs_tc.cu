@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
 // (clustered candidates) fall back to a bitonic sort.  grid = nq, block = 256.
 // ---------------------------------------------------------------------------------------------
 constexpr int GATHER_ALL = 4096;   // keys of one query held in shared memory; more -> overflow (GEMV re-run)
-constexpr int GATHER_SURV = 1024;
+constexpr int GATHER_SURV = 1024;  // also holds the buffer maxima: nctas <= GATHER_SURV
 
 __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int nctas,
                                                         int cap, int kp, u64* __restrict__ lists, int* __restrict__ overflow) {
@@ -380,6 +380,46 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ 
         s_T = 0ull;
     }
     __syncthreads();
+    // how many keys does this query have?  (block reduction of the counts)
+    {
+        int part = 0;
+        for (int b = threadIdx.x; b < nctas; b += nt) part += cnt[b];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if (lane == 0 && part) atomicAdd(&s_m, part);
+    }
+    __syncthreads();
+    const int grand = s_m;
+    __syncthreads();
+    if (threadIdx.x == 0) s_m = 0;
+    u64 T1 = 0ull;
+    if (grand > GATHER_ALL) {
+        // 0. too many keys for shared memory (large shards: the pre-pass samples n/128 rows, so ~140 kp keys pass):
+        //    first a threshold from the buffer maxima -- T1 = kp-th largest head, at least kp keys are >= T1 and
+        //    only ~1.5 % of the keys are -- then the compaction below keeps the keys >= T1 only.
+        u64* heads = surv;  // nctas <= GATHER_SURV slots, free until step 2
+        for (int b = warp; b < nctas; b += nwarps) {
+            const int n = cnt[b];
+            const u64* src = base + (size_t)b * cap;
+            u64 m = 0ull;
+            for (int i = lane; i < n; i += 32) m = umax64(m, src[i]);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) m = umax64(m, __shfl_xor_sync(0xffffffffu, m, off));
+            if (lane == 0) heads[b] = m;
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < nctas; b += nt) {
+            const u64 hb = heads[b];
+            if (hb == 0ull) continue;
+            int r = 0;
+            for (int j = 0; j < nctas; j++) r += heads[j] > hb ? 1 : 0;
+            if (r == kp - 1) s_T = hb;  // fewer than kp non-empty buffers: stays 0, everything is kept
+        }
+        __syncthreads();
+        T1 = s_T;
+        __syncthreads();
+        if (threadIdx.x == 0) s_T = 0ull;
+    }
     // 1. compaction: a warp takes 4 buffers at a time so that their loads are in flight together
     for (int b0 = warp * 4; b0 < nctas; b0 += nwarps * 4) {
         u64 key[4];
@@ -393,7 +433,7 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ 
         for (int u = 0; u < 4; u++) {
             for (int i0 = 0; i0 < nb[u]; i0 += 32) {  // warp-uniform; more than one round only for counts > 32
                 const u64 k = i0 == 0 ? key[u] : ((i0 + lane < nb[u]) ? base[(size_t)(b0 + u) * cap + i0 + lane] : 0ull);
-                const bool valid = k != 0ull;
+                const bool valid = k != 0ull && k >= T1;
                 const unsigned m = __ballot_sync(0xffffffffu, valid);
                 if (m == 0u) continue;
                 int pos = 0;
@@ -538,7 +578,7 @@ cudaError_t tc_launch_gather(const u64* cand, const int* counts, int nctas, int 
     (void)cap_total;
     (void)nqp;
     const size_t gs = (size_t)(GATHER_ALL + GATHER_SURV + 2 * kp) * 8 + (size_t)nctas * 4;
-    if (gs > 200 * 1024) return cudaErrorInvalidValue;
+    if (gs > 200 * 1024 || nctas > GATHER_SURV) return cudaErrorInvalidValue;
     if (gs > 40 * 1024) cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
     tc_gather_kernel<<<nq, 256, gs, st>>>(cand, counts, nctas, cap, kp, lists, overflow);
     g_kernel_launches.fetch_add(1);

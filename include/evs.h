@@ -188,6 +188,8 @@ EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev,
  *                 "tile_rows", "stages", "ctas_per_sm", "profile_scans", "tc_min_nq" (query batches of at
  *                 least this many use the tensor-core scan; 0 = never), "tc_pair_min_nq" (... and of at
  *                 least this many the CTA-pair kernel; 0 = never), "tc_stages", "tc2_slice_tiles".
+ *                 evs_get_option also reads "tc_fallbacks": queries re-run through the GEMV scan so far because a
+ *                 tensor-core candidate buffer overflowed (exactness guard; should stay 0 on ordinary data).
  *                 Unknown names -> EVS_EINVAL.
  * evs_kernel_launches: number of kernels this library has launched in this process.
  * evs_index_time_scan: runs the scan stage alone `iters` times on the index's stream for queries

@@ -462,6 +462,16 @@ def test_metric_size_10m_x_512_properties():
         D2, I2 = idx.search(q, 96)
         results[(storage, "k96")] = (D2, I2)
         assert (np.diff(D2[0].astype(np.float64)) <= 0).all()
+        # the same query inside batches that take the tensor-core scans (one-CTA kernel, CTA-pair kernel): identical
+        # answer for it, and no query of the batch may have needed the GEMV re-run (large shards pass ~9000
+        # candidates per query through the gather: it must hold them)
+        fb0 = evs.get_option("tc_fallbacks")
+        qb = np.concatenate([q, oracle.synth_fill(299, d, 5)])
+        for nqb in (16, 300):
+            Db, Ib = idx.search(qb[:nqb], k)
+            assert np.array_equal(Ib[:1], results[(storage, 1)][1]) and np.array_equal(Db[:1], results[(storage, 1)][0]), nqb
+            assert (np.diff(Db.astype(np.float64), axis=1) <= 0).all() and (Ib >= 0).all()
+        assert evs.get_option("tc_fallbacks") == fb0
         if storage == "f32":
             # sharded: 4 shards on this one GPU -> partials -> merge == unsharded
             xq_t = torch.from_numpy(q).cuda()

@@ -129,10 +129,12 @@ def test_tc_overflow_falls_back_exactly():
     idx = evs.IndexFlatIP(d)
     idx.add(xb)
     evs.set_option("tc_min_nq", 1)
+    fb0 = evs.get_option("tc_fallbacks")
     D, I = idx.search(q, 48)
     Dr, Ir = oracle.canon_search(q, xb, 48)
     assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
     assert I[0].tolist() == list(range(1000, 1048))
+    assert evs.get_option("tc_fallbacks") > fb0  # the guard fired (and only on adversarial data: see below)
 
 
 def test_config3_1m_x_512_bf16_nq4096_recall():
@@ -142,7 +144,9 @@ def test_config3_1m_x_512_bf16_nq4096_recall():
     idx = evs.IndexFlatIP(d, storage="bf16")
     idx.add_synthetic(n, seed=0)
     xq = oracle.synth_fill(nq, d, 1)
+    fb0 = evs.get_option("tc_fallbacks")
     D, I = idx.search(xq, k)
+    assert evs.get_option("tc_fallbacks") == fb0  # no query needed the GEMV re-run
     xb = oracle.synth_fill(n, d, 0)
     sample = np.arange(0, nq, 64)
     Dr, Ir = oracle.canon_search(xq[sample], xb, k)
