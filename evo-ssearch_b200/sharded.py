@@ -143,6 +143,26 @@ class ShardedIndexFlatIP:
         dev = getattr(self.local, "torch_device", None)
         if dev is None:
             dev = torch.device("cuda", self.local.device)
-        xq = torch.from_numpy(x).to(dev, non_blocking=False)
+        if dev.type != "cuda":  # injected CPU engine (tests)
+            D, I = self.search_tensor(torch.from_numpy(x).to(dev), k)
+            return D.cpu().numpy(), I.cpu().numpy()
+        # pinned staging both ways, one synchronisation per call: H2D of the queries, search, D2H of (D, I)
+        st = self._staging(n, d, k)
+        st["q"][:n].copy_(torch.from_numpy(x))
+        xq = st["q"][:n].to(dev, non_blocking=True)
         D, I = self.search_tensor(xq, k)
-        return D.cpu().numpy(), I.cpu().numpy()
+        st["D"][:n].copy_(D, non_blocking=True)
+        st["I"][:n].copy_(I, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return st["D"][:n].numpy().copy(), st["I"][:n].numpy().copy()
+
+    def _staging(self, n: int, d: int, k: int):
+        import torch
+        st = getattr(self, "_stage", None)
+        if st is None or st["q"].shape[0] < n or st["D"].shape[1] != k:
+            cap = max(n, 16)
+            st = {"q": torch.empty((cap, d), dtype=torch.float32).pin_memory(),
+                  "D": torch.empty((cap, k), dtype=torch.float32).pin_memory(),
+                  "I": torch.empty((cap, k), dtype=torch.int64).pin_memory()}
+            self._stage = st
+        return st
