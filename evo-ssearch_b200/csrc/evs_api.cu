@@ -154,6 +154,9 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "tc2_slice_tiles")) {
         if (value < 0 || value > 4096) return fail(EVS_EINVAL, "tc2_slice_tiles must be in [0, 4096]");
         g_tc2_slice_tiles = (int)value;
+    } else if (!strcmp(name, "tc_sample_rows")) {
+        if (value != 0 && (value < 1024 || value > (1 << 24))) return fail(EVS_EINVAL, "tc_sample_rows must be 0 (auto) or in [1024, 2^24]");
+        g_tc_sample_rows = (int)value;
     } else if (!strcmp(name, "tc_stages")) {
         if (value < 2 || value > 14) return fail(EVS_EINVAL, "tc_stages must be in [2, 14]");
         g_tc_max_stages = (int)value;
@@ -175,6 +178,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tc_min_nq")) *value = g_tune.tc_min_nq;
     else if (!strcmp(name, "tc_pair_min_nq")) *value = g_tune.tc_pair_min_nq;
     else if (!strcmp(name, "tc2_slice_tiles")) *value = g_tc2_slice_tiles;
+    else if (!strcmp(name, "tc_sample_rows")) *value = g_tc_sample_rows;
     else if (!strcmp(name, "tc_stages")) *value = g_tc_max_stages;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
     else if (!strcmp(name, "tc_fallbacks")) *value = g_tc_fallbacks.load();  // read-only counter

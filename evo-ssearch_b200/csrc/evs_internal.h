@@ -103,6 +103,8 @@ size_t tc2_workspace_bytes(const Tc2Plan& pl);
 cudaError_t tc2_scan(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, cudaStream_t st);
 cudaError_t tc2_dump_scores(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, float* out, cudaStream_t st);
 extern int g_tc_max_stages;
+extern int g_tc_sample_rows;
+int tc_sample_rows(int nq);
 int tc_max_queries(int d, int is_bf16);
 cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, TcPlan* pl);
 size_t tc_workspace_bytes(const TcPlan& pl);

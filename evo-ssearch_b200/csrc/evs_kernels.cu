@@ -117,14 +117,25 @@ __device__ __forceinline__ void canon32_dot_pair(const float* __restrict__ xa, c
 //   T0 = kp-th largest list HEAD is a lower bound of the kp-th best key (kp heads are >= it), only the
 //   <= kp lists whose head is >= T0 can hold survivors, and only their prefix >= T0 does.  The
 //   survivors (about kp + a few for unordered data, kp*kp at most) are sorted in shared memory.
-// dynamic smem: surv[kp*kp] u64 | heads[L] u64 | sc[kp] f64 | id[kp] i64 | ok[kp] u64 | qs[d] f64
+// dynamic smem: surv[finalize_surv_slots(L, kp)] u64 | heads[L] u64 | sc[kp] f64 | id[kp] i64 | ok[kp] u64 | qs[d] f64
+// (survivor capacity scap = min(L, kp) * kp: with one list per query -- the tensor-core scans -- the kernel needs
+// 7 KB instead of 38 KB of shared memory and eight 256-thread CTAs fit an SM)
+__host__ __device__ inline int finalize_surv_cap(int L, int kp) { return (L < kp ? L : kp) * kp; }
+__host__ __device__ inline int finalize_surv_slots(int L, int kp) {
+    const int scap = finalize_surv_cap(L, kp);
+    int pow2 = kp;
+    while (pow2 < scap) pow2 <<= 1;  // the sort path pads the survivors to a power of two
+    return pow2 > scap + kp ? pow2 : scap + kp;  // the counting path puts kp result slots behind the survivors
+}
+
 __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int t = threadIdx.x, nt = blockDim.x;
     const int warp = t >> 5, lane = t & 31, nwarps = nt >> 5;
     const int kp = p.kp, L = p.L;
-    u64* surv = reinterpret_cast<u64*>(smem_raw);           // [kp*kp]
-    u64* heads = surv + (size_t)kp * kp;                    // [L]
+    const int scap = finalize_surv_cap(L, kp);
+    u64* surv = reinterpret_cast<u64*>(smem_raw);           // [finalize_surv_slots(L, kp)]
+    u64* heads = surv + finalize_surv_slots(L, kp);         // [L]
     double* sc = reinterpret_cast<double*>(heads + L);      // [kp]
     long long* id = reinterpret_cast<long long*>(sc + kp);  // [kp]
     u64* ok = reinterpret_cast<u64*>(id + kp);              // [kp] integer rank keys of the scores
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
     while ((L / (hs * 2)) * 10 >= kp * 23) hs <<= 1;
     for (int attempt = 0; attempt < 2; attempt++) {
     if (attempt == 1) {
-        if (s_nsurv <= kp * kp || hs == 1) break;  // uniform: read after the barrier below
+        if (s_nsurv <= scap || hs == 1) break;  // uniform: read after the barrier below
         __syncthreads();
         if (t == 0) {
             s_nsurv = 0;
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
             if (lane == 0) pos = atomicAdd(&s_nsurv, __popc(m));
             pos = __shfl_sync(0xffffffffu, pos, 0);
             const int dst = pos + __popc(m & ((1u << lane) - 1u));
-            if (keep && dst < kp * kp) surv[dst] = keys[u];
+            if (keep && dst < scap) surv[dst] = keys[u];
         }
     }
     __syncthreads();
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
     // 3. the kp best survivors in descending order -> A[0..kp)
     const int nsurv = s_nsurv;
     const u64* A;
-    if (nsurv <= nt && nsurv + kp <= kp * kp) {
+    if (nsurv <= nt) {
         // usual case (a few more than kp survivors): rank by counting, one barrier instead of a sort
         u64* top = surv + nsurv;  // kp slots behind the survivors
         for (int i = t; i < kp; i += nt) top[i] = 0ull;
@@ -744,7 +755,7 @@ cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
     p.P_ids = reinterpret_cast<long long*>(a.P_ids);
     p.margins = a.margins;
     p.x = a.x;
-    size_t smem = (size_t)a.kp * a.kp * 8 + (size_t)a.L * 8 + (size_t)a.kp * 24 + (size_t)a.d * 8 + 16;
+    size_t smem = (size_t)finalize_surv_slots(a.L, a.kp) * 8 + (size_t)a.L * 8 + (size_t)a.kp * 24 + (size_t)a.d * 8 + 16;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -618,6 +618,11 @@ static cudaError_t launch_tc(bool is_bf16, const CUtensorMap& tdb, const CUtenso
 }
 
 int g_tc_max_stages = 8;  // option "tc_stages"
+int g_tc_sample_rows = 0;  // option "tc_sample_rows": rows the threshold pre-pass scores at least (0 = auto)
+
+// auto: 65536 rows for large batches (the select pass pays for every admitted candidate: 1.1 k' n / sample per query),
+// 32768 for up to 256 queries, where the pre-pass itself is the larger cost (measured: scripts/tc_tune.py)
+int tc_sample_rows(int nq) { return g_tc_sample_rows > 0 ? g_tc_sample_rows : (nq <= 256 ? 32768 : 65536); }
 static int pick_stages(int nk, int npad) {
     int stages = g_tc_max_stages;
     while (stages > 2 && tc_smem_bytes(nk, npad, stages) > 226 * 1024) stages--;
@@ -643,7 +648,7 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     pl->grid = (int)(pl->ntiles < sm_count ? pl->ntiles : sm_count);
     // pre-pass sample: every `stride`-th tile, at least 512 tiles (or all of them)
     long long want = pl->ntiles / 128;
-    if (want < 512) want = 512;
+    if (want < tc_sample_rows(nq) / TC_BM) want = tc_sample_rows(nq) / TC_BM;
     if (want > pl->ntiles) want = pl->ntiles;
     pl->pre_stride = pl->ntiles / want;
     pl->pre_tiles = (pl->ntiles + pl->pre_stride - 1) / pl->pre_stride;

@@ -417,7 +417,7 @@ cudaError_t tc2_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_cou
     slices_for(pl->ntiles, &pl->slice_tiles, &pl->nslices, &pl->grid);
     // pre-pass sample: every `stride`-th pair-tile, at least 256 pair-tiles = 65536 rows (or all of them)
     long long want = pl->ntiles / 128;
-    if (want < 256) want = 256;
+    if (want < tc_sample_rows(nq) / (2 * TC_BM)) want = tc_sample_rows(nq) / (2 * TC_BM);
     if (want > pl->ntiles) want = pl->ntiles;
     pl->pre_stride = pl->ntiles / want;
     pl->pre_tiles = (pl->ntiles + pl->pre_stride - 1) / pl->pre_stride;
