@@ -76,7 +76,7 @@ struct TcPlan {
     int npad, nblocks, nqp, nk, stages, grid, pre_grid, groups, gpow2, cap, cap_total, kp;
     size_t smem;
     long long ntiles, pre_tiles, pre_stride;
-    size_t off_gmax, off_tau0, off_counts, off_overflow, off_cand, off_qbf16, off_end;
+    size_t off_gmax, off_tau0, off_counts, off_overflow, off_spill_cnt, off_cand, off_spill, off_qbf16, off_end;
 };
 struct TcArgs {
     const void* xb;   // database rows (fp32 or bf16)
@@ -94,7 +94,7 @@ struct Tc2Plan {
     int slice_tiles, pre_slice_tiles;
     size_t smem;
     long long ntiles, nslices, pre_tiles, pre_stride, pre_nslices;
-    size_t off_gmax, off_tau0, off_counts, off_overflow, off_cand, off_qbf16, off_end;
+    size_t off_gmax, off_tau0, off_counts, off_overflow, off_spill_cnt, off_cand, off_spill, off_qbf16, off_end;
 };
 extern int g_tc2_slice_tiles;
 int tc2_max_half(int d, int is_bf16);
@@ -102,6 +102,7 @@ cudaError_t tc2_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_cou
 size_t tc2_workspace_bytes(const Tc2Plan& pl);
 cudaError_t tc2_scan(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, cudaStream_t st);
 cudaError_t tc2_dump_scores(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, float* out, cudaStream_t st);
+constexpr int TC_SPILL_CAP = 1024;  // per-query spill list behind the (CTA, query) candidate buffers
 extern int g_tc_max_stages;
 extern int g_tc_sample_rows;
 int tc_sample_rows(int nq);

@@ -51,7 +51,9 @@ struct TcParams {
     u64* cand;            // [nqp][gridDim.x][cap]: the buffers of one query are contiguous for the gather
     int cap;
     int* counts;          // [nqp][gridDim.x]
-    int* overflow;        // [nqp] set to 1 when a buffer overflowed
+    int* overflow;        // [nqp] set to 1 when a buffer AND the query's spill list overflowed
+    int* spill_cnt;       // [nqp] keys offered to the spill list of the query
+    u64* spill;           // [nqp][TC_SPILL_CAP]: where a full (CTA, query) buffer sends its extra keys (clustered rows)
     // MODE_DUMP
     float* dump;          // [n][nqp]
 };
@@ -241,10 +243,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                                 for (int jj = 0; jj < 16; jj++)
                                     if (jj == j) s = __uint_as_float(v[jj]);
                                 int slot = atomicAdd(&cnt_s[c], 1);
-                                if (slot < p.cap)
+                                if (slot < p.cap) {
                                     p.cand[((size_t)(qb + c) * gridDim.x + blockIdx.x) * p.cap + slot] = make_key(s, (uint32_t)row);
-                                else
-                                    p.overflow[qb + c] = 1;
+                                } else {
+                                    const int s2 = atomicAdd(&p.spill_cnt[qb + c], 1);
+                                    if (s2 < TC_SPILL_CAP) p.spill[(size_t)(qb + c) * TC_SPILL_CAP + s2] = make_key(s, (uint32_t)row);
+                                    else p.overflow[qb + c] = 1;
+                                }
                             }
                         }
                     }
@@ -359,21 +364,30 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
 // (clustered candidates) fall back to a bitonic sort.  grid = nq, block = 256.
 // ---------------------------------------------------------------------------------------------
 constexpr int GATHER_ALL = 4096;   // keys of one query held in shared memory; more -> overflow (GEMV re-run)
-constexpr int GATHER_SURV = 1024;  // also holds the buffer maxima: nctas <= GATHER_SURV
+constexpr int GATHER_SURV = 1024;  // also holds the buffer maxima: nctas + 1 <= GATHER_SURV
 
 __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int nctas,
-                                                        int cap, int kp, u64* __restrict__ lists, int* __restrict__ overflow) {
+                                                        int cap, int kp, u64* __restrict__ lists, int* __restrict__ overflow,
+                                                        const int* __restrict__ spill_cnt, const u64* __restrict__ spill) {
     extern __shared__ __align__(16) unsigned char sraw[];
     u64* all = reinterpret_cast<u64*>(sraw);       // GATHER_ALL
     u64* surv = all + GATHER_ALL;                  // GATHER_SURV
     u64* cmax = surv + GATHER_SURV;                // 2 * kp
-    int* cnt = reinterpret_cast<int*>(cmax + 2 * kp);  // nctas
+    int* cnt = reinterpret_cast<int*>(cmax + 2 * kp);  // nctas + 1
     __shared__ int s_n, s_m;
     __shared__ u64 s_T;
     const int c = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nt = blockDim.x, nwarps = nt >> 5;
     const u64* base = cand + (size_t)c * nctas * cap;
     for (int b = threadIdx.x; b < nctas; b += nt) cnt[b] = counts[(size_t)c * nctas + b];
+    // the query's spill list is one more buffer (index nctas): normally empty
+    const u64* sbase = spill + (size_t)c * TC_SPILL_CAP;
+    if (threadIdx.x == 0) {
+        const int sc = spill_cnt[c];
+        cnt[nctas] = sc < TC_SPILL_CAP ? sc : TC_SPILL_CAP;
+    }
+    const int nbuf = nctas + 1;
+    auto buf = [&](int b) { return b < nctas ? base + (size_t)b * cap : sbase; };
     if (threadIdx.x == 0) {
         s_n = 0;
         s_m = 0;
@@ -383,7 +397,7 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ 
     // how many keys does this query have?  (block reduction of the counts)
     {
         int part = 0;
-        for (int b = threadIdx.x; b < nctas; b += nt) part += cnt[b];
+        for (int b = threadIdx.x; b < nbuf; b += nt) part += cnt[b];
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
         if (lane == 0 && part) atomicAdd(&s_m, part);
@@ -398,9 +412,9 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ 
         //    first a threshold from the buffer maxima -- T1 = kp-th largest head, at least kp keys are >= T1 and
         //    only ~1.5 % of the keys are -- then the compaction below keeps the keys >= T1 only.
         u64* heads = surv;  // nctas <= GATHER_SURV slots, free until step 2
-        for (int b = warp; b < nctas; b += nwarps) {
+        for (int b = warp; b < nbuf; b += nwarps) {
             const int n = cnt[b];
-            const u64* src = base + (size_t)b * cap;
+            const u64* src = buf(b);
             u64 m = 0ull;
             for (int i = lane; i < n; i += 32) m = umax64(m, src[i]);
 #pragma unroll
@@ -408,11 +422,11 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ 
             if (lane == 0) heads[b] = m;
         }
         __syncthreads();
-        for (int b = threadIdx.x; b < nctas; b += nt) {
+        for (int b = threadIdx.x; b < nbuf; b += nt) {
             const u64 hb = heads[b];
             if (hb == 0ull) continue;
             int r = 0;
-            for (int j = 0; j < nctas; j++) r += heads[j] > hb ? 1 : 0;
+            for (int j = 0; j < nbuf; j++) r += heads[j] > hb ? 1 : 0;
             if (r == kp - 1) s_T = hb;  // fewer than kp non-empty buffers: stays 0, everything is kept
         }
         __syncthreads();
@@ -421,18 +435,18 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ 
         if (threadIdx.x == 0) s_T = 0ull;
     }
     // 1. compaction: a warp takes 4 buffers at a time so that their loads are in flight together
-    for (int b0 = warp * 4; b0 < nctas; b0 += nwarps * 4) {
+    for (int b0 = warp * 4; b0 < nbuf; b0 += nwarps * 4) {
         u64 key[4];
         int nb[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            nb[u] = (b0 + u < nctas) ? cnt[b0 + u] : 0;
-            key[u] = (lane < nb[u]) ? base[(size_t)(b0 + u) * cap + lane] : 0ull;
+            nb[u] = (b0 + u < nbuf) ? cnt[b0 + u] : 0;
+            key[u] = (lane < nb[u]) ? buf(b0 + u)[lane] : 0ull;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             for (int i0 = 0; i0 < nb[u]; i0 += 32) {  // warp-uniform; more than one round only for counts > 32
-                const u64 k = i0 == 0 ? key[u] : ((i0 + lane < nb[u]) ? base[(size_t)(b0 + u) * cap + i0 + lane] : 0ull);
+                const u64 k = i0 == 0 ? key[u] : ((i0 + lane < nb[u]) ? buf(b0 + u)[i0 + lane] : 0ull);
                 const bool valid = k != 0ull && k >= T1;
                 const unsigned m = __ballot_sync(0xffffffffu, valid);
                 if (m == 0u) continue;
@@ -574,13 +588,13 @@ cudaError_t tc_launch_tau0(const uint32_t* gmax, int groups, int gpow2, int nqp,
 }
 
 cudaError_t tc_launch_gather(const u64* cand, const int* counts, int nctas, int nqp, int cap, int kp, int cap_total, int nq,
-                             u64* lists, int* overflow, cudaStream_t st) {
+                             u64* lists, int* overflow, const int* spill_cnt, const u64* spill, cudaStream_t st) {
     (void)cap_total;
     (void)nqp;
-    const size_t gs = (size_t)(GATHER_ALL + GATHER_SURV + 2 * kp) * 8 + (size_t)nctas * 4;
-    if (gs > 200 * 1024 || nctas > GATHER_SURV) return cudaErrorInvalidValue;
+    const size_t gs = (size_t)(GATHER_ALL + GATHER_SURV + 2 * kp) * 8 + (size_t)(nctas + 1) * 4;
+    if (gs > 200 * 1024 || nctas + 1 > GATHER_SURV) return cudaErrorInvalidValue;
     if (gs > 40 * 1024) cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
-    tc_gather_kernel<<<nq, 256, gs, st>>>(cand, counts, nctas, cap, kp, lists, overflow);
+    tc_gather_kernel<<<nq, 256, gs, st>>>(cand, counts, nctas, cap, kp, lists, overflow, spill_cnt, spill);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -676,7 +690,9 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     pl->off_tau0 = take((size_t)pl->nqp * 4);
     pl->off_counts = take((size_t)pl->grid * pl->nqp * 4);
     pl->off_overflow = take((size_t)pl->nqp * 4);
+    pl->off_spill_cnt = take((size_t)pl->nqp * 4);
     pl->off_cand = take((size_t)pl->grid * pl->nqp * pl->cap * 8);
+    pl->off_spill = take((size_t)pl->nqp * TC_SPILL_CAP * 8);
     pl->off_qbf16 = take((size_t)pl->nqp * d * 2);
     pl->off_end = off;
     return cudaSuccess;
@@ -708,6 +724,8 @@ static cudaError_t tc_prepare(const TcArgs& a, const TcPlan& pl, unsigned char* 
     p->cap = pl.cap;
     p->counts = reinterpret_cast<int*>(ws + pl.off_counts);
     p->overflow = reinterpret_cast<int*>(ws + pl.off_overflow);
+    p->spill_cnt = reinterpret_cast<int*>(ws + pl.off_spill_cnt);
+    p->spill = reinterpret_cast<u64*>(ws + pl.off_spill);
     return cudaSuccess;
 }
 
@@ -727,7 +745,8 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     if ((e = tc_launch_tau0(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp, reinterpret_cast<float*>(ws + pl.off_tau0), st)) !=
         cudaSuccess)
         return e;
-    if ((e = cudaMemsetAsync(ws + pl.off_overflow, 0, (size_t)pl.nqp * 4, st)) != cudaSuccess) return e;
+    // overflow flags and spill counters start at zero (adjacent in the workspace)
+    if ((e = cudaMemsetAsync(ws + pl.off_overflow, 0, pl.off_cand - pl.off_overflow, st)) != cudaSuccess) return e;
     // 2. selection pass over every tile, all query blocks in one persistent launch
     p.ntiles = pl.ntiles;
     p.tile_stride = 1;
@@ -735,7 +754,7 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     if (e != cudaSuccess) return e;
     // 3. per query: gather + sort -> top-kp list
     if ((e = tc_launch_gather(p.cand, p.counts, pl.grid, pl.nqp, pl.cap, pl.kp, pl.cap_total, a.nq,
-                              reinterpret_cast<u64*>(a.lists), p.overflow, st)) != cudaSuccess)
+                              reinterpret_cast<u64*>(a.lists), p.overflow, p.spill_cnt, p.spill, st)) != cudaSuccess)
         return e;
     if (a.overflow_out)
         e = cudaMemcpyAsync(a.overflow_out, ws + pl.off_overflow, (size_t)a.nq * 4, cudaMemcpyDeviceToDevice, st);

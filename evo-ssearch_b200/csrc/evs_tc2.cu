@@ -62,6 +62,8 @@ struct Tc2Params {
     int cap;
     int* counts;           // [nqp][gridDim.x], zeroed before the launch; persists across the items of a CTA
     int* overflow;         // [nqp]
+    int* spill_cnt;        // [nqp]
+    u64* spill;            // [nqp][TC_SPILL_CAP]: extra keys of full (CTA, query) buffers (clustered rows)
     // MODE_DUMP
     float* dump;           // [n][nqp]
 };
@@ -338,10 +340,13 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                                     base = __shfl_sync(0xffffffffu, base, src);
                                     if (hit) {
                                         const int slot = base + __popc(bal & lt_mask);
-                                        if (slot < p.cap)
+                                        if (slot < p.cap) {
                                             p.cand[((size_t)(qb + c) * gridDim.x + blockIdx.x) * p.cap + slot] = make_key(sc, (uint32_t)row);
-                                        else
-                                            p.overflow[qb + c] = 1;
+                                        } else {
+                                            const int s2 = atomicAdd(&p.spill_cnt[qb + c], 1);
+                                            if (s2 < TC_SPILL_CAP) p.spill[(size_t)(qb + c) * TC_SPILL_CAP + s2] = make_key(sc, (uint32_t)row);
+                                            else p.overflow[qb + c] = 1;
+                                        }
                                     }
                                 }
                             }
@@ -448,7 +453,9 @@ cudaError_t tc2_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_cou
     pl->off_tau0 = take((size_t)pl->nqp * 4);
     pl->off_counts = take((size_t)pl->grid * pl->nqp * 4);
     pl->off_overflow = take((size_t)pl->nqp * 4);
+    pl->off_spill_cnt = take((size_t)pl->nqp * 4);
     pl->off_cand = take((size_t)pl->grid * pl->nqp * pl->cap * 8);
+    pl->off_spill = take((size_t)pl->nqp * TC_SPILL_CAP * 8);
     pl->off_qbf16 = take((size_t)pl->nqp * d * 2);
     pl->off_end = off;
     return cudaSuccess;
@@ -501,6 +508,8 @@ static cudaError_t tc2_prepare(const TcArgs& a, const Tc2Plan& pl, unsigned char
     p->cap = pl.cap;
     p->counts = reinterpret_cast<int*>(ws + pl.off_counts);
     p->overflow = reinterpret_cast<int*>(ws + pl.off_overflow);
+    p->spill_cnt = reinterpret_cast<int*>(ws + pl.off_spill_cnt);
+    p->spill = reinterpret_cast<u64*>(ws + pl.off_spill);
     return cudaSuccess;
 }
 
@@ -520,7 +529,7 @@ cudaError_t tc2_scan(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, cuda
     if ((e = tc_launch_tau0(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp, reinterpret_cast<float*>(ws + pl.off_tau0), st)) !=
         cudaSuccess)
         return e;
-    // overflow flags and the per-(CTA, query) counts start at zero (adjacent in the workspace)
+    // the per-(CTA, query) counts, overflow flags and spill counters start at zero (adjacent in the workspace)
     if ((e = cudaMemsetAsync(ws + pl.off_counts, 0, pl.off_cand - pl.off_counts, st)) != cudaSuccess) return e;
     // 2. selection pass over every item
     p.ntiles = pl.ntiles;
@@ -530,7 +539,7 @@ cudaError_t tc2_scan(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, cuda
     if ((e = launch_tc2<MODE_SELECT>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st)) != cudaSuccess) return e;
     // 3. per query: gather + sort -> top-kp list
     if ((e = tc_launch_gather(p.cand, p.counts, pl.grid, pl.nqp, pl.cap, pl.kp, pl.cap_total, a.nq,
-                              reinterpret_cast<u64*>(a.lists), p.overflow, st)) != cudaSuccess)
+                              reinterpret_cast<u64*>(a.lists), p.overflow, p.spill_cnt, p.spill, st)) != cudaSuccess)
         return e;
     if (a.overflow_out)
         e = cudaMemcpyAsync(a.overflow_out, ws + pl.off_overflow, (size_t)a.nq * 4, cudaMemcpyDeviceToDevice, st);

@@ -137,6 +137,30 @@ def test_tc_overflow_falls_back_exactly():
     assert evs.get_option("tc_fallbacks") > fb0  # the guard fired (and only on adversarial data: see below)
 
 
+def test_tc_clustered_rows_use_the_spill_list_not_the_fallback():
+    """Realistic clustering (a burst of near-duplicate images stored in consecutive rows): the few CTAs that own
+    those rows overflow their (CTA, query) buffers; the extra keys go to the query's spill list and the search
+    stays on the tensor-core path (no GEMV re-run), exact as ever."""
+    d, n = 512, 200_000
+    xb = oracle.synth_fill(n, d, 31)
+    q = oracle.synth_fill(300, d, 32)
+    rng = np.random.default_rng(3)
+    burst = q[0][None, :] + 0.02 * rng.standard_normal((700, d)).astype(np.float32)
+    xb[5000:5700] = burst / np.linalg.norm(burst, axis=1, keepdims=True)
+    for storage in ("f32", "bf16"):
+        idx = evs.IndexFlatIP(d, storage=storage)
+        idx.add(xb)
+        evs.set_option("tc_min_nq", 1)
+        fb0 = evs.get_option("tc_fallbacks")
+        for nq in (8, 300):  # one-CTA kernel, CTA-pair kernel
+            D, I = idx.search(q[:nq], 48)
+            sample = [0, 1, nq - 1]
+            Dr, Ir = oracle.canon_search(q[sample], xb, 48)
+            assert np.array_equal(I[sample], Ir) and np.array_equal(D[sample], Dr), (storage, nq)
+            assert set(I[0].tolist()) <= set(range(5000, 5700))
+        assert evs.get_option("tc_fallbacks") == fb0, storage
+
+
 def test_config3_1m_x_512_bf16_nq4096_recall():
     """BASELINE config 3: 1M x 512 bf16, 4096 queries, k = 48: recall@k against the fp32 ground truth
     (bar: >= 0.999; the canonical re-rank makes it exact) checked on a sample of the batch."""
