@@ -154,6 +154,12 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "tc2_slice_tiles")) {
         if (value < 0 || value > 4096) return fail(EVS_EINVAL, "tc2_slice_tiles must be in [0, 4096]");
         g_tc2_slice_tiles = (int)value;
+    } else if (!strcmp(name, "tc_heap_max_nq")) {
+        if (value < 0 || value > 128) return fail(EVS_EINVAL, "tc_heap_max_nq must be in [0, 128]");
+        g_tc_heap_max_nq = (int)value;
+    } else if (!strcmp(name, "tc_heap_pure_max_nq")) {
+        if (value < 0 || value > 128) return fail(EVS_EINVAL, "tc_heap_pure_max_nq must be in [0, 128]");
+        g_tc_heap_pure_max_nq = (int)value;
     } else if (!strcmp(name, "tc_sample_rows")) {
         if (value != 0 && (value < 1024 || value > (1 << 24))) return fail(EVS_EINVAL, "tc_sample_rows must be 0 (auto) or in [1024, 2^24]");
         g_tc_sample_rows = (int)value;
@@ -178,6 +184,8 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tc_min_nq")) *value = g_tune.tc_min_nq;
     else if (!strcmp(name, "tc_pair_min_nq")) *value = g_tune.tc_pair_min_nq;
     else if (!strcmp(name, "tc2_slice_tiles")) *value = g_tc2_slice_tiles;
+    else if (!strcmp(name, "tc_heap_max_nq")) *value = g_tc_heap_max_nq;
+    else if (!strcmp(name, "tc_heap_pure_max_nq")) *value = g_tc_heap_pure_max_nq;
     else if (!strcmp(name, "tc_sample_rows")) *value = g_tc_sample_rows;
     else if (!strcmp(name, "tc_stages")) *value = g_tc_max_stages;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
@@ -453,18 +461,21 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
         ws_need = tc2_workspace_bytes(p2);
     }
     const int64_t last = nq % kTcQueryChunk;  // a shorter final chunk may take the other kernel
+    size_t lists_need = (size_t)first * kp;
     if (!use_pair(first) || (last && !use_pair(last))) {
         TcPlan pl;
-        CU(tc_plan(idx->ntotal, idx->d, bf16, (int)(use_pair(first) ? last : first), kp, idx->sm_count, &pl));
+        const int64_t cn1 = use_pair(first) ? last : first;
+        CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn1, kp, idx->sm_count, &pl));
         if (tc_workspace_bytes(pl) > ws_need) ws_need = tc_workspace_bytes(pl);
+        if (pl.heap && (size_t)cn1 * pl.grid * kp > lists_need) lists_need = (size_t)cn1 * pl.grid * kp;  // one list per CTA
     }
     int rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, ws_need);
     if (rc) return rc;
     if ((rc = ensure_dev(&idx->tc_overflow, &idx->tc_overflow_cap, (size_t)nq))) return rc;
-    const int64_t chunk_cap = nq < kTcQueryChunk ? nq : kTcQueryChunk;
-    if ((rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, (size_t)chunk_cap * kp))) return rc;
+    if ((rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, lists_need))) return rc;
     if ((rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
     idx->last_nq = nq;
+    bool may_overflow = false;  // MODE_HEAP chunks cannot: then nothing below needs the host
     for (int64_t c0 = 0; c0 < nq; c0 += kTcQueryChunk) {
         const int64_t cn = (nq - c0) < kTcQueryChunk ? (nq - c0) : kTcQueryChunk;
         std::pair<cudaEvent_t, cudaEvent_t>* pe = nullptr;
@@ -478,6 +489,7 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
             pe = &idx->prof_events[idx->prof_used++];
             CU(cudaEventRecord(pe->first, st));
         }
+        int lists_per_query = 1;
         {
             TcArgs a;
             a.xb = scan_rows;
@@ -489,6 +501,7 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
             a.lists = idx->lists;
             a.overflow_out = idx->tc_overflow + c0;
             if (use_pair(cn)) {
+                may_overflow = true;
                 Tc2Plan plb;
                 CU(tc2_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, &plb));
                 if (tc2_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
@@ -497,6 +510,12 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
                 TcPlan plb;  // same workspace bound: cn <= the chunk the workspace was sized for
                 CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, &plb));
                 if (tc_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
+                if (plb.heap) {
+                    lists_per_query = plb.grid;
+                    if ((size_t)cn * plb.grid * kp > idx->lists_cap) return fail(EVS_ECUDA, "internal: list workspace too small");
+                } else {
+                    may_overflow = true;
+                }
                 CU(tc_scan_block(a, plb, idx->tc_ws, st));
             }
         }
@@ -504,7 +523,7 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
         if (scan_only) continue;
         FinalizeArgs f;
         f.lists = idx->lists;
-        f.L = 1;
+        f.L = lists_per_query;
         f.kp = kp;
         f.xb = idx->xb32;
         f.xb_is_bf16 = 0;
@@ -520,7 +539,7 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
         f.margins = idx->margins_dev + c0;
         CU(launch_finalize(f, st));
     }
-    if (scan_only) return EVS_OK;
+    if (scan_only || !may_overflow) return EVS_OK;
     // exactness guard: re-run overflowed queries with the GEMV scan
     if ((rc = ensure_pinned(&idx->tc_overflow_pin, &idx->tc_overflow_pin_cap, (size_t)nq))) return rc;
     CU(cudaMemcpyAsync(idx->tc_overflow_pin, idx->tc_overflow, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -74,6 +74,7 @@ struct FinalizeArgs {
 // tensor-core scan (evs_tc.cu)
 struct TcPlan {
     int npad, nblocks, nqp, nk, stages, grid, pre_grid, groups, gpow2, cap, cap_total, kp;
+    int heap;  // 1: MODE_HEAP (small batch, lists [nq][grid][64] come straight out of the scan, L = grid for finalize)
     size_t smem;
     long long ntiles, pre_tiles, pre_stride;
     size_t off_gmax, off_tau0, off_counts, off_overflow, off_spill_cnt, off_cand, off_spill, off_qbf16, off_end;
@@ -105,6 +106,8 @@ cudaError_t tc2_dump_scores(const TcArgs& a, const Tc2Plan& pl, unsigned char* w
 constexpr int TC_SPILL_CAP = 1024;  // per-query spill list behind the (CTA, query) candidate buffers
 extern int g_tc_max_stages;
 extern int g_tc_sample_rows;
+extern int g_tc_heap_max_nq;
+extern int g_tc_heap_pure_max_nq;
 int tc_sample_rows(int nq);
 int tc_max_queries(int d, int is_bf16);
 cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, TcPlan* pl);

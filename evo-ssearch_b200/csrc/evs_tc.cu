@@ -20,6 +20,12 @@
 //   MODE_MAX     per (32-row group, query) maximum -> gmax      (threshold pre-pass over sampled tiles)
 //   MODE_SELECT  every score >= tau0[query] is appended to the (CTA, query) candidate buffer
 //   MODE_DUMP    raw scores to global memory (tests)
+//   MODE_HEAP    small batches (<= 32 queries, k' = 64): every (CTA, query) keeps a running top-k' in shared memory --
+//                a score enters if it beats the CTA's current k'-th best for that query; when more than 128 keys have
+//                piled up the owning epilogue warp bitonic-sorts the slots, keeps 64 and raises the threshold -- and
+//                the CTA writes one sorted k' list per query at the end, exactly what the GEMV scan writes.  No
+//                pre-pass, no threshold kernel, no gather, no overflow case and so no host synchronisation: the whole
+//                search is this launch plus finalize_kernel.
 // tau0[query] = k'-th largest group maximum of the pre-pass: at least k' distinct rows score >= tau0,
 // so it is a valid lower bound of the k'-th best score and the SELECT pass keeps a superset of the
 // top k'.  A (CTA, query) buffer that overflows raises overflow[query]; the host re-runs those queries
@@ -54,6 +60,8 @@ struct TcParams {
     int* overflow;        // [nqp] set to 1 when a buffer AND the query's spill list overflowed
     int* spill_cnt;       // [nqp] keys offered to the spill list of the query
     u64* spill;           // [nqp][TC_SPILL_CAP]: where a full (CTA, query) buffer sends its extra keys (clustered rows)
+    // MODE_HEAP
+    u64* lists;           // [nq][gridDim.x][64] sorted descending, 0 = empty
     // MODE_DUMP
     float* dump;          // [n][nqp]
 };
@@ -88,6 +96,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* tau_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_smem + 4) + 15) & ~(uintptr_t)15);  // float4 reads
     int* cnt_s = reinterpret_cast<int*>(tau_s + NP);
+    u64* heap_s = reinterpret_cast<u64*>(cnt_s + NP);  // MODE_HEAP: [NP][TC_HEAP_SLOTS]; 16-byte aligned (NP % 16 == 0)
 
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(2 * NP)) tmem_cols <<= 1;
@@ -195,6 +204,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+            if (MODE == MODE_HEAP) {  // one block per launch in this mode
+                for (int c = et; c < NP; c += 128) {
+                    // start from the pre-pass bound when there is one (it spares the early sorts: with it a CTA sees
+                    // ~10 admissions per query in all); padded queries never admit anything
+                    tau_s[c] = (qb + c < p.nq) ? (p.tau0 ? p.tau0[qb + c] : -INFINITY) : INFINITY;
+                    cnt_s[c] = 0;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             for (long long i = 0; i < my_tiles; i++, it++) {
                 const int a = (int)(it & 1);
                 const uint32_t aphase = (uint32_t)((it >> 1) & 1);
@@ -219,6 +237,36 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                             uint32_t o = row_ok ? score_to_ordered(__uint_as_float(v[j])) : 0u;
                             o = __reduce_max_sync(0xffffffffu, o);
                             if (lane == j) p.gmax[(size_t)g * p.nqp + qb + c0 + j] = o;
+                        }
+                    } else if (MODE == MODE_HEAP) {
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; j4++) {
+                            const float4 t = *reinterpret_cast<const float4*>(&tau_s[c0 + 4 * j4]);
+                            mask |= (__uint_as_float(v[4 * j4 + 0]) >= t.x ? 1u : 0u) << (4 * j4 + 0);
+                            mask |= (__uint_as_float(v[4 * j4 + 1]) >= t.y ? 1u : 0u) << (4 * j4 + 1);
+                            mask |= (__uint_as_float(v[4 * j4 + 2]) >= t.z ? 1u : 0u) << (4 * j4 + 2);
+                            mask |= (__uint_as_float(v[4 * j4 + 3]) >= t.w ? 1u : 0u) << (4 * j4 + 3);
+                        }
+                        if (!row_ok) mask = 0;
+                        uint32_t cols = __reduce_or_sync(0xffffffffu, mask);  // columns admitted by any row of this warp
+                        while (cols) {
+                            const int j = __ffs(cols) - 1;
+                            cols &= cols - 1;
+                            float sc = 0.f;
+#pragma unroll
+                            for (int jj = 0; jj < 16; jj++)
+                                if (jj == j) sc = __uint_as_float(v[jj]);  // j is warp-uniform
+                            const bool hit = (mask >> j) & 1u;
+                            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                            const int src = __ffs(bal) - 1;
+                            int base = 0;
+                            if (lane == src) base = atomicAdd(&cnt_s[c0 + j], __popc(bal));
+                            base = __shfl_sync(0xffffffffu, base, src);
+                            if (hit) {
+                                const u64 key = make_key(sc, (uint32_t)row);  // 0 (dropped by the sort) for NaN: cannot happen, NaN >= tau is false
+                                heap_s[(size_t)(c0 + j) * TC_HEAP_SLOTS + base + __popc(bal & ((1u << lane) - 1u))] = key;
+                            }
                         }
                     } else {
                         // branch-free filter: 16 compares into a bit mask, one warp-uniform test per group;
@@ -257,6 +305,37 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
+                if (MODE == MODE_HEAP) {
+                    // every warp has appended this tile's admissions (at most 128 per query: room is guaranteed because a
+                    // query never starts a tile with more than 128 keys); warp e now tidies the queries c = e, e+4, ...
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    for (int c = e; c < NP; c += 4) {
+                        const int n = cnt_s[c];
+                        if (n > 128) {  // warp-uniform
+                            u64* hc = heap_s + (size_t)c * TC_HEAP_SLOTS;
+                            for (int i2 = n + lane; i2 < TC_HEAP_SLOTS; i2 += 32) hc[i2] = 0ull;
+                            warp_bitonic_sort_desc(hc, TC_HEAP_SLOTS, lane);
+                            if (lane == 0) {
+                                tau_s[c] = key_score(hc[63]);  // the CTA's 64th best so far: nothing below it can matter
+                                cnt_s[c] = 64;
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            }
+            if (MODE == MODE_HEAP) {
+                // the CTA's answer: one sorted list of 64 keys per query, [query][cta][64] like the GEMV scan's lists
+                for (int c = e; c < NP; c += 4) {
+                    if (qb + c >= p.nq) continue;
+                    const int n = cnt_s[c];
+                    u64* hc = heap_s + (size_t)c * TC_HEAP_SLOTS;
+                    const int pow2 = n <= 64 ? 64 : (n <= 128 ? 128 : TC_HEAP_SLOTS);
+                    for (int i2 = n + lane; i2 < pow2; i2 += 32) hc[i2] = 0ull;
+                    warp_bitonic_sort_desc(hc, pow2, lane);
+                    u64* dst = p.lists + ((size_t)(qb + c) * gridDim.x + blockIdx.x) * 64;
+                    for (int i2 = lane; i2 < 64; i2 += 32) dst[i2] = hc[i2];
+                }
             }
             if (MODE == MODE_SELECT) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // every epilogue warp has finished the block
@@ -609,6 +688,10 @@ int tc_max_queries(int d, int is_bf16) {
     return n < 16 ? 0 : n;
 }
 
+static size_t tc_smem_bytes(int nk, int npad, int stages);
+static size_t tc_smem_bytes_heap(int nk, int npad, int stages) {
+    return tc_smem_bytes(nk, npad, stages) + (size_t)npad * TC_HEAP_SLOTS * 8;
+}
 static size_t tc_smem_bytes(int nk, int npad, int stages) {
     return (size_t)nk * npad * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4) * 8 + 32 + (size_t)npad * 8 + 1024;
 }
@@ -632,11 +715,14 @@ static cudaError_t launch_tc(bool is_bf16, const CUtensorMap& tdb, const CUtenso
 }
 
 int g_tc_max_stages = 8;  // option "tc_stages"
+int g_tc_heap_max_nq = 32;  // option "tc_heap_max_nq": batches up to this size keep their top-k' on chip (MODE_HEAP); 0 = never
+int g_tc_heap_pure_max_nq = 4;  // option "tc_heap_pure_max_nq": ... and up to this size without the threshold pre-pass
 int g_tc_sample_rows = 0;  // option "tc_sample_rows": rows the threshold pre-pass scores at least (0 = auto)
 
 // auto: 65536 rows for large batches (the select pass pays for every admitted candidate: 1.1 k' n / sample per query),
 // 32768 for up to 256 queries, where the pre-pass itself is the larger cost (measured: scripts/tc_tune.py)
 int tc_sample_rows(int nq) { return g_tc_sample_rows > 0 ? g_tc_sample_rows : (nq <= 256 ? 32768 : 65536); }
+static size_t tc_smem_bytes_plain(const TcPlan& pl) { return tc_smem_bytes(pl.nk, pl.npad, pl.stages); }
 static int pick_stages(int nk, int npad) {
     int stages = g_tc_max_stages;
     while (stages > 2 && tc_smem_bytes(nk, npad, stages) > 226 * 1024) stages--;
@@ -658,6 +744,17 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     pl->stages = pick_stages(pl->nk, pl->npad);
     pl->smem = tc_smem_bytes(pl->nk, pl->npad, pl->stages);
     if (pl->smem > 227 * 1024) return cudaErrorInvalidValue;
+    // small batches with k' = 64: running top-k' per (CTA, query) in shared memory, if >= 4 ring stages still fit
+    pl->heap = 0;
+    if (kp == 64 && nq <= g_tc_heap_max_nq && pl->nblocks == 1) {
+        int stages = g_tc_max_stages;
+        while (stages > 2 && tc_smem_bytes_heap(pl->nk, pl->npad, stages) > 226 * 1024) stages--;
+        if (stages >= 4 && tc_smem_bytes_heap(pl->nk, pl->npad, stages) <= 227 * 1024) {
+            pl->heap = nq <= g_tc_heap_pure_max_nq ? 1 : 2;  // 2: thresholds from the pre-pass first
+            pl->stages = stages;
+            pl->smem = tc_smem_bytes_heap(pl->nk, pl->npad, stages);
+        }
+    }
     pl->ntiles = (n + TC_BM - 1) / TC_BM;
     pl->grid = (int)(pl->ntiles < sm_count ? pl->ntiles : sm_count);
     // pre-pass sample: every `stride`-th tile, at least 512 tiles (or all of them)
@@ -737,6 +834,25 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     TcParams p;
     cudaError_t e = tc_prepare(a, pl, ws, &tdb, &tq, &p, st);
     if (e != cudaSuccess) return e;
+    if (pl.heap) {
+        // small batch: the CTAs keep their own top-k' per query on chip and write [nq][grid][64] lists
+        if (pl.heap == 2) {  // pre-pass thresholds first: the running top-k' then hardly ever needs a sort
+            p.ntiles = pl.pre_tiles;
+            p.tile_stride = pl.pre_stride;
+            if ((e = launch_tc<MODE_MAX>(a.is_bf16, tdb, tq, p, pl.pre_grid, tc_smem_bytes_plain(pl), st)) != cudaSuccess) return e;
+            if ((e = tc_launch_tau0(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp, reinterpret_cast<float*>(ws + pl.off_tau0), st)) !=
+                cudaSuccess)
+                return e;
+        } else {
+            p.tau0 = nullptr;
+        }
+        p.ntiles = pl.ntiles;
+        p.tile_stride = 1;
+        p.lists = reinterpret_cast<u64*>(a.lists);
+        if ((e = launch_tc<MODE_HEAP>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st)) != cudaSuccess) return e;
+        if (a.overflow_out) e = cudaMemsetAsync(a.overflow_out, 0, (size_t)a.nq * 4, st);  // this mode cannot overflow
+        return e;
+    }
     // 1. threshold pre-pass over the sampled tiles
     p.ntiles = pl.pre_tiles;
     p.tile_stride = pl.pre_stride;

@@ -7,7 +7,8 @@
 
 namespace evs {
 
-enum { MODE_MAX = 0, MODE_SELECT = 1, MODE_DUMP = 2 };
+enum { MODE_MAX = 0, MODE_SELECT = 1, MODE_DUMP = 2, MODE_HEAP = 3 };
+constexpr int TC_HEAP_SLOTS = 256;  // MODE_HEAP: candidate slots per (CTA, query): k' = 64 kept + 64 slack + one 128-row tile
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers: TMA tensor loads, tcgen05 alloc / mma / commit / ld

@@ -187,7 +187,9 @@ EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev,
  * evs_set_option: "scan_variant" (0 = auto, 1 = direct-load kernel, 2 = bulk-async ring kernel),
  *                 "tile_rows", "stages", "ctas_per_sm", "profile_scans", "tc_min_nq" (query batches of at
  *                 least this many use the tensor-core scan; 0 = never), "tc_pair_min_nq" (... and of at
- *                 least this many the CTA-pair kernel; 0 = never), "tc_stages", "tc2_slice_tiles", "tc_sample_rows".
+ *                 least this many the CTA-pair kernel; 0 = never), "tc_stages", "tc2_slice_tiles", "tc_sample_rows", "tc_heap_max_nq" (batches up to
+ *                 this size keep a running top-k' per CTA in shared memory: no gather, no overflow case, no host sync),
+ *                 "tc_heap_pure_max_nq" (... and up to this size also without the threshold pre-pass).
  *                 evs_get_option also reads "tc_fallbacks": queries re-run through the GEMV scan so far because a
  *                 tensor-core candidate buffer overflowed (exactness guard; should stay 0 on ordinary data).
  *                 Unknown names -> EVS_EINVAL.

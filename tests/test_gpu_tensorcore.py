@@ -14,6 +14,8 @@ def _reset_options():
     yield
     evs.set_option("tc_min_nq", 4)
     evs.set_option("tc_pair_min_nq", 129)
+    evs.set_option("tc_heap_max_nq", 32)
+    evs.set_option("tc_heap_pure_max_nq", 4)
     evs.set_option("tc2_slice_tiles", 0)
     evs.set_option("scan_variant", 0)
 
@@ -119,6 +121,36 @@ def test_tc_search_equals_oracle(storage, d):
     assert np.array_equal(I2, I3) and np.array_equal(D2, D3)
 
 
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_tc_heap_mode_equals_threshold_mode_and_oracle(storage):
+    """Small batches keep a running top-k' per (CTA, query) in shared memory (MODE_HEAP: one scan launch, no
+    pre-pass / gather / host sync).  Same answer as the threshold scheme and as the oracle, for sorted-ascending
+    data (every tile beats the last: the worst case for the on-chip compaction), ties and a ragged tail."""
+    d, n = 512, 150_017
+    xb = oracle.synth_fill(n, d, 41)
+    q = oracle.synth_fill(32, d, 42)
+    order = np.argsort(xb @ q[0])  # rows in ascending score order for query 0: admissions never stop
+    xb = np.ascontiguousarray(xb[order])
+    xb[n - 1] = xb[n - 2]  # exact tie at the very top
+    idx = evs.IndexFlatIP(d, storage=storage)
+    idx.add(xb)
+    evs.set_option("tc_min_nq", 1)
+    for nq, k in ((1, 48), (4, 1), (16, 48), (17, 12), (32, 48)):
+        Dr, Ir = oracle.canon_search(q[:nq], xb, k)
+        for pure in (4, 32):  # with the pre-pass thresholds for nq > 4 (the default), and without any pre-pass
+            evs.set_option("tc_heap_max_nq", 32)
+            evs.set_option("tc_heap_pure_max_nq", pure)
+            fb0 = evs.get_option("tc_fallbacks")
+            D, I = idx.search(q[:nq], k)
+            assert evs.get_option("tc_fallbacks") == fb0  # the on-chip heaps have no overflow case, whatever the data
+            assert np.array_equal(I, Ir) and np.array_equal(D, Dr), (storage, nq, k, pure)
+        evs.set_option("tc_heap_max_nq", 0)  # the threshold scheme (here it needs its GEMV re-run for query 0)
+        D0, I0 = idx.search(q[:nq], k)
+        assert np.array_equal(I0, Ir) and np.array_equal(D0, Dr), (storage, nq, k)
+    evs.set_option("tc_heap_max_nq", 32)
+    assert (idx.last_margins(32) >= 0).all()
+
+
 def test_tc_overflow_falls_back_exactly():
     """Adversarial data: thousands of identical rows all beat the pre-pass threshold -> candidate
     buffers overflow -> those queries are re-run through the GEMV scan; the answer stays exact."""
@@ -129,12 +161,17 @@ def test_tc_overflow_falls_back_exactly():
     idx = evs.IndexFlatIP(d)
     idx.add(xb)
     evs.set_option("tc_min_nq", 1)
+    evs.set_option("tc_heap_max_nq", 0)  # the threshold scheme (the on-chip heaps of small batches cannot overflow)
     fb0 = evs.get_option("tc_fallbacks")
     D, I = idx.search(q, 48)
     Dr, Ir = oracle.canon_search(q, xb, 48)
     assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
     assert I[0].tolist() == list(range(1000, 1048))
     assert evs.get_option("tc_fallbacks") > fb0  # the guard fired (and only on adversarial data: see below)
+    evs.set_option("tc_heap_max_nq", 32)
+    fb1 = evs.get_option("tc_fallbacks")
+    D, I = idx.search(q, 48)
+    assert np.array_equal(I, Ir) and np.array_equal(D, Dr) and evs.get_option("tc_fallbacks") == fb1
 
 
 def test_tc_clustered_rows_use_the_spill_list_not_the_fallback():
@@ -152,7 +189,8 @@ def test_tc_clustered_rows_use_the_spill_list_not_the_fallback():
         idx.add(xb)
         evs.set_option("tc_min_nq", 1)
         fb0 = evs.get_option("tc_fallbacks")
-        for nq in (8, 300):  # one-CTA kernel, CTA-pair kernel
+        for nq, heap in ((8, 32), (8, 0), (300, 32)):  # on-chip heaps, one-CTA threshold kernel, CTA-pair kernel
+            evs.set_option("tc_heap_max_nq", heap)
             D, I = idx.search(q[:nq], 48)
             sample = [0, 1, nq - 1]
             Dr, Ir = oracle.canon_search(q[sample], xb, 48)
