@@ -537,9 +537,15 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
         f.P_scores = out.P_scores ? out.P_scores + (size_t)c0 * k : nullptr;
         f.P_ids = out.P_ids ? out.P_ids + (size_t)c0 * k : nullptr;
         f.margins = idx->margins_dev + c0;
+        if (out.x) {  // exchange mode (only offered for batches that cannot need the host-side repair below)
+            f.x = *out.x;
+            f.x.nq_total = nq;
+            f.x.q_off = c0;
+        }
         CU(launch_finalize(f, st));
     }
     if (scan_only || !may_overflow) return EVS_OK;
+    if (out.x) return fail(EVS_ECUDA, "internal: exchange-mode search took a path that may overflow");
     // exactness guard: re-run overflowed queries with the GEMV scan
     if ((rc = ensure_pinned(&idx->tc_overflow_pin, &idx->tc_overflow_pin_cap, (size_t)nq))) return rc;
     CU(cudaMemcpyAsync(idx->tc_overflow_pin, idx->tc_overflow, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -565,6 +571,17 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
 static bool takes_tc_path(const evs_index* idx, int64_t nq, const ScanTuning& tune) {
     return tune.tc_min_nq > 0 && nq >= tune.tc_min_nq && idx->ntotal >= 65536 &&
            tc_max_queries(idx->d, idx->storage == EVS_STORE_BF16_F32) > 0;
+}
+
+// true when the tensor-core path serves this batch entirely from on-chip heaps (MODE_HEAP): no overflow case, so no
+// host synchronisation and the finalise kernel may write straight into the exchange slots
+static bool tc_path_is_heap(const evs_index* idx, int64_t nq, int64_t k, const ScanTuning& tune) {
+    if (nq > kTcQueryChunk) return false;
+    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
+    if (tune.tc_pair_min_nq > 0 && nq >= tune.tc_pair_min_nq && tc2_max_half(idx->d, bf16) > 0) return false;
+    TcPlan pl;
+    if (tc_plan(idx->ntotal, idx->d, bf16, (int)nq, pick_kp(k), idx->sm_count, &pl) != cudaSuccess) return false;
+    return pl.heap != 0;
 }
 
 static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out,
@@ -928,8 +945,8 @@ extern "C" int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, i
         tune = g_tune;
     }
     SearchOut out;
-    if (idx->ntotal == 0 || takes_tc_path(idx, nq, tune)) {
-        // empty shard / tensor-core scan (host-side overflow repair): partial into local staging, then publish
+    if (idx->ntotal == 0 || (takes_tc_path(idx, nq, tune) && !tc_path_is_heap(idx, nq, k, tune))) {
+        // empty shard / tensor-core scan with host-side overflow repair: partial into local staging, then publish
         out.P_scores = ex->stage_scores;
         out.P_ids = ex->stage_ids;
         if ((rc = search_dev_common(idx, nq, q_dev, k, out, st))) return rc;

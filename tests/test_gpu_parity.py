@@ -294,13 +294,16 @@ def test_peer_exchange_single_rank_equals_search():
         Dr, Ir = idx.search(xq[:40], 48)
         D, I = idx.search_exchange(px, xq_t[:40], 48)
         assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
+        Dr, Ir = idx.search(xq[:16], 48)  # small tensor-core batch (on-chip heaps): finalise writes the slots itself
+        D, I = idx.search_exchange(px, xq_t[:16], 48)
+        assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
     finally:
         evs.set_option("tc_min_nq", 4)
     empty = evs.IndexFlatIP(d)
     D, I = empty.search_exchange(px, xq_t[:2], 5)
     assert (I.cpu().numpy() == -1).all() and (D.cpu().numpy() == np.finfo(np.float32).min).all()
     timed_out, searches = px.status()
-    assert not timed_out and searches == 7
+    assert not timed_out and searches == 8
     with pytest.raises(evs.EvsError):
         idx.search_exchange(px, torch.from_numpy(oracle.synth_fill(301, d, 1)).cuda(), 48)  # beyond max_nq
     px2 = evs.PeerExchange(0, 0, 2, max_nq=4, max_k=48)  # world 2, never connected
