@@ -160,6 +160,8 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "tc_heap_pure_max_nq")) {
         if (value < 0 || value > 128) return fail(EVS_EINVAL, "tc_heap_pure_max_nq must be in [0, 128]");
         g_tc_heap_pure_max_nq = (int)value;
+    } else if (!strcmp(name, "tc2_seamless")) {
+        g_tc2_seamless = value ? 1 : 0;
     } else if (!strcmp(name, "tc_sample_rows")) {
         if (value != 0 && (value < 1024 || value > (1 << 24))) return fail(EVS_EINVAL, "tc_sample_rows must be 0 (auto) or in [1024, 2^24]");
         g_tc_sample_rows = (int)value;
@@ -186,6 +188,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tc2_slice_tiles")) *value = g_tc2_slice_tiles;
     else if (!strcmp(name, "tc_heap_max_nq")) *value = g_tc_heap_max_nq;
     else if (!strcmp(name, "tc_heap_pure_max_nq")) *value = g_tc_heap_pure_max_nq;
+    else if (!strcmp(name, "tc2_seamless")) *value = g_tc2_seamless;
     else if (!strcmp(name, "tc_sample_rows")) *value = g_tc_sample_rows;
     else if (!strcmp(name, "tc_stages")) *value = g_tc_max_stages;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
@@ -452,7 +455,9 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
     const void* scan_rows = bf16 ? idx->xb16 : (const void*)idx->xb32;
     // batches of pair_min_nq or more queries go through the CTA-pair kernel (N up to 256 per MMA, L2-shared slices)
     const bool can_pair = pair_min_nq > 0 && tc2_max_half(idx->d, bf16) > 0 && idx->sm_count >= 2;
-    auto use_pair = [&](int64_t cn) { return can_pair && cn >= pair_min_nq; };
+    // ... and so do batches that would need more than one pass of the one-CTA kernel (fp32 rows: 64 queries per pass)
+    const int one_cta_max = tc_max_queries(idx->d, bf16);
+    auto use_pair = [&](int64_t cn) { return can_pair && (cn >= pair_min_nq || cn > one_cta_max); };
     const int64_t first = nq < kTcQueryChunk ? nq : kTcQueryChunk;
     size_t ws_need = 0;
     if (use_pair(first)) {
@@ -578,7 +583,8 @@ static bool takes_tc_path(const evs_index* idx, int64_t nq, const ScanTuning& tu
 static bool tc_path_is_heap(const evs_index* idx, int64_t nq, int64_t k, const ScanTuning& tune) {
     if (nq > kTcQueryChunk) return false;
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
-    if (tune.tc_pair_min_nq > 0 && nq >= tune.tc_pair_min_nq && tc2_max_half(idx->d, bf16) > 0) return false;
+    if (tune.tc_pair_min_nq > 0 && (nq >= tune.tc_pair_min_nq || nq > tc_max_queries(idx->d, bf16)) && tc2_max_half(idx->d, bf16) > 0)
+        return false;
     TcPlan pl;
     if (tc_plan(idx->ntotal, idx->d, bf16, (int)nq, pick_kp(k), idx->sm_count, &pl) != cudaSuccess) return false;
     return pl.heap != 0;
@@ -1035,7 +1041,7 @@ extern "C" int evs_index_tc_scores_dev(evs_index* idx, int64_t nq, const float* 
         std::lock_guard<std::mutex> lk(g_tune_mu);
         pair_min = g_tune.tc_pair_min_nq;
     }
-    const bool pair = pair_min > 0 && nq >= pair_min && tc2_max_half(idx->d, bf16) > 0;
+    const bool pair = pair_min > 0 && (nq >= pair_min || nq > nb_max) && tc2_max_half(idx->d, bf16) > 0;
     if (nq <= 0 || (!pair && nq > nb_max) || nq > 4096) return fail(EVS_EINVAL, "nq must be in [1, %d]", pair ? 4096 : nb_max);
     if (idx->ntotal == 0) return fail(EVS_EINVAL, "empty index");
     std::lock_guard<std::mutex> lk(idx->mu);

@@ -13,14 +13,16 @@
 //   * work is cut into items (database slice, query block), numbered slice-major and dealt round-robin to the
 //     74 pairs, so the pairs that run at the same time share a handful of slices (a few MB each): the database
 //     streams from HBM once per launch and is re-read from the 126 MB L2 by the other query blocks.
-//   * the query block of the next item is re-loaded (128 KB per CTA, from L2) only when it changes.
+//   * the query block of the next item is re-loaded (128 KB per CTA, from L2) only when it changes, and then K chunk
+//     by K chunk behind the last MMA that reads the old chunk (per-chunk q_full / q_empty barriers), so the tensor
+//     pipe does not drain at item boundaries.
 // Warp roles per CTA (384 threads): warp 0 TMA producer (one lane), warp 1 MMA issuer (one lane, leader CTA
 // only), warp 2 TMEM alloc/dealloc, warps 4-11 epilogue: two warps per TMEM lane quarter (e = warp & 3), which
 // take alternate 32-column groups, so that every SM sub-partition has two epilogue warps to overlap the
 // tcgen05.ld latency of one with the filter arithmetic of the other (one warp per quarter left the MMA issuer
 // waiting on acc_empty 40 % of the time: ncu, profiles/r01_ncu_tc2_select_v1.txt).
-// Barriers: full[s] and q_full collect the TMA bytes of BOTH CTAs on the leader's barrier (cp.async.bulk.tensor
-// .cta_group::2 with the leader's barrier address); empty[s], q_empty and acc_full[a] are signalled in both CTAs
+// Barriers: full[s] and q_full[c] collect the TMA bytes of BOTH CTAs on the leader's barrier (cp.async.bulk.tensor
+// .cta_group::2 with the leader's barrier address); empty[s], q_empty[c] and acc_full[a] are signalled in both CTAs
 // by tcgen05.commit ... multicast::cluster; acc_empty[a] lives in the leader and counts the 16 epilogue warps of
 // the pair (the peer's arrive remotely through mapa + mbarrier.arrive.shared::cluster), each as soon as its last
 // tcgen05.ld of the tile has completed -- before it filters that last group.
@@ -54,6 +56,7 @@ struct Tc2Params {
     long long tile_stride;
     int slice_tiles;       // pair-tiles per slice
     long long nslices;
+    int seamless;          // 1: reload the query block chunk by chunk behind the MMAs (0: drain first; A/B switch)
     // MODE_MAX
     uint32_t* gmax;        // [ntiles * 8][nqp] ordered-uint maxima per 32-row group
     // MODE_SELECT
@@ -125,13 +128,13 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
     unsigned char* q_smem = smem;
     unsigned char* ring = q_smem + (size_t)NK * H * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * TC_STAGE_BYTES);
-    uint64_t* q_full = bars;             // leader's: the query block (both halves) has landed
-    uint64_t* q_empty = bars + 1;        // both: every MMA that reads the resident query block has completed
-    uint64_t* full = bars + 2;           // S, leader's: stage s of BOTH CTAs has landed
+    uint64_t* full = bars;               // S, leader's: stage s of BOTH CTAs has landed
     uint64_t* empty = full + S;          // S, both
     uint64_t* acc_full = empty + S;      // 2, both
-    uint64_t* acc_empty = acc_full + 2;  // 2, leader's, 8 arrivals
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* acc_empty = acc_full + 2;  // 2, leader's, 16 arrivals
+    uint64_t* q_full = acc_empty + 2;    // NK, leader's: K chunk c of the query block (both halves) has landed
+    uint64_t* q_empty = q_full + NK;     // NK, both: every MMA that reads chunk c of the resident block has completed
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(q_empty + NK + (NK & 1));  // keep 16-byte alignment
     float* tau_s = reinterpret_cast<float*>(tmem_base_smem + 4);
     int* cnt_s = reinterpret_cast<int*>(tau_s + NP);
     __nv_bfloat16* tau_b = reinterpret_cast<__nv_bfloat16*>(cnt_s + NP);  // 16-byte aligned: NP is a multiple of 32
@@ -142,8 +145,10 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
     if (threadIdx.x == 0) {
         prefetch_tmap(&tm_db);
         prefetch_tmap(&tm_q);
-        mbar_init(q_full, 1);
-        mbar_init(q_empty, 1);
+        for (int c = 0; c < NK; c++) {
+            mbar_init(&q_full[c], 1);
+            mbar_init(&q_empty[c], 1);
+        }
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -163,7 +168,6 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
-            const uint32_t q_full_leader = mapa_u32(smem_u32(q_full), 0);
             int stage = 0;
             uint32_t phase = 0;
             int cur_b = -1;
@@ -171,11 +175,10 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
             for (long long it = pair; it < nitems; it += npairs) {
                 const long long s = it / p.nqb;
                 const int b = (int)(it % p.nqb);
-                if (b != cur_b) {
-                    if (qloads > 0) mbar_wait(q_empty, (qloads - 1) & 1u);  // the MMAs of the previous block are done with it
-                    if (leader) mbar_arrive_expect_tx(q_full, (uint32_t)(2 * NK * H * 128));
-                    for (int c = 0; c < NK; c++)
-                        tma_load_2d_pair(q_smem + (size_t)c * H * 128, &tm_q, c * EC, b * NP + (int)cta_rank * H, q_full_leader);
+                // a new query block is loaded chunk by chunk, each chunk as soon as the last MMA that reads the old one
+                // has completed (q_empty[c]) and just ahead of the database chunk it will meet: no drain at item boundaries
+                const bool new_block = b != cur_b;
+                if (new_block) {
                     cur_b = b;
                     qloads++;
                 }
@@ -184,6 +187,14 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                 for (long long t = t0; t < t1; t++) {
                     const int row0 = (int)(t * p.tile_stride * (2 * TC_BM) + cta_rank * TC_BM);
                     for (int c = 0; c < NK; c++) {
+                        if (new_block && t == t0) {
+                            if (!p.seamless && c == 0 && qloads > 1)  // A/B: wait for the whole old block first
+                                for (int c2 = 0; c2 < NK; c2++) mbar_wait(&q_empty[c2], (qloads - 2) & 1u);
+                            if (qloads > 1) mbar_wait(&q_empty[c], (qloads - 2) & 1u);
+                            if (leader) mbar_arrive_expect_tx(&q_full[c], (uint32_t)(2 * H * 128));
+                            tma_load_2d_pair(q_smem + (size_t)c * H * 128, &tm_q, c * EC, b * NP + (int)cta_rank * H,
+                                             mapa_u32(smem_u32(&q_full[c]), 0));
+                        }
                         mbar_wait(&empty[stage], phase ^ 1u);
                         if (leader) mbar_arrive_expect_tx(&full[stage], 2 * TC_STAGE_BYTES);
                         tma_load_2d_pair(ring + (size_t)stage * TC_STAGE_BYTES, &tm_db, c * EC, row0,
@@ -209,12 +220,13 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
             for (long long it = pair; it < nitems; it += npairs) {
                 const long long s = it / p.nqb;
                 const int b = (int)(it % p.nqb);
-                if (b != cur_b) {
-                    mbar_wait(q_full, qloads & 1u);
-                    tc_fence_after();
+                const bool new_block = b != cur_b;
+                if (new_block) {
                     cur_b = b;
                     qloads++;
                 }
+                const long long nxt = it + npairs;
+                const bool block_ends = nxt < nitems && (int)(nxt % p.nqb) != b;  // the next item brings another block
                 const long long t0 = s * p.slice_tiles;
                 const long long t1 = (t0 + p.slice_tiles < p.ntiles) ? t0 + p.slice_tiles : p.ntiles;
                 for (long long t = t0; t < t1; t++, tcount++) {
@@ -223,6 +235,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(a * NP);
                     for (int c = 0; c < NK; c++) {
+                        if (new_block && t == t0) mbar_wait(&q_full[c], (qloads - 1) & 1u);  // chunk c of the new block
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(ring + (size_t)stage * TC_STAGE_BYTES);
@@ -233,6 +246,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                                             smem_desc_sw128(b_addr + k * KSTEP_BYTES), idesc, (uint32_t)((c | k) != 0));
                         }
                         umma_commit_pair(&empty[stage], 3);  // frees the ring slot in both CTAs
+                        if (block_ends && t == t1 - 1) umma_commit_pair(&q_empty[c], 3);  // chunk c of the block may be overwritten
                         if (++stage == S) {
                             stage = 0;
                             phase ^= 1u;
@@ -240,8 +254,6 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                     }
                     umma_commit_pair(&acc_full[a], 3);  // accumulator complete -> both epilogues
                 }
-                const long long nxt = it + npairs;
-                if (nxt < nitems && (int)(nxt % p.nqb) != b) umma_commit_pair(q_empty, 3);  // block may be overwritten
             }
         }
         __syncwarp();
@@ -375,7 +387,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
 // host side
 // =============================================================================================
 static size_t tc2_smem_bytes(int nk, int half, int stages) {
-    return (size_t)nk * half * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4) * 8 + 16 + (size_t)half * 20;
+    return (size_t)nk * half * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 * stages + 4 + 2 * nk + (nk & 1)) * 8 + 16 + (size_t)half * 20;
 }
 
 // query rows resident per CTA: the largest multiple of 16 (<= 128) that leaves room for >= 4 ring stages
@@ -389,6 +401,7 @@ int tc2_max_half(int d, int is_bf16) {
 }
 
 int g_tc2_slice_tiles = 0;  // option "tc2_slice_tiles" (0 = auto)
+int g_tc2_seamless = 1;     // option "tc2_seamless"
 
 cudaError_t tc2_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, Tc2Plan* pl) {
     const size_t esz = is_bf16 ? 2 : 4;
@@ -408,12 +421,17 @@ cudaError_t tc2_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_cou
     const int npairs_max = sm_count / 2;
     pl->ntiles = (n + 2 * TC_BM - 1) / (2 * TC_BM);
     auto slices_for = [&](long long ntiles, int* slice_tiles, long long* nslices, int* grid) {
-        // ~16 rounds of items per pair for balance; <= 32 pair-tiles (8 MB of bf16 rows at d = 512) per slice so
-        // that the slices in flight stay L2-resident
+        // ~16 rounds of items per pair for balance, and the slices in flight (npairs / nqb of them, each read by the
+        // nqb pairs that run its query blocks) must stay L2-resident: at most ~64 MB of rows in flight, 32 pair-tiles
+        // per slice
         long long ts = ntiles * pl->nqb / ((long long)npairs_max * 16);
+        const long long tile_bytes = 2LL * TC_BM * d * (long long)esz;
+        long long l2_cap = (64LL << 20) * pl->nqb / ((long long)npairs_max * tile_bytes);
+        if (l2_cap < 2) l2_cap = 2;
+        if (ts > l2_cap) ts = l2_cap;
+        if (ts > 32) ts = 32;
         if (g_tc2_slice_tiles > 0) ts = g_tc2_slice_tiles;
         if (ts < 1) ts = 1;
-        if (ts > 32 && g_tc2_slice_tiles == 0) ts = 32;
         *slice_tiles = (int)ts;
         *nslices = (ntiles + ts - 1) / ts;
         long long items = *nslices * pl->nqb;
@@ -502,6 +520,7 @@ static cudaError_t tc2_prepare(const TcArgs& a, const Tc2Plan& pl, unsigned char
     p->nqp = pl.nqp;
     p->nk = pl.nk;
     p->stages = pl.stages;
+    p->seamless = g_tc2_seamless;
     p->gmax = reinterpret_cast<uint32_t*>(ws + pl.off_gmax);
     p->tau0 = reinterpret_cast<const float*>(ws + pl.off_tau0);
     p->cand = reinterpret_cast<u64*>(ws + pl.off_cand);
