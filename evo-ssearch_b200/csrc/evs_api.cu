@@ -160,8 +160,6 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "tc_heap_pure_max_nq")) {
         if (value < 0 || value > 128) return fail(EVS_EINVAL, "tc_heap_pure_max_nq must be in [0, 128]");
         g_tc_heap_pure_max_nq = (int)value;
-    } else if (!strcmp(name, "tc2_seamless")) {
-        g_tc2_seamless = value ? 1 : 0;
     } else if (!strcmp(name, "tc_sample_rows")) {
         if (value != 0 && (value < 1024 || value > (1 << 24))) return fail(EVS_EINVAL, "tc_sample_rows must be 0 (auto) or in [1024, 2^24]");
         g_tc_sample_rows = (int)value;
@@ -188,7 +186,6 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tc2_slice_tiles")) *value = g_tc2_slice_tiles;
     else if (!strcmp(name, "tc_heap_max_nq")) *value = g_tc_heap_max_nq;
     else if (!strcmp(name, "tc_heap_pure_max_nq")) *value = g_tc_heap_pure_max_nq;
-    else if (!strcmp(name, "tc2_seamless")) *value = g_tc2_seamless;
     else if (!strcmp(name, "tc_sample_rows")) *value = g_tc_sample_rows;
     else if (!strcmp(name, "tc_stages")) *value = g_tc_max_stages;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;

@@ -98,7 +98,6 @@ struct Tc2Plan {
     size_t off_gmax, off_tau0, off_counts, off_overflow, off_spill_cnt, off_cand, off_spill, off_qbf16, off_end;
 };
 extern int g_tc2_slice_tiles;
-extern int g_tc2_seamless;
 int tc2_max_half(int d, int is_bf16);
 cudaError_t tc2_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, Tc2Plan* pl);
 size_t tc2_workspace_bytes(const Tc2Plan& pl);

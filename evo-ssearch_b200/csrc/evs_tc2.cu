@@ -13,16 +13,16 @@
 //   * work is cut into items (database slice, query block), numbered slice-major and dealt round-robin to the
 //     74 pairs, so the pairs that run at the same time share a handful of slices (a few MB each): the database
 //     streams from HBM once per launch and is re-read from the 126 MB L2 by the other query blocks.
-//   * the query block of the next item is re-loaded (128 KB per CTA, from L2) only when it changes, and then K chunk
-//     by K chunk behind the last MMA that reads the old chunk (per-chunk q_full / q_empty barriers), so the tensor
-//     pipe does not drain at item boundaries.
+//   * the query block of the next item is re-loaded (128 KB per CTA, from L2) only when it changes.  (Reloading it K
+//     chunk by K chunk behind the MMAs, with per-chunk barriers, was measured: the extra waits and commits in the
+//     MMA issue loop cost more (+4 % on the select kernel) than the ~3 % drain they remove.)
 // Warp roles per CTA (384 threads): warp 0 TMA producer (one lane), warp 1 MMA issuer (one lane, leader CTA
 // only), warp 2 TMEM alloc/dealloc, warps 4-11 epilogue: two warps per TMEM lane quarter (e = warp & 3), which
 // take alternate 32-column groups, so that every SM sub-partition has two epilogue warps to overlap the
 // tcgen05.ld latency of one with the filter arithmetic of the other (one warp per quarter left the MMA issuer
 // waiting on acc_empty 40 % of the time: ncu, profiles/r01_ncu_tc2_select_v1.txt).
-// Barriers: full[s] and q_full[c] collect the TMA bytes of BOTH CTAs on the leader's barrier (cp.async.bulk.tensor
-// .cta_group::2 with the leader's barrier address); empty[s], q_empty[c] and acc_full[a] are signalled in both CTAs
+// Barriers: full[s] and q_full collect the TMA bytes of BOTH CTAs on the leader's barrier (cp.async.bulk.tensor
+// .cta_group::2 with the leader's barrier address); empty[s], q_empty and acc_full[a] are signalled in both CTAs
 // by tcgen05.commit ... multicast::cluster; acc_empty[a] lives in the leader and counts the 16 epilogue warps of
 // the pair (the peer's arrive remotely through mapa + mbarrier.arrive.shared::cluster), each as soon as its last
 // tcgen05.ld of the tile has completed -- before it filters that last group.
@@ -56,7 +56,6 @@ struct Tc2Params {
     long long tile_stride;
     int slice_tiles;       // pair-tiles per slice
     long long nslices;
-    int seamless;          // 1: reload the query block chunk by chunk behind the MMAs (0: drain first; A/B switch)
     // MODE_MAX
     uint32_t* gmax;        // [ntiles * 8][nqp] ordered-uint maxima per 32-row group
     // MODE_SELECT
@@ -128,13 +127,13 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
     unsigned char* q_smem = smem;
     unsigned char* ring = q_smem + (size_t)NK * H * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * TC_STAGE_BYTES);
-    uint64_t* full = bars;               // S, leader's: stage s of BOTH CTAs has landed
+    uint64_t* q_full = bars;             // leader's: the query block (both halves) has landed
+    uint64_t* q_empty = bars + 1;        // both: every MMA that reads the resident query block has completed
+    uint64_t* full = bars + 2;           // S, leader's: stage s of BOTH CTAs has landed
     uint64_t* empty = full + S;          // S, both
     uint64_t* acc_full = empty + S;      // 2, both
     uint64_t* acc_empty = acc_full + 2;  // 2, leader's, 16 arrivals
-    uint64_t* q_full = acc_empty + 2;    // NK, leader's: K chunk c of the query block (both halves) has landed
-    uint64_t* q_empty = q_full + NK;     // NK, both: every MMA that reads chunk c of the resident block has completed
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(q_empty + NK + (NK & 1));  // keep 16-byte alignment
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* tau_s = reinterpret_cast<float*>(tmem_base_smem + 4);
     int* cnt_s = reinterpret_cast<int*>(tau_s + NP);
     __nv_bfloat16* tau_b = reinterpret_cast<__nv_bfloat16*>(cnt_s + NP);  // 16-byte aligned: NP is a multiple of 32
@@ -145,10 +144,8 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
     if (threadIdx.x == 0) {
         prefetch_tmap(&tm_db);
         prefetch_tmap(&tm_q);
-        for (int c = 0; c < NK; c++) {
-            mbar_init(&q_full[c], 1);
-            mbar_init(&q_empty[c], 1);
-        }
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -168,6 +165,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
+            const uint32_t q_full_leader = mapa_u32(smem_u32(q_full), 0);
             int stage = 0;
             uint32_t phase = 0;
             int cur_b = -1;
@@ -175,10 +173,11 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
             for (long long it = pair; it < nitems; it += npairs) {
                 const long long s = it / p.nqb;
                 const int b = (int)(it % p.nqb);
-                // a new query block is loaded chunk by chunk, each chunk as soon as the last MMA that reads the old one
-                // has completed (q_empty[c]) and just ahead of the database chunk it will meet: no drain at item boundaries
-                const bool new_block = b != cur_b;
-                if (new_block) {
+                if (b != cur_b) {
+                    if (qloads > 0) mbar_wait(q_empty, (qloads - 1) & 1u);  // the MMAs of the previous block are done with it
+                    if (leader) mbar_arrive_expect_tx(q_full, (uint32_t)(2 * NK * H * 128));
+                    for (int c = 0; c < NK; c++)
+                        tma_load_2d_pair(q_smem + (size_t)c * H * 128, &tm_q, c * EC, b * NP + (int)cta_rank * H, q_full_leader);
                     cur_b = b;
                     qloads++;
                 }
@@ -187,14 +186,6 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                 for (long long t = t0; t < t1; t++) {
                     const int row0 = (int)(t * p.tile_stride * (2 * TC_BM) + cta_rank * TC_BM);
                     for (int c = 0; c < NK; c++) {
-                        if (new_block && t == t0) {
-                            if (!p.seamless && c == 0 && qloads > 1)  // A/B: wait for the whole old block first
-                                for (int c2 = 0; c2 < NK; c2++) mbar_wait(&q_empty[c2], (qloads - 2) & 1u);
-                            if (qloads > 1) mbar_wait(&q_empty[c], (qloads - 2) & 1u);
-                            if (leader) mbar_arrive_expect_tx(&q_full[c], (uint32_t)(2 * H * 128));
-                            tma_load_2d_pair(q_smem + (size_t)c * H * 128, &tm_q, c * EC, b * NP + (int)cta_rank * H,
-                                             mapa_u32(smem_u32(&q_full[c]), 0));
-                        }
                         mbar_wait(&empty[stage], phase ^ 1u);
                         if (leader) mbar_arrive_expect_tx(&full[stage], 2 * TC_STAGE_BYTES);
                         tma_load_2d_pair(ring + (size_t)stage * TC_STAGE_BYTES, &tm_db, c * EC, row0,
@@ -220,13 +211,12 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
             for (long long it = pair; it < nitems; it += npairs) {
                 const long long s = it / p.nqb;
                 const int b = (int)(it % p.nqb);
-                const bool new_block = b != cur_b;
-                if (new_block) {
+                if (b != cur_b) {
+                    mbar_wait(q_full, qloads & 1u);
+                    tc_fence_after();
                     cur_b = b;
                     qloads++;
                 }
-                const long long nxt = it + npairs;
-                const bool block_ends = nxt < nitems && (int)(nxt % p.nqb) != b;  // the next item brings another block
                 const long long t0 = s * p.slice_tiles;
                 const long long t1 = (t0 + p.slice_tiles < p.ntiles) ? t0 + p.slice_tiles : p.ntiles;
                 for (long long t = t0; t < t1; t++, tcount++) {
@@ -235,7 +225,6 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(a * NP);
                     for (int c = 0; c < NK; c++) {
-                        if (new_block && t == t0) mbar_wait(&q_full[c], (qloads - 1) & 1u);  // chunk c of the new block
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(ring + (size_t)stage * TC_STAGE_BYTES);
@@ -246,7 +235,6 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                                             smem_desc_sw128(b_addr + k * KSTEP_BYTES), idesc, (uint32_t)((c | k) != 0));
                         }
                         umma_commit_pair(&empty[stage], 3);  // frees the ring slot in both CTAs
-                        if (block_ends && t == t1 - 1) umma_commit_pair(&q_empty[c], 3);  // chunk c of the block may be overwritten
                         if (++stage == S) {
                             stage = 0;
                             phase ^= 1u;
@@ -254,6 +242,8 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                     }
                     umma_commit_pair(&acc_full[a], 3);  // accumulator complete -> both epilogues
                 }
+                const long long nxt = it + npairs;
+                if (nxt < nitems && (int)(nxt % p.nqb) != b) umma_commit_pair(q_empty, 3);  // block may be overwritten
             }
         }
         __syncwarp();
@@ -326,13 +316,18 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                                 for (int j = 0; j < 32; j++) p.dump[(size_t)row * p.nqp + qb + c0 + j] = __uint_as_float(vc[j]);
                             }
                         } else if (MODE == MODE_MAX) {
+                            // column maxima over the warp's 32 rows; lane j keeps column j's, then ONE coalesced store
+                            // (32 predicated single-lane stores cost ptxas-dependent branch/address code per column:
+                            // measured 2.4x on the whole pre-pass)
                             const long long gr = (t * 2 + cta_rank) * 4 + e;  // 32-row group index in the walked list
+                            uint32_t mine = 0u;
 #pragma unroll
                             for (int j = 0; j < 32; j++) {
                                 uint32_t o = row_ok ? score_to_ordered(__uint_as_float(vc[j])) : 0u;
                                 o = __reduce_max_sync(0xffffffffu, o);
-                                if (lane == j) p.gmax[(size_t)gr * p.nqp + qb + c0 + j] = o;
+                                mine = (lane == j) ? o : mine;
                             }
+                            p.gmax[(size_t)gr * p.nqp + qb + c0 + lane] = mine;
                         } else {
                             uint32_t mask = prefilter_mask_bf16(vc, reinterpret_cast<const uint4*>(tau_b + c0));
                             if (!row_ok) mask = 0;
@@ -387,7 +382,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
 // host side
 // =============================================================================================
 static size_t tc2_smem_bytes(int nk, int half, int stages) {
-    return (size_t)nk * half * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 * stages + 4 + 2 * nk + (nk & 1)) * 8 + 16 + (size_t)half * 20;
+    return (size_t)nk * half * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4) * 8 + 16 + (size_t)half * 20;
 }
 
 // query rows resident per CTA: the largest multiple of 16 (<= 128) that leaves room for >= 4 ring stages
@@ -401,7 +396,6 @@ int tc2_max_half(int d, int is_bf16) {
 }
 
 int g_tc2_slice_tiles = 0;  // option "tc2_slice_tiles" (0 = auto)
-int g_tc2_seamless = 1;     // option "tc2_seamless"
 
 cudaError_t tc2_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, Tc2Plan* pl) {
     const size_t esz = is_bf16 ? 2 : 4;
@@ -520,7 +514,6 @@ static cudaError_t tc2_prepare(const TcArgs& a, const Tc2Plan& pl, unsigned char
     p->nqp = pl.nqp;
     p->nk = pl.nk;
     p->stages = pl.stages;
-    p->seamless = g_tc2_seamless;
     p->gmax = reinterpret_cast<uint32_t*>(ws + pl.off_gmax);
     p->tau0 = reinterpret_cast<const float*>(ws + pl.off_tau0);
     p->cand = reinterpret_cast<u64*>(ws + pl.off_cand);

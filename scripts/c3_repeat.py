@@ -13,7 +13,6 @@ def clk():
     except Exception as e:
         return str(e)
 for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
-    evs.set_option("tc2_seamless", rep & 1)
     for _ in range(2):
         idx.search(xq, k)
     torch.cuda.synchronize()
@@ -25,5 +24,5 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 8
     scan = idx.time_scan(xq, k, iters=4)
-    print(json.dumps(dict(rep=rep, seamless=rep & 1, ms=round(ms, 4), qps=round(nq / ms * 1e3), scan_ms=round(scan, 4), clocks=clk())), flush=True)
+    print(json.dumps(dict(rep=rep, ms=round(ms, 4), qps=round(nq / ms * 1e3), scan_ms=round(scan, 4), clocks=clk())), flush=True)
     time.sleep(0.5)
