@@ -1,7 +1,7 @@
+# 8 x B200: sharded parity (both exchanges), the metric at N = 8 / 4 / 2, BASELINE configs 4 and 5.
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-EVS_CHECK_LIGHT=1 timeout 400 $TR --nproc-per-node 8 --master-port 29601 scripts/check_sharded.py 2>&1 | grep -E "OK|MISMATCH|PARITY|Error|error" | tail -14
+EVS_CHECK_LIGHT=1 timeout 400 $TR --nproc-per-node 8 --master-port 29601 scripts/check_sharded.py 2>&1 | grep -E "MISMATCH|PARITY|Error|error" | tail -5
 run() { # name nproc args...
   name=$1; np=$2; shift 2
   timeout 300 $TR --nproc-per-node $np --master-port 29602 bench.py --gpus $np --steps 100 --warmup 5 "$@" > gpurun_out/scale8_$name.log 2>&1
@@ -16,7 +16,9 @@ except Exception as e: print('   parse failed', e)
 run m10_n8_peer 8
 run m10_n8_nccl 8 --exchange nccl
 run m10_n4_peer 4
+run m10_n2_peer 2
 run c5_100m_bf16_nq1 8 --rows 100000000 --storage bf16
 run c5_100m_bf16_nq16 8 --rows 100000000 --storage bf16 --nq 16
+run c5_100m_bf16_nq256 8 --rows 100000000 --storage bf16 --nq 256 --steps 30
 run c4_10m768_nq1 8 --rows 10000000 --dim 768
-run c4_10m768_nq1024 8 --rows 10000000 --dim 768 --nq 1024 --steps 20
+run c4_10m768_bf16_nq1024 8 --rows 10000000 --dim 768 --nq 1024 --storage bf16 --steps 20
