@@ -383,7 +383,7 @@ def run_evs(a) -> int:
            "h2d_bytes_per_step": a.nq * a.dim * 4, "d2h_bytes_per_step": a.nq * a.k * 12,
            "api": "IndexFlatIP.search(numpy) -> numpy via evs_index_search" if world == 1
                   else ("ShardedIndexFlatIP.search(numpy) -> numpy (H2D, scan, NCCL all-gather, merge, D2H)" if a.exchange == "nccl"
-                        else "ShardedIndexFlatIP.search(numpy) -> numpy (H2D, scan, peer-store exchange + merge kernels, D2H)")}
+                        else "ShardedIndexFlatIP.search(numpy) -> numpy via evs_index_search_exchange (H2D, scan, finalise + peer stores, merge, D2H)")}
     # host API and device API must agree on the last step's query
     same = bool(np.array_equal(Ih, I_last.cpu().numpy()) and np.array_equal(Dh, D_last.cpu().numpy()))
 

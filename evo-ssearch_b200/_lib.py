@@ -60,6 +60,7 @@ SIGNATURES = {
     "evs_exchange_status": (_i, [_vp, _pi, _pi64]),
     "evs_exchange_free": (_i, [_vp]),
     "evs_index_search_exchange_dev": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "evs_index_search_exchange": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

@@ -235,15 +235,13 @@ extern "C" int evs_index_free(evs_index* idx) {
     cudaFree(idx->xb16);
     cudaFree(idx->q_dev);
     cudaFree(idx->lists);
-    cudaFree(idx->D_dev);
-    cudaFree(idx->I_dev);
+    cudaFree(idx->I_dev);  // D_dev points into the same allocation
     cudaFree(idx->margins_dev);
     cudaFree(idx->tc_ws);
     cudaFree(idx->tc_overflow);
     cudaFreeHost(idx->tc_overflow_pin);
     cudaFreeHost(idx->q_pin);
-    cudaFreeHost(idx->D_pin);
-    cudaFreeHost(idx->I_pin);
+    cudaFreeHost(idx->I_pin);  // D_pin points into the same allocation
     for (auto& pe : idx->prof_events) {
         cudaEventDestroy(pe.first);
         cudaEventDestroy(pe.second);
@@ -398,7 +396,12 @@ extern "C" int evs_index_add_rows_from(evs_index* dst, const evs_index* src, int
     for (int64_t i = 0; i < n; i++)
         if (rows_host[i] < 0 || rows_host[i] >= src->ntotal)
             return fail(EVS_EINVAL, "row %lld out of range [0, %lld)", (long long)rows_host[i], (long long)src->ntotal);
-    std::lock_guard<std::mutex> lk(dst->mu);
+    // both handles: the source must not be grown (its row storage reallocated) while its rows are read
+    std::unique_lock<std::mutex> lk(dst->mu, std::defer_lock);
+    std::unique_lock<std::mutex> lks(const_cast<evs_index*>(src)->mu, std::defer_lock);
+    std::lock(lk, lks);
+    for (int64_t i = 0; i < n; i++)  // re-checked under the lock
+        if (rows_host[i] >= src->ntotal) return fail(EVS_EINVAL, "row %lld out of range", (long long)rows_host[i]);
     int rc = use_device(dst->device);
     if (rc) return rc;
     if ((rc = grow_for_add_locked(dst, n))) return rc;
@@ -759,50 +762,61 @@ static int ensure_pinned(T** ptr, size_t* cap, size_t need_elems) {
     return EVS_OK;
 }
 
+// host staging shared by evs_index_search and evs_index_search_exchange: queries go caller memory -> pinned -> device in
+// one async copy; (I, D) live in ONE device buffer ([I int64 nq*k][D float32 nq*k]) so that they come back in one copy.
+static int host_stage_locked(evs_index* idx, int64_t nq, int64_t k) {
+    const size_t d = (size_t)idx->d;
+    int rc = ensure_pinned(&idx->q_pin, &idx->q_pin_cap, (size_t)nq * d);
+    if (rc) return rc;
+    if ((rc = ensure_dev(&idx->q_dev, &idx->q_cap, (size_t)nq * d))) return rc;
+    const size_t out_need = (size_t)nq * k;
+    if (idx->out_cap < out_need) {
+        if (idx->I_dev) cudaFree(idx->I_dev);
+        idx->I_dev = nullptr;
+        idx->D_dev = nullptr;
+        idx->out_cap = 0;
+        CU(cudaMalloc(reinterpret_cast<void**>(&idx->I_dev), out_need * (sizeof(int64_t) + sizeof(float))));
+        idx->D_dev = reinterpret_cast<float*>(idx->I_dev + out_need);
+        idx->out_cap = out_need;
+    } else {
+        idx->D_dev = reinterpret_cast<float*>(idx->I_dev + out_need);  // packed for this nq*k
+    }
+    if (idx->out_pin_cap < out_need) {
+        if (idx->I_pin) cudaFreeHost(idx->I_pin);
+        idx->I_pin = nullptr;
+        idx->D_pin = nullptr;
+        idx->out_pin_cap = 0;
+        CU(cudaMallocHost(reinterpret_cast<void**>(&idx->I_pin), out_need * (sizeof(int64_t) + sizeof(float))));
+        idx->out_pin_cap = out_need;
+    }
+    idx->D_pin = reinterpret_cast<float*>(idx->I_pin + out_need);
+    return EVS_OK;
+}
+
+static int host_fetch_locked(evs_index* idx, int64_t nq, int64_t k, float* D_host, int64_t* I_host, cudaStream_t st) {
+    const size_t out_need = (size_t)nq * k;
+    CU(cudaMemcpyAsync(idx->I_pin, idx->I_dev, out_need * (sizeof(int64_t) + sizeof(float)), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(D_host, idx->D_pin, out_need * sizeof(float));
+    memcpy(I_host, idx->I_pin, out_need * sizeof(int64_t));
+    return EVS_OK;
+}
+
 extern "C" int evs_index_search(evs_index* idx, int64_t nq, const float* q_host, int64_t k, float* D_host, int64_t* I_host) {
     int rc = check_search_args(idx, nq, q_host, k, D_host, I_host);
     if (rc || nq == 0) return rc;
     std::lock_guard<std::mutex> lk(idx->mu);
     if ((rc = use_device(idx->device))) return rc;
-    const size_t d = (size_t)idx->d;
-    // stage queries: caller memory -> pinned -> device (one async copy), results come back the same way
-    if ((rc = ensure_pinned(&idx->q_pin, &idx->q_pin_cap, (size_t)nq * d))) return rc;
-    if ((rc = ensure_dev(&idx->q_dev, &idx->q_cap, (size_t)nq * d))) return rc;
-    size_t out_need = (size_t)nq * k;
-    if (idx->out_cap < out_need) {
-        if (idx->D_dev) cudaFree(idx->D_dev);
-        if (idx->I_dev) cudaFree(idx->I_dev);
-        idx->D_dev = nullptr;
-        idx->I_dev = nullptr;
-        idx->out_cap = 0;
-        CU(cudaMalloc(reinterpret_cast<void**>(&idx->D_dev), out_need * sizeof(float)));
-        CU(cudaMalloc(reinterpret_cast<void**>(&idx->I_dev), out_need * sizeof(int64_t)));
-        idx->out_cap = out_need;
-    }
-    if (idx->out_pin_cap < out_need) {
-        if (idx->D_pin) cudaFreeHost(idx->D_pin);
-        if (idx->I_pin) cudaFreeHost(idx->I_pin);
-        idx->D_pin = nullptr;
-        idx->I_pin = nullptr;
-        idx->out_pin_cap = 0;
-        CU(cudaMallocHost(reinterpret_cast<void**>(&idx->D_pin), out_need * sizeof(float)));
-        CU(cudaMallocHost(reinterpret_cast<void**>(&idx->I_pin), out_need * sizeof(int64_t)));
-        idx->out_pin_cap = out_need;
-    }
-    memcpy(idx->q_pin, q_host, (size_t)nq * d * sizeof(float));
+    if ((rc = host_stage_locked(idx, nq, k))) return rc;
+    memcpy(idx->q_pin, q_host, (size_t)nq * idx->d * sizeof(float));
     cudaStream_t st = idx->stream;
     CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
-    CU(cudaMemcpyAsync(idx->q_dev, idx->q_pin, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(idx->q_dev, idx->q_pin, (size_t)nq * idx->d * sizeof(float), cudaMemcpyHostToDevice, st));
     SearchOut out;
     out.D = idx->D_dev;
     out.I = idx->I_dev;
     if ((rc = search_dev_common(idx, nq, idx->q_dev, k, out, st))) return rc;
-    CU(cudaMemcpyAsync(idx->D_pin, idx->D_dev, out_need * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(idx->I_pin, idx->I_dev, out_need * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    memcpy(D_host, idx->D_pin, out_need * sizeof(float));
-    memcpy(I_host, idx->I_pin, out_need * sizeof(int64_t));
-    return EVS_OK;
+    return host_fetch_locked(idx, nq, k, D_host, I_host, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -919,20 +933,9 @@ extern "C" int evs_exchange_free(evs_exchange* ex) {
     return EVS_OK;
 }
 
-extern "C" int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_dev, int64_t k,
-                                             float* D_dev, int64_t* I_dev, void* stream) {
-    int rc = check_search_args(idx, nq, q_dev, k, D_dev, I_dev);
-    if (rc || nq == 0) return rc;
-    if (!ex) return fail(EVS_EINVAL, "ex is NULL");
-    if (!ex->connected) return fail(EVS_EINVAL, "exchange is not connected (evs_exchange_connect)");
-    if (ex->device != idx->device) return fail(EVS_EINVAL, "exchange lives on device %d, index on %d", ex->device, idx->device);
-    if (nq > ex->max_nq || k > ex->max_k)
-        return fail(EVS_ELIMIT, "nq=%lld k=%lld exceed the exchange's capacity (%lld, %lld)", (long long)nq, (long long)k,
-                    (long long)ex->max_nq, (long long)ex->max_k);
-    std::lock_guard<std::mutex> lk(idx->mu);
-    std::lock_guard<std::mutex> lkx(ex->mu);
-    if ((rc = use_device(idx->device))) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
+// enqueue scan -> finalise (-> publish) -> merge for one exchange-mode search; idx->mu and ex->mu are held
+static int search_exchange_enqueue_locked(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_dev, int64_t k, float* D_dev,
+                                          int64_t* I_dev, cudaStream_t st) {
     Exchange x;
     for (int g = 0; g < ex->world; g++) x.peer[g] = ex->peer[g];
     x.rank = ex->rank;
@@ -948,6 +951,7 @@ extern "C" int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, i
         tune = g_tune;
     }
     SearchOut out;
+    int rc;
     if (idx->ntotal == 0 || (takes_tc_path(idx, nq, tune) && !tc_path_is_heap(idx, nq, k, tune))) {
         // empty shard / tensor-core scan with host-side overflow repair: partial into local staging, then publish
         out.P_scores = ex->stage_scores;
@@ -960,6 +964,44 @@ extern "C" int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, i
     }
     CU(launch_merge_exchange(x, nq, (int)k, D_dev, reinterpret_cast<long long*>(I_dev), ex->timed_out(), st));
     return EVS_OK;
+}
+
+static int check_exchange_args(const evs_index* idx, const evs_exchange* ex, int64_t nq, int64_t k) {
+    if (!ex) return fail(EVS_EINVAL, "ex is NULL");
+    if (!ex->connected) return fail(EVS_EINVAL, "exchange is not connected (evs_exchange_connect)");
+    if (ex->device != idx->device) return fail(EVS_EINVAL, "exchange lives on device %d, index on %d", ex->device, idx->device);
+    if (nq > ex->max_nq || k > ex->max_k)
+        return fail(EVS_ELIMIT, "nq=%lld k=%lld exceed the exchange's capacity (%lld, %lld)", (long long)nq, (long long)k,
+                    (long long)ex->max_nq, (long long)ex->max_k);
+    return EVS_OK;
+}
+
+extern "C" int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_dev, int64_t k,
+                                             float* D_dev, int64_t* I_dev, void* stream) {
+    int rc = check_search_args(idx, nq, q_dev, k, D_dev, I_dev);
+    if (rc || nq == 0) return rc;
+    if ((rc = check_exchange_args(idx, ex, nq, k))) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    std::lock_guard<std::mutex> lkx(ex->mu);
+    if ((rc = use_device(idx->device))) return rc;
+    return search_exchange_enqueue_locked(idx, ex, nq, q_dev, k, D_dev, I_dev, (cudaStream_t)stream);
+}
+
+extern "C" int evs_index_search_exchange(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_host, int64_t k, float* D_host,
+                                         int64_t* I_host) {
+    int rc = check_search_args(idx, nq, q_host, k, D_host, I_host);
+    if (rc || nq == 0) return rc;
+    if ((rc = check_exchange_args(idx, ex, nq, k))) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    std::lock_guard<std::mutex> lkx(ex->mu);
+    if ((rc = use_device(idx->device))) return rc;
+    if ((rc = host_stage_locked(idx, nq, k))) return rc;
+    memcpy(idx->q_pin, q_host, (size_t)nq * idx->d * sizeof(float));
+    cudaStream_t st = idx->stream;
+    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+    CU(cudaMemcpyAsync(idx->q_dev, idx->q_pin, (size_t)nq * idx->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = search_exchange_enqueue_locked(idx, ex, nq, idx->q_dev, k, idx->D_dev, idx->I_dev, st))) return rc;
+    return host_fetch_locked(idx, nq, k, D_host, I_host, st);
 }
 
 extern "C" int evs_index_last_margins(evs_index* idx, int64_t nq, float* margins_host) {

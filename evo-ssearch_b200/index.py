@@ -222,6 +222,18 @@ class IndexFlatIP:
                                                   ctypes.c_void_p(st)))
         return D, I
 
+    def search_exchange_host(self, exchange: "PeerExchange", x, k: int):
+        """``search_exchange`` for numpy queries: staging, copies and the one synchronisation are done by the library
+        (``evs_index_search_exchange``).  Collective, like ``search_exchange``."""
+        x = np.ascontiguousarray(np.asarray(x), dtype="float32")
+        n, d = x.shape
+        assert d == self.d and k > 0
+        D = np.empty((n, k), dtype=np.float32)
+        I = np.empty((n, k), dtype=np.int64)
+        check(lib().evs_index_search_exchange(self._h, exchange._h, n, x.ctypes.data_as(ctypes.c_void_p), int(k),
+                                              D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p)))
+        return D, I
+
     def last_margins(self, nq: int) -> np.ndarray:
         """Safety margin per query of the last search (see ``evs_index_last_margins``)."""
         out = np.empty(nq, np.float32)

@@ -143,6 +143,8 @@ class ShardedIndexFlatIP:
         dev = getattr(self.local, "torch_device", None)
         if dev is None:
             dev = torch.device("cuda", self.local.device)
+        if self._px is not None and n <= self._px.max_nq and k <= self._px.max_k:
+            return self.local.search_exchange_host(self._px, x, k)  # all in the library: no torch on this path
         if dev.type != "cuda":  # injected CPU engine (tests)
             D, I = self.search_tensor(torch.from_numpy(x).to(dev), k)
             return D.cpu().numpy(), I.cpu().numpy()

@@ -157,6 +157,9 @@ EVS_API int evs_exchange_status(evs_exchange* ex, int* timed_out, int64_t* searc
 EVS_API int evs_exchange_free(evs_exchange* ex);
 EVS_API int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_dev, int64_t k,
                                   float* D_dev, int64_t* I_dev, void* stream);
+/* the same with host pointers (the sharded counterpart of evs_index_search: pinned staging, one H2D, one D2H, one sync) */
+EVS_API int evs_index_search_exchange(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_host, int64_t k,
+                              float* D_host, int64_t* I_host);
 /* per-query safety margin of the last search on this handle: canonical score of the k-th result
  * minus the scan score of the worst retained candidate (+inf when every row was a candidate).
  * A positive margin larger than the scan's error bound certifies the result exact. */

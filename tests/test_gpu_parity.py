@@ -297,13 +297,18 @@ def test_peer_exchange_single_rank_equals_search():
         Dr, Ir = idx.search(xq[:16], 48)  # small tensor-core batch (on-chip heaps): finalise writes the slots itself
         D, I = idx.search_exchange(px, xq_t[:16], 48)
         assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
+        for nq, kk in ((1, 48), (16, 12), (40, 48)):  # host entry point: staging and the one sync inside the library
+            Dr, Ir = idx.search(xq[:nq], kk)
+            Dh, Ih = idx.search_exchange_host(px, xq[:nq], kk)
+            assert Dh.dtype == np.float32 and Ih.dtype == np.int64
+            assert np.array_equal(Ih, Ir) and np.array_equal(Dh, Dr), (nq, kk)
     finally:
         evs.set_option("tc_min_nq", 4)
     empty = evs.IndexFlatIP(d)
     D, I = empty.search_exchange(px, xq_t[:2], 5)
     assert (I.cpu().numpy() == -1).all() and (D.cpu().numpy() == np.finfo(np.float32).min).all()
     timed_out, searches = px.status()
-    assert not timed_out and searches == 8
+    assert not timed_out and searches == 11
     with pytest.raises(evs.EvsError):
         idx.search_exchange(px, torch.from_numpy(oracle.synth_fill(301, d, 1)).cuda(), 48)  # beyond max_nq
     px2 = evs.PeerExchange(0, 0, 2, max_nq=4, max_k=48)  # world 2, never connected
