@@ -151,6 +151,29 @@ def test_tc_heap_mode_equals_threshold_mode_and_oracle(storage):
     assert (idx.last_margins(32) >= 0).all()
 
 
+@pytest.mark.parametrize("d", [64, 128, 384, 768, 1024])
+def test_tc_paths_across_dims_and_batch_sizes(d):
+    """Every tensor-core route (on-chip heaps with and without pre-pass, thresholds + gather, CTA pairs; k' = 64 and
+    128) on other embedding widths, ragged sizes and both storages: always the oracle's answer, never a re-run."""
+    rng = np.random.default_rng(d)
+    n = int(rng.integers(66_000, 90_000))
+    xb = oracle.synth_fill(n, d, 50 + d)
+    xq = oracle.synth_fill(200, d, 51 + d)
+    evs.set_option("tc_min_nq", 1)
+    for storage in ("f32", "bf16"):
+        idx = evs.IndexFlatIP(d, storage=storage)
+        idx.add(xb)
+        if idx.tc_max_queries() == 0:
+            continue
+        fb0 = evs.get_option("tc_fallbacks")
+        for nq, k in ((3, 48), (7, 5), (29, 48), (32, 100), (45, 48), (130, 12), (200, 48)):
+            D, I = idx.search(xq[:nq], k)
+            sample = np.unique(np.linspace(0, nq - 1, 6).astype(int))
+            Dr, Ir = oracle.canon_search(xq[sample], xb, k)
+            assert np.array_equal(I[sample], Ir) and np.array_equal(D[sample], Dr), (d, storage, nq, k)
+        assert evs.get_option("tc_fallbacks") == fb0, (d, storage)
+
+
 def test_tc_overflow_falls_back_exactly():
     """Adversarial data: thousands of identical rows all beat the pre-pass threshold -> candidate
     buffers overflow -> those queries are re-run through the GEMV scan; the answer stays exact."""
