@@ -56,6 +56,9 @@ struct Tc2Params {
     long long tile_stride;
     int slice_tiles;       // pair-tiles per slice
     long long nslices;
+    int block_major;       // item order: 0 = slice-major, dealt round-robin (select pass: concurrent pairs share slices through L2);
+                           // 1 = block-major, a contiguous run per pair (pre-pass: its 64 MB sample is L2-resident anyway, and a
+                           // pair then keeps the same query block for ~all of its items instead of re-loading it every 3 tiles)
     // MODE_MAX
     uint32_t* gmax;        // [ntiles * 8][nqp] ordered-uint maxima per 32-row group
     // MODE_SELECT
@@ -121,6 +124,22 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
     const bool leader = cta_rank == 0;
     const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const long long nitems = p.nslices * p.nqb;
+    // step -> item (slice, query block) of this pair; false when the pair has no more items
+    const long long run = (nitems + npairs - 1) / npairs;  // block-major: items [pair * run, (pair + 1) * run)
+    auto item_at = [&](long long step, long long& sl, int& bl) -> bool {
+        if (p.block_major) {
+            const long long it = pair * run + step;
+            if (step >= run || it >= nitems) return false;
+            bl = (int)(it / p.nslices);
+            sl = it % p.nslices;
+        } else {
+            const long long it = pair + step * npairs;
+            if (it >= nitems) return false;
+            sl = it / p.nqb;
+            bl = (int)(it % p.nqb);
+        }
+        return true;
+    };
 
     // shared memory: [resident query half: NK chunks x H rows x 128 B][ring: S x 16 KB][barriers][tmem base][tau][cnt]
     if ((smem_u32(smem) & 1023u) != 0u) __trap();  // 128B-swizzled operands need 1024-byte aligned bases
@@ -170,9 +189,10 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
             uint32_t phase = 0;
             int cur_b = -1;
             uint32_t qloads = 0;
-            for (long long it = pair; it < nitems; it += npairs) {
-                const long long s = it / p.nqb;
-                const int b = (int)(it % p.nqb);
+            for (long long step = 0;; step++) {
+                long long s;
+                int b;
+                if (!item_at(step, s, b)) break;
                 if (b != cur_b) {
                     if (qloads > 0) mbar_wait(q_empty, (qloads - 1) & 1u);  // the MMAs of the previous block are done with it
                     if (leader) mbar_arrive_expect_tx(q_full, (uint32_t)(2 * NK * H * 128));
@@ -208,9 +228,10 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
             long long tcount = 0;  // tile counter: accumulator buffer and its phase
             int cur_b = -1;
             uint32_t qloads = 0;
-            for (long long it = pair; it < nitems; it += npairs) {
-                const long long s = it / p.nqb;
-                const int b = (int)(it % p.nqb);
+            for (long long step = 0;; step++) {
+                long long s;
+                int b;
+                if (!item_at(step, s, b)) break;
                 if (b != cur_b) {
                     mbar_wait(q_full, qloads & 1u);
                     tc_fence_after();
@@ -242,8 +263,9 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                     }
                     umma_commit_pair(&acc_full[a], 3);  // accumulator complete -> both epilogues
                 }
-                const long long nxt = it + npairs;
-                if (nxt < nitems && (int)(nxt % p.nqb) != b) umma_commit_pair(q_empty, 3);  // block may be overwritten
+                long long s_next;
+                int b_next;
+                if (item_at(step + 1, s_next, b_next) && b_next != b) umma_commit_pair(q_empty, 3);  // block may be overwritten
             }
         }
         __syncwarp();
@@ -259,9 +281,10 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
         const uint32_t lt_mask = (1u << lane) - 1u;
         long long tcount = 0;
         int cur_b = -1;
-        for (long long it = pair; it < nitems; it += npairs) {
-            const long long s = it / p.nqb;
-            const int b = (int)(it % p.nqb);
+        for (long long step = 0;; step++) {
+            long long s;
+            int b;
+            if (!item_at(step, s, b)) break;
             const int qb = b * NP;
             if (MODE == MODE_SELECT && b != cur_b) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // all epilogue warps have left the previous block
@@ -537,6 +560,7 @@ cudaError_t tc2_scan(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, cuda
     p.tile_stride = pl.pre_stride;
     p.slice_tiles = pl.pre_slice_tiles;
     p.nslices = pl.pre_nslices;
+    p.block_major = 1;
     if ((e = launch_tc2<MODE_MAX>(a.is_bf16, tdb, tq, p, pl.pre_grid, pl.smem, st)) != cudaSuccess) return e;
     if ((e = tc_launch_tau0(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp, reinterpret_cast<float*>(ws + pl.off_tau0), st)) !=
         cudaSuccess)
@@ -548,6 +572,7 @@ cudaError_t tc2_scan(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, cuda
     p.tile_stride = 1;
     p.slice_tiles = pl.slice_tiles;
     p.nslices = pl.nslices;
+    p.block_major = 0;
     if ((e = launch_tc2<MODE_SELECT>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st)) != cudaSuccess) return e;
     // 3. per query: gather + sort -> top-kp list
     if ((e = tc_launch_gather(p.cand, p.counts, pl.grid, pl.nqp, pl.cap, pl.kp, pl.cap_total, a.nq,
