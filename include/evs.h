@@ -114,8 +114,11 @@ EVS_API int evs_index_get_rows(const evs_index* idx, int64_t row0, int64_t n, fl
  *                          (void faiss::IndexFlat::search(idx_t n, const float* x, idx_t k,
  *                           float* distances, idx_t* labels, ...) const).  Host pointers.
  *                          k <= 0 -> EVS_EINVAL (FAISS_THROW_IF_NOT(k > 0)); nq == 0 is a no-op.
- * evs_index_search_dev  same with device pointers for queries and results, enqueued on `stream`
- *                          without a host synchronisation.
+ * evs_index_search_dev  same with device pointers for queries and results, enqueued on `stream`.
+ *                          Batches of up to 32 queries (k <= 48) never synchronise with the host; larger
+ *                          batches synchronise `stream` once, after the results are enqueued, to read the
+ *                          overflow flags of the tensor-core scan (queries whose candidate buffers
+ *                          overflowed -- adversarial data only -- are then re-run exactly).
  * evs_index_search_partial_dev
  *                       row-sharded search, stage 1: this shard's k best as (fp64 canonical score,
  *                          int64 global id) pairs, sorted best first, padded with
