@@ -92,6 +92,12 @@ def test_tc_pair_search_equals_oracle(storage):
     evs.set_option("tc_pair_min_nq", 0)
     D1, I1 = idx.search(xq_all, 100)
     assert np.array_equal(I1, I) and np.array_equal(D1, D)
+    # more queries than one launch set takes (4096): a second, shorter chunk through its own plan
+    evs.set_option("tc_pair_min_nq", 129)
+    big = np.concatenate([xq_all] * 6)[:4100]
+    Db, Ib = idx.search(big, 12)
+    assert np.array_equal(Ib[:700], I[:, :12]) and np.array_equal(Ib[700:1400], I[:, :12]) and np.array_equal(Ib[4096:], I[596:600, :12])
+    assert np.array_equal(Db[4096:], D[596:600, :12])
 
 
 @pytest.mark.parametrize("storage", ["f32", "bf16"])
