@@ -59,6 +59,7 @@ def parse_args():
                     help="N > 1: how shard partials meet -- peer-store exchange kernels over NVLink, or NCCL all-gather + merge")
     ap.add_argument("--no-configs", action="store_true",
                     help="skip the short BASELINE config 2 / 3 legs (1M x 512: fp32 nq 1 and 16; bf16 nq 4096) reported under 'configs'")
+    ap.add_argument("--tc-min-nq", type=int, default=None, help="override the library's tensor-core threshold (experiments)")
     ap.add_argument("--extra", action="store_true", help="also time query batches 1/4/16/64 (reported under 'extra')")
     return ap.parse_args()
 
@@ -322,6 +323,8 @@ def run_evs(a) -> int:
         return float(t.item())
 
     evs.set_option("scan_variant", a.variant)
+    if a.tc_min_nq is not None:
+        evs.set_option("tc_min_nq", a.tc_min_nq)
     index = evs.ShardedIndexFlatIP(a.dim, device=local_rank, storage=a.storage, exchange=a.exchange,
                                    exchange_max_nq=max(64, a.nq), exchange_max_k=a.k)
     t_build = time.perf_counter()
@@ -393,7 +396,9 @@ def run_evs(a) -> int:
     alg_bytes = rows_local * a.dim * esz + a.nq * a.dim * 4 + a.nq * a.k * 12  # SURVEY.md 8(d), per GPU per launch
     peak, peak_src = measured_peak_gbs()
     scan_ms = scan_ms_sum / max(n_prof, 1)
-    passes = -(-a.nq // 4)  # scan launches per search (<= 4 queries per pass at d = 512)
+    tcmin = evs.get_option("tc_min_nq")
+    # database passes per search: one with the tensor-core scan, else <= 4 queries per GEMV pass at d = 512
+    passes = 1 if (tcmin > 0 and a.nq >= tcmin and rows_local >= 65536) else -(-a.nq // 4)
     achieved = alg_bytes * passes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     achieved_alg = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "evs::scan_*_kernel (score + fused top-k')", "achieved": achieved_alg,
@@ -430,7 +435,7 @@ def run_evs(a) -> int:
             "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "nq": a.nq, "k": a.k,
                        "storage": a.storage, "sharding": f"rows/{world}", "rows_per_gpu": rows_local,
                        "exchange": None if world == 1 else a.exchange,
-                       "scan_variant": evs.get_option("scan_variant"),
+                       "scan_variant": evs.get_option("scan_variant"), "tc_min_nq": evs.get_option("tc_min_nq"),
                        "l2": "inputs larger than L2 (database >> 126 MB); a different query every step",
                        "build_s": round(t_build, 3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -45,7 +45,9 @@ static int fail(int code, const char* fmt, ...) {
 static ScanTuning g_tune;
 static std::mutex g_tune_mu;
 static int g_profile_scans = 0;
-static std::atomic<long long> g_tc_fallbacks{0};  // queries re-run through the GEMV scan after a tensor-core overflow  // record CUDA events around every search's scan launches
+static std::atomic<long long> g_tc_fallbacks{0};
+static std::atomic<long long> g_exact_reruns{0};   // queries re-run with the fp32 GEMV scan because the tf32 scan's margin was not certifying
+static int g_tf32_guard_eps_e6 = 150;             // option "tf32_guard_eps_e6": margin (x 1e-6) below which a tf32-scanned result is re-run; 0 = off  // queries re-run through the GEMV scan after a tensor-core overflow  // record CUDA events around every search's scan launches
 
 // ---------------------------------------------------------------------------------------------
 // the handle
@@ -77,6 +79,7 @@ struct evs_index {
     // pinned host staging
     float* q_pin = nullptr;  size_t q_pin_cap = 0;
     float* D_pin = nullptr;  int64_t* I_pin = nullptr; size_t out_pin_cap = 0;
+    float* m_pin = nullptr;  size_t m_pin_cap = 0;     // margins of the last host search (tf32 guard)
 };
 
 static int use_device(int device) {
@@ -160,6 +163,9 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "tc_heap_pure_max_nq")) {
         if (value < 0 || value > 128) return fail(EVS_EINVAL, "tc_heap_pure_max_nq must be in [0, 128]");
         g_tc_heap_pure_max_nq = (int)value;
+    } else if (!strcmp(name, "tf32_guard_eps_e6")) {
+        if (value < 0 || value > 100000) return fail(EVS_EINVAL, "tf32_guard_eps_e6 must be in [0, 100000]");
+        g_tf32_guard_eps_e6 = (int)value;
     } else if (!strcmp(name, "tc_sample_rows")) {
         if (value != 0 && (value < 1024 || value > (1 << 24))) return fail(EVS_EINVAL, "tc_sample_rows must be 0 (auto) or in [1024, 2^24]");
         g_tc_sample_rows = (int)value;
@@ -190,6 +196,8 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tc_stages")) *value = g_tc_max_stages;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
     else if (!strcmp(name, "tc_fallbacks")) *value = g_tc_fallbacks.load();  // read-only counter
+    else if (!strcmp(name, "exact_reruns")) *value = g_exact_reruns.load();  // read-only counter
+    else if (!strcmp(name, "tf32_guard_eps_e6")) *value = g_tf32_guard_eps_e6;
     else return fail(EVS_EINVAL, "unknown option '%s'", name);
     return EVS_OK;
 }
@@ -242,6 +250,7 @@ extern "C" int evs_index_free(evs_index* idx) {
     cudaFreeHost(idx->tc_overflow_pin);
     cudaFreeHost(idx->q_pin);
     cudaFreeHost(idx->I_pin);  // D_pin points into the same allocation
+    cudaFreeHost(idx->m_pin);
     for (auto& pe : idx->prof_events) {
         cudaEventDestroy(pe.first);
         cudaEventDestroy(pe.second);
@@ -802,6 +811,52 @@ static int host_fetch_locked(evs_index* idx, int64_t nq, int64_t k, float* D_hos
     return EVS_OK;
 }
 
+// fp32-storage indexes scan batches of 2+ queries in tf32 on the tensor cores.  The candidate set (k' = 64 or 128 rows by
+// scan score) provably contains the exact top k when  margin = (canonical score of rank k) - (scan score of the worst retained
+// candidate)  exceeds the scan's error: every row that was not retained scored below that candidate.  tf32 products carry
+// ~2^-11 relative truncation per operand: a bias the margin already subtracts (finalize_kernel) plus ~4e-5 rms of scatter on
+// unit vectors; queries whose margin is below tf32_guard_eps (1.5e-4: dense near-ties around rank k, e.g. bursts of
+// near-duplicate images) are re-run with the fp32 GEMV scan.  Host API only: the device
+// API cannot look at the margins without a synchronisation (evs_index_last_margins is there for its callers).
+static bool tf32_guard_applies(const evs_index* idx, int64_t nq) {
+    if (idx->storage != EVS_STORE_F32 || g_tf32_guard_eps_e6 <= 0 || idx->ntotal == 0) return false;
+    ScanTuning tune;
+    {
+        std::lock_guard<std::mutex> lkt(g_tune_mu);
+        tune = g_tune;
+    }
+    return takes_tc_path(idx, nq, tune);  // the GEMV scan accumulates in fp32: nothing to certify
+}
+
+// results (and, when the guard applies, the margins) come back in the same synchronisation; only if a query is not
+// certified is there a second round
+static int host_fetch_guarded_locked(evs_index* idx, int64_t nq, int64_t k, float* D_host, int64_t* I_host, cudaStream_t st) {
+    if (!tf32_guard_applies(idx, nq)) return host_fetch_locked(idx, nq, k, D_host, I_host, st);
+    int rc = ensure_pinned(&idx->m_pin, &idx->m_pin_cap, (size_t)nq);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(idx->m_pin, idx->margins_dev, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if ((rc = host_fetch_locked(idx, nq, k, D_host, I_host, st))) return rc;  // synchronises
+    const float eps = (float)g_tf32_guard_eps_e6 * 1e-6f;
+    int64_t reruns = 0;
+    for (int64_t q = 0; q < nq; q++) {
+        if (idx->m_pin[q] >= eps) continue;  // certified (also +inf: every row was a candidate); NaN margins re-run
+        SearchOut o1;
+        o1.D = idx->D_dev + (size_t)q * k;
+        o1.I = idx->I_dev + (size_t)q * k;
+        float* keep = idx->margins_dev;
+        idx->margins_dev = keep + q;  // the re-run writes this query's margin in place
+        rc = search_enqueue_locked(idx, 1, idx->q_dev + (size_t)q * idx->d, k, o1, st, false, false);
+        idx->margins_dev = keep;
+        idx->last_nq = nq;
+        if (rc) return rc;
+        reruns++;
+    }
+    if (!reruns) return EVS_OK;
+    g_exact_reruns.fetch_add(reruns);
+    CU(cudaEventRecord(idx->ws_free, st));
+    return host_fetch_locked(idx, nq, k, D_host, I_host, st);
+}
+
 extern "C" int evs_index_search(evs_index* idx, int64_t nq, const float* q_host, int64_t k, float* D_host, int64_t* I_host) {
     int rc = check_search_args(idx, nq, q_host, k, D_host, I_host);
     if (rc || nq == 0) return rc;
@@ -816,7 +871,7 @@ extern "C" int evs_index_search(evs_index* idx, int64_t nq, const float* q_host,
     out.D = idx->D_dev;
     out.I = idx->I_dev;
     if ((rc = search_dev_common(idx, nq, idx->q_dev, k, out, st))) return rc;
-    return host_fetch_locked(idx, nq, k, D_host, I_host, st);
+    return host_fetch_guarded_locked(idx, nq, k, D_host, I_host, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
     u64* ok = reinterpret_cast<u64*>(id + kp);              // [kp] integer rank keys of the scores
     double* qs = reinterpret_cast<double*>(ok + kp);        // [d] the query widened once
     __shared__ int s_nsurv, s_nvalid;
+    __shared__ unsigned s_maxerr;  // ordered-uint of the largest (canonical - scan) score difference among the candidates
     __shared__ u64 s_T0;
     const int qi = blockIdx.x;
     const u64* lists = p.lists + (size_t)qi * L * kp;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
     if (t == 0) {
         s_nsurv = 0;
         s_nvalid = 0;
+        s_maxerr = 0u;
         s_T0 = 0ull;
     }
     __syncthreads();
@@ -270,6 +272,10 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
         }
     }
     __syncthreads();
+    // how far the scan under-estimated its own candidates at most (tf32 truncates towards zero: a bias of ~1e-3 relative;
+    // bf16 and fp32 scans scatter around zero): rows that were NOT retained are assumed to be under-estimated no worse
+    if (t < kp && id[t] >= 0 && p.margins) atomicMax(&s_maxerr, score_to_ordered((float)(sc[t] - (double)key_score(A[t]))));
+    __syncthreads();
 
     // 5. rank by counting under (score desc, id asc); ids are unique so ranks are a permutation
     if (t < kp && id[t] >= 0) {
@@ -297,9 +303,11 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
                 p.P_ids[(size_t)qi * p.k + rank] = it + p.id_base;
             }
             if (rank == p.k - 1 && p.margins) {
-                // all kp slots taken -> rows outside the list scored <= the worst retained scan score
-                float worst = key_score(A[kp - 1]);
-                p.margins[qi] = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) : INFINITY;
+                // all kp slots taken -> rows outside the list scored <= the worst retained scan score, i.e. their
+                // canonical score is at most that plus the scan's under-estimate (taken as the largest one observed)
+                const float worst = key_score(A[kp - 1]);
+                const float under = fmaxf(ordered_to_score(s_maxerr), 0.f);
+                p.margins[qi] = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) - under : INFINITY;
             }
         }
     }

@@ -163,9 +163,10 @@ EVS_API int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, int6
 /* the same with host pointers (the sharded counterpart of evs_index_search: pinned staging, one H2D, one D2H, one sync) */
 EVS_API int evs_index_search_exchange(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_host, int64_t k,
                               float* D_host, int64_t* I_host);
-/* per-query safety margin of the last search on this handle: canonical score of the k-th result
- * minus the scan score of the worst retained candidate (+inf when every row was a candidate).
- * A positive margin larger than the scan's error bound certifies the result exact. */
+/* per-query safety margin of the last search on this handle: canonical score of the k-th result minus
+ * (scan score of the worst retained candidate + the largest amount by which the scan under-estimated any
+ * retained candidate); +inf when every row was a candidate.  Rows that were not retained scored below that
+ * candidate, so a margin larger than the spread of the scan's error certifies the result exact. */
 EVS_API int evs_index_last_margins(evs_index* idx, int64_t nq, float* margins_host);
 
 /* ---- persistence: <folder>/.clip_index/index.faiss -------------------------------------------
@@ -196,6 +197,9 @@ EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev,
  *                 least this many the CTA-pair kernel; 0 = never), "tc_stages", "tc2_slice_tiles", "tc_sample_rows", "tc_heap_max_nq" (batches up to
  *                 this size keep a running top-k' per CTA in shared memory: no gather, no overflow case, no host sync),
  *                 "tc_heap_pure_max_nq" (... and up to this size also without the threshold pre-pass).
+ *                 "tf32_guard_eps_e6": fp32-storage indexes scan batches in tf32; evs_index_search re-runs with the
+ *                 fp32 GEMV scan every query whose safety margin (see evs_index_last_margins) is below this many
+ *                 millionths (default 150, 0 = off); "exact_reruns" counts them.
  *                 evs_get_option also reads "tc_fallbacks": queries re-run through the GEMV scan so far because a
  *                 tensor-core candidate buffer overflowed (exactness guard; should stay 0 on ordinary data).
  *                 Unknown names -> EVS_EINVAL.

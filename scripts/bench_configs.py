@@ -62,7 +62,7 @@ if "c1" in which:
 if "c2" in which:
     run("C2 1M x 512 f32", 1_000_000, 512, "f32", (1, 2, 4, 8, 16, 64), 48)
     run("C2 1M x 512 f32 (GEMV only)", 1_000_000, 512, "f32", (4, 16), 48, tc_min_nq=0)
-    evs.set_option("tc_min_nq", 4)
+    evs.set_option("tc_min_nq", 2)
 if "c3" in which:
     run("C3 1M x 512 bf16", 1_000_000, 512, "bf16", (1, 16, 128, 1024, 4096), 48)
 if "m10" in which:

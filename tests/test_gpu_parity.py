@@ -290,7 +290,7 @@ def test_peer_exchange_single_rank_equals_search():
             Dr, Ir = idx.search(xq[:nq], kk)
             D, I = idx.search_exchange(px, xq_t[:nq], kk)
             assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr), (nq, kk)
-        evs.set_option("tc_min_nq", 4)  # tensor-core scan: partial staged locally, then published
+        evs.set_option("tc_min_nq", 2)  # tensor-core scan: partial staged locally, then published
         Dr, Ir = idx.search(xq[:40], 48)
         D, I = idx.search_exchange(px, xq_t[:40], 48)
         assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
@@ -303,7 +303,7 @@ def test_peer_exchange_single_rank_equals_search():
             assert Dh.dtype == np.float32 and Ih.dtype == np.int64
             assert np.array_equal(Ih, Ir) and np.array_equal(Dh, Dr), (nq, kk)
     finally:
-        evs.set_option("tc_min_nq", 4)
+        evs.set_option("tc_min_nq", 2)
     empty = evs.IndexFlatIP(d)
     D, I = empty.search_exchange(px, xq_t[:2], 5)
     assert (I.cpu().numpy() == -1).all() and (D.cpu().numpy() == np.finfo(np.float32).min).all()

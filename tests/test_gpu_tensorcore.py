@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True)
 def _reset_options():
     yield
-    evs.set_option("tc_min_nq", 4)
+    evs.set_option("tc_min_nq", 2)
     evs.set_option("tc_pair_min_nq", 129)
     evs.set_option("tc_heap_max_nq", 32)
     evs.set_option("tc_heap_pure_max_nq", 4)
@@ -178,6 +178,38 @@ def test_tc_paths_across_dims_and_batch_sizes(d):
             Dr, Ir = oracle.canon_search(xq[sample], xb, k)
             assert np.array_equal(I[sample], Ir) and np.array_equal(D[sample], Dr), (d, storage, nq, k)
         assert evs.get_option("tc_fallbacks") == fb0, (d, storage)
+
+
+def test_tf32_margin_guard_reruns_near_tie_queries_exactly():
+    """fp32 storage scans batches in tf32.  80 planted rows whose scores differ by 2e-6 straddle rank 48: tf32 cannot
+    order them, the margin of that query collapses, and the host API re-runs it with the fp32 GEMV scan -- the answer
+    is the oracle's, bit for bit; ordinary queries of the same batch are certified and not re-run."""
+    d, n, k = 512, 120_000, 48
+    xb = oracle.synth_fill(n, d, 61)
+    q = oracle.synth_fill(6, d, 62)
+    rng = np.random.default_rng(9)
+    u = rng.standard_normal((80, d))
+    u -= (u @ q[0].astype(np.float64))[:, None] * q[0]
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    a = 0.9 + 2e-6 * np.arange(80)
+    xb[40_000:40_080] = (a[:, None] * q[0] + np.sqrt(1 - a[:, None] ** 2) * u).astype(np.float32)
+    idx = evs.IndexFlatIP(d)  # fp32 storage
+    idx.add(xb)
+    Dr, Ir = oracle.canon_search(q, xb, k)
+    r0 = evs.get_option("exact_reruns")
+    D, I = idx.search(q, k)  # 6 queries: tensor-core scan (tf32)
+    assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
+    reruns = evs.get_option("exact_reruns") - r0
+    assert 1 <= reruns <= 2, (reruns, idx.last_margins(6))  # query 0 (its near-ties), not the ordinary ones
+    # guard off: the margin still says which query cannot be trusted
+    evs.set_option("tf32_guard_eps_e6", 0)
+    try:
+        D2, I2 = idx.search(q, k)
+        m = idx.last_margins(6)
+        assert m[0] < 1.5e-4 and (m[1:] > 1.5e-4).all(), m
+        assert np.array_equal(I2[1:], Ir[1:]) and np.array_equal(D2[1:], Dr[1:])
+    finally:
+        evs.set_option("tf32_guard_eps_e6", 150)
 
 
 def test_tc_overflow_falls_back_exactly():
