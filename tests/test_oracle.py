@@ -147,3 +147,26 @@ def test_topk_properties(n, d, k, seed):
     D1, I1 = oracle.canon_search(xq, xb, k)
     D2, I2 = oracle.canon_search(xq, xb[perm], k)
     assert np.array_equal(D1, D2)
+
+
+def test_oracle_vs_independent_blas_topk():
+    """An implementation the oracle shares no code with: torch's CPU sgemm (what faiss itself calls for nq >= 20,
+    `exhaustive_inner_product_blas`) followed by torch.topk.  Same ids except where two scores are closer than the
+    fp32 accumulation error, scores within 1e-5 relative -- the tolerance the north_star states for faiss-cpu."""
+    import torch
+    n, d, k, nq = 30_000, 512, 48, 24
+    xb = oracle.synth_fill(n, d, 91)
+    xq = oracle.synth_fill(nq, d, 92)
+    D, I = oracle.canon_search(xq, xb, k)
+    Df, If = oracle.faiss_seq_search(xq, xb, k)
+    S = torch.from_numpy(xq) @ torch.from_numpy(xb).T  # fp32 sgemm, blocked summation order
+    Dt, It = torch.topk(S, k, dim=1)
+    Dt, It = Dt.numpy(), It.numpy()
+    eps = d * 2.0 ** -24
+    for got_D, got_I in ((D, I), (Df, If)):
+        assert np.allclose(got_D, Dt, rtol=1e-5, atol=1e-7)
+        for q in range(nq):
+            for r in np.nonzero(got_I[q] != It[q])[0]:
+                a, b = got_I[q, r], It[q, r]
+                assert abs(oracle.dot_canon32(xb[a], xq[q]) - oracle.dot_canon32(xb[b], xq[q])) <= eps
+    assert (I == It).mean() > 0.99
