@@ -434,6 +434,45 @@ def test_config2_1m_x_512_exact(storage):
         assert (idx.last_margins(16) > 1e-5).all()
 
 
+def test_1m_rows_against_torch_fp32_matmul_topk():
+    """An independent implementation at a size the CPU oracle does not reach in seconds: torch's fp32 matmul on the
+    GPU (TF32 off) + topk over 1M x 512, 64 queries.  Ids equal except pairs closer than the fp32 accumulation
+    error, scores within 1e-5 relative (the north_star's tolerance); every routing (GEMV, on-chip heaps,
+    thresholds + gather) gives the same bits."""
+    import torch
+    n, d, k, nq = 1_000_000, 512, 48, 64
+    idx = evs.IndexFlatIP(d)
+    idx.add_synthetic(n, seed=0)
+    xq = oracle.synth_fill(nq, d, 1)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        xb_t = torch.empty((n, d), dtype=torch.float32, device="cuda")
+        for c0 in range(0, n, 250_000):
+            xb_t[c0:c0 + 250_000] = torch.from_numpy(idx.reconstruct_n(c0, 250_000)).cuda()
+        S = torch.from_numpy(xq).cuda() @ xb_t.T
+        Dt, It = torch.topk(S, k, dim=1)
+        Dt, It = Dt.cpu().numpy(), It.cpu().numpy()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    results = []
+    for lo, hi in ((0, 1), (1, 17), (17, 64)):  # 1 query (GEMV), 16 (on-chip heaps), 47 (thresholds + gather)
+        D, I = idx.search(xq[lo:hi], k)
+        results.append((D, I))
+        assert np.allclose(D, Dt[lo:hi], rtol=RTOL, atol=1e-7)
+        eps = d * 2.0 ** -24
+        for q in range(hi - lo):
+            for r in np.nonzero(I[q] != It[lo + q])[0]:
+                a, b = int(I[q, r]), int(It[lo + q, r])
+                sa = oracle.dot_canon32(idx.reconstruct(a), xq[lo + q])
+                sb = oracle.dot_canon32(idx.reconstruct(b), xq[lo + q])
+                assert abs(sa - sb) <= eps, (lo + q, r, a, b, sa, sb)
+        assert (I == It[lo:hi]).mean() > 0.98
+    Dall, Iall = idx.search(xq, k)  # one batch of 64: same bits as the three routings above
+    assert np.array_equal(Iall, np.concatenate([r[1] for r in results]))
+    assert np.array_equal(Dall, np.concatenate([r[0] for r in results]))
+
+
 def test_metric_size_10m_x_512_properties():
     """10M x 512 (the metric's size): planted neighbours must come back exactly, in order, and the
     result must not depend on scan variant, storage precision or sharding."""
