@@ -24,12 +24,14 @@
 //                a score enters if it beats the CTA's current k'-th best for that query; when more than 128 keys have
 //                piled up the owning epilogue warp bitonic-sorts the slots, keeps 64 and raises the threshold -- and
 //                the CTA writes one sorted k' list per query at the end, exactly what the GEMV scan writes.  No
-//                pre-pass, no threshold kernel, no gather, no overflow case and so no host synchronisation: the whole
-//                search is this launch plus finalize_kernel.
+//                gather, no overflow case and so no host synchronisation.  For 5..32 queries the thresholds start from
+//                the pre-pass bound tau0 (it spares the sorts of the first tiles); for <= 4 queries there is no
+//                pre-pass either and the whole search is this launch plus finalize_kernel.
 // tau0[query] = k'-th largest group maximum of the pre-pass: at least k' distinct rows score >= tau0,
 // so it is a valid lower bound of the k'-th best score and the SELECT pass keeps a superset of the
-// top k'.  A (CTA, query) buffer that overflows raises overflow[query]; the host re-runs those queries
-// through the GEMV path (exactness never depends on the data).
+// top k'.  A (CTA, query) buffer that is full sends its extra keys to the query's spill list (clustered rows); if that
+// overflows too, overflow[query] is raised and the host re-runs the query through the GEMV path (exactness never
+// depends on the data).
 #include <cuda.h>
 #include <float.h>
 
