@@ -210,9 +210,18 @@ def ncu_traffic_per_launch(a, world):
 # ------------------------------------------------------------------------------------------------
 # CPU legs (oracle = test infrastructure; used here only as the timed baseline)
 # ------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Threads the CPU legs use: every core this process may run on.  (torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which would silently turn the all-cores baseline into a single-thread one.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(a, seconds_budget: float = 12.0) -> dict:
     import oracle
-    cores = oracle.max_threads()
+    cores = host_threads()
     rows = min(a.rows, a.cpu_rows)
     xb = oracle.synth_fill(rows, a.dim, seed=0)
     xq = oracle.synth_fill(max(a.nq, 8), a.dim, seed=1)
@@ -249,9 +258,9 @@ def run_reference(a) -> int:
     if rank != 0:
         return 0
     import oracle
-    cores = oracle.max_threads()
+    cores = host_threads()
     rows = min(a.rows, a.cpu_rows)
-    xb = oracle.synth_fill(rows, a.dim, seed=0)
+    xb = oracle.synth_fill(rows, a.dim, seed=0, nthreads=cores)
     xq = oracle.synth_fill(64, a.dim, seed=1)
     scale = rows / a.rows
 
