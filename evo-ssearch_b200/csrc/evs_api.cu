@@ -583,7 +583,8 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
 }
 
 static bool takes_tc_path(const evs_index* idx, int64_t nq, const ScanTuning& tune) {
-    return tune.tc_min_nq > 0 && nq >= tune.tc_min_nq && idx->ntotal >= 65536 &&
+    // TMA row coordinates are int32: shards beyond 2^31 rows (4 TB of bf16 at d = 512: not on this hardware) keep the GEMV scan
+    return tune.tc_min_nq > 0 && nq >= tune.tc_min_nq && idx->ntotal >= 65536 && idx->ntotal < ((int64_t)1 << 31) - 1024 &&
            tc_max_queries(idx->d, idx->storage == EVS_STORE_BF16_F32) > 0;
 }
 
