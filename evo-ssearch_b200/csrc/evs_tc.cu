@@ -724,8 +724,9 @@ int g_tc_heap_pure_max_nq = 4;  // option "tc_heap_pure_max_nq": ... and up to t
 int g_tc_sample_rows = 0;  // option "tc_sample_rows": rows the threshold pre-pass scores at least (0 = auto)
 
 // auto: 65536 rows for large batches (the select pass pays for every admitted candidate: 1.1 k' n / sample per query),
-// 32768 for up to 256 queries, where the pre-pass itself is the larger cost (measured: scripts/tc_tune.py)
-int tc_sample_rows(int nq) { return g_tc_sample_rows > 0 ? g_tc_sample_rows : (nq <= 256 ? 32768 : 65536); }
+// 32768 for up to 256 queries, where the pre-pass itself is the larger cost, 16384 for up to 32 (the on-chip heaps take
+// the extra admissions in their stride); measured: scripts/tc_tune.py and the round-1 sample sweep in DESIGN.md
+int tc_sample_rows(int nq) { return g_tc_sample_rows > 0 ? g_tc_sample_rows : (nq <= 32 ? 16384 : (nq <= 256 ? 32768 : 65536)); }
 static size_t tc_smem_bytes_plain(const TcPlan& pl) { return tc_smem_bytes(pl.nk, pl.npad, pl.stages); }
 static int pick_stages(int nk, int npad) {
     int stages = g_tc_max_stages;
