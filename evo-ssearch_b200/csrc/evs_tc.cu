@@ -720,7 +720,9 @@ static cudaError_t launch_tc(bool is_bf16, const CUtensorMap& tdb, const CUtenso
 
 int g_tc_max_stages = 8;  // option "tc_stages"
 int g_tc_heap_max_nq = 32;  // option "tc_heap_max_nq": batches up to this size keep their top-k' on chip (MODE_HEAP); 0 = never
-int g_tc_heap_pure_max_nq = 4;  // option "tc_heap_pure_max_nq": ... and up to this size without the threshold pre-pass
+int g_tc_heap_pure_max_nq = 0;  // option "tc_heap_pure_max_nq": ... and up to this size without the threshold pre-pass.  Off by
+                                // default: with the 16384-row sample the seeded heaps win at 1M rows for every batch size
+                                // (bf16, 2 queries: 0.195 vs 0.229 ms) and lose 1-2 % at 10M rows for <= 3 queries
 int g_tc_sample_rows = 0;  // option "tc_sample_rows": rows the threshold pre-pass scores at least (0 = auto)
 
 // auto: 65536 rows for large batches (the select pass pays for every admitted candidate: 1.1 k' n / sample per query),

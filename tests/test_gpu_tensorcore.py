@@ -15,7 +15,7 @@ def _reset_options():
     evs.set_option("tc_min_nq", 2)
     evs.set_option("tc_pair_min_nq", 129)
     evs.set_option("tc_heap_max_nq", 32)
-    evs.set_option("tc_heap_pure_max_nq", 4)
+    evs.set_option("tc_heap_pure_max_nq", 0)
     evs.set_option("tc2_slice_tiles", 0)
     evs.set_option("scan_variant", 0)
 
