@@ -116,6 +116,24 @@ size_t tc_workspace_bytes(const TcPlan& pl);
 cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, cudaStream_t st);
 cudaError_t tc_dump_scores(const TcArgs& a, const TcPlan& pl, unsigned char* ws, float* out, cudaStream_t st);
 
+// Launch with programmatic stream serialisation: the kernel may become resident while the preceding kernel of the stream is
+// still draining (its CTAs call griddepcontrol.launch_dependents early); the kernel itself must execute griddepcontrol.wait
+// before it reads anything the predecessor wrote.  Hides launch latency and prologues on the multi-kernel search paths.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int sm_count, const ScanTuning& tune,
                       ScanPlan* plan);
 int max_queries_per_pass(int d, int is_bf16);

@@ -147,14 +147,18 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
     const u64* lists = p.lists + (size_t)qi * L * kp;
     const float* q = p.xq + (size_t)qi * p.d;
 
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the merge kernel of the exchange path may get resident
+    // launched with programmatic stream serialisation: this prologue (the query does not come from the scan) overlaps the
+    // tail of the scan kernel; everything below the wait sees the scan's lists
     for (int i = t; i < p.d; i += nt) qs[i] = (double)q[i];
-    for (int l = t; l < L; l += nt) heads[l] = lists[(size_t)l * kp];
     if (t == 0) {
         s_nsurv = 0;
         s_nvalid = 0;
         s_maxerr = 0u;
         s_T0 = 0ull;
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int l = t; l < L; l += nt) heads[l] = lists[(size_t)l * kp];
     __syncthreads();
     // 1. T0 = kp-th largest head (non-empty keys are unique, so exactly one head has rank kp-1).
     //    `nper` adjacent lanes share one head and split the comparison range.
@@ -396,6 +400,7 @@ __global__ void __launch_bounds__(256) merge_exchange_kernel(Exchange x, long lo
     __shared__ int s_nvalid;
     const long long qi = blockIdx.x;
     unsigned char* local = x.peer[x.rank];
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // launched programmatically behind this rank's finalise / publish kernel
     if (threadIdx.x < x.world) {
         const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(local + 2 * (size_t)x.world * x.slot_bytes) +
                                          (size_t)x.parity * x.world + threadIdx.x;
@@ -740,9 +745,10 @@ cudaError_t launch_merge_exchange(const Exchange& x, long long nq, int k, float*
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    merge_exchange_kernel<<<(unsigned)nq, 256, smem, st>>>(x, nq, k, D, I, timed_out);
-    EVS_LAUNCH_CHECK();
-    return cudaSuccess;
+    cudaError_t le = launch_pdl(merge_exchange_kernel, dim3((unsigned)nq), dim3(256), smem, st, x, nq, k, D, I, timed_out);
+    g_kernel_launches.fetch_add(1);
+    if (le != cudaSuccess) return le;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
@@ -770,9 +776,10 @@ cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
     // small batches: 1024 threads shorten the single CTA's critical path; large batches: 256 threads
     // so that several queries share an SM
     const int threads = a.nq <= 296 ? 1024 : 256;
-    finalize_kernel<<<(unsigned)a.nq, threads, smem, st>>>(p);
-    EVS_LAUNCH_CHECK();
-    return cudaSuccess;
+    cudaError_t le = launch_pdl(finalize_kernel, dim3((unsigned)a.nq), dim3((unsigned)threads), smem, st, p);
+    g_kernel_launches.fetch_add(1);
+    if (le != cudaSuccess) return le;
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

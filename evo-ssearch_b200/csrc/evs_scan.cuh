@@ -178,6 +178,7 @@ __device__ __forceinline__ void cta_merge_and_store(u64* sel_base, int nwarps_se
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NQ, int NV>
 __global__ void __launch_bounds__(256) scan_direct_kernel(ScanParams p) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // finalize_kernel may get resident while this grid streams
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename RawVec<T>::type raw_t;
     // rows in flight per warp, sized so that query registers + raw vectors stay near 100 registers

@@ -84,6 +84,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages, NK = p.nk, NP = p.npad;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a dependent launched programmatically may get resident early
 
     // 128B-swizzled operands need 1024-byte aligned bases: align by hand (1 KiB of slack is allocated)
     unsigned char* q_smem = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
@@ -123,6 +124,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    // everything above (barriers, TMEM, descriptor prefetch) may have overlapped the preceding kernel of the stream
+    // (programmatic launch); the queries (bf16 copy), thresholds and counters below are that kernel's output
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tiles of this CTA (the same list for every query block)
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -372,6 +376,8 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
     const int c = blockIdx.x * 8 + warp;
     int* hist = hist_all[warp];
     const int pitch = groups + 1;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // gmax is the pre-pass kernel's output
     if (staged) {
         const int q = threadIdx.x & 7;
         for (int i = threadIdx.x >> 3; i < groups; i += 32) tile[q * pitch + i] = __ldg(gmax + (size_t)i * npad + blockIdx.x * 8 + q);
@@ -665,8 +671,10 @@ cudaError_t tc_launch_tau0(const uint32_t* gmax, int groups, int gpow2, int nqp,
     const int staged = tile_bytes <= 160 * 1024;
     if (staged && tile_bytes > 40 * 1024)
         cudaFuncSetAttribute(tc_tau0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes);
-    tc_tau0_kernel<<<nqp / 8, 256, staged ? tile_bytes : 0, st>>>(gmax, groups, nqp, nq, kp, tau0, staged);
+    cudaError_t e = launch_pdl(tc_tau0_kernel, dim3((unsigned)(nqp / 8)), dim3(256), staged ? tile_bytes : (size_t)0, st, gmax, groups, nqp, nq,
+                               kp, tau0, staged);
     g_kernel_launches.fetch_add(1);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
@@ -706,8 +714,9 @@ static cudaError_t launch_tc_mode(const CUtensorMap& tdb, const CUtensorMap& tq,
     auto kern = tc_scan_kernel<T, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 256, smem, st>>>(tdb, tq, p);
+    e = launch_pdl(kern, dim3((unsigned)grid), dim3(256), smem, st, tdb, tq, p);
     g_kernel_launches.fetch_add(1);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
