@@ -129,7 +129,7 @@ __host__ __device__ inline int finalize_surv_slots(int L, int kp) {
 }
 
 __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int t = threadIdx.x, nt = blockDim.x;
     const int warp = t >> 5, lane = t & 31, nwarps = nt >> 5;
     const int kp = p.kp, L = p.L;
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256) publish_partials_kernel(Exchange x, long 
 // =============================================================================================
 __global__ void __launch_bounds__(256) merge_exchange_kernel(Exchange x, long long nq, int k, float* __restrict__ D,
                                                             long long* __restrict__ I, int* __restrict__ timed_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = x.world * k;
     double* sc = reinterpret_cast<double*>(smem_raw);
     long long* id = reinterpret_cast<long long*>(sc + m);
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(int nparts, long lo
                                                             const double* __restrict__ scores,
                                                             const long long* __restrict__ ids, long long part_stride,
                                                             float* __restrict__ D, long long* __restrict__ I) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = nparts * k;
     double* sc = reinterpret_cast<double*>(smem_raw);
     long long* id = reinterpret_cast<long long*>(sc + m);
@@ -506,7 +506,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 
 template <typename T, bool VEC16>
 __global__ void __launch_bounds__(256) l2_normalize_kernel(T* __restrict__ x, long long n, int d) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
     float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * d;
