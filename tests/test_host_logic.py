@@ -76,3 +76,72 @@ def test_side_files_are_plain_pickles(tmp_path):
     assert pickle.load(open(tmp_path / "paths.pkl", "rb")) == paths
     assert pickle.load(open(tmp_path / "metadata.pkl", "rb"))[1]["size"] == 3
     assert evs.config.INDEX_FOLDER_NAME == os.getenv("EVOSSEARCH_INDEX_FOLDER", ".clip_index")
+
+
+class _NumpyIndex:
+    """Host stand-in for IndexFlatIP with the methods the lifecycle functions use (no device, no search): lets the
+    planning logic of create_index / update_index -- which file keeps its row, which is embedded, in what order -- run
+    on CPU.  The arithmetic paths are covered by the GPU tests."""
+
+    def __init__(self, d, device=None, storage=None):
+        self.d, self.device, self.storage = d, 0, storage or "f32"
+        self.rows = np.zeros((0, d), np.float32)
+
+    @property
+    def ntotal(self):
+        return self.rows.shape[0]
+
+    def add(self, x):
+        self.rows = np.concatenate([self.rows, np.asarray(x, np.float32)])
+
+    def add_rows_from(self, src, ids):
+        self.rows = np.concatenate([self.rows, src.rows[np.asarray(ids, np.int64)]])
+
+
+class _CountingEncoder:
+    d = 8
+
+    def __init__(self):
+        self.calls = []
+
+    def get_image_embedding(self, image_path):
+        name = os.path.basename(str(image_path))
+        self.calls.append(name)
+        if name.startswith("broken"):
+            raise OSError("cannot identify image file")
+        rng = np.random.default_rng(abs(hash((name, os.path.getsize(image_path)))) % (2 ** 32))
+        v = rng.standard_normal(self.d).astype(np.float32)
+        return v / np.linalg.norm(v)
+
+
+def test_incremental_reindex_plan_on_cpu(tmp_path, monkeypatch):
+    monkeypatch.setattr(lifecycle, "IndexFlatIP", _NumpyIndex)
+    store = {}
+    monkeypatch.setattr(lifecycle, "write_index", lambda index, fname: store.__setitem__(fname, index) or open(fname, "wb").close())
+    monkeypatch.setattr(lifecycle, "read_index", lambda fname: store[fname])
+    lifecycle.evict_index()
+    for i in range(10):
+        (tmp_path / f"img_{i}.jpg").write_bytes(b"x" * (i + 1))
+    (tmp_path / "broken.png").write_bytes(b"b")
+    (tmp_path / "notes.txt").write_bytes(b"t")
+    enc = _CountingEncoder()
+    index, paths, meta = lifecycle.create_index(tmp_path, enc, batch_size=4)
+    assert index.ntotal == len(paths) == len(meta) == 10 and len(enc.calls) == 11
+    lifecycle.save_index(index, paths, meta, tmp_path)
+    # unchanged folder: only the unreadable file is retried, rows and order are kept
+    enc.calls.clear()
+    i1, p1, m1, st = lifecycle.update_index(tmp_path, enc)
+    assert enc.calls == ["broken.png"] and st == {"kept": 10, "embedded": 0, "removed": 0, "failed": 1}
+    assert p1 == paths and m1 == meta and np.array_equal(i1.rows, index.rows)
+    # one deleted, one changed, two new
+    os.remove(tmp_path / "img_3.jpg")
+    (tmp_path / "img_5.jpg").write_bytes(b"changed!")
+    (tmp_path / "new_a.jpg").write_bytes(b"a")
+    (tmp_path / "new_b.webp").write_bytes(b"bb")
+    enc.calls.clear()
+    i2, p2, m2, st = lifecycle.update_index(tmp_path, enc, batch_size=2)
+    assert sorted(enc.calls) == ["broken.png", "img_5.jpg", "new_a.jpg", "new_b.webp"]
+    assert st == {"kept": 8, "embedded": 3, "removed": 1, "failed": 1}
+    fresh, pf, mf = lifecycle.create_index(tmp_path, _CountingEncoder())
+    assert p2 == pf and m2 == mf and np.array_equal(i2.rows, fresh.rows)  # interchangeable with a full rebuild
+    lifecycle.evict_index()
