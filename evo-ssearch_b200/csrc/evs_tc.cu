@@ -238,14 +238,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                         }
                     } else if (MODE == MODE_MAX) {
                         const long long g = ((blockIdx.x + i * gridDim.x) * 4 + e);  // 32-row group index of this launch
-                        uint32_t mine = 0u;  // lane j keeps column j's maximum, then one coalesced 64-byte store
+                        float mine = -INFINITY;  // lane j keeps column j's maximum, then one coalesced 64-byte store
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
-                            uint32_t o = row_ok ? score_to_ordered(__uint_as_float(v[j])) : 0u;
-                            o = __reduce_max_sync(0xffffffffu, o);
-                            mine = (lane == j) ? o : mine;
+                            const float m = warp_max_f32(row_ok ? __uint_as_float(v[j]) : -INFINITY);
+                            mine = (lane == j) ? m : mine;
                         }
-                        if (lane < 16) p.gmax[(size_t)g * p.nqp + qb + c0 + lane] = mine;
+                        if (lane < 16) p.gmax[(size_t)g * p.nqp + qb + c0 + lane] = group_max_to_ordered(mine);
                     } else if (MODE == MODE_HEAP) {
                         uint32_t mask = 0;
 #pragma unroll

@@ -343,14 +343,13 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant
                             // (32 predicated single-lane stores cost ptxas-dependent branch/address code per column:
                             // measured 2.4x on the whole pre-pass)
                             const long long gr = (t * 2 + cta_rank) * 4 + e;  // 32-row group index in the walked list
-                            uint32_t mine = 0u;
+                            float mine = -INFINITY;
 #pragma unroll
                             for (int j = 0; j < 32; j++) {
-                                uint32_t o = row_ok ? score_to_ordered(__uint_as_float(vc[j])) : 0u;
-                                o = __reduce_max_sync(0xffffffffu, o);
-                                mine = (lane == j) ? o : mine;
+                                const float m = warp_max_f32(row_ok ? __uint_as_float(vc[j]) : -INFINITY);
+                                mine = (lane == j) ? m : mine;
                             }
-                            p.gmax[(size_t)gr * p.nqp + qb + c0 + lane] = mine;
+                            p.gmax[(size_t)gr * p.nqp + qb + c0 + lane] = group_max_to_ordered(mine);
                         } else {
                             uint32_t mask = prefilter_mask_bf16(vc, reinterpret_cast<const uint4*>(tau_b + c0));
                             if (!row_ok) mask = 0;

@@ -159,6 +159,14 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         : "r"(taddr)
         : "memory");
 }
+// warp-wide fp32 maximum in one instruction (sm_100a: SASS CREDUX.MAX.F32); NaN lanes are ignored unless all are NaN
+__device__ __forceinline__ float warp_max_f32(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+// group maximum -> the ordered-uint the threshold kernel ranks; 0 = "no usable value" (every row out of range, or NaN only)
+__device__ __forceinline__ uint32_t group_max_to_ordered(float m) { return m == -INFINITY ? 0u : score_to_ordered(m); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- host helpers shared by the two scans (defined in evs_tc.cu) --------------------------------
