@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libevs.so")
 
-EVS_OK, EVS_EINVAL, EVS_ENODEV, EVS_ECUDA, EVS_ENOMEM, EVS_EIO, EVS_EFORMAT, EVS_ELIMIT = 0, -1, -2, -3, -4, -5, -6, -7
+EVS_OK, EVS_EINVAL, EVS_ENODEV, EVS_ECUDA, EVS_ENOMEM, EVS_EIO, EVS_EFORMAT, EVS_ELIMIT, EVS_ETIMEOUT = 0, -1, -2, -3, -4, -5, -6, -7, -8
 EVS_F32, EVS_F16, EVS_BF16 = 0, 1, 2
 EVS_STORE_F32, EVS_STORE_BF16_F32 = 0, 1
 EVS_MAX_K = 112
@@ -61,6 +61,12 @@ SIGNATURES = {
     "evs_exchange_free": (_i, [_vp]),
     "evs_index_search_exchange_dev": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "evs_index_search_exchange": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "evs_index_set_storage": (_i, [_vp, _i]),
+    "evs_index_max_row_norm": (_i, [_vp, _pf]),
+    "evs_index_guard_stats": (_i, [_vp, _pi64, _pi64]),
+    "evs_index_read_rows": (_i, [_c.c_char_p, _i, _i, _i64, _i64, _c.POINTER(_vp), _pi64]),
+    "evs_index_file_info": (_i, [_c.c_char_p, _pi, _pi64]),
+    "evs_index_scan_clocks": (_i, [_vp, _vp, _i64, _pi64]),
 }
 
 _lib = None

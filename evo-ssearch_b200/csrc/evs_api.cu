@@ -44,16 +44,22 @@ static int fail(int code, const char* fmt, ...) {
 
 static ScanTuning g_tune;
 static std::mutex g_tune_mu;
-static int g_profile_scans = 0;
-static std::atomic<long long> g_tc_fallbacks{0};
-static std::atomic<long long> g_exact_reruns{0};   // queries re-run with the fp32 GEMV scan because the tf32 scan's margin was not certifying
-static int g_tf32_guard_eps_e6 = 150;             // option "tf32_guard_eps_e6": margin (x 1e-6) below which a tf32-scanned result is re-run; 0 = off  // queries re-run through the GEMV scan after a tensor-core overflow  // record CUDA events around every search's scan launches
+static int g_profile_scans = 0;                    // record CUDA events around every search's scan launches
+static std::atomic<long long> g_tc_fallbacks{0};   // queries re-run through the GEMV scan after a tensor-core buffer overflow
+static std::atomic<long long> g_exact_reruns{0};   // queries the HOST re-ran with the fp32 GEMV scan because the finalise could not
+                                                   // certify them (the device-side re-runs are counted per handle: evs_index_guard_stats)
+static int g_tf32_guard_eps_e6 = 150;              // option "tf32_guard_eps_e6": STATISTICAL error bound (x 1e-6, relative to |q| max|x|)
+                                                   // of the single-tf32 scans (fp32 rows, batches beyond the 3xTF32 range); 0 = off
 
 // ---------------------------------------------------------------------------------------------
 // the handle
 // ---------------------------------------------------------------------------------------------
 static const int kQueryChunk = 256;     // GEMV path: queries finalised per launch (bounds the list workspace)
 static const int kTcQueryChunk = 4096;  // tensor-core path: queries per launch set
+
+// per-handle device words (idx->words): counters the kernels share across searches
+enum { W_TICKET = 0, W_NEXT_CHUNK = 1, W_GUARD_COUNT0 = 2, W_GUARD_COUNT1 = 3, W_UNCERT = 4 /* u64 */, W_RERUNS = 6 /* u64 */,
+       W_MAX_NORM = 8 /* float */, W_WORDS = 16 };
 
 struct evs_index {
     int d = 0, device = 0, storage = EVS_STORE_F32;
@@ -63,7 +69,7 @@ struct evs_index {
     int sm_count = 0;
     cudaStream_t stream = nullptr;    // the handle's own stream
     cudaEvent_t ws_free = nullptr;    // recorded after each search: the workspace may be reused after it
-    std::mutex mu;                    // serialises add/search on this handle (Flask threads)
+    mutable std::mutex mu;            // serialises add/search/write/get_rows on this handle (Flask threads)
     // workspace (device)
     float* q_dev = nullptr;  size_t q_cap = 0;         // staged queries [chunk][d]
     void* lists = nullptr;   size_t lists_cap = 0;     // candidate lists
@@ -73,6 +79,14 @@ struct evs_index {
     int* tc_overflow = nullptr; size_t tc_overflow_cap = 0; // [nq] overflow flags of the tensor-core scan
     int* tc_overflow_pin = nullptr; size_t tc_overflow_pin_cap = 0;
     int64_t last_nq = 0;
+    unsigned* words = nullptr;        // W_WORDS device words shared by the kernels across searches (ticket, chunk counter, guard
+                                      // counters, uncertified / re-run counters, the largest row norm)
+    int* guard_slot = nullptr; size_t guard_slot_cap = 0;   // [max(nq, 32)] slot per query, then [max(nq, 32)] the re-run queue
+    unsigned long long* guard_lists = nullptr; size_t guard_lists_cap = 0;  // lists of the device-side exact re-run
+    unsigned long long guard_seq = 0;                       // guarded searches so far (parity of the counter in use)
+    unsigned long long* cta_clock = nullptr; size_t cta_clock_cap = 0; int cta_clock_n = 0;  // option "scan_clock"
+    cudaStream_t last_stream = nullptr; bool have_last_stream = false;  // the stream the workspace was last used on
+    TmapCache tmaps;
     // optional per-search timing of the scan stage (option "profile_scans")
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
@@ -158,7 +172,7 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
         if (value < 0 || value > 4096) return fail(EVS_EINVAL, "tc2_slice_tiles must be in [0, 4096]");
         g_tc2_slice_tiles = (int)value;
     } else if (!strcmp(name, "tc_heap_max_nq")) {
-        if (value < 0 || value > 128) return fail(EVS_EINVAL, "tc_heap_max_nq must be in [0, 128]");
+        if (value < 0 || value > 32) return fail(EVS_EINVAL, "tc_heap_max_nq must be in [0, 32]");
         g_tc_heap_max_nq = (int)value;
     } else if (!strcmp(name, "tc_heap_pure_max_nq")) {
         if (value < 0 || value > 128) return fail(EVS_EINVAL, "tc_heap_pure_max_nq must be in [0, 128]");
@@ -174,6 +188,22 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
         g_tc_max_stages = (int)value;
     } else if (!strcmp(name, "profile_scans")) {
         g_profile_scans = value ? 1 : 0;
+    } else if (!strcmp(name, "fuse_finalize")) {
+        g_tune.fuse_finalize = value ? 1 : 0;
+    } else if (!strcmp(name, "scan_dynamic")) {
+        g_tune.scan_dynamic = value ? 1 : 0;
+    } else if (!strcmp(name, "scan_chunk_groups")) {
+        if (value < 1 || value > 64) return fail(EVS_EINVAL, "scan_chunk_groups must be in [1, 64]");
+        g_tune.scan_chunk_groups = (int)value;
+    } else if (!strcmp(name, "scan_clock")) {
+        g_tune.scan_clock = value ? 1 : 0;
+    } else if (!strcmp(name, "x3")) {
+        g_tune.x3 = value ? 1 : 0;
+    } else if (!strcmp(name, "x3_max_nq")) {
+        if (value < 0 || value > 32) return fail(EVS_EINVAL, "x3_max_nq must be in [0, 32]");
+        g_tune.x3_max_nq = (int)value;
+    } else if (!strcmp(name, "guard")) {
+        g_tune.guard = value ? 1 : 0;
     } else {
         return fail(EVS_EINVAL, "unknown option '%s'", name);
     }
@@ -198,6 +228,13 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tc_fallbacks")) *value = g_tc_fallbacks.load();  // read-only counter
     else if (!strcmp(name, "exact_reruns")) *value = g_exact_reruns.load();  // read-only counter
     else if (!strcmp(name, "tf32_guard_eps_e6")) *value = g_tf32_guard_eps_e6;
+    else if (!strcmp(name, "fuse_finalize")) *value = g_tune.fuse_finalize;
+    else if (!strcmp(name, "scan_dynamic")) *value = g_tune.scan_dynamic;
+    else if (!strcmp(name, "scan_chunk_groups")) *value = g_tune.scan_chunk_groups;
+    else if (!strcmp(name, "scan_clock")) *value = g_tune.scan_clock;
+    else if (!strcmp(name, "x3")) *value = g_tune.x3;
+    else if (!strcmp(name, "x3_max_nq")) *value = g_tune.x3_max_nq;
+    else if (!strcmp(name, "guard")) *value = g_tune.guard;
     else return fail(EVS_EINVAL, "unknown option '%s'", name);
     return EVS_OK;
 }
@@ -227,9 +264,14 @@ extern "C" int evs_index_create(int d, int device, int storage, evs_index** out)
     idx->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ws_free, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&idx->words), W_WORDS * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(idx->words, 0, W_WORDS * sizeof(unsigned));
     if (e != cudaSuccess) {
+        cudaFree(idx->words);
+        if (idx->ws_free) cudaEventDestroy(idx->ws_free);
+        if (idx->stream) cudaStreamDestroy(idx->stream);
         delete idx;
-        return fail(EVS_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+        return fail(EVS_ECUDA, "stream/event/workspace creation failed: %s", cudaGetErrorString(e));
     }
     *out = idx;
     return EVS_OK;
@@ -238,7 +280,7 @@ extern "C" int evs_index_create(int d, int device, int storage, evs_index** out)
 extern "C" int evs_index_free(evs_index* idx) {
     if (!idx) return EVS_OK;
     cudaSetDevice(idx->device);
-    if (idx->stream) cudaStreamSynchronize(idx->stream);
+    cudaDeviceSynchronize();  // searches may still be in flight on the caller's streams
     cudaFree(idx->xb32);
     cudaFree(idx->xb16);
     cudaFree(idx->q_dev);
@@ -247,6 +289,10 @@ extern "C" int evs_index_free(evs_index* idx) {
     cudaFree(idx->margins_dev);
     cudaFree(idx->tc_ws);
     cudaFree(idx->tc_overflow);
+    cudaFree(idx->words);
+    cudaFree(idx->guard_slot);
+    cudaFree(idx->guard_lists);
+    cudaFree(idx->cta_clock);
     cudaFreeHost(idx->tc_overflow_pin);
     cudaFreeHost(idx->q_pin);
     cudaFreeHost(idx->I_pin);  // D_pin points into the same allocation
@@ -296,9 +342,16 @@ static int grow_locked(evs_index* idx, int64_t rows) {
         }
     }
     if (idx->ntotal > 0) {
-        CU(cudaMemcpyAsync(n32, idx->xb32, (size_t)idx->ntotal * d * sizeof(float), cudaMemcpyDeviceToDevice, idx->stream));
-        if (n16) CU(cudaMemcpyAsync(n16, idx->xb16, (size_t)idx->ntotal * d * 2, cudaMemcpyDeviceToDevice, idx->stream));
-        CU(cudaStreamSynchronize(idx->stream));
+        cudaError_t e = cudaMemcpyAsync(n32, idx->xb32, (size_t)idx->ntotal * d * sizeof(float), cudaMemcpyDeviceToDevice, idx->stream);
+        if (e == cudaSuccess && n16)
+            e = cudaMemcpyAsync(n16, idx->xb16, (size_t)idx->ntotal * d * 2, cudaMemcpyDeviceToDevice, idx->stream);
+        const cudaError_t es = cudaStreamSynchronize(idx->stream);  // also on the error path: nothing may still read the old rows
+        if (e == cudaSuccess) e = es;
+        if (e != cudaSuccess) {
+            cudaFree(n32);
+            cudaFree(n16);
+            return fail(EVS_ECUDA, "copying the rows into the grown storage failed: %s", cudaGetErrorString(e));
+        }
     }
     cudaFree(idx->xb32);
     cudaFree(idx->xb16);
@@ -324,6 +377,9 @@ static int finish_add_locked(evs_index* idx, int64_t n) {
                               reinterpret_cast<unsigned char*>(idx->xb16) + (size_t)idx->ntotal * d * 2, (long long)n * idx->d,
                               idx->sm_count, idx->stream));
     }
+    // the largest row norm scales the certification bound of the searches (finalize_query)
+    CU(launch_row_norm_max(idx->xb32 + (size_t)idx->ntotal * d, (long long)n, idx->d, reinterpret_cast<float*>(idx->words + W_MAX_NORM),
+                           idx->sm_count, idx->stream));
     CU(cudaStreamSynchronize(idx->stream));
     idx->ntotal += n;
     return EVS_OK;
@@ -428,6 +484,7 @@ extern "C" int evs_index_add_rows_from(evs_index* dst, const evs_index* src, int
 
 extern "C" int evs_index_get_rows(const evs_index* idx, int64_t row0, int64_t n, float* out_host) {
     if (!idx || (!out_host && n > 0)) return fail(EVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);  // a concurrent add() that regrows frees xb32
     if (row0 < 0 || n < 0 || row0 + n > idx->ntotal) return fail(EVS_EINVAL, "rows [%lld,%lld) out of range", (long long)row0, (long long)(row0 + n));
     if (n == 0) return EVS_OK;
     int rc = use_device(idx->device);
@@ -447,21 +504,239 @@ struct SearchOut {
     const Exchange* x = nullptr;  // exchange mode: the finalise kernel stores the partial into every rank's slot
 };
 
-// Enqueue the search of `nq` device-resident queries on stream `st`; outputs are device pointers.
-// idx->mu is held by the caller.
+// Which scan serves a batch.  Decided ONCE per search from one snapshot of the tuning options and passed down, so that the
+// exchange entry points and the search itself can never disagree (they used to read the options twice).
+enum { PATH_GEMV = 0, PATH_TC_HEAP = 1, PATH_TC_SYNC = 2 };
+struct PathInfo {
+    int kind = PATH_GEMV;
+    int kp = 64;
+    bool x3 = false;     // PATH_TC_HEAP over fp32 rows: 3xTF32 split scan, `blk` queries per launch set
+    bool guard = false;  // results are certified on the device and uncertified queries re-run exactly (fp32 storage, batches)
+    int blk = 0;         // PATH_TC_HEAP: queries per launch set
+    float err_coef = 0.f;  // scan error bound relative to |q| * max|x| (0 = not certified: bf16 storage)
+};
+
+// scan error models, relative to |q| * |x|.  fp32 GEMV: 4 partial chains of d/128 FMAs per lane, 3 + 5
+// additions to combine: (d/128 + 9) roundings of 2^-24, stated generously.  3xTF32: three dropped terms of 2^-20 each plus
+// one fp32 accumulation per MMA (3 per 8 elements of K), each taken as a full 2^-23 truncation of the running sum.
+static float gemv_err_coef(int d) { return (float)((d / 32 + 8) * ldexp(1.0, -24)); }
+static float x3_err_coef(int d) { return (float)(3.0 * ldexp(1.0, -20) + (3.0 * d / 8.0 + 8.0) * ldexp(1.0, -23)); }
+
+static bool takes_tc_path(const evs_index* idx, int64_t nq, const ScanTuning& tune) {
+    // TMA row coordinates are int32: shards beyond 2^31 rows (4 TB of bf16 at d = 512: not on this hardware) keep the GEMV scan
+    return tune.tc_min_nq > 0 && nq >= tune.tc_min_nq && idx->ntotal >= 65536 && idx->ntotal < ((int64_t)1 << 31) - 1024 &&
+           tc_max_queries(idx->d, idx->storage == EVS_STORE_BF16_F32) > 0;
+}
+
+static PathInfo plan_path(const evs_index* idx, int64_t nq, int64_t k, const ScanTuning& tune, bool allow_tc) {
+    PathInfo pi;
+    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
+    pi.kp = pick_kp(k);
+    pi.err_coef = bf16 ? 0.f : gemv_err_coef(idx->d);
+    if (!allow_tc || !takes_tc_path(idx, nq, tune)) return pi;
+    pi.guard = !bf16 && tune.guard != 0;
+    // small fp32 batches: 3xTF32 on-chip-heap blocks (fp32-class scan error, no host synchronisation)
+    const int x3max = (!bf16 && tune.x3 && pi.kp == 64) ? tc_x3_max_queries(idx->d) : 0;
+    if (x3max > 0 && nq <= tune.x3_max_nq) {
+        pi.kind = PATH_TC_HEAP;
+        pi.x3 = true;
+        pi.blk = x3max;
+        pi.err_coef = x3_err_coef(idx->d);
+        return pi;
+    }
+    pi.err_coef = bf16 ? 0.f : (float)g_tf32_guard_eps_e6 * 1e-6f;  // single tf32: statistical bound (option), not a proof
+    if (pi.err_coef <= 0.f) pi.guard = false;
+    pi.kind = PATH_TC_SYNC;
+    if (nq <= kTcQueryChunk) {
+        const bool pair = tune.tc_pair_min_nq > 0 && (nq >= tune.tc_pair_min_nq || nq > tc_max_queries(idx->d, bf16)) &&
+                          tc2_max_half(idx->d, bf16) > 0 && idx->sm_count >= 2;
+        TcPlan pl;
+        if (!pair && tc_plan(idx->ntotal, idx->d, bf16, (int)nq, pi.kp, idx->sm_count, 0, &pl) == cudaSuccess && pl.heap) {
+            pi.kind = PATH_TC_HEAP;
+            pi.blk = (int)nq;
+        }
+    }
+    return pi;
+}
+
+static const int kGuardCap = 32;  // queries one device-side guard re-run can take (the on-chip-heap batches are <= 32 queries)
+
 template <typename T>
 static int ensure_pinned(T** ptr, size_t* cap, size_t need_elems);
 
-static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out,
-                                 cudaStream_t st, bool scan_only = false, bool allow_tc = true);
+// The workspace of a handle is used by one search at a time.  Searches enqueued on the SAME stream are ordered by the stream
+// (no event between them: an event record would also break the programmatic overlap of consecutive searches); a search on
+// another stream first waits for everything enqueued on the previous one.
+static int ws_acquire(evs_index* idx, cudaStream_t st) {
+    if (idx->have_last_stream && idx->last_stream != st) {
+        cudaError_t e = cudaEventRecord(idx->ws_free, idx->last_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, idx->ws_free, 0);
+        if (e != cudaSuccess) {  // the previous stream is gone: be safe
+            cudaGetLastError();
+            CU(cudaDeviceSynchronize());
+        }
+    }
+    idx->last_stream = st;
+    idx->have_last_stream = true;
+    return EVS_OK;
+}
 
-// Tensor-core path for a batch: one database pass per block of up to tc_max_queries queries.
-// Queries whose candidate buffers overflowed are re-run through the GEMV path (needs one host sync).
-static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st,
-                            bool scan_only, int profile, int pair_min_nq) {
-    const int kp = pick_kp(k);
+static FinalizeParams make_finalize(evs_index* idx, const void* lists, int L, int kp, const float* xq, int64_t k, const SearchOut& out,
+                                    int64_t c0, int64_t nq_total, float err_coef) {
+    FinalizeParams f;
+    f.lists = reinterpret_cast<const unsigned long long*>(lists);
+    f.L = L;
+    f.kp = kp;
+    f.xb = idx->xb32;
+    f.xb_is_bf16 = 0;
+    f.xq = xq;
+    f.d = idx->d;
+    f.k = (int)k;
+    f.id_base = idx->id_base;
+    f.D = out.D ? out.D + (size_t)c0 * k : nullptr;
+    f.I = out.I ? reinterpret_cast<long long*>(out.I + (size_t)c0 * k) : nullptr;
+    f.P_scores = out.P_scores ? out.P_scores + (size_t)c0 * k : nullptr;
+    f.P_ids = out.P_ids ? reinterpret_cast<long long*>(out.P_ids + (size_t)c0 * k) : nullptr;
+    f.margins = idx->margins_dev + c0;
+    if (out.x) {
+        f.x = *out.x;
+        f.x.nq_total = nq_total;
+        f.x.q_off = c0;
+    }
+    f.err_coef = err_coef;
+    f.max_norm = reinterpret_cast<const float*>(idx->words + W_MAX_NORM);
+    f.uncertified = reinterpret_cast<unsigned long long*>(idx->words + W_UNCERT);
+    return f;
+}
+
+struct ProfileScope {  // optional CUDA event pair around the scan launches of one search (option "profile_scans")
+    std::pair<cudaEvent_t, cudaEvent_t>* pe = nullptr;
+    int begin(evs_index* idx, int profile, cudaStream_t st) {
+        if (!profile || idx->prof_used >= 65536) return EVS_OK;
+        if (idx->prof_used == idx->prof_events.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            CU(cudaEventCreate(&a));
+            CU(cudaEventCreate(&b));
+            idx->prof_events.emplace_back(a, b);
+        }
+        pe = &idx->prof_events[idx->prof_used++];
+        CU(cudaEventRecord(pe->first, st));
+        return EVS_OK;
+    }
+    int end(cudaStream_t st) {
+        if (pe) CU(cudaEventRecord(pe->second, st));
+        return EVS_OK;
+    }
+};
+
+static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st,
+                                 const ScanTuning& tune, const PathInfo& pi, bool scan_only = false, int kp_override = 0);
+
+static TcArgs make_tc_args(evs_index* idx, const float* xq, int64_t nq, void* lists, int* overflow_out) {
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
-    const void* scan_rows = bf16 ? idx->xb16 : (const void*)idx->xb32;
+    TcArgs a;
+    a.xb = bf16 ? idx->xb16 : (const void*)idx->xb32;
+    a.is_bf16 = bf16;
+    a.n = idx->ntotal;
+    a.d = idx->d;
+    a.xq = xq;
+    a.nq = (int)nq;
+    a.lists = lists;
+    a.overflow_out = overflow_out;
+    a.tmaps = &idx->tmaps;
+    return a;
+}
+
+// Small batches served from on-chip heaps (MODE_HEAP): one launch set per block of pi.blk queries (the whole batch, or the
+// 3xTF32 block size for fp32 rows), ONE finalise over the per-CTA lists of all queries, and -- fp32 storage -- the
+// device-side guard: the finalise certifies each result against the scan's error bound, uncertified queries are queued,
+// an fp32 GEMV re-run (k' = 128) walks the queue inside one launch that returns at once when the queue is empty, and a
+// predicated second finalise overwrites their results.  No host synchronisation anywhere.
+static int search_tc_heap_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st,
+                                 const ScanTuning& tune, const PathInfo& pi, bool scan_only, int profile) {
+    const int kp = 64;
+    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
+    const int blk = pi.blk;
+    TcPlan pl0;
+    CU(tc_plan(idx->ntotal, idx->d, bf16, (int)(nq < blk ? nq : blk), kp, idx->sm_count, pi.x3, &pl0));
+    if (!pl0.heap) return fail(EVS_ECUDA, "internal: the on-chip-heap path was planned for a batch it cannot serve");
+    const int grid = pl0.grid;
+    int rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc_workspace_bytes(pl0));
+    if (rc) return rc;
+    if ((rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, (size_t)nq * grid * kp))) return rc;
+    if ((rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
+    idx->last_nq = nq;
+    const bool guard = pi.guard && !scan_only && out.x == nullptr && nq <= kGuardCap;
+    ScanPlan gp;
+    ScanTuning gt = tune;
+    gt.scan_variant = 1;
+    const int gq = max_queries_per_pass(idx->d, 0);
+    if (guard) {
+        CU(plan_scan(idx->ntotal, idx->d, 0, 128, gq, idx->sm_count, gt, &gp));
+        if (gp.variant != 1) return fail(EVS_ECUDA, "internal: no vectorised GEMV scan for the guard at d = %d", idx->d);
+        if ((rc = ensure_dev(&idx->guard_slot, &idx->guard_slot_cap, (size_t)(nq > kGuardCap ? nq : kGuardCap) * 2))) return rc;
+        if ((rc = ensure_dev(&idx->guard_lists, &idx->guard_lists_cap, (size_t)kGuardCap * gp.grid * 128))) return rc;
+    }
+    ProfileScope prof;
+    if ((rc = prof.begin(idx, profile, st))) return rc;
+    for (int64_t b0 = 0; b0 < nq; b0 += blk) {
+        const int64_t cn = (nq - b0) < blk ? (nq - b0) : blk;
+        TcPlan plb;
+        CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, pi.x3, &plb));
+        if (!plb.heap || plb.grid != grid || tc_workspace_bytes(plb) > idx->tc_ws_cap)
+            return fail(EVS_ECUDA, "internal: inconsistent plans for the blocks of one on-chip-heap batch");
+        TcArgs a = make_tc_args(idx, q_dev + (size_t)b0 * idx->d, cn,
+                                reinterpret_cast<unsigned long long*>(idx->lists) + (size_t)b0 * grid * kp, nullptr);
+        CU(tc_scan_block(a, plb, idx->tc_ws, st));
+    }
+    if ((rc = prof.end(st))) return rc;
+    if (scan_only) return EVS_OK;
+    FinalizeParams f = make_finalize(idx, idx->lists, grid, kp, q_dev, k, out, 0, nq, pi.err_coef);
+    int* gslot = idx->guard_slot;
+    int* gqueue = idx->guard_slot ? idx->guard_slot + (nq > kGuardCap ? nq : kGuardCap) : nullptr;
+    int* gcount = nullptr;
+    if (guard) {
+        const int par = (int)(++idx->guard_seq & 1ull);
+        gcount = reinterpret_cast<int*>(idx->words) + W_GUARD_COUNT0 + par;
+        f.guard_count = gcount;
+        f.guard_count_next = reinterpret_cast<int*>(idx->words) + W_GUARD_COUNT0 + (par ^ 1);
+        f.guard_slot = gslot;
+        f.guard_q = gqueue;
+        f.guard_cap = kGuardCap;
+    }
+    CU(launch_finalize(f, nq, st));
+    if (!guard) return EVS_OK;
+    ScanArgs ga;
+    ga.xb = idx->xb32;
+    ga.is_bf16 = 0;
+    ga.n = idx->ntotal;
+    ga.d = idx->d;
+    ga.xq = q_dev;
+    ga.q0 = 0;
+    ga.nq_pass = gq;
+    ga.lists = idx->guard_lists;
+    ga.kp = 128;
+    ga.qmap = gqueue;
+    ga.nactive = gcount;
+    ga.qcap = kGuardCap;
+    CU(launch_scan(ga, &gp, st));
+    FinalizeParams f2 = make_finalize(idx, idx->guard_lists, gp.grid, 128, q_dev, k, out, 0, nq, gemv_err_coef(idx->d));
+    f2.pred_slot = gslot;
+    f2.guard_cap = kGuardCap;
+    f2.reruns = reinterpret_cast<unsigned long long*>(idx->words + W_RERUNS);
+    CU(launch_finalize(f2, nq, st));
+    return EVS_OK;
+}
+
+// Tensor-core path for larger batches: one database pass per block of up to tc_max_queries queries (one-CTA kernel) or the
+// CTA-pair kernel.  These scans select by thresholds into bounded candidate buffers; a query whose buffers overflowed
+// (adversarial data) -- and, for fp32 storage, a query the finalise could not certify against the scan's error bound -- is
+// re-run through the fp32 GEMV scan with k' = 128.  Both flags come back in ONE host synchronisation.
+static int search_tc_sync_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st,
+                                 const ScanTuning& tune, const PathInfo& pi, bool scan_only, int profile) {
+    const int kp = pi.kp;
+    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
+    const int pair_min_nq = tune.tc_pair_min_nq;
     // batches of pair_min_nq or more queries go through the CTA-pair kernel (N up to 256 per MMA, L2-shared slices)
     const bool can_pair = pair_min_nq > 0 && tc2_max_half(idx->d, bf16) > 0 && idx->sm_count >= 2;
     // ... and so do batches that would need more than one pass of the one-CTA kernel (fp32 rows: 64 queries per pass)
@@ -479,7 +754,7 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
     if (!use_pair(first) || (last && !use_pair(last))) {
         TcPlan pl;
         const int64_t cn1 = use_pair(first) ? last : first;
-        CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn1, kp, idx->sm_count, &pl));
+        CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn1, kp, idx->sm_count, 0, &pl));
         if (tc_workspace_bytes(pl) > ws_need) ws_need = tc_workspace_bytes(pl);
         if (pl.heap && (size_t)cn1 * pl.grid * kp > lists_need) lists_need = (size_t)cn1 * pl.grid * kp;  // one list per CTA
     }
@@ -488,85 +763,68 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
     if ((rc = ensure_dev(&idx->tc_overflow, &idx->tc_overflow_cap, (size_t)nq))) return rc;
     if ((rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, lists_need))) return rc;
     if ((rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
+    const bool guard = pi.guard && !scan_only;
+    if (guard && (rc = ensure_dev(&idx->guard_slot, &idx->guard_slot_cap, (size_t)(nq > kGuardCap ? nq : kGuardCap) * 2))) return rc;
+    int* gcount = nullptr;
+    int* gcount_next = nullptr;
+    if (guard) {
+        const int par = (int)(++idx->guard_seq & 1ull);
+        gcount = reinterpret_cast<int*>(idx->words) + W_GUARD_COUNT0 + par;
+        gcount_next = reinterpret_cast<int*>(idx->words) + W_GUARD_COUNT0 + (par ^ 1);
+    }
     idx->last_nq = nq;
-    bool may_overflow = false;  // MODE_HEAP chunks cannot: then nothing below needs the host
     for (int64_t c0 = 0; c0 < nq; c0 += kTcQueryChunk) {
         const int64_t cn = (nq - c0) < kTcQueryChunk ? (nq - c0) : kTcQueryChunk;
-        std::pair<cudaEvent_t, cudaEvent_t>* pe = nullptr;
-        if (profile && idx->prof_used < 65536) {
-            if (idx->prof_used == idx->prof_events.size()) {
-                cudaEvent_t a = nullptr, b = nullptr;
-                CU(cudaEventCreate(&a));
-                CU(cudaEventCreate(&b));
-                idx->prof_events.emplace_back(a, b);
-            }
-            pe = &idx->prof_events[idx->prof_used++];
-            CU(cudaEventRecord(pe->first, st));
-        }
+        ProfileScope prof;
+        if ((rc = prof.begin(idx, profile, st))) return rc;
         int lists_per_query = 1;
         {
-            TcArgs a;
-            a.xb = scan_rows;
-            a.is_bf16 = bf16;
-            a.n = idx->ntotal;
-            a.d = idx->d;
-            a.xq = q_dev + (size_t)c0 * idx->d;
-            a.nq = (int)cn;
-            a.lists = idx->lists;
-            a.overflow_out = idx->tc_overflow + c0;
+            TcArgs a = make_tc_args(idx, q_dev + (size_t)c0 * idx->d, cn, idx->lists, idx->tc_overflow + c0);
             if (use_pair(cn)) {
-                may_overflow = true;
                 Tc2Plan plb;
                 CU(tc2_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, &plb));
                 if (tc2_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
                 CU(tc2_scan(a, plb, idx->tc_ws, st));
             } else {
                 TcPlan plb;  // same workspace bound: cn <= the chunk the workspace was sized for
-                CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, &plb));
+                CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, 0, &plb));
                 if (tc_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
                 if (plb.heap) {
                     lists_per_query = plb.grid;
                     if ((size_t)cn * plb.grid * kp > idx->lists_cap) return fail(EVS_ECUDA, "internal: list workspace too small");
-                } else {
-                    may_overflow = true;
                 }
                 CU(tc_scan_block(a, plb, idx->tc_ws, st));
             }
         }
-        if (pe) CU(cudaEventRecord(pe->second, st));
+        if ((rc = prof.end(st))) return rc;
         if (scan_only) continue;
-        FinalizeArgs f;
-        f.lists = idx->lists;
-        f.L = lists_per_query;
-        f.kp = kp;
-        f.xb = idx->xb32;
-        f.xb_is_bf16 = 0;
-        f.xq = q_dev + (size_t)c0 * idx->d;
-        f.nq = cn;
-        f.d = idx->d;
-        f.k = (int)k;
-        f.id_base = idx->id_base;
-        f.D = out.D ? out.D + (size_t)c0 * k : nullptr;
-        f.I = out.I ? out.I + (size_t)c0 * k : nullptr;
-        f.P_scores = out.P_scores ? out.P_scores + (size_t)c0 * k : nullptr;
-        f.P_ids = out.P_ids ? out.P_ids + (size_t)c0 * k : nullptr;
-        f.margins = idx->margins_dev + c0;
-        if (out.x) {  // exchange mode (only offered for batches that cannot need the host-side repair below)
-            f.x = *out.x;
-            f.x.nq_total = nq;
-            f.x.q_off = c0;
+        FinalizeParams f = make_finalize(idx, idx->lists, lists_per_query, kp, q_dev + (size_t)c0 * idx->d, k, out, c0, nq, pi.err_coef);
+        if (guard) {  // certification only: the queue is read by the host below, nothing is re-run on the device
+            f.guard_count = gcount;
+            f.guard_count_next = gcount_next;
+            f.guard_slot = idx->guard_slot + c0;
+            f.guard_q = idx->guard_slot + (nq > kGuardCap ? nq : kGuardCap);
+            f.guard_cap = 0;  // slots are not used: every uncertified query gets guard_slot = -2
         }
-        CU(launch_finalize(f, st));
+        if (out.x) return fail(EVS_ECUDA, "internal: exchange-mode search took a path that needs the host");
+        CU(launch_finalize(f, cn, st));
     }
-    if (scan_only || !may_overflow) return EVS_OK;
-    if (out.x) return fail(EVS_ECUDA, "internal: exchange-mode search took a path that may overflow");
-    // exactness guard: re-run overflowed queries with the GEMV scan
-    if ((rc = ensure_pinned(&idx->tc_overflow_pin, &idx->tc_overflow_pin_cap, (size_t)nq))) return rc;
+    if (scan_only) return EVS_OK;
+    // exactness guards: re-run overflowed and uncertified queries with the fp32 GEMV scan
+    const size_t words = guard ? 2 * (size_t)nq : (size_t)nq;
+    if ((rc = ensure_pinned(&idx->tc_overflow_pin, &idx->tc_overflow_pin_cap, words))) return rc;
     CU(cudaMemcpyAsync(idx->tc_overflow_pin, idx->tc_overflow, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (guard)
+        CU(cudaMemcpyAsync(idx->tc_overflow_pin + nq, idx->guard_slot, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    ScanTuning t1 = tune;
+    PathInfo p1 = plan_path(idx, 1, k, t1, false);
     for (int64_t q = 0; q < nq; q++) {
-        if (!idx->tc_overflow_pin[q]) continue;
-        g_tc_fallbacks.fetch_add(1);
+        const bool over = idx->tc_overflow_pin[q] != 0;
+        const bool uncert = guard && idx->tc_overflow_pin[nq + q] != -1;
+        if (!over && !uncert) continue;
+        if (over) g_tc_fallbacks.fetch_add(1);
+        else g_exact_reruns.fetch_add(1);
         SearchOut o1;
         o1.D = out.D ? out.D + (size_t)q * k : nullptr;
         o1.I = out.I ? out.I + (size_t)q * k : nullptr;
@@ -574,7 +832,7 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
         o1.P_ids = out.P_ids ? out.P_ids + (size_t)q * k : nullptr;
         float* keep = idx->margins_dev;
         idx->margins_dev = keep + q;  // the re-run writes this query's margin in place
-        rc = search_enqueue_locked(idx, 1, q_dev + (size_t)q * idx->d, k, o1, st, false, false);
+        rc = search_enqueue_locked(idx, 1, q_dev + (size_t)q * idx->d, k, o1, st, t1, p1, false, k <= 112 ? 128 : 0);
         idx->margins_dev = keep;
         idx->last_nq = nq;
         if (rc) return rc;
@@ -582,65 +840,43 @@ static int search_tc_locked(evs_index* idx, int64_t nq, const float* q_dev, int6
     return EVS_OK;
 }
 
-static bool takes_tc_path(const evs_index* idx, int64_t nq, const ScanTuning& tune) {
-    // TMA row coordinates are int32: shards beyond 2^31 rows (4 TB of bf16 at d = 512: not on this hardware) keep the GEMV scan
-    return tune.tc_min_nq > 0 && nq >= tune.tc_min_nq && idx->ntotal >= 65536 && idx->ntotal < ((int64_t)1 << 31) - 1024 &&
-           tc_max_queries(idx->d, idx->storage == EVS_STORE_BF16_F32) > 0;
-}
-
-// true when the tensor-core path serves this batch entirely from on-chip heaps (MODE_HEAP): no overflow case, so no
-// host synchronisation and the finalise kernel may write straight into the exchange slots
-static bool tc_path_is_heap(const evs_index* idx, int64_t nq, int64_t k, const ScanTuning& tune) {
-    if (nq > kTcQueryChunk) return false;
-    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
-    if (tune.tc_pair_min_nq > 0 && (nq >= tune.tc_pair_min_nq || nq > tc_max_queries(idx->d, bf16)) && tc2_max_half(idx->d, bf16) > 0)
-        return false;
-    TcPlan pl;
-    if (tc_plan(idx->ntotal, idx->d, bf16, (int)nq, pick_kp(k), idx->sm_count, &pl) != cudaSuccess) return false;
-    return pl.heap != 0;
-}
-
-static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out,
-                                 cudaStream_t st, bool scan_only, bool allow_tc) {
-    const int kp = pick_kp(k);
-    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
-    const void* scan_rows = bf16 ? idx->xb16 : (const void*)idx->xb32;
-    ScanTuning tune;
+static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st,
+                                 const ScanTuning& tune, const PathInfo& pi, bool scan_only, int kp_override) {
     int profile;
     {
         std::lock_guard<std::mutex> lk(g_tune_mu);
-        tune = g_tune;
         profile = g_profile_scans && !scan_only;
     }
-    if (allow_tc && takes_tc_path(idx, nq, tune))
-        return search_tc_locked(idx, nq, q_dev, k, out, st, scan_only, profile, tune.tc_pair_min_nq);
-    const int qpp = max_queries_per_pass(idx->d, bf16);
+    if (pi.kind == PATH_TC_HEAP) return search_tc_heap_locked(idx, nq, q_dev, k, out, st, tune, pi, scan_only, profile);
+    if (pi.kind == PATH_TC_SYNC) return search_tc_sync_locked(idx, nq, q_dev, k, out, st, tune, pi, scan_only, profile);
+    const int kp = kp_override ? kp_override : pi.kp;
+    const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
+    const bool scan_bf16 = bf16 && kp_override == 0;  // an exact re-run always scans the fp32 rows
+    const void* scan_rows = scan_bf16 ? idx->xb16 : (const void*)idx->xb32;
+    const int qpp = max_queries_per_pass(idx->d, scan_bf16);
     ScanPlan plan;
-    CU(plan_scan(idx->ntotal, idx->d, bf16, kp, qpp, idx->sm_count, tune, &plan));
+    CU(plan_scan(idx->ntotal, idx->d, scan_bf16, kp, qpp, idx->sm_count, tune, &plan));
     const int64_t chunk_cap = nq < kQueryChunk ? nq : kQueryChunk;
     int rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, (size_t)chunk_cap * plan.grid * kp);
     if (rc) return rc;
-    if (allow_tc && (rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
-    idx->last_nq = nq;
+    if (kp_override == 0) {
+        if ((rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
+        idx->last_nq = nq;
+    }
+    // single-query searches (what the app issues, oldapp.py:2005): the scan's last CTA finalises -- one launch in all
+    const bool fused = tune.fuse_finalize && nq == 1 && plan.variant == 1 && !scan_only;
+    const float err_coef = scan_bf16 ? 0.f : gemv_err_coef(idx->d);
 
     for (int64_t c0 = 0; c0 < nq; c0 += kQueryChunk) {
         const int64_t cn = (nq - c0) < kQueryChunk ? (nq - c0) : kQueryChunk;
         const float* qc = q_dev + (size_t)c0 * idx->d;
-        std::pair<cudaEvent_t, cudaEvent_t>* pe = nullptr;
-        if (profile && idx->prof_used < 65536) {
-            if (idx->prof_used == idx->prof_events.size()) {
-                cudaEvent_t a = nullptr, b = nullptr;
-                CU(cudaEventCreate(&a));
-                CU(cudaEventCreate(&b));
-                idx->prof_events.emplace_back(a, b);
-            }
-            pe = &idx->prof_events[idx->prof_used++];
-            CU(cudaEventRecord(pe->first, st));
-        }
+        ProfileScope prof;
+        if ((rc = prof.begin(idx, profile, st))) return rc;
+        FinalizeParams f = make_finalize(idx, idx->lists, plan.grid, kp, qc, k, out, c0, nq, err_coef);
         for (int64_t p0 = 0; p0 < cn; p0 += qpp) {
             ScanArgs a;
             a.xb = scan_rows;
-            a.is_bf16 = bf16;
+            a.is_bf16 = scan_bf16;
             a.n = idx->ntotal;
             a.d = idx->d;
             a.xq = qc;
@@ -648,33 +884,25 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
             a.nq_pass = (int)((cn - p0) < qpp ? (cn - p0) : qpp);
             a.lists = idx->lists;
             a.kp = kp;
+            if (fused) {
+                a.fuse = &f;
+                a.ticket = idx->words + W_TICKET;
+                if (tune.scan_dynamic) {
+                    a.next_chunk = idx->words + W_NEXT_CHUNK;
+                    a.chunk_groups = tune.scan_chunk_groups > 0 ? tune.scan_chunk_groups : 2;
+                }
+                if (tune.scan_clock) {
+                    if ((rc = ensure_dev(&idx->cta_clock, &idx->cta_clock_cap, (size_t)plan.grid * 2))) return rc;
+                    idx->cta_clock_n = plan.grid;
+                    a.cta_clock = idx->cta_clock;
+                }
+            }
             // the plan's shared-memory size was computed for qpp queries per pass: large enough for fewer
             CU(launch_scan(a, &plan, st));
         }
-        if (pe) CU(cudaEventRecord(pe->second, st));
-        if (scan_only) continue;
-        FinalizeArgs f;
-        f.lists = idx->lists;
-        f.L = plan.grid;
-        f.kp = kp;
-        f.xb = idx->xb32;
-        f.xb_is_bf16 = 0;
-        f.xq = qc;
-        f.nq = cn;
-        f.d = idx->d;
-        f.k = (int)k;
-        f.id_base = idx->id_base;
-        f.D = out.D ? out.D + (size_t)c0 * k : nullptr;
-        f.I = out.I ? out.I + (size_t)c0 * k : nullptr;
-        f.P_scores = out.P_scores ? out.P_scores + (size_t)c0 * k : nullptr;
-        f.P_ids = out.P_ids ? out.P_ids + (size_t)c0 * k : nullptr;
-        f.margins = idx->margins_dev + c0;
-        if (out.x) {
-            f.x = *out.x;
-            f.x.nq_total = nq;
-            f.x.q_off = c0;
-        }
-        CU(launch_finalize(f, st));
+        if ((rc = prof.end(st))) return rc;
+        if (scan_only || fused) continue;
+        CU(launch_finalize(f, cn, st));
     }
     return EVS_OK;
 }
@@ -702,10 +930,16 @@ static int check_search_args(const evs_index* idx, int64_t nq, const void* q, in
     return EVS_OK;
 }
 
-// order stream `st` after the previous user of the handle's workspace, run, and mark the workspace busy until done
-static int search_dev_common(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st) {
-    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
-    int rc;
+static ScanTuning tune_snapshot() {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    return g_tune;
+}
+
+// order stream `st` after the previous user of the handle's workspace and enqueue the search
+static int search_dev_common(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st,
+                             const ScanTuning& tune, const PathInfo& pi) {
+    int rc = ws_acquire(idx, st);
+    if (rc) return rc;
     if (idx->ntotal == 0) {
         long long count = (long long)nq * k;
         int grid = (int)((count + 255) / 256 < 1024 ? (count + 255) / 256 : 1024);
@@ -714,12 +948,9 @@ static int search_dev_common(evs_index* idx, int64_t nq, const float* q_dev, int
         g_kernel_launches.fetch_add(1);
         CU(cudaGetLastError());
         idx->last_nq = 0;
-        rc = EVS_OK;
-    } else {
-        rc = search_enqueue_locked(idx, nq, q_dev, k, out, st);
+        return EVS_OK;
     }
-    CU(cudaEventRecord(idx->ws_free, st));
-    return rc;
+    return search_enqueue_locked(idx, nq, q_dev, k, out, st, tune, pi);
 }
 
 extern "C" int evs_index_search_dev(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, float* D_dev, int64_t* I_dev,
@@ -731,7 +962,8 @@ extern "C" int evs_index_search_dev(evs_index* idx, int64_t nq, const float* q_d
     SearchOut out;
     out.D = D_dev;
     out.I = I_dev;
-    return search_dev_common(idx, nq, q_dev, k, out, (cudaStream_t)stream);
+    const ScanTuning tune = tune_snapshot();
+    return search_dev_common(idx, nq, q_dev, k, out, (cudaStream_t)stream, tune, plan_path(idx, nq, k, tune, true));
 }
 
 extern "C" int evs_index_search_partial_dev(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, double* out_scores_dev,
@@ -743,7 +975,8 @@ extern "C" int evs_index_search_partial_dev(evs_index* idx, int64_t nq, const fl
     SearchOut out;
     out.P_scores = out_scores_dev;
     out.P_ids = out_ids_dev;
-    return search_dev_common(idx, nq, q_dev, k, out, (cudaStream_t)stream);
+    const ScanTuning tune = tune_snapshot();
+    return search_dev_common(idx, nq, q_dev, k, out, (cudaStream_t)stream, tune, plan_path(idx, nq, k, tune, true));
 }
 
 extern "C" int evs_merge_partials_dev(int device, int nparts, int64_t nq, int64_t k, const double* scores_dev,
@@ -812,52 +1045,6 @@ static int host_fetch_locked(evs_index* idx, int64_t nq, int64_t k, float* D_hos
     return EVS_OK;
 }
 
-// fp32-storage indexes scan batches of 2+ queries in tf32 on the tensor cores.  The candidate set (k' = 64 or 128 rows by
-// scan score) provably contains the exact top k when  margin = (canonical score of rank k) - (scan score of the worst retained
-// candidate)  exceeds the scan's error: every row that was not retained scored below that candidate.  tf32 products carry
-// ~2^-11 relative truncation per operand: a bias the margin already subtracts (finalize_kernel) plus ~4e-5 rms of scatter on
-// unit vectors; queries whose margin is below tf32_guard_eps (1.5e-4: dense near-ties around rank k, e.g. bursts of
-// near-duplicate images) are re-run with the fp32 GEMV scan.  Host API only: the device
-// API cannot look at the margins without a synchronisation (evs_index_last_margins is there for its callers).
-static bool tf32_guard_applies(const evs_index* idx, int64_t nq) {
-    if (idx->storage != EVS_STORE_F32 || g_tf32_guard_eps_e6 <= 0 || idx->ntotal == 0) return false;
-    ScanTuning tune;
-    {
-        std::lock_guard<std::mutex> lkt(g_tune_mu);
-        tune = g_tune;
-    }
-    return takes_tc_path(idx, nq, tune);  // the GEMV scan accumulates in fp32: nothing to certify
-}
-
-// results (and, when the guard applies, the margins) come back in the same synchronisation; only if a query is not
-// certified is there a second round
-static int host_fetch_guarded_locked(evs_index* idx, int64_t nq, int64_t k, float* D_host, int64_t* I_host, cudaStream_t st) {
-    if (!tf32_guard_applies(idx, nq)) return host_fetch_locked(idx, nq, k, D_host, I_host, st);
-    int rc = ensure_pinned(&idx->m_pin, &idx->m_pin_cap, (size_t)nq);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(idx->m_pin, idx->margins_dev, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if ((rc = host_fetch_locked(idx, nq, k, D_host, I_host, st))) return rc;  // synchronises
-    const float eps = (float)g_tf32_guard_eps_e6 * 1e-6f;
-    int64_t reruns = 0;
-    for (int64_t q = 0; q < nq; q++) {
-        if (idx->m_pin[q] >= eps) continue;  // certified (also +inf: every row was a candidate); NaN margins re-run
-        SearchOut o1;
-        o1.D = idx->D_dev + (size_t)q * k;
-        o1.I = idx->I_dev + (size_t)q * k;
-        float* keep = idx->margins_dev;
-        idx->margins_dev = keep + q;  // the re-run writes this query's margin in place
-        rc = search_enqueue_locked(idx, 1, idx->q_dev + (size_t)q * idx->d, k, o1, st, false, false);
-        idx->margins_dev = keep;
-        idx->last_nq = nq;
-        if (rc) return rc;
-        reruns++;
-    }
-    if (!reruns) return EVS_OK;
-    g_exact_reruns.fetch_add(reruns);
-    CU(cudaEventRecord(idx->ws_free, st));
-    return host_fetch_locked(idx, nq, k, D_host, I_host, st);
-}
-
 extern "C" int evs_index_search(evs_index* idx, int64_t nq, const float* q_host, int64_t k, float* D_host, int64_t* I_host) {
     int rc = check_search_args(idx, nq, q_host, k, D_host, I_host);
     if (rc || nq == 0) return rc;
@@ -866,13 +1053,16 @@ extern "C" int evs_index_search(evs_index* idx, int64_t nq, const float* q_host,
     if ((rc = host_stage_locked(idx, nq, k))) return rc;
     memcpy(idx->q_pin, q_host, (size_t)nq * idx->d * sizeof(float));
     cudaStream_t st = idx->stream;
-    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+    if ((rc = ws_acquire(idx, st))) return rc;
     CU(cudaMemcpyAsync(idx->q_dev, idx->q_pin, (size_t)nq * idx->d * sizeof(float), cudaMemcpyHostToDevice, st));
     SearchOut out;
     out.D = idx->D_dev;
     out.I = idx->I_dev;
-    if ((rc = search_dev_common(idx, nq, idx->q_dev, k, out, st))) return rc;
-    return host_fetch_guarded_locked(idx, nq, k, D_host, I_host, st);
+    const ScanTuning tune = tune_snapshot();
+    rc = search_dev_common(idx, nq, idx->q_dev, k, out, st, tune, plan_path(idx, nq, k, tune, true));
+    if (!rc) rc = host_fetch_locked(idx, nq, k, D_host, I_host, st);
+    if (rc) cudaStreamSynchronize(st);  // the pinned query buffer may still be in flight: it is reused by the next call
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -882,17 +1072,18 @@ struct evs_exchange {
     int device = 0, rank = 0, world = 0;
     int64_t max_nq = 0, max_k = 0;
     size_t slot_bytes = 0, total_bytes = 0;
-    unsigned char* local = nullptr;     // [2][world][slot_bytes] slots, [2][world] u64 flags, done counter, timeout flag
+    unsigned char* local = nullptr;     // [2][world][slot_bytes] slots, [2][world] u64 flags, done counter
     unsigned char* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool opened[8] = {false, false, false, false, false, false, false, false};
     bool connected = false;
     unsigned long long seq = 0;
     double* stage_scores = nullptr;     // local partial staging for the paths that cannot write the slots themselves
     int64_t* stage_ids = nullptr;
+    volatile int* status_host = nullptr;  // host-mapped word the merge kernel writes on failure (1 timeout, 2 peer failed)
+    int* status_dev = nullptr;
     std::mutex mu;
     size_t flags_off() const { return 2 * (size_t)world * slot_bytes; }
     unsigned* done() const { return reinterpret_cast<unsigned*>(local + flags_off() + 2 * (size_t)world * 8); }
-    int* timed_out() const { return reinterpret_cast<int*>(local + flags_off() + 2 * (size_t)world * 8 + 8); }
 };
 
 extern "C" int evs_exchange_create(int device, int rank, int world, int64_t max_nq, int64_t max_k, evs_exchange** out) {
@@ -920,11 +1111,19 @@ extern "C" int evs_exchange_create(int device, int rank, int world, int64_t max_
     if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->total_bytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ex->stage_scores), (size_t)max_nq * max_k * 8);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ex->stage_ids), (size_t)max_nq * max_k * 8);
+    void* sh = nullptr;
+    if (e == cudaSuccess) e = cudaHostAlloc(&sh, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        memset(sh, 0, 64);
+        ex->status_host = reinterpret_cast<volatile int*>(sh);
+        e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&ex->status_dev), sh, 0);
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         cudaFree(ex->local);
         cudaFree(ex->stage_scores);
         cudaFree(ex->stage_ids);
+        if (sh) cudaFreeHost(sh);
         delete ex;
         return fail(e == cudaErrorMemoryAllocation ? EVS_ENOMEM : EVS_ECUDA, "exchange allocation failed: %s", cudaGetErrorString(e));
     }
@@ -966,12 +1165,12 @@ extern "C" int evs_exchange_connect(evs_exchange* ex, const void* handles, int64
     return EVS_OK;
 }
 
+// *timed_out = the failure word (0 ok, 1 = a merge gave up waiting for a rank, 2 = a rank reported that it failed a search);
+// reading it does not clear it -- the next search call on this exchange reports and clears it
 extern "C" int evs_exchange_status(evs_exchange* ex, int* timed_out, int64_t* searches) {
     if (!ex) return fail(EVS_EINVAL, "ex is NULL");
     std::lock_guard<std::mutex> lk(ex->mu);
-    int rc = use_device(ex->device);
-    if (rc) return rc;
-    if (timed_out) CU(cudaMemcpy(timed_out, ex->timed_out(), sizeof(int), cudaMemcpyDeviceToHost));
+    if (timed_out) *timed_out = *ex->status_host;
     if (searches) *searches = (int64_t)ex->seq;
     return EVS_OK;
 }
@@ -985,8 +1184,18 @@ extern "C" int evs_exchange_free(evs_exchange* ex) {
     cudaFree(ex->local);
     cudaFree(ex->stage_scores);
     cudaFree(ex->stage_ids);
+    if (ex->status_host) cudaFreeHost(const_cast<int*>(ex->status_host));
     delete ex;
     return EVS_OK;
+}
+
+// a failure an earlier search of this exchange ran into (seen by its merge kernel) is reported once, by the next call
+static int exchange_take_failure(evs_exchange* ex) {
+    const int s = *ex->status_host;
+    if (s == 0) return EVS_OK;
+    *ex->status_host = 0;
+    return fail(EVS_ETIMEOUT, s == 2 ? "a peer rank failed a collective search: its results were padding, not a merge without that shard"
+                                     : "a collective search waited ~10 s for a rank that never arrived: its results were padding");
 }
 
 // enqueue scan -> finalise (-> publish) -> merge for one exchange-mode search; idx->mu and ex->mu are held
@@ -996,30 +1205,41 @@ static int search_exchange_enqueue_locked(evs_index* idx, evs_exchange* ex, int6
     for (int g = 0; g < ex->world; g++) x.peer[g] = ex->peer[g];
     x.rank = ex->rank;
     x.world = ex->world;
-    x.seq = ++ex->seq;              // every rank calls in the same order: the sequence numbers agree
+    x.seq = ex->seq + 1;             // every rank calls in the same order: the sequence numbers agree
     x.parity = (int)(x.seq & 1ull);  // two generations of slots: a fast rank may start search s+1 while a slow one merges s
     x.slot_bytes = ex->slot_bytes;
     x.done = ex->done();
     x.nq_total = nq;
-    ScanTuning tune;
-    {
-        std::lock_guard<std::mutex> lkt(g_tune_mu);
-        tune = g_tune;
-    }
+    x.status = ex->status_dev;
+    const ScanTuning tune = tune_snapshot();  // ONE snapshot decides the path here and inside the search
+    const PathInfo pi = plan_path(idx, nq, k, tune, true);
+    // empty shard / scans that need the host (overflow repair) / device-guarded batches (their second finalise may still
+    // overwrite results): the partial goes to local staging and a publish kernel stores it into the peers' slots;
+    // otherwise the finalise kernel stores this shard's k best straight into every rank's slot
+    const bool staged = idx->ntotal == 0 || pi.kind == PATH_TC_SYNC || (pi.kind == PATH_TC_HEAP && pi.guard);
     SearchOut out;
-    int rc;
-    if (idx->ntotal == 0 || (takes_tc_path(idx, nq, tune) && !tc_path_is_heap(idx, nq, k, tune))) {
-        // empty shard / tensor-core scan with host-side overflow repair: partial into local staging, then publish
+    if (staged) {
         out.P_scores = ex->stage_scores;
         out.P_ids = ex->stage_ids;
-        if ((rc = search_dev_common(idx, nq, q_dev, k, out, st))) return rc;
-        CU(launch_publish_partials(x, nq, (int)k, ex->stage_scores, reinterpret_cast<const long long*>(ex->stage_ids), st));
     } else {
-        out.x = &x;  // the finalise kernel stores this shard's k best straight into every rank's slot
-        if ((rc = search_dev_common(idx, nq, q_dev, k, out, st))) return rc;
+        out.x = &x;
     }
-    CU(launch_merge_exchange(x, nq, (int)k, D_dev, reinterpret_cast<long long*>(I_dev), ex->timed_out(), st));
-    return EVS_OK;
+    int rc = search_dev_common(idx, nq, q_dev, k, out, st, tune, pi);
+    cudaError_t e = cudaSuccess;
+    if (!rc && staged) e = launch_publish_partials(x, nq, (int)k, ex->stage_scores, reinterpret_cast<const long long*>(ex->stage_ids), st);
+    if (!rc && e == cudaSuccess) e = launch_merge_exchange(x, nq, (int)k, D_dev, reinterpret_cast<long long*>(I_dev), st);
+    if (!rc && e != cudaSuccess) rc = fail(EVS_ECUDA, "exchange launch failed: %s", cudaGetErrorString(e));
+    ex->seq = x.seq;  // stay in step with the peers whatever happened
+    if (rc) {
+        // this rank cannot deliver its partial: tell the peers (poisoned flag) instead of leaving them to wait ~10 s, or to
+        // merge without this shard
+        char keep[sizeof(t_err)];
+        memcpy(keep, t_err, sizeof(keep));
+        launch_publish_poison(x, st);
+        cudaGetLastError();
+        memcpy(t_err, keep, sizeof(keep));
+    }
+    return rc;
 }
 
 static int check_exchange_args(const evs_index* idx, const evs_exchange* ex, int64_t nq, int64_t k) {
@@ -1040,7 +1260,11 @@ extern "C" int evs_index_search_exchange_dev(evs_index* idx, evs_exchange* ex, i
     std::lock_guard<std::mutex> lk(idx->mu);
     std::lock_guard<std::mutex> lkx(ex->mu);
     if ((rc = use_device(idx->device))) return rc;
-    return search_exchange_enqueue_locked(idx, ex, nq, q_dev, k, D_dev, I_dev, (cudaStream_t)stream);
+    // asynchronous entry point: a failure seen by an EARLIER search's merge kernel is reported here (once), before this
+    // search is enqueued -- every rank still enqueues its searches in step
+    const int late = exchange_take_failure(ex);
+    rc = search_exchange_enqueue_locked(idx, ex, nq, q_dev, k, D_dev, I_dev, (cudaStream_t)stream);
+    return rc ? rc : late;
 }
 
 extern "C" int evs_index_search_exchange(evs_index* idx, evs_exchange* ex, int64_t nq, const float* q_host, int64_t k, float* D_host,
@@ -1054,10 +1278,15 @@ extern "C" int evs_index_search_exchange(evs_index* idx, evs_exchange* ex, int64
     if ((rc = host_stage_locked(idx, nq, k))) return rc;
     memcpy(idx->q_pin, q_host, (size_t)nq * idx->d * sizeof(float));
     cudaStream_t st = idx->stream;
-    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+    if ((rc = ws_acquire(idx, st))) return rc;
     CU(cudaMemcpyAsync(idx->q_dev, idx->q_pin, (size_t)nq * idx->d * sizeof(float), cudaMemcpyHostToDevice, st));
-    if ((rc = search_exchange_enqueue_locked(idx, ex, nq, idx->q_dev, k, idx->D_dev, idx->I_dev, st))) return rc;
-    return host_fetch_locked(idx, nq, k, D_host, I_host, st);
+    rc = search_exchange_enqueue_locked(idx, ex, nq, idx->q_dev, k, idx->D_dev, idx->I_dev, st);
+    if (!rc) rc = host_fetch_locked(idx, nq, k, D_host, I_host, st);
+    if (rc) {
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    return exchange_take_failure(ex);  // synchronous entry point: this search's own failure, if any
 }
 
 extern "C" int evs_index_last_margins(evs_index* idx, int64_t nq, float* margins_host) {
@@ -1067,7 +1296,7 @@ extern "C" int evs_index_last_margins(evs_index* idx, int64_t nq, float* margins
     if (nq == 0) return EVS_OK;
     int rc = use_device(idx->device);
     if (rc) return rc;
-    CU(cudaEventSynchronize(idx->ws_free));
+    if (idx->have_last_stream) CU(cudaStreamSynchronize(idx->last_stream));
     CU(cudaMemcpy(margins_host, idx->margins_dev, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost));
     return EVS_OK;
 }
@@ -1082,15 +1311,16 @@ extern "C" int evs_index_time_scan(evs_index* idx, int64_t nq, const float* q_de
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
-    CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+    if ((rc = ws_acquire(idx, st))) return rc;
     SearchOut none;
-    rc = search_enqueue_locked(idx, nq, q_dev, k, none, st, true);  // warm-up
+    const ScanTuning tune = tune_snapshot();
+    const PathInfo pi = plan_path(idx, nq, k, tune, true);
+    rc = search_enqueue_locked(idx, nq, q_dev, k, none, st, tune, pi, true);  // warm-up
     if (!rc) {
         cudaEventRecord(e0, st);
-        for (int i = 0; i < iters && !rc; i++) rc = search_enqueue_locked(idx, nq, q_dev, k, none, st, true);
+        for (int i = 0; i < iters && !rc; i++) rc = search_enqueue_locked(idx, nq, q_dev, k, none, st, tune, pi, true);
         cudaEventRecord(e1, st);
     }
-    cudaEventRecord(idx->ws_free, st);
     cudaError_t e = cudaStreamSynchronize(st);
     float ms = 0.f;
     if (!rc && e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
@@ -1120,6 +1350,41 @@ extern "C" int evs_index_scan_profile(evs_index* idx, int64_t* count, double* to
     return EVS_OK;
 }
 
+extern "C" int evs_index_guard_stats(evs_index* idx, int64_t* reruns, int64_t* uncertified) {
+    if (!idx) return fail(EVS_EINVAL, "idx is NULL");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    if (idx->have_last_stream) CU(cudaStreamSynchronize(idx->last_stream));
+    unsigned long long w[2] = {0, 0};
+    CU(cudaMemcpy(w, idx->words + W_UNCERT, sizeof(w), cudaMemcpyDeviceToHost));  // W_UNCERT, W_RERUNS are adjacent u64
+    if (uncertified) *uncertified = (int64_t)w[0];
+    if (reruns) *reruns = (int64_t)w[1];
+    return EVS_OK;
+}
+
+extern "C" int evs_index_max_row_norm(evs_index* idx, float* max_norm) {
+    if (!idx || !max_norm) return fail(EVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    CU(cudaMemcpy(max_norm, idx->words + W_MAX_NORM, sizeof(float), cudaMemcpyDeviceToHost));
+    return EVS_OK;
+}
+
+extern "C" int evs_index_scan_clocks(evs_index* idx, uint64_t* out_host, int64_t cap_ctas, int64_t* nctas) {
+    if (!idx || !nctas) return fail(EVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    *nctas = idx->cta_clock_n;
+    if (!out_host || idx->cta_clock_n == 0) return EVS_OK;
+    if (cap_ctas < idx->cta_clock_n) return fail(EVS_EINVAL, "buffer holds %lld CTAs, need %d", (long long)cap_ctas, idx->cta_clock_n);
+    if (idx->have_last_stream) CU(cudaStreamSynchronize(idx->last_stream));
+    CU(cudaMemcpy(out_host, idx->cta_clock, (size_t)idx->cta_clock_n * 16, cudaMemcpyDeviceToHost));
+    return EVS_OK;
+}
+
 extern "C" int evs_index_tc_max_queries(const evs_index* idx, int* max_queries) {
     if (!idx || !max_queries) return fail(EVS_EINVAL, "NULL argument");
     *max_queries = tc_max_queries(idx->d, idx->storage == EVS_STORE_BF16_F32);
@@ -1131,26 +1396,17 @@ extern "C" int evs_index_tc_scores_dev(evs_index* idx, int64_t nq, const float* 
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
     const int nb_max = tc_max_queries(idx->d, bf16);
     if (nb_max == 0) return fail(EVS_ELIMIT, "d = %d is not supported by the tensor-core scan", idx->d);
-    int pair_min;
-    {
-        std::lock_guard<std::mutex> lk(g_tune_mu);
-        pair_min = g_tune.tc_pair_min_nq;
-    }
+    const ScanTuning tune = tune_snapshot();
+    const int pair_min = tune.tc_pair_min_nq;
     const bool pair = pair_min > 0 && (nq >= pair_min || nq > nb_max) && tc2_max_half(idx->d, bf16) > 0;
+    // fp32 rows, small batches: the scores of the 3xTF32 split scan the searches use
+    const int x3 = (!bf16 && !pair && tune.x3 && nq <= tc_x3_max_queries(idx->d)) ? 1 : 0;
     if (nq <= 0 || (!pair && nq > nb_max) || nq > 4096) return fail(EVS_EINVAL, "nq must be in [1, %d]", pair ? 4096 : nb_max);
     if (idx->ntotal == 0) return fail(EVS_EINVAL, "empty index");
     std::lock_guard<std::mutex> lk(idx->mu);
     int rc = use_device(idx->device);
     if (rc) return rc;
-    TcArgs a;
-    a.xb = bf16 ? idx->xb16 : (const void*)idx->xb32;
-    a.is_bf16 = bf16;
-    a.n = idx->ntotal;
-    a.d = idx->d;
-    a.xq = q_dev;
-    a.nq = (int)nq;
-    a.lists = nullptr;
-    a.overflow_out = nullptr;
+    TcArgs a = make_tc_args(idx, q_dev, nq, nullptr, nullptr);
     cudaStream_t st = (cudaStream_t)stream;
     if (pair) {
         Tc2Plan pl;
@@ -1158,19 +1414,18 @@ extern "C" int evs_index_tc_scores_dev(evs_index* idx, int64_t nq, const float* 
         *npad = pl.nqp;
         if (!out_dev) return EVS_OK;  // pitch query
         if ((rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc2_workspace_bytes(pl)))) return rc;
-        CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+        if ((rc = ws_acquire(idx, st))) return rc;
         CU(tc2_dump_scores(a, pl, idx->tc_ws, out_dev, st));
         *npad = pl.nqp;
     } else {
         TcPlan pl;
-        CU(tc_plan(idx->ntotal, idx->d, bf16, (int)nq, 64, idx->sm_count, &pl));
+        CU(tc_plan(idx->ntotal, idx->d, bf16, (int)nq, 64, idx->sm_count, x3, &pl));
         *npad = pl.npad;
         if (!out_dev) return EVS_OK;  // pitch query
         if ((rc = ensure_dev(&idx->tc_ws, &idx->tc_ws_cap, tc_workspace_bytes(pl)))) return rc;
-        CU(cudaStreamWaitEvent(st, idx->ws_free, 0));
+        if ((rc = ws_acquire(idx, st))) return rc;
         CU(tc_dump_scores(a, pl, idx->tc_ws, out_dev, st));
     }
-    CU(cudaEventRecord(idx->ws_free, st));
     return EVS_OK;
 }
 
@@ -1250,6 +1505,7 @@ static const size_t kIoChunk = (size_t)64 << 20;
 
 extern "C" int evs_index_write(const evs_index* idx, const char* path) {
     if (!idx || !path) return fail(EVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);  // save_index may race a re-index on another Flask thread
     int rc = use_device(idx->device);
     if (rc) return rc;
     FILE* f = fopen(path, "wb");
@@ -1289,7 +1545,9 @@ extern "C" int evs_index_write(const evs_index* idx, const char* path) {
     return EVS_OK;
 }
 
-extern "C" int evs_index_read(const char* path, int device, int storage, evs_index** out) {
+// Read rows [row_lo, row_hi) of the file's payload (row_hi < 0: to the end) into a new index whose id_base is row_lo:
+// the loader of one shard of a row-sharded index -- every rank reads only its own byte range of index.faiss.
+static int read_rows(const char* path, int device, int storage, int64_t row_lo, int64_t row_hi, evs_index** out, int64_t* ntotal_file) {
     if (!path || !out) return fail(EVS_EINVAL, "NULL argument");
     *out = nullptr;
     FILE* f = fopen(path, "rb");
@@ -1318,17 +1576,28 @@ extern "C" int evs_index_read(const char* path, int device, int storage, evs_ind
         fclose(f);
         return fail(EVS_EFORMAT, "'%s': truncated payload", path);
     }
+    if (ntotal_file) *ntotal_file = h.ntotal;
+    if (row_hi < 0 || row_hi > h.ntotal) row_hi = h.ntotal;
+    if (row_lo < 0 || row_lo > row_hi) {
+        fclose(f);
+        return fail(EVS_EINVAL, "rows [%lld, %lld) out of range for '%s' (%lld rows)", (long long)row_lo, (long long)row_hi, path,
+                    (long long)h.ntotal);
+    }
+    const int64_t nrows = row_hi - row_lo;
     evs_index* idx = nullptr;
     int rc = evs_index_create(h.d, device, storage, &idx);
     if (rc) {
         fclose(f);
         return rc;
     }
-    size_t total = (size_t)h.count * sizeof(float);
+    idx->id_base = row_lo;
+    size_t total = (size_t)nrows * (size_t)h.d * sizeof(float);
     if (total) {
-        {
+        if (fseeko(f, (off_t)(sizeof(h) + (size_t)row_lo * (size_t)h.d * sizeof(float)), SEEK_SET) != 0)
+            rc = fail(EVS_EIO, "'%s': seek failed: %s", path, strerror(errno));
+        if (!rc) {
             std::lock_guard<std::mutex> lk(idx->mu);
-            rc = grow_locked(idx, h.ntotal);
+            rc = grow_locked(idx, nrows);
         }
         void* pin[2] = {nullptr, nullptr};
         size_t chunk = total < kIoChunk ? total : kIoChunk;
@@ -1355,7 +1624,7 @@ extern "C" int evs_index_read(const char* path, int device, int storage, evs_ind
         }
         if (!rc) {
             std::lock_guard<std::mutex> lk(idx->mu);
-            rc = finish_add_locked(idx, h.ntotal);
+            rc = finish_add_locked(idx, nrows);
         } else {
             cudaStreamSynchronize(idx->stream);
         }
@@ -1370,5 +1639,66 @@ extern "C" int evs_index_read(const char* path, int device, int storage, evs_ind
         return rc;
     }
     *out = idx;
+    return EVS_OK;
+}
+
+extern "C" int evs_index_read(const char* path, int device, int storage, evs_index** out) {
+    return read_rows(path, device, storage, 0, -1, out, nullptr);
+}
+
+extern "C" int evs_index_read_rows(const char* path, int device, int storage, int64_t row_lo, int64_t row_hi, evs_index** out,
+                                   int64_t* ntotal_file) {
+    return read_rows(path, device, storage, row_lo, row_hi, out, ntotal_file);
+}
+
+extern "C" int evs_index_file_info(const char* path, int* d, int64_t* ntotal) {
+    if (!path) return fail(EVS_EINVAL, "path is NULL");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(EVS_EIO, "cannot open '%s': %s", path, strerror(errno));
+    FlatHeader h;
+    const bool ok = fread(&h, sizeof(h), 1, f) == 1;
+    fclose(f);
+    if (!ok) return fail(EVS_EFORMAT, "'%s': truncated header", path);
+    if (memcmp(h.fourcc, "IxFI", 4) && memcmp(h.fourcc, "IxF2", 4) && memcmp(h.fourcc, "IxFl", 4))
+        return fail(EVS_EFORMAT, "'%s': not a flat index (fourcc %.4s)", path, h.fourcc);
+    if (h.d <= 0 || h.ntotal < 0 || h.count != (uint64_t)h.ntotal * (uint64_t)h.d)
+        return fail(EVS_EFORMAT, "'%s': inconsistent header", path);
+    if (d) *d = h.d;
+    if (ntotal) *ntotal = h.ntotal;
+    return EVS_OK;
+}
+
+// Switch the scan precision of an index in place: EVS_STORE_BF16_F32 derives the bf16 scan copy (large batches over
+// fp32-storage indexes otherwise scan in tf32 straight from the fp32 rows: twice the bytes through L2 for no gain in
+// accuracy after the canonical re-score); EVS_STORE_F32 drops it.
+extern "C" int evs_index_set_storage(evs_index* idx, int storage) {
+    if (!idx) return fail(EVS_EINVAL, "idx is NULL");
+    if (storage != EVS_STORE_F32 && storage != EVS_STORE_BF16_F32) return fail(EVS_EINVAL, "unknown storage %d", storage);
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    if (storage == idx->storage) return EVS_OK;
+    CU(cudaDeviceSynchronize());  // no search may be in flight while the scan rows change
+    if (storage == EVS_STORE_F32) {
+        cudaFree(idx->xb16);
+        idx->xb16 = nullptr;
+        idx->storage = storage;
+        return EVS_OK;
+    }
+    if (idx->capacity > 0) {
+        void* n16 = nullptr;
+        cudaError_t e = cudaMalloc(&n16, (size_t)idx->capacity * idx->d * 2);
+        if (e != cudaSuccess) return fail(EVS_ENOMEM, "cudaMalloc of the bf16 copy failed: %s", cudaGetErrorString(e));
+        if (idx->ntotal > 0) {
+            e = launch_f32_to_bf16(idx->xb32, n16, (long long)idx->ntotal * idx->d, idx->sm_count, idx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(idx->stream);
+            if (e != cudaSuccess) {
+                cudaFree(n16);
+                return fail(EVS_ECUDA, "bf16 layout kernel failed: %s", cudaGetErrorString(e));
+            }
+        }
+        idx->xb16 = n16;
+    }
+    idx->storage = storage;
     return EVS_OK;
 }

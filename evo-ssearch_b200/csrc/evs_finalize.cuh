@@ -1,0 +1,373 @@
+// evs_finalize.cuh -- the per-query finalise step as a device function.
+//
+// Input: L candidate lists of one query (kp keys each, sorted descending, 0 = empty) as the scans write them.
+// Work:  pick the kp best keys of the union, re-score them in the canonical fp64 order (CANON-32),
+//        rank by (score desc, id asc), emit the k best as final (D, I), as a shard partial, or straight into every
+//        rank's exchange slot over NVLink; compute the safety margin and decide whether the result is certified.
+// Callers: finalize_kernel (one CTA per query, evs_kernels.cu) and -- for single-query searches -- the LAST CTA of
+//        the GEMV scan itself (evs_scan.cuh, ticket counter), which removes a launch from the latency path of
+//        index.search(q.reshape(1,-1), k) (/root/reference/oldapp.py:2005, :2112).
+#pragma once
+#include <float.h>
+
+#include "evs_common.cuh"
+#include "evs_internal.h"
+
+namespace evs {
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// The canonical order on integers (DSETP is quarter-rate on B200, and short-circuit logic branches):
+// map the score to an order-preserving u64 (-0.0 folded onto +0.0 so that equal doubles stay equal).
+__device__ __forceinline__ u64 score_rank_key(double s) { return f64_to_ordered(s == 0.0 ? 0.0 : s); }
+__device__ __forceinline__ int better_i(u64 oa, long long ia, u64 ob, long long ib) {
+    return (int)(oa > ob) | ((int)(oa == ob) & (int)(ia < ib));
+}
+// exact fp32 -> fp64 widening with integer ops for normal numbers (F2F.F64.F32 issues at 1/8 rate)
+__device__ __forceinline__ double widen_f32(float f) {
+    const uint32_t u = __float_as_uint(f);
+    const uint32_t e = (u >> 23) & 0xFFu;
+    if (e == 0u || e == 255u) return (double)f;  // zero, subnormal, inf, nan: the slow exact path
+    const uint32_t hi = (u & 0x80000000u) | ((e + 896u) << 20) | ((u & 0x007FFFFFu) >> 3);
+    const uint32_t lo = u << 29;
+    return __hiloint2double((int)hi, (int)lo);
+}
+
+__device__ __forceinline__ double canon32_dot_bf16(const __nv_bfloat16* __restrict__ x, const double* __restrict__ q,
+                                                   int d, int lane) {
+    double acc = 0.0;
+    const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+    for (int i = lane; i < d; i += 32) acc = fma((double)__uint_as_float(((uint32_t)xs[i]) << 16), q[i], acc);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
+    return acc;
+}
+
+// CANON-32 of TWO rows at once with the row loads batched (same accumulation order per row; the two
+// rows' load latencies and fp64 chains overlap).  A null row pointer yields -DBL_MAX.
+__device__ __forceinline__ void canon32_dot_pair(const float* __restrict__ xa, const float* __restrict__ xb,
+                                                 const double* __restrict__ qs, int d, int lane, double& ra, double& rb) {
+    double acca = 0.0, accb = 0.0;
+    for (int base = 0; base < d; base += 512) {
+        float va[16], vb[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            int i = base + lane + 32 * u;
+            va[u] = (xa && i < d) ? __ldg(xa + i) : 0.f;
+            vb[u] = (xb && i < d) ? __ldg(xb + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            int i = base + lane + 32 * u;
+            if (i < d) {
+                const double qv = qs[i];
+                acca = fma(widen_f32(va[u]), qv, acca);
+                accb = fma(widen_f32(vb[u]), qv, accb);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        acca = acca + __shfl_xor_sync(0xffffffffu, acca, off);
+        accb = accb + __shfl_xor_sync(0xffffffffu, accb, off);
+    }
+    ra = xa ? acca : -DBL_MAX;
+    rb = xb ? accb : -DBL_MAX;
+}
+
+// The L per-CTA lists are sorted, so the global top-kp is found without merging them all:
+//   T0 = kp-th largest list HEAD is a lower bound of the kp-th best key (kp heads are >= it), only the
+//   <= kp lists whose head is >= T0 can hold survivors, and only their prefix >= T0 does.  The
+//   survivors (about kp + a few for unordered data, kp*kp at most) are sorted in shared memory.
+// shared memory (finalize_smem_bytes): FinalizeShared | surv[finalize_surv_slots(L, kp)] u64 | heads[L] u64 | sc[kp] f64 |
+//   id[kp] i64 | ok[kp] u64 | qs[d] f64
+// (survivor capacity scap = min(L, kp) * kp: with one list per query -- the tensor-core scans -- the kernel needs
+// 7 KB instead of 38 KB of shared memory and eight 256-thread CTAs fit an SM)
+__host__ __device__ inline int finalize_surv_cap(int L, int kp) { return (L < kp ? L : kp) * kp; }
+__host__ __device__ inline int finalize_surv_slots(int L, int kp) {
+    const int scap = finalize_surv_cap(L, kp);
+    int pow2 = kp;
+    while (pow2 < scap) pow2 <<= 1;  // the sort path pads the survivors to a power of two
+    return pow2 > scap + kp ? pow2 : scap + kp;  // the counting path puts kp result slots behind the survivors
+}
+struct FinalizeShared {
+    int nsurv, nvalid;
+    unsigned maxerr;  // ordered-uint of the largest (canonical - scan) score difference among the candidates
+    int pad0;
+    u64 T0;
+    double qnorm2;    // |q|^2
+};
+__host__ __device__ inline size_t finalize_smem_bytes(int L, int kp, int d) {
+    return sizeof(FinalizeShared) + (size_t)finalize_surv_slots(L, kp) * 8 + (size_t)L * 8 + (size_t)kp * 24 + (size_t)d * 8;
+}
+
+// the part that does not depend on the scan's output: the query widened to fp64 (may run before griddepcontrol.wait)
+__device__ __forceinline__ void finalize_prologue(const FinalizeParams& p, long long qi, unsigned char* smem_raw) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    FinalizeShared* sh = reinterpret_cast<FinalizeShared*>(smem_raw);
+    double* qs = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) +
+                                           ((size_t)finalize_surv_slots(p.L, p.kp) + p.L + 3 * (size_t)p.kp) * 8);
+    const float* q = p.xq + (size_t)qi * p.d;
+    for (int i = t; i < p.d; i += nt) qs[i] = (double)q[i];
+    if (t == 0) {
+        sh->nsurv = 0;
+        sh->nvalid = 0;
+        sh->maxerr = 0u;
+        sh->T0 = 0ull;
+        sh->qnorm2 = 0.0;
+    }
+}
+
+// Finalise query `qi` (index into xq / the outputs) from the lists at `lists` ([L][kp]).  Called by every thread of the
+// CTA (a multiple of 32 threads, at least 64) after finalize_prologue and a point where the lists are visible.
+__device__ __forceinline__ void finalize_query(const FinalizeParams& p, long long qi, const u64* __restrict__ lists,
+                                               unsigned char* smem_raw) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int warp = t >> 5, lane = t & 31, nwarps = nt >> 5;
+    const int kp = p.kp, L = p.L;
+    const int scap = finalize_surv_cap(L, kp);
+    FinalizeShared* sh = reinterpret_cast<FinalizeShared*>(smem_raw);
+    u64* surv = reinterpret_cast<u64*>(smem_raw + sizeof(FinalizeShared));  // [finalize_surv_slots(L, kp)]
+    u64* heads = surv + finalize_surv_slots(L, kp);         // [L]
+    double* sc = reinterpret_cast<double*>(heads + L);      // [kp]
+    long long* id = reinterpret_cast<long long*>(sc + kp);  // [kp]
+    u64* ok = reinterpret_cast<u64*>(id + kp);              // [kp] integer rank keys of the scores
+    double* qs = reinterpret_cast<double*>(ok + kp);        // [d] the query widened once
+
+    // lists were written by other SMs (possibly during this very kernel): read them past L1
+    for (int l = t; l < L; l += nt) heads[l] = __ldcg(lists + (size_t)l * kp);
+    if (qi == 0 && t == 0 && p.guard_count_next) *p.guard_count_next = 0;  // ready for the next guarded search of this handle
+    __syncthreads();
+    if (p.err_coef > 0.f && warp == 0) {  // |q|^2 for the certification bound (qs is complete: barrier above)
+        double s2 = 0.0;
+        for (int i = lane; i < p.d; i += 32) s2 = fma(qs[i], qs[i], s2);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        if (lane == 0) sh->qnorm2 = s2;
+    }
+    // 1. T0 = kp-th largest head (non-empty keys are unique, so exactly one head has rank kp-1).
+    //    `nper` adjacent lanes share one head and split the comparison range.
+    //    Only every `hs`-th head is ranked (about 2.3*kp of them): still a valid bound (kp keys are >= it),
+    //    a quarter of the comparisons, a few more survivors.  If the survivors then overflow their
+    //    buffer the bound is recomputed from every head (then at most kp lists qualify: <= kp*kp keys).
+    int hs = 1;
+    while ((L / (hs * 2)) * 10 >= kp * 23) hs <<= 1;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (attempt == 1) {
+            if (sh->nsurv <= scap || hs == 1) break;  // uniform: read after the barrier below
+            __syncthreads();
+            if (t == 0) {
+                sh->nsurv = 0;
+                sh->T0 = 0ull;
+            }
+            hs = 1;
+            __syncthreads();
+        }
+        const int Ls = (L + hs - 1) / hs;  // sampled heads: lists 0, hs, 2hs, ...
+        if (Ls >= kp) {
+            int nper = 1;
+            while (nper < 32 && nper * 2 * Ls <= nt) nper <<= 1;
+            const int part = t & (nper - 1);
+            for (int l0 = 0; l0 < Ls; l0 += nt / nper) {
+                const int l = l0 + t / nper;
+                const u64 h = l < Ls ? heads[l * hs] : 0ull;
+                int r = 0;
+                if (h != 0ull)
+                    for (int j = part; j < Ls; j += nper) r += heads[j * hs] > h ? 1 : 0;
+                for (int off = 1; off < nper; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+                if (h != 0ull && part == 0 && r == kp - 1) sh->T0 = h;
+            }
+        }
+        __syncthreads();
+        const u64 T0 = sh->T0;  // 0: fewer than kp non-empty lists -> every key survives (at most kp*kp)
+        // 2. survivors: one warp per qualifying list, prefix >= T0
+        for (int l = warp; l < L; l += nwarps) {
+            const u64 h = heads[l];
+            if (h == 0ull || h < T0) continue;  // warp-uniform
+            const u64* src = lists + (size_t)l * kp;
+            u64 keys[4];  // kp <= 128: all loads of the list issued before the first use
+#pragma unroll
+            for (int u = 0; u < 4; u++) keys[u] = (32 * u + lane < kp) ? __ldcg(src + 32 * u + lane) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const bool keep = keys[u] != 0ull && keys[u] >= T0;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m == 0u) break;
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&sh->nsurv, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const int dst = pos + __popc(m & ((1u << lane) - 1u));
+                if (keep && dst < scap) surv[dst] = keys[u];
+            }
+        }
+        __syncthreads();
+    }  // attempt
+    // 3. the kp best survivors in descending order -> A[0..kp)
+    const int nsurv = sh->nsurv;
+    const u64* A;
+    if (nsurv <= nt) {
+        // usual case (a few more than kp survivors): rank by counting, one barrier instead of a sort
+        u64* top = surv + nsurv;  // kp slots behind the survivors
+        for (int i = t; i < kp; i += nt) top[i] = 0ull;
+        __syncthreads();
+        if (t < nsurv) {
+            const u64 key = surv[t];
+            int r = 0;
+            for (int j = 0; j < nsurv; j++) r += surv[j] > key ? 1 : 0;
+            if (r < kp) top[r] = key;
+        }
+        __syncthreads();
+        A = top;
+    } else {
+        int pow2 = kp;
+        while (pow2 < nsurv) pow2 <<= 1;
+        for (int i = nsurv + t; i < pow2; i += nt) surv[i] = 0ull;
+        for (int size = 2; size <= pow2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int e = t; e < (pow2 >> 1); e += nt) {
+                    int i = ((e / stride) * (stride << 1)) + (e % stride);
+                    cmpx_desc(surv, i, i + stride, (i & size) == 0);
+                }
+            }
+        }
+        __syncthreads();
+        A = surv;  // A[0..kp) = the kp best scan keys
+    }
+
+    // 4. canonical re-score of the kp candidates (a warp takes two candidates at a time)
+    for (int c = 2 * warp; c < kp; c += 2 * nwarps) {
+        const u64 ka = A[c], kb = (c + 1 < kp) ? A[c + 1] : 0ull;
+        const long long rowa = ka ? (long long)key_row(ka) : -1, rowb = kb ? (long long)key_row(kb) : -1;
+        double sa = -DBL_MAX, sb = -DBL_MAX;
+        if (p.xb_is_bf16) {
+            const __nv_bfloat16* xb16 = reinterpret_cast<const __nv_bfloat16*>(p.xb);
+            if (ka) sa = canon32_dot_bf16(xb16 + (size_t)rowa * p.d, qs, p.d, lane);
+            if (kb) sb = canon32_dot_bf16(xb16 + (size_t)rowb * p.d, qs, p.d, lane);
+        } else {
+            const float* xb32 = reinterpret_cast<const float*>(p.xb);
+            canon32_dot_pair(ka ? xb32 + (size_t)rowa * p.d : nullptr, kb ? xb32 + (size_t)rowb * p.d : nullptr, qs, p.d, lane,
+                             sa, sb);
+        }
+        if (lane == 0) {
+            sc[c] = sa;
+            id[c] = rowa;
+            ok[c] = rowa >= 0 ? score_rank_key(sa) : 0ull;
+            if (c + 1 < kp) {
+                sc[c + 1] = sb;
+                id[c + 1] = rowb;
+                ok[c + 1] = rowb >= 0 ? score_rank_key(sb) : 0ull;
+            }
+        }
+    }
+    __syncthreads();
+    // how far the scan under-estimated its own candidates at most (tf32 truncates towards zero: a bias of ~1e-3 relative;
+    // bf16 and fp32 scans scatter around zero)
+    const bool want_margin = p.margins != nullptr || p.guard_count != nullptr || p.pred_slot != nullptr;
+    for (int c = t; c < kp; c += nt)
+        if (id[c] >= 0 && want_margin) atomicMax(&sh->maxerr, score_to_ordered((float)(sc[c] - (double)key_score(A[c]))));
+    __syncthreads();
+
+    // 5. rank by counting under (score desc, id asc); ids are unique so ranks are a permutation
+    for (int c = t; c < kp; c += nt) {
+        if (id[c] < 0) continue;
+        atomicAdd(&sh->nvalid, 1);
+        const double st = sc[c];
+        const long long it = id[c];
+        const u64 ot = ok[c];
+        int rank = 0;
+        // empty slots have id -1 and key 0: a real candidate never loses to them -> mask by id >= 0 arithmetically
+        for (int j = 0; j < kp; j++) rank += better_i(ok[j], id[j], ot, it) & (int)(id[j] >= 0);
+        if (rank < p.k) {
+            if (p.D) {
+                p.D[(size_t)qi * p.k + rank] = (float)st;
+                p.I[(size_t)qi * p.k + rank] = it + p.id_base;
+            } else if (p.x.world > 0) {
+                const size_t e = (size_t)(p.x.q_off + qi) * p.k + rank;
+                for (int g = 0; g < p.x.world; g++) {  // the same 16 bytes to every rank's slot for this shard
+                    unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
+                    reinterpret_cast<double*>(slot)[e] = st;
+                    reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = it + p.id_base;
+                }
+            } else {
+                p.P_scores[(size_t)qi * p.k + rank] = st;
+                p.P_ids[(size_t)qi * p.k + rank] = it + p.id_base;
+            }
+            if (rank == p.k - 1 && want_margin) {
+                // All kp slots taken -> every row outside the list has a scan score <= the worst retained one, so its
+                // true score is at most that plus the scan's error.  margin = canonical score of rank k minus (worst
+                // retained scan score + the largest under-estimate observed on the retained candidates); the result is
+                // CERTIFIED exact when margin > E = err_coef * |q| * max|x|, E being the error bound of the scan that
+                // produced the lists (fp32 GEMV / 3xTF32: a few 1e-6; single tf32 / bf16: the caller's statistical eps).
+                const float worst = key_score(A[kp - 1]);
+                const float under = fmaxf(ordered_to_score(sh->maxerr), 0.f);
+                const float margin = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) - under : INFINITY;
+                if (p.margins) p.margins[qi] = margin;
+                if (p.err_coef > 0.f) {
+                    const float mx = p.max_norm ? *p.max_norm : 1.f;
+                    const float E = p.err_coef * (float)sqrt(sh->qnorm2) * mx;
+                    const bool certified = margin > E;  // false for NaN
+                    if (!certified) {
+                        if (p.guard_count) {  // first phase: queue the query for the exact re-run
+                            const int slot = atomicAdd(p.guard_count, 1);
+                            if (slot < p.guard_cap) {
+                                p.guard_slot[qi] = slot;
+                                p.guard_q[slot] = (int)qi;
+                            } else {
+                                p.guard_slot[qi] = -2;  // flagged only: the host re-runs it (guard_cap = 0), or the queue is full
+                                if (p.guard_cap > 0 && p.uncertified) atomicAdd(p.uncertified, 1ull);
+                            }
+                        } else if (p.uncertified) {  // second phase (or no re-run available): best effort, counted
+                            atomicAdd(p.uncertified, 1ull);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // 6. padding (-FLT_MAX,-1) / (-DBL_MAX,-1) for the slots no candidate ranked into
+    const int nvalid = sh->nvalid;
+    for (int r = nvalid + t; r < p.k; r += nt) {
+        if (p.D) {
+            p.D[(size_t)qi * p.k + r] = -FLT_MAX;
+            p.I[(size_t)qi * p.k + r] = -1;
+        } else if (p.x.world > 0) {
+            const size_t e = (size_t)(p.x.q_off + qi) * p.k + r;
+            for (int g = 0; g < p.x.world; g++) {
+                unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
+                reinterpret_cast<double*>(slot)[e] = -DBL_MAX;
+                reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = -1;
+            }
+        } else {
+            p.P_scores[(size_t)qi * p.k + r] = -DBL_MAX;
+            p.P_ids[(size_t)qi * p.k + r] = -1;
+        }
+    }
+    if (t == 0 && p.margins && nvalid < p.k) p.margins[qi] = INFINITY;  // every row was a candidate
+    if (p.x.world > 0 && p.D == nullptr) {
+        // publish: when the last query's CTA has written its part, raise this shard's flag on every rank
+        __syncthreads();
+        if (t == 0) {
+            __threadfence_system();
+            const unsigned prev = atomicAdd(p.x.done, 1u);
+            if (prev == (unsigned)p.x.nq_total - 1u) {  // counts across the launches of one search
+                *p.x.done = 0u;
+                __threadfence_system();
+                for (int g = 0; g < p.x.world; g++) {
+                    unsigned long long* flags = reinterpret_cast<unsigned long long*>(p.x.peer[g] + 2 * (size_t)p.x.world * p.x.slot_bytes);
+                    st_release_sys_u64(flags + (size_t)p.x.parity * p.x.world + p.x.rank, p.x.seq);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace evs

@@ -1,5 +1,6 @@
-// evs_internal.h -- host-side declarations shared by evs_kernels.cu and evs_api.cu.
+// evs_internal.h -- host-side declarations shared by evs_kernels.cu, evs_tc*.cu and evs_api.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -19,6 +20,13 @@ struct ScanTuning {
     int tc_min_nq = 2;     // query batches of at least this many use the tensor-core scan (0 = never); measured
                            // (scripts/small_nq_sweep.py): from 2 queries on it beats the CUDA-core GEMV for fp32 and bf16 rows
     int tc_pair_min_nq = 129;  // ... and of at least this many the CTA-pair kernel (evs_tc2.cu); 0 = never
+    int fuse_finalize = 1;     // single-query GEMV searches: the scan's last CTA finalises (no second launch)
+    int scan_dynamic = 1;      // ... and rows are dealt dynamically, `scan_chunk_groups` row groups per grab
+    int scan_chunk_groups = 2;
+    int scan_clock = 0;        // diagnostics: record per-CTA start / end-of-scan-loop times of fused single-query scans
+    int x3 = 1;                // fp32 rows, batches up to x3_max_nq queries: 3xTF32 split scan (fp32-class scan error)
+    int x3_max_nq = 32;
+    int guard = 1;             // certify fp32-storage batch results on the device and re-run uncertified queries exactly
 };
 
 struct ScanPlan {
@@ -29,22 +37,11 @@ struct ScanPlan {
     int tile_rows, stages;
 };
 
-struct ScanArgs {
-    const void* xb;
-    int is_bf16;
-    long long n;
-    int d;
-    const float* xq;
-    int q0;
-    int nq_pass;  // 1..4 queries handled by this launch
-    void* lists;  // u64 [nq_chunk][grid][kp]
-    int kp;
-};
-
 // Peer-store exchange of shard partials (row sharding): every rank owns a symmetric buffer
 //   [2 parities][world shards][slot_bytes]  gather slots (float64 scores [nq*k] then int64 ids [nq*k])
-//   [2 parities][world shards] uint64       arrival flags holding the search sequence number
+//   [2 parities][world shards] uint64       arrival flags: the search sequence number; bit 63 = that rank FAILED the search
 // and sees all ranks' buffers through peer-mapped pointers.
+constexpr unsigned long long kExchangePoison = 1ull << 63;
 struct Exchange {
     unsigned char* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int rank = 0, world = 0, parity = 0;
@@ -53,29 +50,82 @@ struct Exchange {
     unsigned* done = nullptr;  // local counter of finished finalize CTAs
     long long nq_total = 0;    // queries of the whole search (a search may be finalised in several launches)
     long long q_off = 0;       // first query of this launch
+    int* status = nullptr;     // host-mapped: 1 = a merge gave up waiting for a rank (~10 s), 2 = a rank reported failure
 };
 
-struct FinalizeArgs {
-    const void* lists;
-    int L, kp;
-    const void* xb;
-    int xb_is_bf16;
-    const float* xq;
-    long long nq;
-    int d, k;
-    long long id_base;
-    float* D;
-    int64_t* I;
-    double* P_scores;
-    int64_t* P_ids;
-    float* margins;
+// everything the finalise step needs (evs_finalize.cuh: finalize_query).  Plain data, filled by evs_api.cu.
+struct FinalizeParams {
+    const unsigned long long* lists = nullptr;  // [nq][L][kp]  (guard phase 2: [slot][L][kp], slot = pred_slot[query])
+    int L = 0;
+    int kp = 0;
+    const void* xb = nullptr;  // rows used for the canonical re-score (the fp32 master copy)
+    int xb_is_bf16 = 0;
+    const float* xq = nullptr;  // [nq][d]
+    int d = 0;
+    int k = 0;
+    long long id_base = 0;
+    // mode 0: final results
+    float* D = nullptr;         // [nq][k]
+    long long* I = nullptr;     // [nq][k]
+    // mode 1: shard partial
+    double* P_scores = nullptr;  // [nq][k]
+    long long* P_ids = nullptr;  // [nq][k]
+    float* margins = nullptr;    // [nq] (may be null)
+    // mode 2: shard partial written straight into every rank's gather buffer over NVLink (peer stores); x.world > 0
     Exchange x;
+    // certification: the result of a query is certified when  margin > err_coef * |q| * max|x|  (see finalize_query)
+    float err_coef = 0.f;             // error bound of the scan that produced the lists, relative to |q|*|x|; 0 = do not certify
+    const float* max_norm = nullptr;  // device: largest row norm of the index (null -> 1)
+    // guard, first phase: uncertified queries are queued for the exact re-run
+    int* guard_count = nullptr;       // device counter (null -> no guard)
+    int* guard_count_next = nullptr;  // the counter the NEXT guarded search will use: zeroed here (no memset node in the chain)
+    int* guard_slot = nullptr;        // [nq]: slot of the query in the re-run queue, -1 = certified, -2 = uncertified but not queued
+    int* guard_q = nullptr;           // [guard_cap]: query of each slot
+    int guard_cap = 0;                // 0: flag only (the host re-runs)
+    // guard, second phase: only the queries with pred_slot[q] >= 0 are finalised again, from the re-run's lists
+    const int* pred_slot = nullptr;
+    unsigned long long* uncertified = nullptr;  // device counter: results that stayed uncertified
+    unsigned long long* reruns = nullptr;       // device counter: queries finalised again from the exact re-run
+};
+
+struct ScanArgs {
+    const void* xb = nullptr;
+    int is_bf16 = 0;
+    long long n = 0;
+    int d = 0;
+    const float* xq = nullptr;
+    int q0 = 0;
+    int nq_pass = 1;  // 1..4 queries handled by this launch
+    void* lists = nullptr;  // u64 [nq_chunk][grid][kp]
+    int kp = 64;
+    // direct variant only (all optional):
+    const FinalizeParams* fuse = nullptr;  // single-query launch: the last CTA finalises the query (needs `ticket`)
+    unsigned* ticket = nullptr;
+    unsigned* next_chunk = nullptr;        // dynamic row dealing (with `ticket` only: the last CTA resets the counter)
+    int chunk_groups = 0;
+    const int* qmap = nullptr;             // guard re-run: queries qmap[0 .. *nactive), nq_pass at a time
+    const int* nactive = nullptr;
+    int qcap = 0;
+    unsigned long long* cta_clock = nullptr;
+};
+
+// host-encoded TMA descriptors are cached per (base pointer, rows, d, element type, box rows)
+struct TmapCache {
+    struct Entry {
+        const void* base = nullptr;
+        long long rows = 0;
+        int d = 0, f32 = 0, box = 0;
+        CUtensorMap map;
+    };
+    Entry e[16];
+    int next = 0;
 };
 
 // tensor-core scan (evs_tc.cu)
 struct TcPlan {
     int npad, nblocks, nqp, nk, stages, grid, pre_grid, groups, gpow2, cap, cap_total, kp;
-    int heap;  // 1: MODE_HEAP (small batch, lists [nq][grid][64] come straight out of the scan, L = grid for finalize)
+    int heap;  // 1: MODE_HEAP (small batch, lists [nq][grid][64] come straight out of the scan, L = grid for finalize); 2: ... seeded by a pre-pass
+    int x3;    // 3xTF32: fp32 rows split hi + lo on the fly, queries split once; scan error ~1e-6 instead of ~1e-3
     size_t smem;
     long long ntiles, pre_tiles, pre_stride;
     size_t off_gmax, off_tau0, off_counts, off_overflow, off_spill_cnt, off_cand, off_spill, off_qbf16, off_end;
@@ -89,6 +139,7 @@ struct TcArgs {
     int nq;
     void* lists;      // out: u64 [nq][kp]
     int* overflow_out;  // out (optional): int [nq]
+    TmapCache* tmaps = nullptr;
 };
 // CTA-pair tensor-core scan for large batches (evs_tc2.cu)
 struct Tc2Plan {
@@ -111,14 +162,16 @@ extern int g_tc_heap_max_nq;
 extern int g_tc_heap_pure_max_nq;
 int tc_sample_rows(int nq);
 int tc_max_queries(int d, int is_bf16);
-cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, TcPlan* pl);
+int tc_x3_max_queries(int d);  // queries one 3xTF32 pass serves (0 = dimension not supported)
+cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, int x3, TcPlan* pl);
 size_t tc_workspace_bytes(const TcPlan& pl);
 cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, cudaStream_t st);
 cudaError_t tc_dump_scores(const TcArgs& a, const TcPlan& pl, unsigned char* ws, float* out, cudaStream_t st);
 
 // Launch with programmatic stream serialisation: the kernel may become resident while the preceding kernel of the stream is
-// still draining (its CTAs call griddepcontrol.launch_dependents early); the kernel itself must execute griddepcontrol.wait
-// before it reads anything the predecessor wrote.  Hides launch latency and prologues on the multi-kernel search paths.
+// still draining (once its CTAs have called griddepcontrol.launch_dependents); the kernel itself must execute
+// griddepcontrol.wait before it reads anything a predecessor wrote.  Hides launch latency and prologues on the
+// multi-kernel search paths.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -138,11 +191,12 @@ cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int 
                       ScanPlan* plan);
 int max_queries_per_pass(int d, int is_bf16);
 cudaError_t launch_scan(const ScanArgs& a, ScanPlan* plan, cudaStream_t st);
-cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st);
+cudaError_t launch_finalize(const FinalizeParams& p, long long nq, cudaStream_t st);
+size_t finalize_smem_bytes_host(int L, int kp, int d);
 cudaError_t launch_publish_partials(const Exchange& x, long long nq, int k, const double* scores, const long long* ids,
                                     cudaStream_t st);
-cudaError_t launch_merge_exchange(const Exchange& x, long long nq, int k, float* D, long long* I, int* timed_out,
-                                  cudaStream_t st);
+cudaError_t launch_publish_poison(const Exchange& x, cudaStream_t st);
+cudaError_t launch_merge_exchange(const Exchange& x, long long nq, int k, float* D, long long* I, cudaStream_t st);
 cudaError_t launch_merge_partials(int nparts, long long nq, int k, const double* scores, const long long* ids,
                                   long long part_stride, float* D,
                                   long long* I, cudaStream_t st);
@@ -153,5 +207,10 @@ cudaError_t launch_gather_rows(const float* src, const long long* ids_dev, float
                                cudaStream_t st);
 cudaError_t launch_synth_fill(float* out, long long n, int d, unsigned long long seed, long long row_base, int sm_count,
                               cudaStream_t st);
+// max_norm[0] = max(max_norm[0], largest |row|) over rows [0, n): float bits compared as unsigned (norms are >= 0);
+// NaN rows are ignored
+cudaError_t launch_row_norm_max(const float* rows, long long n, int d, float* max_norm, int sm_count, cudaStream_t st);
+// small device fills used on the search path instead of memset nodes
+cudaError_t launch_fill_i32(int* p, long long count, int value, cudaStream_t st);
 
 }  // namespace evs

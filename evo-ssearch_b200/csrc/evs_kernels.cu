@@ -19,338 +19,31 @@ namespace evs {
 std::atomic<long long> g_kernel_launches{0};
 
 // =============================================================================================
-// finalize
+// finalize: one CTA per query around finalize_query (evs_finalize.cuh).  grid = nq, block = 1024 or 256.
+// Launched with programmatic stream serialisation behind the scan: the prologue (the query widened to fp64 -- it does
+// not come from the scan) overlaps the scan's tail; everything below the wait sees the scan's lists.
+// Guard second phase (pred_slot != null): only the queries the first finalise queued are finalised again, from the
+// lists of the exact re-run; every other CTA returns at once.
 // =============================================================================================
-struct FinalizeParams {
-    const u64* lists;  // [nq][L][kp]
-    int L;
-    int kp;
-    const void* xb;    // rows used for the canonical re-score (fp32 master, or bf16 when there is none)
-    int xb_is_bf16;
-    const float* xq;   // [nq][d]
-    int d;
-    int k;
-    long long id_base;
-    // mode 0: final results
-    float* D;          // [nq][k]
-    long long* I;      // [nq][k]
-    // mode 1: shard partial
-    double* P_scores;  // [nq][k]
-    long long* P_ids;  // [nq][k]
-    float* margins;    // [nq] (may be null)
-    // mode 2: shard partial written straight into every rank's gather buffer over NVLink (peer stores)
-    Exchange x;
-};
-
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ bool cand_better(double sa, long long ia, double sb, long long ib) {
-    return (sa > sb) || (sa == sb && ia < ib);
-}
-// The same order on integers (DSETP is quarter-rate on B200, and short-circuit logic branches):
-// map the score to an order-preserving u64 (-0.0 folded onto +0.0 so that equal doubles stay equal).
-__device__ __forceinline__ u64 score_rank_key(double s) { return f64_to_ordered(s == 0.0 ? 0.0 : s); }
-__device__ __forceinline__ int better_i(u64 oa, long long ia, u64 ob, long long ib) {
-    return (int)(oa > ob) | ((int)(oa == ob) & (int)(ia < ib));
-}
-// exact fp32 -> fp64 widening with integer ops for normal numbers (F2F.F64.F32 issues at 1/8 rate)
-__device__ __forceinline__ double widen_f32(float f) {
-    const uint32_t u = __float_as_uint(f);
-    const uint32_t e = (u >> 23) & 0xFFu;
-    if (e == 0u || e == 255u) return (double)f;  // zero, subnormal, inf, nan: the slow exact path
-    const uint32_t hi = (u & 0x80000000u) | ((e + 896u) << 20) | ((u & 0x007FFFFFu) >> 3);
-    const uint32_t lo = u << 29;
-    return __hiloint2double((int)hi, (int)lo);
-}
-
-__device__ __forceinline__ double canon32_dot_bf16(const __nv_bfloat16* __restrict__ x, const double* __restrict__ q,
-                                                   int d, int lane) {
-    double acc = 0.0;
-    const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
-    for (int i = lane; i < d; i += 32) acc = fma((double)__uint_as_float(((uint32_t)xs[i]) << 16), q[i], acc);
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
-    return acc;
-}
-
-// CANON-32 of TWO rows at once with the row loads batched (same accumulation order per row; the two
-// rows' load latencies and fp64 chains overlap).  A null row pointer yields -DBL_MAX.
-__device__ __forceinline__ void canon32_dot_pair(const float* __restrict__ xa, const float* __restrict__ xb,
-                                                 const double* __restrict__ qs, int d, int lane, double& ra, double& rb) {
-    double acca = 0.0, accb = 0.0;
-    for (int base = 0; base < d; base += 512) {
-        float va[16], vb[16];
-#pragma unroll
-        for (int u = 0; u < 16; u++) {
-            int i = base + lane + 32 * u;
-            va[u] = (xa && i < d) ? __ldg(xa + i) : 0.f;
-            vb[u] = (xb && i < d) ? __ldg(xb + i) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 16; u++) {
-            int i = base + lane + 32 * u;
-            if (i < d) {
-                const double qv = qs[i];
-                acca = fma(widen_f32(va[u]), qv, acca);
-                accb = fma(widen_f32(vb[u]), qv, accb);
-            }
-        }
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        acca = acca + __shfl_xor_sync(0xffffffffu, acca, off);
-        accb = accb + __shfl_xor_sync(0xffffffffu, accb, off);
-    }
-    ra = xa ? acca : -DBL_MAX;
-    rb = xb ? accb : -DBL_MAX;
-}
-
-// grid = nq, block = 1024.
-// The L per-CTA lists are sorted, so the global top-kp is found without merging them all:
-//   T0 = kp-th largest list HEAD is a lower bound of the kp-th best key (kp heads are >= it), only the
-//   <= kp lists whose head is >= T0 can hold survivors, and only their prefix >= T0 does.  The
-//   survivors (about kp + a few for unordered data, kp*kp at most) are sorted in shared memory.
-// dynamic smem: surv[finalize_surv_slots(L, kp)] u64 | heads[L] u64 | sc[kp] f64 | id[kp] i64 | ok[kp] u64 | qs[d] f64
-// (survivor capacity scap = min(L, kp) * kp: with one list per query -- the tensor-core scans -- the kernel needs
-// 7 KB instead of 38 KB of shared memory and eight 256-thread CTAs fit an SM)
-__host__ __device__ inline int finalize_surv_cap(int L, int kp) { return (L < kp ? L : kp) * kp; }
-__host__ __device__ inline int finalize_surv_slots(int L, int kp) {
-    const int scap = finalize_surv_cap(L, kp);
-    int pow2 = kp;
-    while (pow2 < scap) pow2 <<= 1;  // the sort path pads the survivors to a power of two
-    return pow2 > scap + kp ? pow2 : scap + kp;  // the counting path puts kp result slots behind the survivors
-}
-
 __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int t = threadIdx.x, nt = blockDim.x;
-    const int warp = t >> 5, lane = t & 31, nwarps = nt >> 5;
-    const int kp = p.kp, L = p.L;
-    const int scap = finalize_surv_cap(L, kp);
-    u64* surv = reinterpret_cast<u64*>(smem_raw);           // [finalize_surv_slots(L, kp)]
-    u64* heads = surv + finalize_surv_slots(L, kp);         // [L]
-    double* sc = reinterpret_cast<double*>(heads + L);      // [kp]
-    long long* id = reinterpret_cast<long long*>(sc + kp);  // [kp]
-    u64* ok = reinterpret_cast<u64*>(id + kp);              // [kp] integer rank keys of the scores
-    double* qs = reinterpret_cast<double*>(ok + kp);        // [d] the query widened once
-    __shared__ int s_nsurv, s_nvalid;
-    __shared__ unsigned s_maxerr;  // ordered-uint of the largest (canonical - scan) score difference among the candidates
-    __shared__ u64 s_T0;
-    const int qi = blockIdx.x;
-    const u64* lists = p.lists + (size_t)qi * L * kp;
-    const float* q = p.xq + (size_t)qi * p.d;
-
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the merge kernel of the exchange path may get resident
-    // launched with programmatic stream serialisation: this prologue (the query does not come from the scan) overlaps the
-    // tail of the scan kernel; everything below the wait sees the scan's lists
-    for (int i = t; i < p.d; i += nt) qs[i] = (double)q[i];
-    if (t == 0) {
-        s_nsurv = 0;
-        s_nvalid = 0;
-        s_maxerr = 0u;
-        s_T0 = 0ull;
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int l = t; l < L; l += nt) heads[l] = lists[(size_t)l * kp];
-    __syncthreads();
-    // 1. T0 = kp-th largest head (non-empty keys are unique, so exactly one head has rank kp-1).
-    //    `nper` adjacent lanes share one head and split the comparison range.
-    //    Only every `hs`-th head is ranked (about 2.3*kp of them): still a valid bound (kp keys are >= it),
-    //    a quarter of the comparisons, a few more survivors.  If the survivors then overflow their
-    //    buffer the bound is recomputed from every head (then at most kp lists qualify: <= kp*kp keys).
-    int hs = 1;
-    while ((L / (hs * 2)) * 10 >= kp * 23) hs <<= 1;
-    for (int attempt = 0; attempt < 2; attempt++) {
-    if (attempt == 1) {
-        if (s_nsurv <= scap || hs == 1) break;  // uniform: read after the barrier below
-        __syncthreads();
-        if (t == 0) {
-            s_nsurv = 0;
-            s_T0 = 0ull;
-        }
-        hs = 1;
-        __syncthreads();
-    }
-    const int Ls = (L + hs - 1) / hs;  // sampled heads: lists 0, hs, 2hs, ...
-    if (Ls >= kp) {
-        int nper = 1;
-        while (nper < 32 && nper * 2 * Ls <= nt) nper <<= 1;
-        const int part = t & (nper - 1);
-        for (int l0 = 0; l0 < Ls; l0 += nt / nper) {
-            const int l = l0 + t / nper;
-            const u64 h = l < Ls ? heads[l * hs] : 0ull;
-            int r = 0;
-            if (h != 0ull)
-                for (int j = part; j < Ls; j += nper) r += heads[j * hs] > h ? 1 : 0;
-            for (int off = 1; off < nper; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
-            if (h != 0ull && part == 0 && r == kp - 1) s_T0 = h;
-        }
-    }
-    __syncthreads();
-    const u64 T0 = s_T0;  // 0: fewer than kp non-empty lists -> every key survives (at most kp*kp)
-    // 2. survivors: one warp per qualifying list, prefix >= T0
-    for (int l = warp; l < L; l += nwarps) {
-        const u64 h = heads[l];
-        if (h == 0ull || h < T0) continue;  // warp-uniform
-        const u64* src = lists + (size_t)l * kp;
-        u64 keys[4];  // kp <= 128: all loads of the list issued before the first use
-#pragma unroll
-        for (int u = 0; u < 4; u++) keys[u] = (32 * u + lane < kp) ? src[32 * u + lane] : 0ull;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const bool keep = keys[u] != 0ull && keys[u] >= T0;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m == 0u) break;
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(&s_nsurv, __popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            const int dst = pos + __popc(m & ((1u << lane) - 1u));
-            if (keep && dst < scap) surv[dst] = keys[u];
-        }
-    }
-    __syncthreads();
-    }  // attempt
-    // 3. the kp best survivors in descending order -> A[0..kp)
-    const int nsurv = s_nsurv;
-    const u64* A;
-    if (nsurv <= nt) {
-        // usual case (a few more than kp survivors): rank by counting, one barrier instead of a sort
-        u64* top = surv + nsurv;  // kp slots behind the survivors
-        for (int i = t; i < kp; i += nt) top[i] = 0ull;
-        __syncthreads();
-        if (t < nsurv) {
-            const u64 key = surv[t];
-            int r = 0;
-            for (int j = 0; j < nsurv; j++) r += surv[j] > key ? 1 : 0;
-            if (r < kp) top[r] = key;
-        }
-        __syncthreads();
-        A = top;
+    const long long qi = blockIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel of the chain may get resident
+    const u64* lists;
+    if (p.pred_slot != nullptr) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int slot = p.pred_slot[qi];
+        if (slot < 0 || slot >= p.guard_cap) return;  // certified by the first phase (the usual case): CTA-uniform
+        lists = p.lists + (size_t)slot * p.L * p.kp;
+        if (threadIdx.x == 0 && p.reruns) atomicAdd(p.reruns, 1ull);
+        finalize_prologue(p, qi, smem_raw);
     } else {
-        int pow2 = kp;
-        while (pow2 < nsurv) pow2 <<= 1;
-        for (int i = nsurv + t; i < pow2; i += nt) surv[i] = 0ull;
-        for (int size = 2; size <= pow2; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                __syncthreads();
-                for (int e = t; e < (pow2 >> 1); e += nt) {
-                    int i = ((e / stride) * (stride << 1)) + (e % stride);
-                    cmpx_desc(surv, i, i + stride, (i & size) == 0);
-                }
-            }
-        }
-        __syncthreads();
-        A = surv;  // A[0..kp) = the kp best scan keys
+        finalize_prologue(p, qi, smem_raw);
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (threadIdx.x == 0 && p.guard_slot) p.guard_slot[qi] = -1;  // overwritten below (barriers in between) if uncertified
+        lists = p.lists + (size_t)qi * p.L * p.kp;
     }
-
-    // 4. canonical re-score of the kp candidates (a warp takes two candidates at a time)
-    for (int c = 2 * warp; c < kp; c += 2 * nwarps) {
-        const u64 ka = A[c], kb = (c + 1 < kp) ? A[c + 1] : 0ull;
-        const long long rowa = ka ? (long long)key_row(ka) : -1, rowb = kb ? (long long)key_row(kb) : -1;
-        double sa = -DBL_MAX, sb = -DBL_MAX;
-        if (p.xb_is_bf16) {
-            const __nv_bfloat16* xb16 = reinterpret_cast<const __nv_bfloat16*>(p.xb);
-            if (ka) sa = canon32_dot_bf16(xb16 + (size_t)rowa * p.d, qs, p.d, lane);
-            if (kb) sb = canon32_dot_bf16(xb16 + (size_t)rowb * p.d, qs, p.d, lane);
-        } else {
-            const float* xb32 = reinterpret_cast<const float*>(p.xb);
-            canon32_dot_pair(ka ? xb32 + (size_t)rowa * p.d : nullptr, kb ? xb32 + (size_t)rowb * p.d : nullptr, qs, p.d, lane,
-                             sa, sb);
-        }
-        if (lane == 0) {
-            sc[c] = sa;
-            id[c] = rowa;
-            ok[c] = rowa >= 0 ? score_rank_key(sa) : 0ull;
-            if (c + 1 < kp) {
-                sc[c + 1] = sb;
-                id[c + 1] = rowb;
-                ok[c + 1] = rowb >= 0 ? score_rank_key(sb) : 0ull;
-            }
-        }
-    }
-    __syncthreads();
-    // how far the scan under-estimated its own candidates at most (tf32 truncates towards zero: a bias of ~1e-3 relative;
-    // bf16 and fp32 scans scatter around zero): rows that were NOT retained are assumed to be under-estimated no worse
-    if (t < kp && id[t] >= 0 && p.margins) atomicMax(&s_maxerr, score_to_ordered((float)(sc[t] - (double)key_score(A[t]))));
-    __syncthreads();
-
-    // 5. rank by counting under (score desc, id asc); ids are unique so ranks are a permutation
-    if (t < kp && id[t] >= 0) {
-        atomicAdd(&s_nvalid, 1);
-        const double st = sc[t];
-        const long long it = id[t];
-        const u64 ot = ok[t];
-        int rank = 0;
-        // empty slots have id -1 and key 0: a real candidate never loses to them (its key is > 0 or, for
-        // -DBL_MAX-like scores, ties are broken by id < -1 being impossible) -> mask by id >= 0 arithmetically
-        for (int j = 0; j < kp; j++) rank += better_i(ok[j], id[j], ot, it) & (int)(id[j] >= 0);
-        if (rank < p.k) {
-            if (p.D) {
-                p.D[(size_t)qi * p.k + rank] = (float)st;
-                p.I[(size_t)qi * p.k + rank] = it + p.id_base;
-            } else if (p.x.world > 0) {
-                const size_t e = (size_t)(p.x.q_off + qi) * p.k + rank;
-                for (int g = 0; g < p.x.world; g++) {  // the same 16 bytes to every rank's slot for this shard
-                    unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
-                    reinterpret_cast<double*>(slot)[e] = st;
-                    reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = it + p.id_base;
-                }
-            } else {
-                p.P_scores[(size_t)qi * p.k + rank] = st;
-                p.P_ids[(size_t)qi * p.k + rank] = it + p.id_base;
-            }
-            if (rank == p.k - 1 && p.margins) {
-                // all kp slots taken -> rows outside the list scored <= the worst retained scan score, i.e. their
-                // canonical score is at most that plus the scan's under-estimate (taken as the largest one observed)
-                const float worst = key_score(A[kp - 1]);
-                const float under = fmaxf(ordered_to_score(s_maxerr), 0.f);
-                p.margins[qi] = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) - under : INFINITY;
-            }
-        }
-    }
-    __syncthreads();
-    // 6. padding (-FLT_MAX,-1) / (-DBL_MAX,-1) for the slots no candidate ranked into
-    const int nvalid = s_nvalid;
-    for (int r = nvalid + t; r < p.k; r += nt) {
-        if (p.D) {
-            p.D[(size_t)qi * p.k + r] = -FLT_MAX;
-            p.I[(size_t)qi * p.k + r] = -1;
-        } else if (p.x.world > 0) {
-            const size_t e = (size_t)(p.x.q_off + qi) * p.k + r;
-            for (int g = 0; g < p.x.world; g++) {
-                unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
-                reinterpret_cast<double*>(slot)[e] = -DBL_MAX;
-                reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = -1;
-            }
-        } else {
-            p.P_scores[(size_t)qi * p.k + r] = -DBL_MAX;
-            p.P_ids[(size_t)qi * p.k + r] = -1;
-        }
-    }
-    if (t == 0 && p.margins && nvalid < p.k) p.margins[qi] = INFINITY;
-    if (p.x.world > 0) {
-        // publish: when the last query's CTA has written its part, raise this shard's flag on every rank
-        __syncthreads();
-        if (t == 0) {
-            __threadfence_system();
-            const unsigned prev = atomicAdd(p.x.done, 1u);
-            if (prev == (unsigned)p.x.nq_total - 1u) {  // counts across the launches of one search
-                *p.x.done = 0u;
-                __threadfence_system();
-                for (int g = 0; g < p.x.world; g++) {
-                    unsigned long long* flags = reinterpret_cast<unsigned long long*>(p.x.peer[g] + 2 * (size_t)p.x.world * p.x.slot_bytes);
-                    st_release_sys_u64(flags + (size_t)p.x.parity * p.x.world + p.x.rank, p.x.seq);
-                }
-            }
-        }
-    }
+    finalize_query(p, qi, lists, smem_raw);
 }
 
 // =============================================================================================
@@ -386,35 +79,75 @@ __global__ void __launch_bounds__(256) publish_partials_kernel(Exchange x, long 
 }
 
 // =============================================================================================
+// poison: this rank could not run search `x.seq` (an allocation or a launch failed after its peers may already be waiting):
+// raise its flag with bit 63 set on every rank, so that the peers' merges report the failure instead of waiting ~10 s or
+// returning a result that silently misses this shard.  grid = 1, block = 32.
+// =============================================================================================
+__global__ void publish_poison_kernel(Exchange x) {
+    if (threadIdx.x == 0) {
+        *x.done = 0u;
+        __threadfence_system();
+        for (int g = 0; g < x.world; g++) {
+            unsigned long long* flags = reinterpret_cast<unsigned long long*>(x.peer[g] + 2 * (size_t)x.world * x.slot_bytes);
+            st_release_sys_u64(flags + (size_t)x.parity * x.world + x.rank, x.seq | kExchangePoison);
+        }
+    }
+}
+
+// =============================================================================================
 // merge after the peer-store exchange: wait until every shard's flag for this search has arrived in the
 // LOCAL gather buffer, then rank the world*k partials of each query.  grid = nq, block = 256.
 // Every rank runs this kernel on its own GPU; the flags are written by the other GPUs' finalize kernels.
+// A rank that never arrives (~10 s watchdog) or that reported failure (poisoned flag) makes the whole result
+// padding (-FLT_MAX, -1) and sets *x.status (host-mapped): stale slots are never merged.
 // =============================================================================================
 __global__ void __launch_bounds__(256) merge_exchange_kernel(Exchange x, long long nq, int k, float* __restrict__ D,
-                                                            long long* __restrict__ I, int* __restrict__ timed_out) {
+                                                            long long* __restrict__ I) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = x.world * k;
     double* sc = reinterpret_cast<double*>(smem_raw);
     long long* id = reinterpret_cast<long long*>(sc + m);
     u64* ok = reinterpret_cast<u64*>(id + m);
-    __shared__ int s_nvalid;
+    __shared__ int s_nvalid, s_fail;
     const long long qi = blockIdx.x;
     unsigned char* local = x.peer[x.rank];
+    if (threadIdx.x == 0) {
+        s_nvalid = 0;
+        s_fail = 0;
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");  // launched programmatically behind this rank's finalise / publish kernel
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __syncthreads();
     if (threadIdx.x < x.world) {
         const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(local + 2 * (size_t)x.world * x.slot_bytes) +
                                          (size_t)x.parity * x.world + threadIdx.x;
         const long long t0 = clock64();
-        while (ld_acquire_sys_u64(flag) < x.seq) {
-            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a rank never arrived; report instead of hanging
-                *timed_out = 1;
+        for (;;) {
+            const unsigned long long v = ld_acquire_sys_u64(flag);
+            const unsigned long long vs = v & ~kExchangePoison;
+            if (vs >= x.seq) {
+                if (vs == x.seq && (v & kExchangePoison)) atomicMax(&s_fail, 2);  // that rank failed this search
+                break;
+            }
+            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a rank never arrived
+                atomicMax(&s_fail, 1);
                 break;
             }
             __nanosleep(64);
         }
     }
-    if (threadIdx.x == 0) s_nvalid = 0;
     __syncthreads();
+    if (s_fail) {  // CTA-uniform: report, never merge what sits in the slots (it is an older search's partial)
+        for (int r = threadIdx.x; r < k; r += blockDim.x) {
+            D[(size_t)qi * k + r] = -FLT_MAX;
+            I[(size_t)qi * k + r] = -1;
+        }
+        if (threadIdx.x == 0 && x.status) {
+            *reinterpret_cast<volatile int*>(x.status) = s_fail;
+            __threadfence_system();
+        }
+        return;
+    }
     for (int e = threadIdx.x; e < m; e += blockDim.x) {
         const int part = e / k, r = e % k;
         const unsigned char* slot = local + ((size_t)x.parity * x.world + part) * x.slot_bytes;
@@ -600,6 +333,40 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 }
 
 // =============================================================================================
+// largest row norm of rows [0, n): one warp per row, fp32 sum of squares (an upper-bound estimate is all the
+// certification needs: it is inflated by 1e-6 relative on use), atomicMax on the float bits (norms are >= 0, so the
+// unsigned order of the bits is the numeric order).  NaN rows are ignored.
+// =============================================================================================
+__global__ void __launch_bounds__(256) row_norm_max_kernel(const float* __restrict__ rows, long long n, int d, float* __restrict__ max_norm) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float best = 0.f;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        const float* x = rows + (size_t)r * d;
+        float s = 0.f;
+        if ((d & 3) == 0) {
+            for (int i = lane; i < (d >> 2); i += 32) {
+                const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(x) + i);
+                s = fmaf(v.x, v.x, s);
+                s = fmaf(v.y, v.y, s);
+                s = fmaf(v.z, v.z, s);
+                s = fmaf(v.w, v.w, s);
+            }
+        } else {
+            for (int i = lane; i < d; i += 32) s = fmaf(x[i], x[i], s);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (s == s) best = fmaxf(best, s);
+    }
+    if (lane == 0 && best > 0.f) atomicMax(reinterpret_cast<unsigned*>(max_norm), __float_as_uint(sqrtf(best) * 1.000001f));
+}
+
+__global__ void fill_i32_kernel(int* __restrict__ p, long long count, int value) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) p[i] = value;
+}
+
+// =============================================================================================
 // synthetic rows: value(seed, global row, col) -- same integer function as oracle/orc_synth_fill
 // =============================================================================================
 __device__ __forceinline__ u64 splitmix64(u64 z) {
@@ -653,6 +420,19 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(float* __restrict__ out
 static int clamp_grid(long long want, int cap) {
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
+}
+
+// opt a kernel in to more than 48 KB of dynamic shared memory once per (kernel, device): `table` is a per-kernel array
+template <typename K>
+static cudaError_t ensure_smem_optin(K kern, size_t smem, size_t (&table)[16]) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& have = table[dev & 15];
+    if (smem <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) have = smem;
+    return e;
 }
 
 cudaError_t launch_l2_normalize(void* x, long long n, int d, int dtype, int sm_count, cudaStream_t st) {
@@ -738,45 +518,53 @@ cudaError_t launch_publish_partials(const Exchange& x, long long nq, int k, cons
     return cudaSuccess;
 }
 
-cudaError_t launch_merge_exchange(const Exchange& x, long long nq, int k, float* D, long long* I, int* timed_out,
-                                  cudaStream_t st) {
+cudaError_t launch_publish_poison(const Exchange& x, cudaStream_t st) {
+    publish_poison_kernel<<<1, 32, 0, st>>>(x);
+    EVS_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_merge_exchange(const Exchange& x, long long nq, int k, float* D, long long* I, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     size_t smem = (size_t)x.world * k * 24;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t le = launch_pdl(merge_exchange_kernel, dim3((unsigned)nq), dim3(256), smem, st, x, nq, k, D, I, timed_out);
+    cudaError_t le = launch_pdl(merge_exchange_kernel, dim3((unsigned)nq), dim3(256), smem, st, x, nq, k, D, I);
     g_kernel_launches.fetch_add(1);
     if (le != cudaSuccess) return le;
     return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
-    if (a.nq <= 0) return cudaSuccess;
-    FinalizeParams p;
-    p.lists = reinterpret_cast<const u64*>(a.lists);
-    p.L = a.L;
-    p.kp = a.kp;
-    p.xb = a.xb;
-    p.xb_is_bf16 = a.xb_is_bf16;
-    p.xq = a.xq;
-    p.d = a.d;
-    p.k = a.k;
-    p.id_base = a.id_base;
-    p.D = a.D;
-    p.I = reinterpret_cast<long long*>(a.I);
-    p.P_scores = a.P_scores;
-    p.P_ids = reinterpret_cast<long long*>(a.P_ids);
-    p.margins = a.margins;
-    p.x = a.x;
-    size_t smem = (size_t)finalize_surv_slots(a.L, a.kp) * 8 + (size_t)a.L * 8 + (size_t)a.kp * 24 + (size_t)a.d * 8 + 16;
+cudaError_t launch_row_norm_max(const float* rows, long long n, int d, float* max_norm, int sm_count, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    int grid = clamp_grid((n * 32 + 255) / 256, sm_count * 8);
+    row_norm_max_kernel<<<grid, 256, 0, st>>>(rows, n, d, max_norm);
+    EVS_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_fill_i32(int* p, long long count, int value, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    int grid = clamp_grid((count + 255) / 256, 64);
+    fill_i32_kernel<<<grid, 256, 0, st>>>(p, count, value);
+    EVS_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+size_t finalize_smem_bytes_host(int L, int kp, int d) { return finalize_smem_bytes(L, kp, d) + 16; }
+
+cudaError_t launch_finalize(const FinalizeParams& p, long long nq, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    size_t smem = finalize_smem_bytes_host(p.L, p.kp, p.d);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t optin[16] = {};
+    cudaError_t oe = ensure_smem_optin(finalize_kernel, smem, optin);
+    if (oe != cudaSuccess) return oe;
     // small batches: 1024 threads shorten the single CTA's critical path; large batches: 256 threads
     // so that several queries share an SM
-    const int threads = a.nq <= 296 ? 1024 : 256;
-    cudaError_t le = launch_pdl(finalize_kernel, dim3((unsigned)a.nq), dim3((unsigned)threads), smem, st, p);
+    const int threads = nq <= 296 ? 1024 : 256;
+    cudaError_t le = launch_pdl(finalize_kernel, dim3((unsigned)nq), dim3((unsigned)threads), smem, st, p);
     g_kernel_launches.fetch_add(1);
     if (le != cudaSuccess) return le;
     return cudaGetLastError();
@@ -798,18 +586,44 @@ static cudaError_t launch_scan_t(const ScanArgs& a, ScanPlan* plan, cudaStream_t
     p.tile_rows = plan->tile_rows;
     p.stages = plan->stages;
     p.lists_stride_q = plan->grid * a.kp;
+    p.ticket = nullptr;
+    p.next_chunk = nullptr;
+    p.chunk_groups = 1;
+    p.qmap = a.qmap;
+    p.nactive = a.nactive;
+    p.qcap = a.qcap;
+    p.cta_clock = nullptr;
     if (plan->variant == 2) {
+        if (a.fuse || a.nactive) return cudaErrorInvalidValue;  // the ring variant neither fuses nor re-runs
         auto kern = scan_ring_kernel<T, NQ, NV>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
         kern<<<plan->grid, plan->threads, plan->smem_bytes, st>>>(p);
-    } else {
-        auto kern = scan_direct_kernel<T, NQ, NV>;
-        if (plan->smem_bytes > 48 * 1024)
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-        kern<<<plan->grid, plan->threads, plan->smem_bytes, st>>>(p);
+        EVS_LAUNCH_CHECK();
+        return cudaSuccess;
     }
-    EVS_LAUNCH_CHECK();
-    return cudaSuccess;
+    FinalizeParams f;
+    size_t smem = plan->smem_bytes;
+    if (a.fuse != nullptr && NQ == 1 && a.ticket != nullptr) {
+        f = *a.fuse;
+        p.ticket = a.ticket;
+        p.cta_clock = a.cta_clock;
+        if (a.next_chunk != nullptr && a.chunk_groups > 0) {
+            p.next_chunk = a.next_chunk;
+            p.chunk_groups = a.chunk_groups;
+        }
+        const size_t fs = finalize_smem_bytes_host(f.L, f.kp, f.d);
+        if (fs > smem) smem = fs;
+    } else if (a.fuse != nullptr) {
+        return cudaErrorInvalidValue;
+    }
+    auto kern = scan_direct_kernel<T, NQ, NV>;
+    static size_t optin[16] = {};  // per instantiation
+    cudaError_t oe = ensure_smem_optin(kern, smem, optin);
+    if (oe != cudaSuccess) return oe;
+    cudaError_t le = launch_pdl(kern, dim3((unsigned)plan->grid), dim3((unsigned)plan->threads), smem, st, p, f);
+    g_kernel_launches.fetch_add(1);
+    if (le != cudaSuccess) return le;
+    return cudaGetLastError();
 }
 
 template <typename T, int NV>
@@ -835,6 +649,14 @@ static cudaError_t launch_scan_generic(const ScanArgs& a, ScanPlan* plan, cudaSt
     p.tile_rows = 0;
     p.stages = 0;
     p.lists_stride_q = plan->grid * a.kp;
+    p.ticket = nullptr;
+    p.next_chunk = nullptr;
+    p.chunk_groups = 1;
+    p.qmap = nullptr;
+    p.nactive = nullptr;
+    p.qcap = 0;
+    p.cta_clock = nullptr;
+    if (a.fuse || a.nactive) return cudaErrorInvalidValue;
     for (int qi = 0; qi < a.nq_pass; qi++) {
         p.q0 = a.q0 + qi;
         scan_generic_kernel<T><<<plan->grid, plan->threads, plan->smem_bytes, st>>>(p);

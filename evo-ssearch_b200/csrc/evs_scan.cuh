@@ -17,6 +17,7 @@
 //                 read conflict-free 16-byte vectors from the ring.
 #pragma once
 #include "evs_common.cuh"
+#include "evs_finalize.cuh"
 
 namespace evs {
 
@@ -31,6 +32,14 @@ struct ScanParams {
     int kp;            // candidates kept per list (64 or 128)
     int tile_rows;     // ring variant: rows per stage
     int stages;        // ring variant: ring depth
+    // direct variant only:
+    unsigned* ticket;  // non-null (single-query launches): the LAST CTA to retire finalises the query in this launch
+    unsigned* next_chunk;  // non-null: rows are dealt dynamically, `chunk_groups` row groups per grab (evens out the tail)
+    int chunk_groups;
+    const int* qmap;   // guard re-run: the launch walks the queries qmap[0 .. *nactive), NQ at a time, and writes the
+    const int* nactive;  //   lists of queue slot s at lists[s * lists_stride_q ...]; null = queries q0 .. q0+NQ-1
+    int qcap;          // capacity of qmap
+    unsigned long long* cta_clock;  // diagnostics (option "scan_clock"): [gridDim.x][2] globaltimer at CTA start / end of its scan loop
 };
 
 template <typename T> struct Elem;
@@ -46,11 +55,17 @@ struct QueryRegs {
     static constexpr int VEC = Elem<T>::VEC;
     float v[NQ][NV][VEC];
     __device__ __forceinline__ void load(const float* __restrict__ xq, int q0, int d, int lane) {
+        int qidx[NQ];
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) qidx[qi] = q0 + qi;
+        load_idx(xq, qidx, d, lane);
+    }
+    __device__ __forceinline__ void load_idx(const float* __restrict__ xq, const int (&qidx)[NQ], int d, int lane) {
 #pragma unroll
         for (int qi = 0; qi < NQ; qi++)
 #pragma unroll
             for (int j = 0; j < NV; j++) {
-                const float4* src = reinterpret_cast<const float4*>(xq + (size_t)(q0 + qi) * d + VEC * (lane + 32 * j));
+                const float4* src = reinterpret_cast<const float4*>(xq + (size_t)qidx[qi] * d + VEC * (lane + 32 * j));
 #pragma unroll
                 for (int h = 0; h < VEC / 4; h++) {
                     float4 t = src[h];
@@ -153,7 +168,9 @@ struct WarpSelect {
 // CTA epilogue shared by both variants: tree-merge the consumer warps' sorted lists, write one list
 // per query.  `nwarps_sel` warps own buffers sel_base + warp * NQ * capw.  Called by ALL threads.
 template <int NQ>
-__device__ __forceinline__ void cta_merge_and_store(u64* sel_base, int nwarps_sel, int kp, const ScanParams& p) {
+__device__ __forceinline__ void cta_merge_and_store(u64* sel_base, int nwarps_sel, int kp, const ScanParams& p, int slot0 = -1,
+                                                    int nvalid = NQ) {
+    if (slot0 < 0) slot0 = p.q0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int capw = 2 * kp;
     for (int step = 1; step < nwarps_sel; step <<= 1) {
@@ -166,20 +183,41 @@ __device__ __forceinline__ void cta_merge_and_store(u64* sel_base, int nwarps_se
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NQ * kp; i += blockDim.x) {
+    for (int i = threadIdx.x; i < nvalid * kp; i += blockDim.x) {
         int qi = i / kp, r = i % kp;
-        p.lists[(size_t)(p.q0 + qi) * p.lists_stride_q + (size_t)blockIdx.x * kp + r] = sel_base[(size_t)qi * capw + r];
+        p.lists[(size_t)(slot0 + qi) * p.lists_stride_q + (size_t)blockIdx.x * kp + r] = sel_base[(size_t)qi * capw + r];
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Variant 1: direct loads.  grid = ctas, block = 32 * warps.  Warps walk groups of RPG rows.
-// dynamic smem: warps * NQ * 2*kp * 8 bytes.
+// dynamic smem: max(warps * NQ * 2*kp * 8, finalize_smem_bytes when the finalise is fused) bytes.
+//
+// Launched with programmatic stream serialisation: the CTAs may become resident while the preceding kernel of the
+// stream drains and wait (griddepcontrol.wait) until it has completed before they read anything.
+//   * rows are dealt statically (group g to warp g mod W) or -- next_chunk != null -- dynamically: a warp's first chunk
+//     is static, every further one comes from a global counter, fetched one chunk ahead so that the atomic's latency
+//     hides behind the loads.  A static deal leaves the SMs that the memory system serves more slowly still streaming
+//     while the others idle; at 1.25M rows per GPU (the metric at N = 8) that tail is several percent of the scan.
+//   * ticket != null (single-query searches): the last CTA to retire finalises the query right here (merge of the
+//     per-CTA lists, canonical fp64 re-score, ranking, output / peer stores): no second launch on the latency path.
+//   * nactive != null: guard re-run of the queries queued by the first finalise (evs_finalize.cuh), NQ at a time.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NQ, int NV>
-__global__ void __launch_bounds__(256) scan_direct_kernel(ScanParams p) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // finalize_kernel may get resident while this grid streams
+struct ScanOcc {  // CTAs per SM the register allocation is held to (the measured optimum: 2 for fp32 rows, 4 for bf16 rows)
+    static constexpr int value = NQ == 1 ? ((sizeof(T) == 2 && NV <= 2) ? 4 : 2) : 1;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <typename T, int NQ, int NV>
+__global__ void __launch_bounds__(256, ScanOcc<T, NQ, NV>::value) scan_direct_kernel(ScanParams p, FinalizeParams f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_last;
     typedef typename RawVec<T>::type raw_t;
     // rows in flight per warp, sized so that query registers + raw vectors stay near 100 registers
     constexpr int QREGS = NQ * NV * Elem<T>::VEC;
@@ -189,42 +227,105 @@ __global__ void __launch_bounds__(256) scan_direct_kernel(ScanParams p) {
     const int nwarps = blockDim.x >> 5;
     u64* sel_base = reinterpret_cast<u64*>(smem_raw);
 
-    QueryRegs<T, NQ, NV> q;
-    q.load(p.xq, p.q0, p.d, lane);
-    WarpSelect<NQ> sel;
-    sel.init(sel_base + (size_t)warp * NQ * 2 * p.kp, p.kp);
+    // The queries (and, for a guard re-run, the queue) may be the output of the preceding kernel of the stream, which may
+    // itself have triggered this launch early: nothing is read before it has completed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // only now may the next kernel of the stream (finalise / merge / the next search's scan) become resident: its own
+    // prologue may read the queries too, and they are complete from here on
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    unsigned long long t_start = 0;
+    if (p.cta_clock && threadIdx.x == 0) t_start = globaltimer_ns();
 
+    int nact = NQ;
+    if (p.nactive) {
+        nact = *p.nactive;
+        if (nact > p.qcap) nact = p.qcap;
+        if (nact <= 0) return;  // nothing queued (the usual case): grid-uniform
+    }
     const long long total_warps = (long long)gridDim.x * nwarps;
     const long long gw = (long long)blockIdx.x * nwarps + warp;
     const long long ngroups = (p.n + RPG - 1) / RPG;
     const size_t row_vecs = (size_t)p.d / Elem<T>::VEC;  // 16-byte vectors per row
     const raw_t* base = reinterpret_cast<const raw_t*>(p.xb);
 
-    for (long long g = gw; g < ngroups; g += total_warps) {
-        const long long r0 = g * RPG;
-        raw_t raw[RPG][NV];
+    for (int g0 = 0; g0 < nact; g0 += NQ) {
+        int qidx[NQ];
 #pragma unroll
-        for (int r = 0; r < RPG; r++) {
-            long long row = r0 + r < p.n ? r0 + r : p.n - 1;  // clamp: tail rows are re-read, not offered
-            const raw_t* src = base + (size_t)row * row_vecs + lane;
-#pragma unroll
-            for (int j = 0; j < NV; j++) {
-                if constexpr (sizeof(T) == 4) raw[r][j] = ldg_stream_f4(src + 32 * j);
-                else raw[r][j] = ldg_stream_u4(src + 32 * j);
-            }
+        for (int qi = 0; qi < NQ; qi++) {
+            int sl = g0 + qi < nact ? g0 + qi : nact - 1;  // a short last group repeats its last query (lists not stored)
+            qidx[qi] = p.nactive ? p.qmap[sl] : p.q0 + sl;
         }
+        QueryRegs<T, NQ, NV> q;
+        q.load_idx(p.xq, qidx, p.d, lane);
+        WarpSelect<NQ> sel;
+        sel.init(sel_base + (size_t)warp * NQ * 2 * p.kp, p.kp);
+
+        auto do_group = [&](long long g) {
+            const long long r0 = g * RPG;
+            raw_t raw[RPG][NV];
 #pragma unroll
-        for (int r = 0; r < RPG; r++) {
-            float s[NQ];
-            row_scores<T, NQ, NV>(raw[r], q, s);
-            if (r0 + r < p.n) {
+            for (int r = 0; r < RPG; r++) {
+                long long row = r0 + r < p.n ? r0 + r : p.n - 1;  // clamp: tail rows are re-read, not offered
+                const raw_t* src = base + (size_t)row * row_vecs + lane;
 #pragma unroll
-                for (int qi = 0; qi < NQ; qi++) sel.offer(qi, s[qi], (uint32_t)(r0 + r), lane);
+                for (int j = 0; j < NV; j++) {
+                    if constexpr (sizeof(T) == 4) raw[r][j] = ldg_stream_f4(src + 32 * j);
+                    else raw[r][j] = ldg_stream_u4(src + 32 * j);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPG; r++) {
+                float s[NQ];
+                row_scores<T, NQ, NV>(raw[r], q, s);
+                if (r0 + r < p.n) {
+#pragma unroll
+                    for (int qi = 0; qi < NQ; qi++) sel.offer(qi, s[qi], (uint32_t)(r0 + r), lane);
+                }
+            }
+        };
+
+        if (p.next_chunk != nullptr && p.nactive == nullptr) {
+            const long long C = p.chunk_groups;
+            const long long nchunks = (ngroups + C - 1) / C;
+            long long chunk = gw;
+            while (chunk < nchunks) {
+                long long next = 0;
+                if (lane == 0) next = total_warps + (long long)atomicAdd(p.next_chunk, 1u);  // consumed after this chunk
+                const long long gend = (chunk + 1) * C < ngroups ? (chunk + 1) * C : ngroups;
+                for (long long g = chunk * C; g < gend; g++) do_group(g);
+                chunk = __shfl_sync(0xffffffffu, next, 0);
+            }
+        } else {
+            for (long long g = gw; g < ngroups; g += total_warps) do_group(g);
+        }
+        if (p.cta_clock && threadIdx.x == 0 && g0 == 0) {
+            p.cta_clock[2 * blockIdx.x] = t_start;
+            p.cta_clock[2 * blockIdx.x + 1] = globaltimer_ns();
+        }
+        sel.finish(lane);
+        const int left = nact - g0;
+        cta_merge_and_store<NQ>(sel_base, nwarps, p.kp, p, p.nactive ? g0 : p.q0, left < NQ ? left : NQ);
+        __syncthreads();  // the selection buffers are reused by the next group / by the finalise below
+    }
+
+    if constexpr (NQ == 1) {
+        if (p.ticket != nullptr) {
+            __threadfence();  // this thread's list stores are visible device-wide before the CTA takes its ticket
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+            __syncthreads();
+            if (s_last) {  // CTA-uniform: every other CTA's list is complete
+                if (threadIdx.x == 0) {
+                    *p.ticket = 0u;  // ready for the next search (its CTAs take tickets only after this kernel has completed)
+                    if (p.next_chunk) *p.next_chunk = 0u;
+                }
+                __threadfence();
+                finalize_prologue(f, p.q0, smem_raw);
+                __syncthreads();
+                finalize_query(f, p.q0, f.lists + (size_t)p.q0 * f.L * f.kp, smem_raw);
             }
         }
     }
-    sel.finish(lane);
-    cta_merge_and_store<NQ>(sel_base, nwarps, p.kp, p);
 }
 
 // ---------------------------------------------------------------------------------------------

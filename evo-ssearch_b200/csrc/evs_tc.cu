@@ -75,28 +75,40 @@ struct TcParams {
 //   then barriers, TMEM base address, tau0[npad], cnt[npad]
 // ---------------------------------------------------------------------------------------------
 
-template <typename T, int MODE>
-__global__ void __launch_bounds__(256, 1)
+// X3 (fp32 rows only): 3xTF32 split scan.  tf32 keeps 11 significant bits of each operand, a ~1e-3 relative error that
+// is far above fp32 noise; here every operand is split  v = hi + lo  (hi = the tf32 part, lo = v - hi exactly) and each
+// K step issues  D += A_hi*Q_hi + A_hi*Q_lo + A_lo*Q_hi : the dropped terms are ~2^-20 relative, i.e. fp32-class scores
+// from the tensor cores.  The queries are split once (tc_split_queries, both halves resident in shared memory); the
+// database tile is split on the fly by four converter warps (8-11): hi overwrites the staged tile in place, lo goes to
+// a two-deep side ring; the MMA issuer waits for the converted stage instead of the raw one.  The tensor pipe is a few
+// percent busy at these batch sizes, so the three MMAs per K step hide under the HBM stream.
+template <typename T, int MODE, bool X3>
+__global__ void __launch_bounds__(X3 ? 384 : 256, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant__ CUtensorMap tm_q, TcParams p) {
+    static_assert(!X3 || sizeof(T) == 4, "the 3xTF32 split applies to fp32 rows");
     constexpr bool TF32 = sizeof(T) == 4;
+    constexpr int QH = X3 ? 2 : 1;             // resident query copies (hi, lo)
+    constexpr int LO_STAGES = 2;
     constexpr int EC = 128 / sizeof(T);        // elements per 128-byte chunk
     constexpr int KSTEP_BYTES = 32;            // one MMA consumes 32 bytes of K per row (16 bf16 / 8 tf32)
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages, NK = p.nk, NP = p.npad;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a dependent launched programmatically may get resident early
 
     // 128B-swizzled operands need 1024-byte aligned bases: align by hand (1 KiB of slack is allocated)
-    unsigned char* q_smem = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-    unsigned char* ring = q_smem + (size_t)NK * NP * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * TC_STAGE_BYTES);
+    unsigned char* q_smem = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);  // X3: [hi: NK chunks][lo: NK chunks]
+    unsigned char* ring = q_smem + (size_t)QH * NK * NP * 128;
+    unsigned char* lo_ring = ring + (size_t)S * TC_STAGE_BYTES;  // X3: LO_STAGES x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? (size_t)LO_STAGES * TC_STAGE_BYTES : 0));
     uint64_t* q_full = bars;             // 1: the query block has landed
     uint64_t* q_empty = bars + 1;        // 1: every MMA that reads the query block has completed
     uint64_t* full = bars + 2;           // S
     uint64_t* empty = full + S;          // S
     uint64_t* acc_full = empty + S;      // 2
     uint64_t* acc_empty = acc_full + 2;  // 2
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* lo_full = acc_empty + 2;   // LO_STAGES (X3): the converter warps have split the stage
+    uint64_t* lo_empty = lo_full + LO_STAGES;  // LO_STAGES (X3): the MMAs that read the lo tile have completed
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(lo_empty + LO_STAGES);
     float* tau_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_smem + 4) + 15) & ~(uintptr_t)15);  // float4 reads
     int* cnt_s = reinterpret_cast<int*>(tau_s + NP);
     u64* heap_s = reinterpret_cast<u64*>(cnt_s + NP);  // MODE_HEAP: [NP][TC_HEAP_SLOTS]; 16-byte aligned (NP % 16 == 0)
@@ -117,6 +129,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], 4);
         }
+        for (int a = 0; a < LO_STAGES; a++) {
+            mbar_init(&lo_full[a], 4);  // one arrival per converter warp
+            mbar_init(&lo_empty[a], 1);
+        }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_base_smem, tmem_cols);
@@ -127,6 +143,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
     // everything above (barriers, TMEM, descriptor prefetch) may have overlapped the preceding kernel of the stream
     // (programmatic launch); the queries (bf16 copy), thresholds and counters below are that kernel's output
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // dependents (tau0 / finalise, whose prologues read the queries) may get resident from here on: the kernel that
+    // produced the queries -- possibly one that triggered THIS launch early -- has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // tiles of this CTA (the same list for every query block)
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -138,8 +157,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
             uint32_t phase = 0;
             for (int b = 0; b < p.nblocks; b++) {
                 if (b > 0) mbar_wait(q_empty, (uint32_t)((b - 1) & 1));  // previous block's MMAs are done with it
-                mbar_arrive_expect_tx(q_full, (uint32_t)(NK * NP * 128));
+                mbar_arrive_expect_tx(q_full, (uint32_t)(QH * NK * NP * 128));
                 for (int c = 0; c < NK; c++) tma_load_2d(q_smem + (size_t)c * NP * 128, &tm_q, c * EC, b * NP, q_full);
+                if (X3)  // the lo halves of the queries are rows [nqp, 2 nqp) of the split query matrix
+                    for (int c = 0; c < NK; c++)
+                        tma_load_2d(q_smem + (size_t)(NK + c) * NP * 128, &tm_q, c * EC, p.nqp + b * NP, q_full);
                 for (long long i = 0; i < my_tiles; i++) {
                     const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
                     const int row0 = (int)(tile * TC_BM);
@@ -160,8 +182,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         // ================= MMA issuer =================
         if (lane == 0 && my_tiles > 0) {
             const uint32_t idesc = make_idesc(TF32, TC_BM, NP);
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, lo_stage = 0;
+            uint32_t phase = 0, lo_phase = 0;
             long long it = 0;  // tile counter across blocks: accumulator buffer and its phase
             for (int b = 0; b < p.nblocks; b++) {
                 mbar_wait(q_full, (uint32_t)(b & 1));
@@ -174,13 +196,32 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                     const uint32_t d_tmem = tmem_base + (uint32_t)(a * NP);
                     for (int c = 0; c < NK; c++) {
                         mbar_wait(&full[stage], phase);
+                        if (X3) mbar_wait(&lo_full[lo_stage], lo_phase);  // hi written in place, lo in the side ring
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(ring + (size_t)stage * TC_STAGE_BYTES);
                         const uint32_t b_addr = smem_u32(q_smem + (size_t)c * NP * 128);
+                        if (X3) {
+                            const uint32_t al_addr = smem_u32(lo_ring + (size_t)lo_stage * TC_STAGE_BYTES);
+                            const uint32_t bl_addr = smem_u32(q_smem + (size_t)(NK + c) * NP * 128);
 #pragma unroll
-                        for (int k = 0; k < 128 / KSTEP_BYTES; k++) {
-                            umma<TF32>(d_tmem, smem_desc_sw128(a_addr + k * KSTEP_BYTES),
-                                       smem_desc_sw128(b_addr + k * KSTEP_BYTES), idesc, (uint32_t)((c | k) != 0));
+                            for (int k = 0; k < 128 / KSTEP_BYTES; k++) {
+                                const uint64_t ah = smem_desc_sw128(a_addr + k * KSTEP_BYTES), al = smem_desc_sw128(al_addr + k * KSTEP_BYTES);
+                                const uint64_t bh = smem_desc_sw128(b_addr + k * KSTEP_BYTES), bl = smem_desc_sw128(bl_addr + k * KSTEP_BYTES);
+                                umma<TF32>(d_tmem, ah, bh, idesc, (uint32_t)((c | k) != 0));
+                                umma<TF32>(d_tmem, ah, bl, idesc, 1u);
+                                umma<TF32>(d_tmem, al, bh, idesc, 1u);
+                            }
+                            umma_commit(&lo_empty[lo_stage]);
+                            if (++lo_stage == LO_STAGES) {
+                                lo_stage = 0;
+                                lo_phase ^= 1u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 128 / KSTEP_BYTES; k++) {
+                                umma<TF32>(d_tmem, smem_desc_sw128(a_addr + k * KSTEP_BYTES),
+                                           smem_desc_sw128(b_addr + k * KSTEP_BYTES), idesc, (uint32_t)((c | k) != 0));
+                            }
                         }
                         umma_commit(&empty[stage]);  // frees the ring slot when these MMAs have read it
                         if (++stage == S) {
@@ -194,7 +235,49 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (X3 && warp >= 8) {
+        // ================= converter warps (3xTF32): split every staged tile into hi (in place) + lo =================
+        const int ct = threadIdx.x - 256;  // 0..127
+        int stage = 0, lo_stage = 0;
+        uint32_t phase = 0, lo_phase = 0;
+        for (int b = 0; b < p.nblocks; b++) {
+            for (long long i = 0; i < my_tiles; i++) {
+                for (int c = 0; c < NK; c++) {
+                    mbar_wait(&full[stage], phase);                 // the raw fp32 tile has landed (TMA)
+                    mbar_wait(&lo_empty[lo_stage], lo_phase ^ 1u);  // the MMAs that read this lo slot are done
+                    float4* raw4 = reinterpret_cast<float4*>(ring + (size_t)stage * TC_STAGE_BYTES);
+                    float4* lo4 = reinterpret_cast<float4*>(lo_ring + (size_t)lo_stage * TC_STAGE_BYTES);
+#pragma unroll
+                    for (int u = 0; u < TC_STAGE_BYTES / 16 / 128; u++) {  // 8 vectors per thread, element-wise: any swizzle
+                        const float4 v = raw4[ct + 128 * u];
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                        // exact: the low 13 mantissa bits.  (inf - inf would turn an infinite element into NaN: keep hi only)
+                        l.x = fabsf(v.x) <= FLT_MAX ? v.x - h.x : 0.f;
+                        l.y = fabsf(v.y) <= FLT_MAX ? v.y - h.y : 0.f;
+                        l.z = fabsf(v.z) <= FLT_MAX ? v.z - h.z : 0.f;
+                        l.w = fabsf(v.w) <= FLT_MAX ? v.w - h.w : 0.f;
+                        raw4[ct + 128 * u] = h;  // explicit: the result does not depend on how the MMA narrows fp32 bits
+                        lo4[ct + 128 * u] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> the MMA's async-proxy reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&lo_full[lo_stage]);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                    if (++lo_stage == LO_STAGES) {
+                        lo_stage = 0;
+                        lo_phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
         // ================= epilogue =================
         const int e = warp & 3;                 // TMEM lane quarter
         const int row_in_tile = e * 32 + lane;  // this thread's row
@@ -622,6 +705,29 @@ __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ src, __nv_bflo
         dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// 3xTF32: split the queries once.  dst = fp32 [2 * nqp][d]: rows [0, nqp) hold hi = tf32(q) (round to nearest), rows
+// [nqp, 2 nqp) hold lo = q - hi (exact); rows beyond nq are zero (the TMA box of a partial block reads them).
+__global__ void tc_split_queries_kernel(const float* __restrict__ xq, float* __restrict__ dst, int nq, int nqp, int d) {
+    const long long total = (long long)nqp * d;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / d);
+        float hi = 0.f, lo = 0.f;
+        if (row < nq) {
+            const float v = xq[i];
+            if (fabsf(v) <= FLT_MAX) {
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                hi = __uint_as_float(u & 0xFFFFE000u);
+                lo = v - hi;
+            } else {
+                hi = v;
+            }
+        }
+        dst[i] = hi;
+        dst[total + i] = lo;
+    }
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
@@ -654,6 +760,36 @@ cudaError_t tc_make_tmap(CUtensorMap* map, const void* base, long long rows, int
                      gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// the same through the handle's descriptor cache (encoding two descriptors costs a few microseconds per search)
+static cudaError_t tc_get_tmap(TmapCache* cache, CUtensorMap* map, const void* base, long long rows, int d, bool is_f32, int box_rows) {
+    if (cache) {
+        for (auto& e : cache->e)
+            if (e.base == base && e.rows == rows && e.d == d && e.f32 == (int)is_f32 && e.box == box_rows) {
+                *map = e.map;
+                return cudaSuccess;
+            }
+    }
+    cudaError_t err = tc_make_tmap(map, base, rows, d, is_f32, box_rows);
+    if (err != cudaSuccess || !cache) return err;
+    TmapCache::Entry& e = cache->e[cache->next];
+    cache->next = (cache->next + 1) % 16;
+    e.base = base;
+    e.rows = rows;
+    e.d = d;
+    e.f32 = (int)is_f32;
+    e.box = box_rows;
+    e.map = *map;
+    return cudaSuccess;
+}
+
+static cudaError_t tc_split_queries(const float* xq, void* dst, int nq, int nqp, int d, cudaStream_t st) {
+    const long long total = (long long)nqp * d;
+    long long blocks = (total + 255) / 256;
+    tc_split_queries_kernel<<<(int)(blocks < 1024 ? blocks : 1024), 256, 0, st>>>(xq, reinterpret_cast<float*>(dst), nq, nqp, d);
+    g_kernel_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 cudaError_t tc_queries_to_bf16(const float* xq, void* dst, long long count, cudaStream_t st) {
@@ -699,31 +835,40 @@ int tc_max_queries(int d, int is_bf16) {
     return n < 16 ? 0 : n;
 }
 
-static size_t tc_smem_bytes(int nk, int npad, int stages);
+static size_t tc_smem_bytes(int nk, int npad, int stages) {
+    return (size_t)nk * npad * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4 + 4) * 8 + 32 + (size_t)npad * 8 + 1024;
+}
 static size_t tc_smem_bytes_heap(int nk, int npad, int stages) {
     return tc_smem_bytes(nk, npad, stages) + (size_t)npad * TC_HEAP_SLOTS * 8;
 }
-static size_t tc_smem_bytes(int nk, int npad, int stages) {
-    return (size_t)nk * npad * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4) * 8 + 32 + (size_t)npad * 8 + 1024;
+// 3xTF32: two resident query copies (hi, lo) and the two-deep lo ring of the converter warps
+static size_t tc_smem_bytes_x3(int nk, int npad, int stages, bool heap) {
+    return tc_smem_bytes(nk, npad, stages) + (size_t)nk * npad * 128 + 2 * (size_t)TC_STAGE_BYTES +
+           (heap ? (size_t)npad * TC_HEAP_SLOTS * 8 : 0);
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool X3>
 static cudaError_t launch_tc_mode(const CUtensorMap& tdb, const CUtensorMap& tq, const TcParams& p, int grid, size_t smem,
                                   cudaStream_t st) {
-    auto kern = tc_scan_kernel<T, MODE>;
+    auto kern = tc_scan_kernel<T, MODE, X3>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = launch_pdl(kern, dim3((unsigned)grid), dim3(256), smem, st, tdb, tq, p);
+    e = launch_pdl(kern, dim3((unsigned)grid), dim3(X3 ? 384 : 256), smem, st, tdb, tq, p);
     g_kernel_launches.fetch_add(1);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
 template <int MODE>
-static cudaError_t launch_tc(bool is_bf16, const CUtensorMap& tdb, const CUtensorMap& tq, const TcParams& p, int grid,
+static cudaError_t launch_tc(bool is_bf16, int x3, const CUtensorMap& tdb, const CUtensorMap& tq, const TcParams& p, int grid,
                              size_t smem, cudaStream_t st) {
-    return is_bf16 ? launch_tc_mode<__nv_bfloat16, MODE>(tdb, tq, p, grid, smem, st)
-                   : launch_tc_mode<float, MODE>(tdb, tq, p, grid, smem, st);
+    if (x3) {
+        if (is_bf16) return cudaErrorInvalidValue;
+        if constexpr (MODE == MODE_SELECT) return cudaErrorInvalidValue;  // the 3xTF32 scan serves the on-chip-heap batches only
+        else return launch_tc_mode<float, MODE, true>(tdb, tq, p, grid, smem, st);
+    }
+    return is_bf16 ? launch_tc_mode<__nv_bfloat16, MODE, false>(tdb, tq, p, grid, smem, st)
+                   : launch_tc_mode<float, MODE, false>(tdb, tq, p, grid, smem, st);
 }
 
 int g_tc_max_stages = 8;  // option "tc_stages"
@@ -737,7 +882,18 @@ int g_tc_sample_rows = 0;  // option "tc_sample_rows": rows the threshold pre-pa
 // 32768 for up to 256 queries, where the pre-pass itself is the larger cost, 16384 for up to 32 (the on-chip heaps take
 // the extra admissions in their stride); measured: scripts/tc_tune.py and the round-1 sample sweep in DESIGN.md
 int tc_sample_rows(int nq) { return g_tc_sample_rows > 0 ? g_tc_sample_rows : (nq <= 32 ? 16384 : (nq <= 256 ? 32768 : 65536)); }
-static size_t tc_smem_bytes_plain(const TcPlan& pl) { return tc_smem_bytes(pl.nk, pl.npad, pl.stages); }
+static size_t tc_smem_bytes_plain(const TcPlan& pl) {
+    return pl.x3 ? tc_smem_bytes_x3(pl.nk, pl.npad, pl.stages, false) : tc_smem_bytes(pl.nk, pl.npad, pl.stages);
+}
+
+// queries one 3xTF32 pass serves: both query halves, the on-chip heaps, the lo ring and >= 4 raw stages must fit
+int tc_x3_max_queries(int d) {
+    if (((size_t)d * 4) % 128) return 0;
+    const int nk = (int)((size_t)d * 4 / 128);
+    for (int npad = 32; npad >= 16; npad -= 16)
+        if (tc_smem_bytes_x3(nk, npad, 4, true) <= 227 * 1024) return npad;
+    return 0;
+}
 static int pick_stages(int nk, int npad) {
     int stages = g_tc_max_stages;
     while (stages > 2 && tc_smem_bytes(nk, npad, stages) > 226 * 1024) stages--;
@@ -748,10 +904,12 @@ size_t tc_workspace_bytes(const TcPlan& pl) { return pl.off_end; }
 
 // Plan a launch set for `nq` queries over `n` rows: blocks of npad <= tc_max_queries queries are walked
 // inside one persistent launch, so the fixed costs (launches, prologues, pre-pass) are paid once.
-cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, TcPlan* pl) {
+cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_count, int x3, TcPlan* pl) {
     const size_t esz = is_bf16 ? 2 : 4;
-    const int nbmax = tc_max_queries(d, is_bf16);
+    const int nbmax = x3 ? tc_x3_max_queries(d) : tc_max_queries(d, is_bf16);
     if (nbmax == 0 || nq <= 0) return cudaErrorInvalidValue;
+    if (x3 && (is_bf16 || kp != 64 || nq > nbmax)) return cudaErrorInvalidValue;  // one on-chip-heap block of fp32 rows
+    pl->x3 = x3 ? 1 : 0;
     pl->npad = nq >= nbmax ? nbmax : (nq + 15) / 16 * 16;
     pl->nblocks = (nq + pl->npad - 1) / pl->npad;
     pl->nqp = pl->nblocks * pl->npad;
@@ -761,7 +919,14 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     if (pl->smem > 227 * 1024) return cudaErrorInvalidValue;
     // small batches with k' = 64: running top-k' per (CTA, query) in shared memory, if >= 4 ring stages still fit
     pl->heap = 0;
-    if (kp == 64 && nq <= g_tc_heap_max_nq && pl->nblocks == 1) {
+    if (x3) {
+        int stages = g_tc_max_stages;
+        while (stages > 2 && tc_smem_bytes_x3(pl->nk, pl->npad, stages, true) > 226 * 1024) stages--;
+        if (stages < 4 || tc_smem_bytes_x3(pl->nk, pl->npad, stages, true) > 227 * 1024) return cudaErrorInvalidValue;
+        pl->heap = nq <= g_tc_heap_pure_max_nq ? 1 : 2;
+        pl->stages = stages;
+        pl->smem = tc_smem_bytes_x3(pl->nk, pl->npad, stages, true);
+    } else if (kp == 64 && nq <= g_tc_heap_max_nq && pl->nblocks == 1) {
         int stages = g_tc_max_stages;
         while (stages > 2 && tc_smem_bytes_heap(pl->nk, pl->npad, stages) > 226 * 1024) stages--;
         if (stages >= 4 && tc_smem_bytes_heap(pl->nk, pl->npad, stages) <= 227 * 1024) {
@@ -805,22 +970,28 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     pl->off_spill_cnt = take((size_t)pl->nqp * 4);
     pl->off_cand = take((size_t)pl->grid * pl->nqp * pl->cap * 8);
     pl->off_spill = take((size_t)pl->nqp * TC_SPILL_CAP * 8);
-    pl->off_qbf16 = take((size_t)pl->nqp * d * 2);
+    pl->off_qbf16 = take(x3 ? (size_t)2 * pl->nqp * d * 4 : (size_t)pl->nqp * d * 2);  // bf16 copy of the queries / their hi + lo split
     pl->off_end = off;
     return cudaSuccess;
 }
 
 static cudaError_t tc_prepare(const TcArgs& a, const TcPlan& pl, unsigned char* ws, CUtensorMap* tdb, CUtensorMap* tq,
                               TcParams* p, cudaStream_t st) {
-    cudaError_t e = tc_make_tmap(tdb, a.xb, a.n, a.d, !a.is_bf16, TC_BM);
+    cudaError_t e = tc_get_tmap(a.tmaps, tdb, a.xb, a.n, a.d, !a.is_bf16, TC_BM);
     if (e != cudaSuccess) return e;
     const void* qsrc = a.xq;
+    long long qrows = a.nq;
     if (a.is_bf16) {
         void* qb = ws + pl.off_qbf16;
         if ((e = tc_queries_to_bf16(a.xq, qb, (long long)a.nq * a.d, st)) != cudaSuccess) return e;
         qsrc = qb;
+    } else if (pl.x3) {
+        void* qs = ws + pl.off_qbf16;
+        if ((e = tc_split_queries(a.xq, qs, a.nq, pl.nqp, a.d, st)) != cudaSuccess) return e;
+        qsrc = qs;
+        qrows = 2LL * pl.nqp;
     }
-    if ((e = tc_make_tmap(tq, qsrc, a.nq, a.d, !a.is_bf16, pl.npad)) != cudaSuccess) return e;
+    if ((e = tc_get_tmap(a.tmaps, tq, qsrc, qrows, a.d, !a.is_bf16, pl.npad)) != cudaSuccess) return e;
     *p = TcParams{};
     p->n = a.n;
     p->d = a.d;
@@ -854,7 +1025,7 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
         if (pl.heap == 2) {  // pre-pass thresholds first: the running top-k' then hardly ever needs a sort
             p.ntiles = pl.pre_tiles;
             p.tile_stride = pl.pre_stride;
-            if ((e = launch_tc<MODE_MAX>(a.is_bf16, tdb, tq, p, pl.pre_grid, tc_smem_bytes_plain(pl), st)) != cudaSuccess) return e;
+            if ((e = launch_tc<MODE_MAX>(a.is_bf16, pl.x3, tdb, tq, p, pl.pre_grid, tc_smem_bytes_plain(pl), st)) != cudaSuccess) return e;
             if ((e = tc_launch_tau0(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp, reinterpret_cast<float*>(ws + pl.off_tau0), st)) !=
                 cudaSuccess)
                 return e;
@@ -864,14 +1035,14 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
         p.ntiles = pl.ntiles;
         p.tile_stride = 1;
         p.lists = reinterpret_cast<u64*>(a.lists);
-        if ((e = launch_tc<MODE_HEAP>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st)) != cudaSuccess) return e;
+        if ((e = launch_tc<MODE_HEAP>(a.is_bf16, pl.x3, tdb, tq, p, pl.grid, pl.smem, st)) != cudaSuccess) return e;
         if (a.overflow_out) e = cudaMemsetAsync(a.overflow_out, 0, (size_t)a.nq * 4, st);  // this mode cannot overflow
         return e;
     }
     // 1. threshold pre-pass over the sampled tiles
     p.ntiles = pl.pre_tiles;
     p.tile_stride = pl.pre_stride;
-    e = launch_tc<MODE_MAX>(a.is_bf16, tdb, tq, p, pl.pre_grid, pl.smem, st);
+    e = launch_tc<MODE_MAX>(a.is_bf16, 0, tdb, tq, p, pl.pre_grid, pl.smem, st);
     if (e != cudaSuccess) return e;
     if ((e = tc_launch_tau0(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp, reinterpret_cast<float*>(ws + pl.off_tau0), st)) !=
         cudaSuccess)
@@ -881,7 +1052,7 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     // 2. selection pass over every tile, all query blocks in one persistent launch
     p.ntiles = pl.ntiles;
     p.tile_stride = 1;
-    e = launch_tc<MODE_SELECT>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st);
+    e = launch_tc<MODE_SELECT>(a.is_bf16, 0, tdb, tq, p, pl.grid, pl.smem, st);
     if (e != cudaSuccess) return e;
     // 3. per query: gather + sort -> top-kp list
     if ((e = tc_launch_gather(p.cand, p.counts, pl.grid, pl.nqp, pl.cap, pl.kp, pl.cap_total, a.nq,
@@ -901,7 +1072,7 @@ cudaError_t tc_dump_scores(const TcArgs& a, const TcPlan& pl, unsigned char* ws,
     p.ntiles = pl.ntiles;
     p.tile_stride = 1;
     p.dump = out;
-    return launch_tc<MODE_DUMP>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st);
+    return launch_tc<MODE_DUMP>(a.is_bf16, pl.x3, tdb, tq, p, pl.grid, tc_smem_bytes_plain(pl), st);
 }
 
 }  // namespace evs

@@ -109,6 +109,38 @@ class IndexFlatIP:
     def reserve(self, nrows: int) -> None:
         check(lib().evs_index_reserve(self._h, int(nrows)))
 
+    def set_storage(self, storage: str) -> None:
+        """Switch the scan precision in place: ``"bf16"`` derives the bf16 scan copy of an fp32-storage index (large
+        query batches then run the bf16 tensor-core scan instead of tf32 from the fp32 rows), ``"f32"`` drops it."""
+        if storage not in _STORAGE:
+            raise ValueError(f"storage must be one of {sorted(_STORAGE)}")
+        check(lib().evs_index_set_storage(self._h, _STORAGE[storage]))
+        self.storage = "bf16" if _STORAGE[storage] == EVS_STORE_BF16_F32 else "f32"
+
+    @property
+    def max_row_norm(self) -> float:
+        """Largest row norm (it scales the certification bound of the searches)."""
+        v = ctypes.c_float(0)
+        check(lib().evs_index_max_row_norm(self._h, ctypes.byref(v)))
+        return v.value
+
+    def guard_stats(self):
+        """``(reruns, uncertified)``: queries finalised again from the device-side exact re-run, and results that
+        stayed uncertified, since the index was created."""
+        r, u = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(lib().evs_index_guard_stats(self._h, ctypes.byref(r), ctypes.byref(u)))
+        return r.value, u.value
+
+    def scan_clocks(self) -> np.ndarray:
+        """Diagnostics (option ``scan_clock``): ``uint64[nctas, 2]`` start / end-of-scan-loop times (ns) of the CTAs of
+        the last fused single-query scan."""
+        n = ctypes.c_int64(0)
+        check(lib().evs_index_scan_clocks(self._h, None, 0, ctypes.byref(n)))
+        out = np.zeros((n.value, 2), np.uint64)
+        if n.value:
+            check(lib().evs_index_scan_clocks(self._h, out.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n)))
+        return out
+
     def reset(self) -> None:
         """faiss ``Index.reset``: drop all vectors."""
         base = self.id_base
@@ -339,6 +371,25 @@ def read_index(fname: str, *, device: Optional[int] = None, storage: Optional[st
     h = ctypes.c_void_p()
     check(lib().evs_index_read(os.fsencode(str(fname)), dev, _STORAGE[storage], ctypes.byref(h)))
     return IndexFlatIP(0, _handle=h)
+
+
+def read_index_rows(fname: str, row_lo: int, row_hi: int, *, device: Optional[int] = None,
+                    storage: Optional[str] = None) -> Tuple[IndexFlatIP, int]:
+    """The shard loader: rows ``[row_lo, row_hi)`` of an ``index.faiss`` (only that byte range of the file is read)
+    -> ``(index with id_base = row_lo, rows in the file)``."""
+    storage = default_storage() if storage is None else storage
+    dev = default_device() if device is None else int(device)
+    h, n = ctypes.c_void_p(), ctypes.c_int64(0)
+    check(lib().evs_index_read_rows(os.fsencode(str(fname)), dev, _STORAGE[storage], int(row_lo), int(row_hi),
+                                    ctypes.byref(h), ctypes.byref(n)))
+    return IndexFlatIP(0, _handle=h), n.value
+
+
+def index_file_info(fname: str) -> Tuple[int, int]:
+    """``(d, ntotal)`` from the 45-byte header of an ``index.faiss``."""
+    d, n = ctypes.c_int(0), ctypes.c_int64(0)
+    check(lib().evs_index_file_info(os.fsencode(str(fname)), ctypes.byref(d), ctypes.byref(n)))
+    return d.value, n.value
 
 
 def normalize_L2(x) -> None:

@@ -23,16 +23,66 @@ from __future__ import annotations
 import os
 import pickle
 import threading
+from collections import OrderedDict
 from pathlib import Path
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, List, Optional, Tuple
 
 import numpy as np
 
+from . import _lib
 from .config import config
 from .index import IndexFlatIP, read_index, write_index
 
+# Resident indexes: an LRU keyed by the resolved path of index.faiss, bounded by a byte budget (HBM held by the cached
+# indexes on this GPU; EVS_CACHE_BYTES, default 120 GiB of the B200's 180 GB).  An entry is valid while the
+# (mtime_ns, size) of index.faiss, paths.pkl AND metadata.pkl are unchanged -- save_index writes the three files one
+# after the other, so index.faiss alone would pin "new vectors, old paths" if another process loaded in between.
 _cache_lock = threading.Lock()
-_cache: Dict[str, Tuple[Tuple[int, int], IndexFlatIP, list, Optional[list]]] = {}
+_cache: "OrderedDict[str, tuple]" = OrderedDict()  # key -> (signature, index, paths, metadata, bytes)
+CACHE_BUDGET_BYTES = int(os.environ.get("EVS_CACHE_BYTES", str(120 << 30)))
+load_stats = {"loads": 0, "bytes": 0, "seconds": 0.0, "evictions": 0}  # what the loader did (bench / tests)
+
+
+def _index_bytes(index) -> int:
+    per_row = index.d * (6 if getattr(index, "storage", "f32") == "bf16" else 4)
+    local = getattr(index, "local", index)  # a sharded index holds only its block on this GPU
+    return int(local.ntotal) * per_row
+
+
+def _signature(index_path: Path):
+    sig = []
+    for name in ("index.faiss", "paths.pkl", "metadata.pkl"):
+        try:
+            st = os.stat(index_path / name)
+            sig.append((st.st_mtime_ns, st.st_size))
+        except OSError:
+            sig.append(None)
+    return tuple(sig)
+
+
+def _cache_put(key: str, sig, index, paths, meta) -> None:
+    nbytes = _index_bytes(index)
+    with _cache_lock:
+        _cache.pop(key, None)
+        _cache[key] = (sig, index, paths, meta, nbytes)
+        total = sum(e[4] for e in _cache.values())
+        while total > CACHE_BUDGET_BYTES and len(_cache) > 1:  # least recently used first; never the entry just added
+            _, old = _cache.popitem(last=False)
+            total -= old[4]
+            load_stats["evictions"] += 1
+
+
+def _want_sharded(sharded: Optional[bool]) -> bool:
+    if sharded is not None:
+        return bool(sharded)
+    env = os.environ.get("EVS_SHARDED", "auto").lower()
+    if env in ("0", "no", "false"):
+        return False
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:  # noqa: BLE001
+        return False
 
 
 def _walk(folder_path: Path) -> List[Path]:
@@ -203,16 +253,34 @@ def save_index(index: IndexFlatIP, image_paths, image_metadata, folder_path) -> 
         pickle.dump(image_metadata, f)
     # the index just written is the resident one for this folder
     key = str((index_path / "index.faiss").resolve())
-    st = os.stat(key)
-    with _cache_lock:
-        _cache[key] = ((st.st_mtime_ns, st.st_size), index, list(image_paths), image_metadata)
+    _cache_put(key, _signature(index_path), index, list(image_paths), image_metadata)
 
 
-def load_index(folder_path):
+def _read_resident(fname: Path, sharded: bool):
+    """index.faiss -> HBM.  Sharded: every rank reads only its own row block of the file (collective call)."""
+    import time
+    t0 = time.perf_counter()
+    if sharded:
+        from .sharded import ShardedIndexFlatIP
+        index = ShardedIndexFlatIP.read_index(str(fname), exchange=os.environ.get("EVS_EXCHANGE", "peer"))
+    else:
+        index = read_index(str(fname))
+    load_stats["loads"] += 1
+    load_stats["bytes"] += int(getattr(index, "local", index).ntotal) * index.d * 4
+    load_stats["seconds"] += time.perf_counter() - t0
+    return index
+
+
+def load_index(folder_path, sharded: Optional[bool] = None):
     """``(index, image_paths, image_metadata)`` or ``(None, None, None)`` (oldapp.py:108-135).
 
     Any failure -- missing folder, corrupt file, unreadable pickle -- yields the ``None`` triple, as the
-    reference's blanket ``except`` does.  A hit in the resident cache costs one ``stat``.
+    reference's blanket ``except`` does.  A hit in the resident cache costs three ``stat`` calls.
+
+    ``sharded`` (default: automatic -- true when ``torch.distributed`` is initialised with more than one rank; env
+    ``EVS_SHARDED=0`` forces it off): the index is row-sharded over the ranks' GPUs, each rank streaming only its own
+    block of ``index.faiss`` into its HBM, and the returned object is a ``ShardedIndexFlatIP`` with the same
+    ``search(x, k)``.  Then ``load_index`` and the searches are collective calls.
     """
     index_path = Path(folder_path) / config.INDEX_FOLDER_NAME
     if not index_path.exists():
@@ -220,13 +288,22 @@ def load_index(folder_path):
     try:
         fname = index_path / "index.faiss"
         key = str(fname.resolve())
-        st = os.stat(key)
-        sig = (st.st_mtime_ns, st.st_size)
+        sig = _signature(index_path)
+        if sig[0] is None:
+            return None, None, None
+        use_shards = _want_sharded(sharded)
         with _cache_lock:
             hit = _cache.get(key)
-        if hit is not None and hit[0] == sig:
-            return hit[1], hit[2], hit[3]
-        index = read_index(str(fname))
+            if hit is not None and hit[0] == sig and hasattr(hit[1], "local") == use_shards:
+                _cache.move_to_end(key)
+                return hit[1], hit[2], hit[3]
+        try:
+            index = _read_resident(fname, use_shards)
+        except _lib.EvsError as e:
+            if e.code != _lib.EVS_ENOMEM:
+                raise
+            evict_index()  # HBM is full of other folders' indexes: drop them and try once more
+            index = _read_resident(fname, use_shards)
         with open(index_path / "paths.pkl", "rb") as f:
             image_paths = pickle.load(f)
         image_metadata = None
@@ -237,8 +314,7 @@ def load_index(folder_path):
                     image_metadata = pickle.load(f)
             except Exception:  # noqa: BLE001 - backwards compatible, as the reference
                 image_metadata = None
-        with _cache_lock:
-            _cache[key] = (sig, index, image_paths, image_metadata)
+        _cache_put(key, sig, index, image_paths, image_metadata)
         return index, image_paths, image_metadata
     except Exception:  # noqa: BLE001 - the reference swallows everything here
         return None, None, None
@@ -248,6 +324,7 @@ def evict_index(folder_path=None) -> None:
     """Drop one folder's resident index (or all of them) and free its HBM."""
     with _cache_lock:
         if folder_path is None:
+            load_stats["evictions"] += len(_cache)
             _cache.clear()
         else:
             key = str((Path(folder_path) / config.INDEX_FOLDER_NAME / "index.faiss").resolve())

@@ -111,6 +111,42 @@ class ShardedIndexFlatIP:
             self.local.add_synthetic(hi - lo, seed, normalize)
         self._ntotal = n_total
 
+    # -- persistence ----------------------------------------------------------------------------
+    @classmethod
+    def read_index(cls, fname: str, *, group=None, device: Optional[int] = None, storage: Optional[str] = None,
+                   exchange: str = "nccl", exchange_max_nq: int = 1024, exchange_max_k: int = 48) -> "ShardedIndexFlatIP":
+        """``faiss.read_index(path)`` (oldapp.py:117) for a row-sharded index: every rank reads ONLY its own block of
+        ``index.faiss`` -- bytes ``[45 + 4*d*lo, 45 + 4*d*hi)`` -- through the library's double-buffered pinned path
+        (``evs_index_read_rows``); no rank ever holds the whole database.  Collective: call on every rank."""
+        from .index import index_file_info, read_index_rows
+        d, n = index_file_info(fname)
+        self = cls(d, group=group, device=device, storage=storage, exchange=exchange, exchange_max_nq=exchange_max_nq,
+                   exchange_max_k=exchange_max_k)
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        shard, n_file = read_index_rows(fname, lo, hi, device=self.local.device, storage=self.local.storage)
+        assert n_file == n and shard.id_base == lo and shard.ntotal == hi - lo
+        self.local = shard  # the handle created by __init__ was empty
+        self._ntotal = n
+        return self
+
+    def write_index(self, fname: str) -> None:
+        """``faiss.write_index`` for a sharded index: rank 0 writes the header, every rank its own block, in rank order
+        (one writer at a time; the file is byte-identical to the single-GPU one).  Collective."""
+        import struct
+        for r in range(self.world):
+            if r == self.rank:
+                lo, hi = shard_bounds(self._ntotal, self.world, self.rank)
+                with open(fname, "wb" if r == 0 else "r+b") as f:
+                    if r == 0:
+                        f.write(b"IxFI" + struct.pack("<iqqqBiQ", self.d, self._ntotal, 1 << 20, 1 << 20, 1, 0,
+                                                      self._ntotal * self.d))
+                    f.seek(45 + 4 * self.d * lo)
+                    step = max(1, (64 << 20) // (4 * self.d))
+                    for r0 in range(0, hi - lo, step):
+                        f.write(self.local.reconstruct_n(r0, min(step, hi - lo - r0)).tobytes())
+            if self.world > 1:
+                self._dist.barrier(group=self.group)
+
     # -- search -------------------------------------------------------------------------------
     def search_tensor(self, xq, k: int):
         """``xq``: ``(nq, d)`` tensor on this rank's device, identical on every rank -> tensors ``(D, I)``."""

@@ -41,7 +41,7 @@ extern "C" {
 #define EVS_API
 #endif
 
-#define EVS_VERSION 100 /* 0.1.0 */
+#define EVS_VERSION 200 /* 0.2.0 */
 
 /* error codes */
 #define EVS_OK 0
@@ -52,6 +52,7 @@ extern "C" {
 #define EVS_EIO (-5)      /* file could not be opened / read / written                  */
 #define EVS_EFORMAT (-6)  /* not a flat index.faiss file, or corrupt                    */
 #define EVS_ELIMIT (-7)   /* outside the limits of this build (k > EVS_MAX_K, ...)      */
+#define EVS_ETIMEOUT (-8) /* a collective (row-sharded) search lost a rank: it never arrived, or reported failure */
 
 /* element types of device buffers */
 #define EVS_F32 0
@@ -87,6 +88,11 @@ EVS_API int evs_index_storage(const evs_index* idx, int* storage);
 /* global id of local row 0 (row sharding: this handle owns rows [base, base+ntotal)) */
 EVS_API int evs_index_set_id_base(evs_index* idx, int64_t base);
 EVS_API int evs_index_id_base(const evs_index* idx, int64_t* base);
+/* switch the scan precision in place: EVS_STORE_BF16_F32 derives the bf16 scan copy of an fp32-storage index (large query
+ * batches otherwise scan in tf32 straight from the fp32 rows), EVS_STORE_F32 drops it.  Waits for searches in flight. */
+EVS_API int evs_index_set_storage(evs_index* idx, int storage);
+/* largest row norm of the index (maintained by add; it scales the certification bound of the searches) */
+EVS_API int evs_index_max_row_norm(evs_index* idx, float* max_norm);
 
 /* ---- add ------------------------------------------------------------------------------------
  * evs_index_add         <- index.add(embeddings_array)              oldapp.py:88
@@ -117,8 +123,22 @@ EVS_API int evs_index_get_rows(const evs_index* idx, int64_t row0, int64_t n, fl
  * evs_index_search_dev  same with device pointers for queries and results, enqueued on `stream`.
  *                          Batches of up to 32 queries (k <= 48) never synchronise with the host; larger
  *                          batches synchronise `stream` once, after the results are enqueued, to read the
- *                          overflow flags of the tensor-core scan (queries whose candidate buffers
- *                          overflowed -- adversarial data only -- are then re-run exactly).
+ *                          overflow flags of the tensor-core scan and the certification flags of the finalise
+ *                          (queries whose candidate buffers overflowed -- adversarial data only -- or whose
+ *                          result could not be certified are then re-run with the fp32 GEMV scan).
+ *                          A single query is ONE kernel launch: the scan's last CTA finalises.
+ *
+ * Exactness of fp32-storage indexes (every entry point: host, device, partial, exchange):
+ *   1 query        fp32 CUDA-core GEMV scan;
+ *   2..32 queries  3xTF32 tensor-core scan (each operand split hi + lo, three MMAs per K step: fp32-class scan error,
+ *                  ~1e-6 on unit vectors), on-chip top-k';
+ *   more           single-tf32 tensor-core scan (~1e-3 scan error; candidates k' = 64/128 then ranked exactly).
+ *   The finalise kernel certifies every result: margin > E, E = (error bound of that scan) * |q| * max|x|
+ *   (see evs_index_last_margins).  Uncertified queries are re-run with the fp32 GEMV scan and k' = 128 -- on the
+ *   device for batches of up to 32 queries (a queue the finalise fills, a re-run launch that returns at once when it is
+ *   empty, a predicated second finalise: no host synchronisation), by the host otherwise.  For the 3xTF32 and GEMV
+ *   scans E is an error model of the arithmetic; for the single-tf32 scans it is the statistical
+ *   option "tf32_guard_eps_e6".  bf16 storage is the recall mode (north_star: recall@k >= 0.999): not certified.
  * evs_index_search_partial_dev
  *                       row-sharded search, stage 1: this shard's k best as (fp64 canonical score,
  *                          int64 global id) pairs, sorted best first, padded with
@@ -148,7 +168,10 @@ EVS_API int evs_merge_partials_dev(int device, int nparts, int64_t nq, int64_t k
  *   evs_exchange_create   allocate the local buffer for at most max_nq queries x max_k results.
  *   evs_exchange_handle   64-byte IPC handle of the local buffer (all-gather these out of band).
  *   evs_exchange_connect  map the peers' buffers from `world` handles laid out by rank.
- *   evs_exchange_status   *timed_out = 1 if some merge waited ~10 s for a rank that never arrived.
+ *   evs_exchange_status   *timed_out = 1 if some merge waited ~10 s for a rank that never arrived, 2 if a rank reported that
+ *                         it failed a search.  In both cases that search's results are padding (-FLT_MAX, -1), never a
+ *                         merge of stale slots, and the search call that sees it returns EVS_ETIMEOUT (the host entry
+ *                         point for its own search; the asynchronous device entry point on the next call) and clears it.
  * world == 1 needs no connect.  One process per GPU (two ranks of one exchange must not share a GPU).
  */
 #define EVS_IPC_HANDLE_BYTES 64
@@ -166,8 +189,11 @@ EVS_API int evs_index_search_exchange(evs_index* idx, evs_exchange* ex, int64_t 
 /* per-query safety margin of the last search on this handle: canonical score of the k-th result minus
  * (scan score of the worst retained candidate + the largest amount by which the scan under-estimated any
  * retained candidate); +inf when every row was a candidate.  Rows that were not retained scored below that
- * candidate, so a margin larger than the spread of the scan's error certifies the result exact. */
+ * candidate, so a margin larger than the scan's error bound certifies the result exact. */
 EVS_API int evs_index_last_margins(evs_index* idx, int64_t nq, float* margins_host);
+/* counters of this handle: queries finalised again from the device-side exact re-run, and results that stayed
+ * uncertified (more than k' - k rows within the scan error of rank k: ties at fp32 resolution) */
+EVS_API int evs_index_guard_stats(evs_index* idx, int64_t* reruns, int64_t* uncertified);
 
 /* ---- persistence: <folder>/.clip_index/index.faiss -------------------------------------------
  * evs_index_write       <- faiss.write_index(index, path)           oldapp.py:98
@@ -178,6 +204,14 @@ EVS_API int evs_index_last_margins(evs_index* idx, int64_t nq, float* margins_ho
  */
 EVS_API int evs_index_write(const evs_index* idx, const char* path);
 EVS_API int evs_index_read(const char* path, int device, int storage, evs_index** out);
+/* evs_index_read_rows   the shard loader of a row-sharded index: reads ONLY rows
+ *                          [row_lo, row_hi) of the payload -- bytes [45 + 4 d row_lo, 45 + 4 d row_hi) -- through the
+ *                          same double-buffered pinned path; the new handle's id_base is row_lo.  row_hi < 0 = to the
+ *                          end.  *ntotal_file (optional) = rows in the file.
+ * evs_index_file_info   header only: d and ntotal of an index.faiss (to lay out the shards before reading). */
+EVS_API int evs_index_read_rows(const char* path, int device, int storage, int64_t row_lo, int64_t row_hi, evs_index** out,
+                        int64_t* ntotal_file);
+EVS_API int evs_index_file_info(const char* path, int* d, int64_t* ntotal);
 
 /* ---- stand-alone kernels ---------------------------------------------------------------------
  * evs_l2_normalize_dev  <- x /= x.norm(dim=-1, keepdim=True)        oldapp.py:35, :43, :51
@@ -197,9 +231,14 @@ EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev,
  *                 least this many the CTA-pair kernel; 0 = never), "tc_stages", "tc2_slice_tiles", "tc_sample_rows", "tc_heap_max_nq" (batches up to
  *                 this size keep a running top-k' per CTA in shared memory: no gather, no overflow case, no host sync),
  *                 "tc_heap_pure_max_nq" (... and up to this size also without the threshold pre-pass).
- *                 "tf32_guard_eps_e6": fp32-storage indexes scan batches in tf32; evs_index_search re-runs with the
- *                 fp32 GEMV scan every query whose safety margin (see evs_index_last_margins) is below this many
- *                 millionths (default 150, 0 = off); "exact_reruns" counts them.
+ *                 "x3" (default 1) / "x3_max_nq" (default 32): fp32 rows, batches up to that many queries use the 3xTF32
+ *                 split scan; "guard" (default 1): certify fp32-storage batch results and re-run uncertified queries;
+ *                 "tf32_guard_eps_e6": the statistical error bound, in millionths relative to |q| max|x|, that the
+ *                 single-tf32 scans (fp32 rows, batches beyond the 3xTF32 range) are certified against (default 150,
+ *                 0 = off); "exact_reruns" counts the queries the host re-ran (evs_index_guard_stats: the device's).
+ *                 "fuse_finalize" (default 1): single-query searches finalise inside the scan's last CTA;
+ *                 "scan_dynamic" / "scan_chunk_groups": dynamic row dealing of that scan; "scan_clock": record per-CTA
+ *                 scan times (evs_index_scan_clocks).
  *                 evs_get_option also reads "tc_fallbacks": queries re-run through the GEMV scan so far because a
  *                 tensor-core candidate buffer overflowed (exactness guard; should stay 0 on ordinary data).
  *                 Unknown names -> EVS_EINVAL.
@@ -216,6 +255,10 @@ EVS_API int evs_index_time_scan(evs_index* idx, int64_t nq, const float* q_dev, 
  * the stream it runs on.  This call waits for them, returns how many searches were recorded since the
  * last call and the sum of their scan durations in ms, and resets the record. */
 EVS_API int evs_index_scan_profile(evs_index* idx, int64_t* count, double* total_ms);
+/* With option "scan_clock" = 1 every fused single-query scan records, per CTA, the %globaltimer at its start and at the
+ * end of its scan loop: out_host = uint64 [nctas][2] of the last such search (ns); a call with out_host = NULL only returns
+ * the count.  Diagnostics for the tail of the streaming scan. */
+EVS_API int evs_index_scan_clocks(evs_index* idx, uint64_t* out_host, int64_t cap_ctas, int64_t* nctas);
 /* Diagnostics for the tensor-core scans (tcgen05): raw scan scores of every row against nq queries,
  * out_dev = float32 [ntotal][pitch]; the pitch (queries padded per block) is returned in *npad, and a call
  * with out_dev = NULL only returns it.  nq <= evs_index_tc_max_queries() uses the one-CTA kernel; batches of

@@ -25,13 +25,13 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/evs.h but not exported by libevs.so"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert _lib.lib().evs_version() == 100
+    assert _lib.lib().evs_version() == 200
 
 
 def test_header_constants_match_binding():
     text = open(os.path.join(ROOT, "include", "evs.h")).read()
     consts = dict(re.findall(r"#define\s+(EVS_\w+)\s+\(?(-?\d+)\)?", text))
-    for name in ("EVS_OK", "EVS_EINVAL", "EVS_ENODEV", "EVS_ECUDA", "EVS_ENOMEM", "EVS_EIO", "EVS_EFORMAT", "EVS_ELIMIT",
+    for name in ("EVS_OK", "EVS_EINVAL", "EVS_ENODEV", "EVS_ECUDA", "EVS_ENOMEM", "EVS_EIO", "EVS_EFORMAT", "EVS_ELIMIT", "EVS_ETIMEOUT",
                  "EVS_F32", "EVS_F16", "EVS_BF16", "EVS_STORE_F32", "EVS_STORE_BF16_F32", "EVS_MAX_K"):
         assert int(consts[name]) == getattr(_lib, name), name
 
