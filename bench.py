@@ -2,7 +2,7 @@
 """bench.py -- flat inner-product top-k queries/sec at 10M x 512, k = 48 (BASELINE.json `metric`).
 
     python bench.py [--gpus N --steps K --warmup W]            the CUDA path (one process per GPU)
-    python bench.py --impl reference [...]                     the CPU reference arm (oracle port)
+    python bench.py --impl reference [...]                     the CPU reference arm (oracle port, ALL rows)
 
 A "step" is ONE search call: a batch of `--nq` queries (default 1 -- what the app issues,
 oldapp.py:2005, and the case the north_star's roofline target names) scored against all rows, top-48
@@ -17,6 +17,10 @@ One JSON line is printed by rank 0:
             of (D, I) inside the timed region
   roofline  the scan kernel: algorithmic bytes per launch / its mean duration (CUDA events recorded by
             libevs around every scan launch inside the timed region) against the measured HBM peak
+  parity    answers, not speed: host API == device API on the last step's query; self-match property at full size (a query
+            equal to database row r must return r first with score ~1); at N > 1 rank 0 ALSO holds the unsharded database
+            and the sharded (D, I) must equal the single-GPU (D, I) bit for bit
+  configs   the other BASELINE configurations that fit this launch (C1 latency, C2, C3 at N = 1; C4 at N >= 2; C5 at N = 8)
   cpu_baseline  the CPU oracle (a labelled port of faiss-cpu's flat-IP scan; faiss itself is not
             installable here) timed on this box's host cores on a bounded row sample
 """
@@ -53,13 +57,15 @@ def parse_args():
     ap.add_argument("--k", type=int, default=48)
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--variant", type=int, default=0, help="scan kernel: 0 auto, 1 direct loads, 2 bulk-async ring")
-    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="row sample for the CPU baseline")
+    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="row sample for the cpu_baseline leg of the CUDA arm")
+    ap.add_argument("--ref-rows", type=int, default=0, help="rows the reference arm scans per step (0 = all of --rows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how shard partials meet -- peer-store exchange kernels over NVLink, or NCCL all-gather + merge")
-    ap.add_argument("--no-configs", action="store_true",
-                    help="skip the short BASELINE config 2 / 3 legs (1M x 512: fp32 nq 1 and 16; bf16 nq 4096) reported under 'configs'")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations reported under 'configs'")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (N > 1: the unsharded copy on rank 0)")
     ap.add_argument("--tc-min-nq", type=int, default=None, help="override the library's tensor-core threshold (experiments)")
+    ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="evs.set_option before the run (experiments)")
     ap.add_argument("--extra", action="store_true", help="also time query batches 1/4/16/64 (reported under 'extra')")
     return ap.parse_args()
 
@@ -69,54 +75,101 @@ def workload_name(a) -> str:
 
 
 # ------------------------------------------------------------------------------------------------
-# clocks during the timed region
+# clocks during the timed region: NVML polled in-process every few milliseconds (the timed region of the metric is
+# 10-60 ms long: nvidia-smi's 100 ms loop sees nothing of it); nvidia-smi is the fallback
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("hw_power_brake_slowdown", 0x80))
 
-    def __init__(self, gpu_index: int):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index: int, period_s: float = 0.004):
+        self.gpu, self.period = gpu_index, period_s
+        self.sm, self.power, self.reasons = [], [], set()
+        self.max_sm = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.source = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # torch may see a permuted / masked device list: map through CUDA_VISIBLE_DEVICES when it is a plain list
+            phys = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis and all(p.strip().isdigit() for p in vis.split(",")):
+                phys = int(vis.split(",")[self.gpu])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = f"NVML in-process, {self.period * 1e3:.0f} ms period"
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+            self.source = "nvidia-smi -lms 100 (NVML unavailable)"
+        self._thread = threading.Thread(target=self._poll_nvml if self.nvml else self._poll_smi, daemon=True)
+        self._thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001 - older binding name
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def _poll_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                     "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.source = "unavailable"
+            return
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        os.set_blocking(proc.stdout.fileno(), False)
+        buf = ""
+        while not self._stop.is_set():
+            try:
+                chunk = proc.stdout.read()
+            except Exception:  # noqa: BLE001
+                chunk = None
+            if chunk:
+                buf += chunk
+                *lines, buf = buf.split("\n")
+                for ln in lines:
+                    f = [x.strip() for x in ln.split(",")]
+                    if len(f) < 7:
+                        continue
+                    try:
+                        self.sm.append(float(f[0]))
+                        self.max_sm = max(self.max_sm or 0.0, float(f[1]))
+                        self.power.append(float(f[2]))
+                    except ValueError:
+                        continue
+                    for nm, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(nm)
+            self._stop.wait(0.05)
+        proc.terminate()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=5)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm),
+                "reasons": sorted(self.reasons), "source": self.source}
 
 
 def measured_peak_gbs():
@@ -140,30 +193,66 @@ def measured_peak_tflops():
     return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
-def config_legs(evs, torch, dev, k):
-    """BASELINE configs 2 and 3 on this GPU, device-timed (CUDA events on torch's stream around back-to-back
-    IndexFlatIP.search calls with device-resident queries).  Each leg carries its own roofline: HBM for the
+def scan_arithmetic(evs, storage: str, nq: int, rows_per_gpu: int, dim: int) -> str:
+    """Which arithmetic scans a batch (mirrors plan_path in evs_api.cu); the final ranking is always the fp64 re-score."""
+    tcmin = evs.get_option("tc_min_nq")
+    if not (tcmin > 0 and nq >= tcmin and rows_per_gpu >= 65536):
+        return ("bf16 rows, " if storage == "bf16" else "") + "fp32 CUDA-core GEMV (FFMA), fp32 accumulate"
+    if storage == "bf16":
+        return "bf16 tensor-core scan (tcgen05.mma kind::f16), fp32 accumulate"
+    if evs.get_option("x3") and nq <= evs.get_option("x3_max_nq") and dim * 4 % 128 == 0 and dim <= 768:
+        return "3xTF32 tensor-core scan (tcgen05.mma kind::tf32, hi/lo split operands, 3 MMAs per K step), fp32 accumulate"
+    return "single-tf32 tensor-core scan (tcgen05.mma kind::tf32) + statistical certification + fp32 GEMV re-run of uncertified queries"
+
+
+def device_timed(torch, dev, fn, reps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / reps
+
+
+def config_legs_single(evs, torch, dev, k):
+    """BASELINE configs 1, 2 and 3 on this GPU.  C1 (the reference's own scale) is a latency leg: microseconds per
+    query through the host API and on the device.  C2 / C3 are device-timed (CUDA events on torch's stream around
+    back-to-back IndexFlatIP.search calls with device-resident queries) and carry their own roofline: HBM for the
     streaming cases, dense bf16 tensor throughput for the 4096-query batch."""
     hbm_peak, _ = measured_peak_gbs()
     tf_burst, tf_sust, tf_src = measured_peak_tflops()
     out = []
 
-    def queries(d, nq):
+    def queries(d, nq, seed=1):
         qi = evs.IndexFlatIP(d, device=dev.index)
-        qi.add_synthetic(nq, seed=1)
-        return torch.from_numpy(qi.reconstruct_n(0, nq)).to(dev)
+        qi.add_synthetic(nq, seed=seed)
+        return qi.reconstruct_n(0, nq)
 
-    def timed(idx, xq, reps):
-        for _ in range(3):
-            idx.search(xq, k)
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            idx.search(xq, k)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1) / reps
+    # ---- C1: 10k x 512, 1 query, k = 12 (what the application really runs) ----
+    idx = evs.IndexFlatIP(512, device=dev.index)
+    idx.add_synthetic(10_000, seed=0)
+    qh = queries(512, 64)
+    qd = torch.from_numpy(qh).to(dev)
+    for i in range(20):
+        idx.search(qh[i % 64:i % 64 + 1], 12)
+    t0 = time.perf_counter()
+    reps = 2000
+    for i in range(reps):
+        idx.search(qh[i % 64:i % 64 + 1], 12)
+    host_us = (time.perf_counter() - t0) / reps * 1e6
+    l0 = evs.kernel_launches()
+    dev_us = device_timed(torch, dev, lambda: idx.search(qd[:1], 12), 500, 20) * 1e3
+    launches = (evs.kernel_launches() - l0) / 520
+    out.append({"config": "C1: 10000x512 f32, nq=1, k=12", "e2e_us_per_query": host_us, "e2e_queries_per_s": 1e6 / host_us,
+                "device_us_per_query": dev_us, "kernel_launches_per_query": launches,
+                "note": "e2e = IndexFlatIP.search(numpy) -> numpy: pinned H2D, ONE kernel (scan + fused finalise), D2H, sync; "
+                        "device = back-to-back searches of a device-resident query, CUDA events (launch-bound: includes the "
+                        "Python/ctypes call per search)"})
+    del idx
 
     for tag, rows, d, storage, nqs in (("C2", 1_000_000, 512, "f32", (1, 16)), ("C3", 1_000_000, 512, "bf16", (4096,))):
         idx = evs.IndexFlatIP(d, device=dev.index, storage=storage)
@@ -171,16 +260,25 @@ def config_legs(evs, torch, dev, k):
         idx.add_synthetic(rows, seed=0)
         esz = 2 if storage == "bf16" else 4
         for nq in nqs:
-            xq = queries(d, nq)
-            ms = timed(idx, xq, 50 if nq <= 64 else 5)
+            xq = torch.from_numpy(queries(d, nq)).to(dev)
+            ms = device_timed(torch, dev, lambda: idx.search(xq, k), 50 if nq <= 64 else 5)
             scan_ms = idx.time_scan(xq, k, iters=20 if nq <= 64 else 3)
             rec = {"config": f"{tag}: {rows}x{d} {storage}, nq={nq}, k={k}", "ms_per_search": ms, "queries_per_s": nq / ms * 1e3,
-                   "scan_ms": scan_ms}
+                   "scan_ms": scan_ms, "scan_arithmetic": scan_arithmetic(evs, storage, nq, rows, d)}
             if nq <= 64:
                 alg = rows * d * esz + nq * d * 4 + nq * k * 12
                 ach = alg / (scan_ms * 1e-3) / 1e9
                 rec["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                                    "frac_whole_search": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+                if storage == "f32" and nq > 1:
+                    # the same batch on the fp32 CUDA-core GEMV (4 queries per database pass at d = 512), for the record
+                    old = evs.get_option("tc_min_nq")
+                    evs.set_option("tc_min_nq", 0)
+                    gms = device_timed(torch, dev, lambda: idx.search(xq, k), 20)
+                    evs.set_option("tc_min_nq", old)
+                    rec["fp32_gemv_ms_per_search"] = gms
+                    rec["fp32_gemv_queries_per_s"] = nq / gms * 1e3
+                    rec["guard"] = dict(zip(("device_reruns", "uncertified"), idx.guard_stats()))
             else:
                 flops = 2.0 * nq * rows * d
                 ach = flops / (scan_ms * 1e-3) / 1e12
@@ -188,8 +286,69 @@ def config_legs(evs, torch, dev, k):
                                    "frac_of_sustained": ach / tf_sust, "peak_source": tf_src,
                                    "frac_whole_search": flops / (ms * 1e-3) / 1e12 / tf_burst,
                                    "kernel": "evs::tc2_scan_kernel (tcgen05.mma cta_group::2) incl. threshold pre-pass, tau0, gather"}
+                rec["tc_fallbacks"] = evs.get_option("tc_fallbacks")
             out.append(rec)
         del idx
+    return out
+
+
+def config_legs_sharded(evs, torch, dist, dev, world, rank, a, barrier, max_over_ranks):
+    """BASELINE configs 4 (10M x 768 over 2/4/8 GPUs, 1 and 1024 queries) and -- at 8 GPUs -- 5 (100M x 512 bf16, 1 and 16
+    queries): device-timed like the metric (CUDA events between barriers, max over ranks), with the per-GPU roofline."""
+    hbm_peak, _ = measured_peak_gbs()
+    tf_burst, _, _ = measured_peak_tflops()
+    legs = [("C4", 10_000_000, 768, "f32", 1, 40), ("C4", 10_000_000, 768, "bf16", 1024, 10)]
+    if world >= 8:
+        legs += [("C5", 100_000_000, 512, "bf16", 1, 40), ("C5", 100_000_000, 512, "bf16", 16, 20)]
+    out = []
+    cur = None
+    index = None
+    for tag, rows, d, storage, nq, steps in legs:
+        if cur != (rows, d, storage):
+            del index
+            torch.cuda.empty_cache()
+            index = evs.ShardedIndexFlatIP(d, device=dev.index, storage=storage, exchange=a.exchange,
+                                           exchange_max_nq=1024, exchange_max_k=a.k)
+            index.add_synthetic(rows, seed=0)
+            cur = (rows, d, storage)
+        lo, hi = evs.shard_bounds(rows, world, rank)
+        qi = evs.IndexFlatIP(d, device=dev.index)
+        qi.add_synthetic(8 * nq, seed=1)
+        qd = torch.from_numpy(qi.reconstruct_n(0, 8 * nq).reshape(8, nq, d)).to(dev)
+        del qi
+        for i in range(3):
+            index.search_tensor(qd[i % 8], a.k)
+        index.local.scan_profile()
+        evs.set_option("profile_scans", 1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            index.search_tensor(qd[i % 8], a.k)
+        e1.record()
+        barrier()
+        evs.set_option("profile_scans", 0)
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        n_prof, scan_sum = index.local.scan_profile()
+        scan_ms = scan_sum / max(n_prof, 1)
+        esz = 2 if storage == "bf16" else 4
+        rec = {"config": f"{tag}: {rows}x{d} {storage} over {world} GPUs, nq={nq}, k={a.k}", "ms_per_search": ms,
+               "queries_per_s": nq / ms * 1e3, "scan_ms_rank0": scan_ms, "rows_per_gpu": hi - lo,
+               "scan_arithmetic": scan_arithmetic(evs, storage, nq, hi - lo, d)}
+        if nq <= 64:
+            alg = (hi - lo) * d * esz + nq * d * 4 + nq * a.k * 12
+            ach = alg / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+            rec["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                               "frac_of_nominal_8TBs": ach / 8000.0,
+                               "frac_whole_search": alg / (ms * 1e-3) / 1e9 / hbm_peak, "per": "GPU (rank 0)"}
+        else:
+            flops = 2.0 * nq * (hi - lo) * d
+            ach = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
+            rec["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst,
+                               "frac_whole_search": flops / (ms * 1e-3) / 1e12 / tf_burst, "per": "GPU (rank 0)"}
+        out.append(rec)
+    del index
+    torch.cuda.empty_cache()
     return out
 
 
@@ -223,7 +382,7 @@ def cpu_baseline(a, seconds_budget: float = 12.0) -> dict:
     import oracle
     cores = host_threads()
     rows = min(a.rows, a.cpu_rows)
-    xb = oracle.synth_fill(rows, a.dim, seed=0)
+    xb = oracle.synth_fill(rows, a.dim, seed=0, nthreads=cores)
     xq = oracle.synth_fill(max(a.nq, 8), a.dim, seed=1)
     scale = rows / a.rows  # a flat scan is linear in rows: q/s at the full size = q/s on the sample * rows/full
 
@@ -246,7 +405,8 @@ def cpu_baseline(a, seconds_budget: float = 12.0) -> dict:
     return {
         "value": all_qps * scale, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": f"{rows} of {a.rows} rows x {a.dim}, nq={a.nq}, k={a.k}; q/s scaled by {scale:g} (flat scan is linear in rows); "
-                  f"all-cores row-split scan of the oracle port (faiss-cpu not installable)",
+                  f"all-cores row-split scan of the oracle port (faiss-cpu not installable); the reference ARM (--impl reference) "
+                  f"scans all rows",
         "faiss_threading_value": seq_qps * scale,
         "faiss_threading_note": "same port with faiss's own threading (parallel over queries only: one thread scans "
                                 "the database for a single query)",
@@ -254,13 +414,18 @@ def cpu_baseline(a, seconds_budget: float = 12.0) -> dict:
 
 
 def run_reference(a) -> int:
+    """The CPU reference arm: the oracle port of faiss-cpu IndexFlatIP on this box's host cores, on the SAME workload --
+    every step scans all --rows rows (no sampling, no scaling)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import oracle
     cores = host_threads()
-    rows = min(a.rows, a.cpu_rows)
+    rows = a.ref_rows if a.ref_rows > 0 else a.rows
+    rows = min(rows, a.rows)
+    t_fill = time.perf_counter()
     xb = oracle.synth_fill(rows, a.dim, seed=0, nthreads=cores)
+    t_fill = time.perf_counter() - t_fill
     xq = oracle.synth_fill(64, a.dim, seed=1)
     scale = rows / a.rows
 
@@ -278,17 +443,22 @@ def run_reference(a) -> int:
     # faiss's own threading for the same call, for the record (short)
     t1 = time.perf_counter()
     reps = 0
-    while reps < 3 or time.perf_counter() - t1 < 3.0:
+    while reps < 2 or time.perf_counter() - t1 < 3.0:
         oracle.faiss_seq_search(np.roll(xq, -reps, axis=0)[:a.nq], xb, a.k, simd=True, nthreads=cores)
         reps += 1
     seq_qps = reps * a.nq / (time.perf_counter() - t1) * scale
-    sample = (f"each step scans {rows} of {a.rows} rows x {a.dim} (nq={a.nq}, k={a.k}) with all {cores} host threads "
-              f"(rows split across threads); q/s scaled by {scale:g} to the full row count")
+    if rows == a.rows:
+        sample = (f"each step scans ALL {a.rows} rows x {a.dim} (nq={a.nq}, k={a.k}) with all {cores} host threads "
+                  f"(rows split across threads); no sampling, no scaling")
+    else:
+        sample = (f"each step scans {rows} of {a.rows} rows x {a.dim} (nq={a.nq}, k={a.k}) with all {cores} host threads; "
+                  f"q/s scaled by {scale:g} (--ref-rows)")
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3 / scale, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "nq": a.nq, "k": a.k,
+                   "rows_scanned_per_step": rows, "build_s": round(t_fill, 2),
                    "engine": "oracle port of faiss-cpu IndexFlatIP (faiss not installable in this image)"},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "faiss_threading_value": seq_qps},
@@ -334,6 +504,9 @@ def run_evs(a) -> int:
     evs.set_option("scan_variant", a.variant)
     if a.tc_min_nq is not None:
         evs.set_option("tc_min_nq", a.tc_min_nq)
+    for kv in a.set:
+        name, val = kv.split("=")
+        evs.set_option(name, int(val))
     index = evs.ShardedIndexFlatIP(a.dim, device=local_rank, storage=a.storage, exchange=a.exchange,
                                    exchange_max_nq=max(64, a.nq), exchange_max_k=a.k)
     t_build = time.perf_counter()
@@ -373,6 +546,7 @@ def run_evs(a) -> int:
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.02)
     ms_total, launches, (D_last, I_last) = timed_device(q_dev, a.steps, a.warmup, profile=True)
     n_prof, scan_ms_sum = index.local.scan_profile()
     clocks = sampler.stop() if rank == 0 else None
@@ -395,9 +569,46 @@ def run_evs(a) -> int:
            "h2d_bytes_per_step": a.nq * a.dim * 4, "d2h_bytes_per_step": a.nq * a.k * 12,
            "api": "IndexFlatIP.search(numpy) -> numpy via evs_index_search" if world == 1
                   else ("ShardedIndexFlatIP.search(numpy) -> numpy (H2D, scan, NCCL all-gather, merge, D2H)" if a.exchange == "nccl"
-                        else "ShardedIndexFlatIP.search(numpy) -> numpy via evs_index_search_exchange (H2D, scan, finalise + peer stores, merge, D2H)")}
-    # host API and device API must agree on the last step's query
-    same = bool(np.array_equal(Ih, I_last.cpu().numpy()) and np.array_equal(Dh, D_last.cpu().numpy()))
+                        else "ShardedIndexFlatIP.search(numpy) -> numpy via evs_index_search_exchange (H2D, scan + fused finalise + peer stores, merge, D2H)")}
+
+    # ---- parity: answers, not speed ----
+    parity = {"host_equals_device_result": bool(np.array_equal(Ih, I_last.cpu().numpy()) and np.array_equal(Dh, D_last.cpu().numpy()))}
+    if not a.no_parity:
+        # (1) self-match at full size: the query IS database row r (regenerated from its global id) -> r first, score ~ 1
+        probe_rows = [0, a.rows // 7, a.rows // 2 + 3, (a.rows * 6) // 7, a.rows - 1]
+        ok_self = True
+        for r in probe_rows:
+            pi = evs.IndexFlatIP(a.dim, device=local_rank)
+            pi.id_base = r
+            pi.add_synthetic(1, seed=0)
+            qrow = pi.reconstruct_n(0, 1)
+            del pi
+            Dp, Ip = index.search(qrow, a.k)
+            ok_self = ok_self and int(Ip[0, 0]) == r and abs(float(Dp[0, 0]) - 1.0) < 1e-5 and bool((np.diff(Dp[0].astype(np.float64)) <= 0).all())
+        parity["self_match_at_full_size"] = bool(ok_self)
+        parity["self_match_rows"] = probe_rows
+        # (2) N > 1: rank 0 also holds the whole database on its GPU; sharded (D, I) == single-GPU (D, I), bit for bit
+        if world > 1:
+            nchk = min(8, pool)
+            sharded = [index.search(q_host[i], a.k) for i in range(nchk)]
+            same = True
+            if rank == 0:
+                single = evs.IndexFlatIP(a.dim, device=local_rank, storage=a.storage)
+                single.reserve(a.rows)
+                single.add_synthetic(a.rows, seed=0)
+                for i in range(nchk):
+                    Ds, Is = single.search(q_host[i], a.k)
+                    same = same and bool(np.array_equal(Is, sharded[i][1]) and np.array_equal(Ds, sharded[i][0]))
+                del single
+                torch.cuda.empty_cache()
+            t = torch.tensor([1 if same else 0], device=dev)
+            dist.broadcast(t, src=0)
+            parity["sharded_equals_single_gpu"] = bool(int(t.item()) == 1)
+            parity["sharded_equals_single_gpu_queries"] = nchk
+            if index._px is not None:
+                failed, searches = index._px.status()
+                parity["exchange_failures"] = int(failed)
+        parity["guard"] = dict(zip(("device_reruns", "uncertified"), index.local.guard_stats()))
 
     # ---- roofline of the dominant kernel (the scan) ----
     rows_local = hi - lo
@@ -407,15 +618,21 @@ def run_evs(a) -> int:
     scan_ms = scan_ms_sum / max(n_prof, 1)
     tcmin = evs.get_option("tc_min_nq")
     # database passes per search: one with the tensor-core scan, else <= 4 queries per GEMV pass at d = 512
-    passes = 1 if (tcmin > 0 and a.nq >= tcmin and rows_local >= 65536) else -(-a.nq // 4)
+    tc = tcmin > 0 and a.nq >= tcmin and rows_local >= 65536
+    passes = (-(-a.nq // 16) if (a.storage == "f32" and a.nq <= 32 and evs.get_option("x3")) else 1) if tc else -(-a.nq // 4)
     achieved = alg_bytes * passes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     achieved_alg = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "evs::scan_*_kernel (score + fused top-k')", "achieved": achieved_alg,
-                "peak": peak, "unit": "GB/s", "frac": achieved_alg / peak, "traffic": ncu_traffic_per_launch(a, world),
+    fused = a.nq == 1 and evs.get_option("fuse_finalize") == 1
+    roofline = {"bound": "hbm",
+                "kernel": "evs::scan_direct_kernel (score + fused top-k' + the last CTA's finalise: ONE launch per search)" if fused
+                          else "evs scan kernels (score + fused top-k')",
+                "achieved": achieved_alg, "peak": peak, "unit": "GB/s", "frac": achieved_alg / peak,
+                "traffic": ncu_traffic_per_launch(a, world),
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved_alg / 8000.0,
                 "algorithmic_bytes_per_search_per_gpu": alg_bytes, "scan_ms_per_search": scan_ms,
                 "scan_launches_per_search": passes, "searches_timed": n_prof,
                 "hbm_read_rate_incl_repasses": achieved,
+                "scan_arithmetic": scan_arithmetic(evs, a.storage, a.nq, rows_local, a.dim),
                 "scan_share_of_step": scan_ms / (ms_total / a.steps) if ms_total > 0 else None}
 
     extra = None
@@ -427,10 +644,13 @@ def run_evs(a) -> int:
             extra[f"nq{nq}"] = {"queries_per_s": max(10, a.steps // 4) * nq / (ms * 1e-3)}
 
     configs = None
-    if world == 1 and not a.no_configs:
+    if not a.no_configs:
         del index
         torch.cuda.empty_cache()
-        configs = config_legs(evs, torch, dev, a.k)
+        if world == 1:
+            configs = config_legs_single(evs, torch, dev, a.k)
+        else:
+            configs = config_legs_sharded(evs, torch, dist, dev, world, rank, a, barrier, max_over_ranks)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -445,10 +665,11 @@ def run_evs(a) -> int:
                        "storage": a.storage, "sharding": f"rows/{world}", "rows_per_gpu": rows_local,
                        "exchange": None if world == 1 else a.exchange,
                        "scan_variant": evs.get_option("scan_variant"), "tc_min_nq": evs.get_option("tc_min_nq"),
+                       "fuse_finalize": evs.get_option("fuse_finalize"), "scan_dynamic": evs.get_option("scan_dynamic"),
                        "l2": "inputs larger than L2 (database >> 126 MB); a different query every step",
                        "build_s": round(t_build, 3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "host_equals_device_result": same,
+            "parity": parity, "host_equals_device_result": parity["host_equals_device_result"],
         }
         if extra:
             line["extra"] = extra

@@ -53,6 +53,7 @@ SIGNATURES = {
     "evs_index_time_scan": (_i, [_vp, _i64, _vp, _i64, _i, _pf]),
     "evs_index_scan_profile": (_i, [_vp, _pi64, _c.POINTER(_c.c_double)]),
     "evs_index_tc_max_queries": (_i, [_vp, _pi]),
+    "evs_index_tc_x3_max_queries": (_i, [_vp, _pi]),
     "evs_index_tc_scores_dev": (_i, [_vp, _i64, _vp, _vp, _pi, _vp]),
     "evs_exchange_create": (_i, [_i, _i, _i, _i64, _i64, _c.POINTER(_vp)]),
     "evs_exchange_handle": (_i, [_vp, _vp, _i64]),

@@ -737,6 +737,7 @@ static int search_tc_sync_locked(evs_index* idx, int64_t nq, const float* q_dev,
     const int kp = pi.kp;
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
     const int pair_min_nq = tune.tc_pair_min_nq;
+    if (out.x) return fail(EVS_ECUDA, "internal: exchange-mode search took a path that needs the host");
     // batches of pair_min_nq or more queries go through the CTA-pair kernel (N up to 256 per MMA, L2-shared slices)
     const bool can_pair = pair_min_nq > 0 && tc2_max_half(idx->d, bf16) > 0 && idx->sm_count >= 2;
     // ... and so do batches that would need more than one pass of the one-CTA kernel (fp32 rows: 64 queries per pass)
@@ -806,7 +807,6 @@ static int search_tc_sync_locked(evs_index* idx, int64_t nq, const float* q_dev,
             f.guard_q = idx->guard_slot + (nq > kGuardCap ? nq : kGuardCap);
             f.guard_cap = 0;  // slots are not used: every uncertified query gets guard_slot = -2
         }
-        if (out.x) return fail(EVS_ECUDA, "internal: exchange-mode search took a path that needs the host");
         CU(launch_finalize(f, cn, st));
     }
     if (scan_only) return EVS_OK;
@@ -1388,6 +1388,13 @@ extern "C" int evs_index_scan_clocks(evs_index* idx, uint64_t* out_host, int64_t
 extern "C" int evs_index_tc_max_queries(const evs_index* idx, int* max_queries) {
     if (!idx || !max_queries) return fail(EVS_EINVAL, "NULL argument");
     *max_queries = tc_max_queries(idx->d, idx->storage == EVS_STORE_BF16_F32);
+    return EVS_OK;
+}
+
+extern "C" int evs_index_tc_x3_max_queries(const evs_index* idx, int* max_queries) {
+    if (!idx || !max_queries) return fail(EVS_EINVAL, "NULL argument");
+    const ScanTuning tune = tune_snapshot();
+    *max_queries = (idx->storage == EVS_STORE_F32 && tune.x3) ? tc_x3_max_queries(idx->d) : 0;
     return EVS_OK;
 }
 

@@ -288,6 +288,12 @@ class IndexFlatIP:
         check(lib().evs_index_tc_max_queries(self._h, ctypes.byref(v)))
         return v.value
 
+    def tc_x3_max_queries(self) -> int:
+        """Queries one 3xTF32 pass serves for this index (0: bf16 storage, option off, or dimension not supported)."""
+        v = ctypes.c_int(0)
+        check(lib().evs_index_tc_x3_max_queries(self._h, ctypes.byref(v)))
+        return v.value
+
     def tc_scores(self, xq_cuda):
         """Diagnostics: raw tensor-core scan scores, ``float32[ntotal, nq]`` CUDA tensor."""
         import torch

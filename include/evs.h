@@ -265,6 +265,8 @@ EVS_API int evs_index_scan_clocks(evs_index* idx, uint64_t* out_host, int64_t ca
  * at least option "tc_pair_min_nq" queries (<= 4096) the CTA-pair kernel (cta_group::2).  bf16 storage scores
  * bf16 rows x bf16-rounded queries, fp32 storage scores in tf32; both accumulate in fp32. */
 EVS_API int evs_index_tc_max_queries(const evs_index* idx, int* max_queries);
+/* queries one 3xTF32 pass serves (0: bf16 storage, option "x3" off, or a dimension whose split query block does not fit) */
+EVS_API int evs_index_tc_x3_max_queries(const evs_index* idx, int* max_queries);
 EVS_API int evs_index_tc_scores_dev(evs_index* idx, int64_t nq, const float* q_dev, float* out_dev, int* npad, void* stream);
 
 #ifdef __cplusplus

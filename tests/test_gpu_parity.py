@@ -30,8 +30,11 @@ NEG = np.float32(-np.finfo(np.float32).max)
 @pytest.fixture(autouse=True)
 def _reset_options():
     yield
-    for name in ("scan_variant", "tile_rows", "stages", "ctas_per_sm"):
+    for name in ("scan_variant", "tile_rows", "stages", "ctas_per_sm", "scan_clock"):
         evs.set_option(name, 0)
+    evs.set_option("fuse_finalize", 1)
+    evs.set_option("scan_dynamic", 1)
+    evs.set_option("scan_chunk_groups", 2)
 
 
 def _index(xb, storage="f32", variant=0):
@@ -314,6 +317,115 @@ def test_peer_exchange_single_rank_equals_search():
     px2 = evs.PeerExchange(0, 0, 2, max_nq=4, max_k=48)  # world 2, never connected
     with pytest.raises(evs.EvsError):
         idx.search_exchange(px2, xq_t[:1], 48)
+
+
+def test_single_query_search_is_one_launch_whatever_the_scan_options():
+    """What the app issues (oldapp.py:2005): one query.  The GEMV scan's last CTA finalises, so the whole search is ONE
+    kernel launch; dealing the rows statically or dynamically, fused or not, f32 or bf16 rows gives the same bits."""
+    d, n, k = 512, 300_007, 48
+    q = oracle.synth_fill(3, d, 7)
+    for storage in ("f32", "bf16"):
+        idx = evs.IndexFlatIP(d, storage=storage)
+        idx.add_synthetic(n, seed=11)
+        xb = idx.reconstruct_n(0, n)
+        Dr, Ir = oracle.canon_search(q, xb, k)
+        for fuse, dyn, chunk in ((1, 1, 2), (1, 1, 1), (1, 1, 7), (1, 0, 2), (0, 0, 2)):
+            evs.set_option("fuse_finalize", fuse)
+            evs.set_option("scan_dynamic", dyn)
+            evs.set_option("scan_chunk_groups", chunk)
+            for qi in range(3):
+                l0 = evs.kernel_launches()
+                D, I = idx.search(q[qi:qi + 1], k)
+                assert evs.kernel_launches() - l0 == (1 if fuse else 2), (storage, fuse, dyn, chunk)
+                assert np.array_equal(I, Ir[qi:qi + 1]) and np.array_equal(D, Dr[qi:qi + 1]), (storage, fuse, dyn, chunk, qi)
+        # per-CTA scan clocks (diagnostics): one record per CTA, ends after starts
+        evs.set_option("fuse_finalize", 1)
+        evs.set_option("scan_clock", 1)
+        idx.search(q[:1], k)
+        clk = idx.scan_clocks()
+        evs.set_option("scan_clock", 0)
+        assert clk.shape[0] >= 148 and (clk[:, 1] >= clk[:, 0]).all()
+
+
+def test_back_to_back_device_searches_overlap_safely():
+    """Consecutive searches enqueued on one stream without any host synchronisation: every kernel is launched with
+    programmatic stream serialisation (the next search's CTAs become resident while the previous one drains and wait for
+    it before they read or write anything shared: lists, ticket, chunk counter).  200 single-query searches and 60 small
+    batches, all checked afterwards."""
+    import torch
+    d, n, k = 512, 200_003, 48
+    idx = evs.IndexFlatIP(d)
+    idx.add_synthetic(n, seed=13)
+    xb = idx.reconstruct_n(0, n)
+    q = oracle.synth_fill(40, d, 14)
+    qt = torch.from_numpy(q).cuda()
+    Dr, Ir = oracle.canon_search(q, xb, k)
+    outs = [idx.search(qt[i % 40:i % 40 + 1], k) for i in range(200)]
+    outs16 = [idx.search(qt[(i % 3) * 8:(i % 3) * 8 + 16], k) for i in range(60)]
+    torch.cuda.synchronize()
+    for i, (D, I) in enumerate(outs):
+        j = i % 40
+        assert np.array_equal(I.cpu().numpy(), Ir[j:j + 1]) and np.array_equal(D.cpu().numpy(), Dr[j:j + 1]), i
+    for i, (D, I) in enumerate(outs16):
+        j = (i % 3) * 8
+        assert np.array_equal(I.cpu().numpy(), Ir[j:j + 16]) and np.array_equal(D.cpu().numpy(), Dr[j:j + 16]), i
+
+
+def test_read_rows_is_the_shard_loader(tmp_path):
+    """evs_index_read_rows reads only rows [lo, hi) of index.faiss: G shard handles loaded that way answer exactly like
+    the whole file loaded on one GPU (partials + merge), ids are global, and the header-only query agrees."""
+    import torch
+    from evo_ssearch_b200.index import index_file_info, read_index_rows
+    d, n, k = 512, 70_003, 48
+    xb = oracle.synth_fill(n, d, 41)
+    xq = oracle.synth_fill(5, d, 42)
+    whole = _index(xb)
+    path = str(tmp_path / "index.faiss")
+    evs.write_index(whole, path)
+    assert index_file_info(path) == (d, n)
+    Ds, Is = whole.search(xq, k)
+    xq_t = torch.from_numpy(xq).cuda()
+    for G in (1, 3):
+        S, I = [], []
+        for g in range(G):
+            lo, hi = evs.shard_bounds(n, G, g)
+            sh, n_file = read_index_rows(path, lo, hi)
+            assert n_file == n and sh.ntotal == hi - lo and sh.id_base == lo
+            assert np.array_equal(sh.reconstruct_n(0, min(7, hi - lo)), xb[lo:lo + min(7, hi - lo)])
+            s, i = sh.search_partial(xq_t, k)
+            S.append(s)
+            I.append(i)
+        D, Ifin = evs.merge_partials(torch.stack(S), torch.stack(I), k)
+        assert np.array_equal(Ifin.cpu().numpy(), Is) and np.array_equal(D.cpu().numpy(), Ds), G
+    empty, _ = read_index_rows(path, n, n)
+    assert empty.ntotal == 0 and empty.id_base == n
+    with pytest.raises(evs.EvsError):
+        read_index_rows(path, 10, 5)
+
+
+def test_set_storage_derives_and_drops_the_bf16_scan_copy():
+    d, n, k = 512, 100_000, 48
+    idx = evs.IndexFlatIP(d)
+    idx.add_synthetic(n, seed=21)
+    xb = idx.reconstruct_n(0, n)
+    q = oracle.synth_fill(200, d, 22)
+    Dr, Ir = oracle.canon_search(q[:8], xb, k)
+    ref = evs.IndexFlatIP(d, storage="bf16")
+    ref.add(xb)
+    idx.set_storage("bf16")
+    assert idx.storage == "bf16"
+    for nq in (1, 8, 200):
+        D, I = idx.search(q[:nq], k)
+        D2, I2 = ref.search(q[:nq], k)
+        assert np.array_equal(I, I2) and np.array_equal(D, D2), nq
+        assert np.array_equal(I[:min(nq, 8)], Ir[:min(nq, 8)])
+    idx.add(xb[:1000])  # the derived copy follows later adds
+    assert idx.search(q[:3], k)[1].shape == (3, k)
+    idx.set_storage("f32")
+    assert idx.storage == "f32"
+    D, I = idx.search(q[:8], k)
+    Dr2, Ir2 = oracle.canon_search(q[:8], np.concatenate([xb, xb[:1000]]), k)
+    assert np.array_equal(I, Ir2) and np.array_equal(D, Dr2)
 
 
 def test_concurrent_search_threads():

@@ -18,6 +18,10 @@ def _reset_options():
     evs.set_option("tc_heap_pure_max_nq", 0)
     evs.set_option("tc2_slice_tiles", 0)
     evs.set_option("scan_variant", 0)
+    evs.set_option("x3", 1)
+    evs.set_option("x3_max_nq", 32)
+    evs.set_option("guard", 1)
+    evs.set_option("tf32_guard_eps_e6", 150)
 
 
 @pytest.mark.parametrize("storage,d", [("bf16", 512), ("f32", 512), ("bf16", 768), ("f32", 768), ("bf16", 1024), ("bf16", 64)])
@@ -36,11 +40,22 @@ def test_tc_raw_scores_match_torch(storage, d):
         if storage == "bf16":
             ref = (xb.bfloat16().double() @ xq.bfloat16().double().T).float()  # exact products of the rounded inputs
             tol = 2e-6  # only fp32 accumulation order differs
+        elif nq <= idx.tc_x3_max_queries():
+            ref = (xb.double() @ xq.double().T).float()
+            tol = 2e-6  # 3xTF32 split scan: fp32-class error (the dropped terms are ~2^-20 relative, plus fp32 accumulation)
         else:
             ref = (xb.double() @ xq.double().T).float()
-            tol = 5e-4  # tf32 truncates each operand to 10 mantissa bits: ~4e-5 rms on unit vectors, ~4 sigma max
+            tol = 5e-4  # single tf32 truncates each operand to 10 mantissa bits: ~4e-5 rms on unit vectors, ~4 sigma max
         err = (got - ref).abs().max().item()
         assert err <= tol, (storage, d, nq, err)
+    if storage == "f32" and idx.tc_x3_max_queries() > 0:
+        # the same batch with the split switched off is a plain tf32 scan: three orders of magnitude further from fp64
+        evs.set_option("x3", 0)
+        xq = torch.from_numpy(oracle.synth_fill(16, d, 4)).cuda()
+        err1 = (idx.tc_scores(xq) - (xb.double() @ xq.double().T).float()).abs().max().item()
+        evs.set_option("x3", 1)
+        err3 = (idx.tc_scores(xq) - (xb.double() @ xq.double().T).float()).abs().max().item()
+        assert err3 <= 2e-6 and err1 > 20 * err3, (d, err1, err3)
 
 
 @pytest.mark.parametrize("storage,d", [("bf16", 512), ("f32", 512), ("bf16", 768), ("bf16", 64)])
@@ -180,36 +195,117 @@ def test_tc_paths_across_dims_and_batch_sizes(d):
         assert evs.get_option("tc_fallbacks") == fb0, (d, storage)
 
 
-def test_tf32_margin_guard_reruns_near_tie_queries_exactly():
-    """fp32 storage scans batches in tf32.  80 planted rows whose scores differ by 2e-6 straddle rank 48: tf32 cannot
-    order them, the margin of that query collapses, and the host API re-runs it with the fp32 GEMV scan -- the answer
-    is the oracle's, bit for bit; ordinary queries of the same batch are certified and not re-run."""
-    d, n, k = 512, 120_000, 48
+def _planted(spacing, d=512, n=120_000, nq=6):
+    """`n` unit rows, 80 of which score 0.9 + spacing * i against query 0: they straddle rank 48."""
     xb = oracle.synth_fill(n, d, 61)
-    q = oracle.synth_fill(6, d, 62)
+    q = oracle.synth_fill(max(nq, 6), d, 62)[:nq]
     rng = np.random.default_rng(9)
     u = rng.standard_normal((80, d))
     u -= (u @ q[0].astype(np.float64))[:, None] * q[0]
     u /= np.linalg.norm(u, axis=1, keepdims=True)
-    a = 0.9 + 2e-6 * np.arange(80)
+    a = 0.9 + spacing * np.arange(80)
     xb[40_000:40_080] = (a[:, None] * q[0] + np.sqrt(1 - a[:, None] ** 2) * u).astype(np.float32)
-    idx = evs.IndexFlatIP(d)  # fp32 storage
+    return xb, q
+
+
+@pytest.mark.parametrize("x3", [1, 0])
+def test_device_guard_reruns_near_tie_queries_exactly_on_every_entry_point(x3):
+    """fp32 storage, small batches.  The finalise kernel certifies every result against the error bound of the scan that
+    produced the candidates (3xTF32: a few 1e-5 relative to |q| max|x| as a bound, ~1e-6 in fact; single tf32 with
+    x3 = 0: the statistical 1.5e-4); a query whose margin is inside the bound -- 80 planted rows closer together than the
+    scan can resolve straddle rank 48 -- is queued, re-run ON THE DEVICE with the fp32 GEMV scan (k' = 128) and finalised
+    again.  Same answer, bit for bit the oracle's, through the host API, the CUDA-tensor API, the shard-partial API and the
+    exchange API; no host synchronisation is involved; ordinary queries of the batch are not re-run."""
+    import torch
+    k = 48
+    xb, q = _planted(2e-7 if x3 else 2e-6)
+    evs.set_option("x3", x3)
+    idx = evs.IndexFlatIP(512)  # fp32 storage
+    idx.add(xb)
+    assert abs(idx.max_row_norm - 1.0) < 1e-3
+    Dr, Ir = oracle.canon_search(q, xb, k)
+    qt = torch.from_numpy(q).cuda()
+
+    def check(D, I, what):
+        assert np.array_equal(I, Ir) and np.array_equal(D, Dr), what
+    r0, u0 = idx.guard_stats()
+    check(*idx.search(q, k), "host")
+    r1, u1 = idx.guard_stats()
+    assert 1 <= r1 - r0 <= 2 and u1 == u0, (r1 - r0, u1 - u0, idx.last_margins(6))  # query 0, not the ordinary ones
+    D, I = idx.search(qt, k)
+    check(D.cpu().numpy(), I.cpu().numpy(), "cuda tensor")
+    S, I = idx.search_partial(qt, k)
+    check(S.cpu().numpy().astype(np.float32), I.cpu().numpy(), "partial")
+    px = evs.PeerExchange(0, 0, 1, max_nq=16, max_k=48)
+    D, I = idx.search_exchange(px, qt, k)
+    check(D.cpu().numpy(), I.cpu().numpy(), "exchange (device)")
+    check(*idx.search_exchange_host(px, q, k), "exchange (host)")
+    r2, u2 = idx.guard_stats()
+    assert 4 <= r2 - r1 <= 8 and u2 == u0
+    assert evs.get_option("exact_reruns") == evs.get_option("exact_reruns")  # the host re-ran nothing: all on the device
+    # guard off: the margin still says which query cannot be trusted, and nothing is re-run
+    evs.set_option("guard", 0)
+    D2, I2 = idx.search(q, k)
+    m = idx.last_margins(6)
+    bound = 1.5e-4 if not x3 else 3e-5
+    assert m[0] < bound and (m[1:] > bound).all(), m
+    assert np.array_equal(I2[1:], Ir[1:]) and np.array_equal(D2[1:], Dr[1:])
+    assert idx.guard_stats() == (r2, u2)
+
+
+def test_host_side_guard_for_batches_beyond_the_heap_range():
+    """40 fp32 queries: single-tf32 threshold scan (the host synchronises once for the overflow flags anyway); the
+    certification flags come back in the same synchronisation and uncertified queries are re-run with the fp32 GEMV scan,
+    through the host API and the CUDA-tensor API alike."""
+    import torch
+    k = 48
+    xb, q = _planted(2e-6, nq=40)
+    idx = evs.IndexFlatIP(512)
     idx.add(xb)
     Dr, Ir = oracle.canon_search(q, xb, k)
-    r0 = evs.get_option("exact_reruns")
-    D, I = idx.search(q, k)  # 6 queries: tensor-core scan (tf32)
+    e0 = evs.get_option("exact_reruns")
+    D, I = idx.search(q, k)
     assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
-    reruns = evs.get_option("exact_reruns") - r0
-    assert 1 <= reruns <= 2, (reruns, idx.last_margins(6))  # query 0 (its near-ties), not the ordinary ones
-    # guard off: the margin still says which query cannot be trusted
-    evs.set_option("tf32_guard_eps_e6", 0)
-    try:
-        D2, I2 = idx.search(q, k)
-        m = idx.last_margins(6)
-        assert m[0] < 1.5e-4 and (m[1:] > 1.5e-4).all(), m
-        assert np.array_equal(I2[1:], Ir[1:]) and np.array_equal(D2[1:], Dr[1:])
-    finally:
-        evs.set_option("tf32_guard_eps_e6", 150)
+    e1 = evs.get_option("exact_reruns")
+    assert 1 <= e1 - e0 <= 3, e1 - e0
+    Dt, It = idx.search(torch.from_numpy(q).cuda(), k)
+    assert np.array_equal(It.cpu().numpy(), Ir) and np.array_equal(Dt.cpu().numpy(), Dr)
+    assert evs.get_option("exact_reruns") - e1 == e1 - e0
+
+
+def test_certification_scales_with_the_norms():
+    """IndexFlatIP.add accepts any scale: the bound is relative to |q| * max|x|, so un-normalised data neither triggers
+    spurious re-runs nor escapes the guard."""
+    k = 48
+    xb, q = _planted(2e-7)
+    idx = evs.IndexFlatIP(512)
+    idx.add(xb * np.float32(8.0))
+    assert abs(idx.max_row_norm - 8.0) < 1e-2
+    q8 = q * np.float32(4.0)
+    Dr, Ir = oracle.canon_search(q8, xb * np.float32(8.0), k)
+    r0, u0 = idx.guard_stats()
+    D, I = idx.search(q8, k)
+    assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
+    r1, u1 = idx.guard_stats()
+    assert 1 <= r1 - r0 <= 2 and u1 == u0  # the planted query only: power-of-two scaling leaves every margin/bound ratio as it was
+
+
+@pytest.mark.parametrize("nq", [2, 16, 17, 32])
+def test_x3_blocks_equal_oracle(nq):
+    """fp32 storage, 2..32 queries = one or two 3xTF32 blocks of 16: results are the oracle's, the margins are far above
+    the scan's error bound on ordinary data (nothing is re-run), and no buffer can overflow."""
+    d, n, k = 512, 150_001, 48
+    idx = evs.IndexFlatIP(d)
+    idx.add_synthetic(n, seed=5)
+    xb = idx.reconstruct_n(0, n)
+    q = oracle.synth_fill(nq, d, 6)
+    r0 = idx.guard_stats()
+    fb0 = evs.get_option("tc_fallbacks")
+    D, I = idx.search(q, k)
+    Dr, Ir = oracle.canon_search(q, xb, k)
+    assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
+    assert (idx.last_margins(nq) > 1e-4).all()
+    assert idx.guard_stats() == r0 and evs.get_option("tc_fallbacks") == fb0
 
 
 def test_tc_overflow_falls_back_exactly():

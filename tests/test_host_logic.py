@@ -145,3 +145,38 @@ def test_incremental_reindex_plan_on_cpu(tmp_path, monkeypatch):
     fresh, pf, mf = lifecycle.create_index(tmp_path, _CountingEncoder())
     assert p2 == pf and m2 == mf and np.array_equal(i2.rows, fresh.rows)  # interchangeable with a full rebuild
     lifecycle.evict_index()
+
+
+def test_resident_cache_is_an_lru_with_a_byte_budget(tmp_path, monkeypatch):
+    """the resident cache must not grow without bound, and its signature covers all three files."""
+    from evo_ssearch_b200 import lifecycle
+
+    class Fake:
+        storage = "f32"
+
+        def __init__(self, n, d=4):
+            self.ntotal, self.d = n, d
+
+    monkeypatch.setattr(lifecycle, "CACHE_BUDGET_BYTES", 16 * 100 * 2 + 8)  # room for two 100-row indexes of d = 4
+    lifecycle.evict_index()
+    ev0 = lifecycle.load_stats["evictions"]
+    for name in ("a", "b", "c"):
+        lifecycle._cache_put(name, ("sig",), Fake(100), [], None)
+    assert list(lifecycle._cache) == ["b", "c"] and lifecycle.load_stats["evictions"] == ev0 + 1
+    lifecycle._cache_put("b", ("sig2",), Fake(100), [], None)  # re-put moves to the recent end
+    lifecycle._cache_put("d", ("sig",), Fake(100), [], None)
+    assert list(lifecycle._cache) == ["b", "d"]
+    lifecycle._cache_put("huge", ("sig",), Fake(10_000), [], None)  # larger than the budget: kept alone, never evicts itself
+    assert list(lifecycle._cache) == ["huge"]
+    lifecycle.evict_index()
+    assert not lifecycle._cache
+    # the signature changes when ANY of the three files changes
+    ip = tmp_path / ".clip_index"
+    ip.mkdir()
+    (ip / "index.faiss").write_bytes(b"x")
+    s0 = lifecycle._signature(ip)
+    assert s0[0] is not None and s0[1] is None and s0[2] is None
+    (ip / "paths.pkl").write_bytes(b"yy")
+    s1 = lifecycle._signature(ip)
+    assert s1 != s0 and s1[0] == s0[0]
+    assert lifecycle._want_sharded(False) is False and lifecycle._want_sharded(None) is False  # no process group here

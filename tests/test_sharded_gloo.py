@@ -35,6 +35,13 @@ class OracleShard:
         import oracle
         self.add(oracle.synth_fill(n, self.d, seed, row_base=self.id_base + self.xb.shape[0], normalize=normalize))
 
+    @property
+    def ntotal(self):
+        return self.xb.shape[0]
+
+    def reconstruct_n(self, n0, ni):
+        return self.xb[n0:n0 + ni]
+
     def search_partial(self, xq, k):
         import oracle
         q = xq.numpy()
@@ -83,6 +90,12 @@ def _worker(rank, world, port, n, d, nq, k, out):
         sh2 = evs.ShardedIndexFlatIP(d, local_index=OracleShard(d), merge=oracle_merge)
         sh2.add_synthetic(n, 21)
         ok = ok and bool(np.array_equal(sh2.local.xb, oracle.synth_fill(n, d, 21)[lo:hi]))
+        # sharded write_index: header by rank 0, every rank its own block -> the single-GPU file, byte for byte
+        from oracle import faiss_io
+        path = os.path.join(os.environ["EVS_TEST_TMP"], f"sharded_{n}.faiss")
+        sh.write_index(path)
+        dist.barrier()
+        ok = ok and open(path, "rb").read() == faiss_io.pack_index_flat(xb)
         out[rank] = ok
     finally:
         dist.destroy_process_group()
@@ -97,8 +110,9 @@ def _free_port():
 
 
 @pytest.mark.parametrize("n,k", [(1001, 48), (5, 12)])  # uneven shards; shards with fewer than k rows
-def test_two_rank_sharded_search_equals_single(n, k):
+def test_two_rank_sharded_search_equals_single(n, k, tmp_path):
     world = 2
+    os.environ["EVS_TEST_TMP"] = str(tmp_path)
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), n, 64, 3, k, out), nprocs=world, join=True)
