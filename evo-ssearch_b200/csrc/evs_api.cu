@@ -514,6 +514,7 @@ struct PathInfo {
     bool guard = false;  // results are certified on the device and uncertified queries re-run exactly (fp32 storage, batches)
     int blk = 0;         // PATH_TC_HEAP: queries per launch set
     float err_coef = 0.f;  // scan error bound relative to |q| * max|x| (0 = not certified: bf16 storage)
+    bool fused = false;  // PATH_GEMV, one query: the scan's last CTA finalises (and, in exchange mode, merges): ONE launch
 };
 
 // scan error models, relative to |q| * |x|.  fp32 GEMV: 4 partial chains of d/128 FMAs per lane, 3 + 5
@@ -533,11 +534,23 @@ static PathInfo plan_path(const evs_index* idx, int64_t nq, int64_t k, const Sca
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
     pi.kp = pick_kp(k);
     pi.err_coef = bf16 ? 0.f : gemv_err_coef(idx->d);
-    if (!allow_tc || !takes_tc_path(idx, nq, tune)) return pi;
-    pi.guard = !bf16 && tune.guard != 0;
+    if (!allow_tc || !takes_tc_path(idx, nq, tune)) {
+        if (nq == 1 && tune.fuse_finalize && idx->ntotal > 0) {
+            ScanPlan plan;
+            pi.fused = plan_scan(idx->ntotal, idx->d, bf16, pi.kp, 1, idx->sm_count, tune, &plan) == cudaSuccess && plan.variant == 1;
+        }
+        return pi;
+    }
+    // the device-side guard re-runs with the vectorised fp32 GEMV scan: dimensions it does not cover are certified and
+    // counted (evs_index_guard_stats) but not re-run
+    ScanPlan gplan;
+    ScanTuning gt = tune;
+    gt.scan_variant = 1;
+    const bool gemv_ok = plan_scan(idx->ntotal, idx->d, 0, 128, 1, idx->sm_count, gt, &gplan) == cudaSuccess && gplan.variant == 1;
+    pi.guard = !bf16 && tune.guard != 0 && gemv_ok;
     // small fp32 batches: 3xTF32 on-chip-heap blocks (fp32-class scan error, no host synchronisation)
     const int x3max = (!bf16 && tune.x3 && pi.kp == 64) ? tc_x3_max_queries(idx->d) : 0;
-    if (x3max > 0 && nq <= tune.x3_max_nq) {
+    if (x3max > 0 && nq <= tune.x3_max_nq && nq <= g_tc_heap_max_nq) {
         pi.kind = PATH_TC_HEAP;
         pi.x3 = true;
         pi.blk = x3max;
@@ -864,7 +877,8 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
         idx->last_nq = nq;
     }
     // single-query searches (what the app issues, oldapp.py:2005): the scan's last CTA finalises -- one launch in all
-    const bool fused = tune.fuse_finalize && nq == 1 && plan.variant == 1 && !scan_only;
+    const bool fused = (kp_override ? (tune.fuse_finalize && nq == 1 && plan.variant == 1) : pi.fused) && !scan_only;
+    if (out.x && out.x->merge_D && !fused) return fail(EVS_ECUDA, "internal: the exchange expected a fused single-query search");
     const float err_coef = scan_bf16 ? 0.f : gemv_err_coef(idx->d);
 
     for (int64_t c0 = 0; c0 < nq; c0 += kQueryChunk) {
@@ -892,7 +906,7 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
                     a.chunk_groups = tune.scan_chunk_groups > 0 ? tune.scan_chunk_groups : 2;
                 }
                 if (tune.scan_clock) {
-                    if ((rc = ensure_dev(&idx->cta_clock, &idx->cta_clock_cap, (size_t)plan.grid * 2))) return rc;
+                    if ((rc = ensure_dev(&idx->cta_clock, &idx->cta_clock_cap, (size_t)plan.grid * 2 + 8))) return rc;
                     idx->cta_clock_n = plan.grid;
                     a.cta_clock = idx->cta_clock;
                 }
@@ -1217,17 +1231,22 @@ static int search_exchange_enqueue_locked(evs_index* idx, evs_exchange* ex, int6
     // overwrite results): the partial goes to local staging and a publish kernel stores it into the peers' slots;
     // otherwise the finalise kernel stores this shard's k best straight into every rank's slot
     const bool staged = idx->ntotal == 0 || pi.kind == PATH_TC_SYNC || (pi.kind == PATH_TC_HEAP && pi.guard);
+    const bool one_launch = !staged && pi.kind == PATH_GEMV && pi.fused;  // scan + finalise + peer stores + wait + merge
     SearchOut out;
     if (staged) {
         out.P_scores = ex->stage_scores;
         out.P_ids = ex->stage_ids;
     } else {
+        if (one_launch) {
+            x.merge_D = D_dev;
+            x.merge_I = reinterpret_cast<long long*>(I_dev);
+        }
         out.x = &x;
     }
     int rc = search_dev_common(idx, nq, q_dev, k, out, st, tune, pi);
     cudaError_t e = cudaSuccess;
     if (!rc && staged) e = launch_publish_partials(x, nq, (int)k, ex->stage_scores, reinterpret_cast<const long long*>(ex->stage_ids), st);
-    if (!rc && e == cudaSuccess) e = launch_merge_exchange(x, nq, (int)k, D_dev, reinterpret_cast<long long*>(I_dev), st);
+    if (!rc && e == cudaSuccess && !one_launch) e = launch_merge_exchange(x, nq, (int)k, D_dev, reinterpret_cast<long long*>(I_dev), st);
     if (!rc && e != cudaSuccess) rc = fail(EVS_ECUDA, "exchange launch failed: %s", cudaGetErrorString(e));
     ex->seq = x.seq;  // stay in step with the peers whatever happened
     if (rc) {
@@ -1382,6 +1401,8 @@ extern "C" int evs_index_scan_clocks(evs_index* idx, uint64_t* out_host, int64_t
     if (cap_ctas < idx->cta_clock_n) return fail(EVS_EINVAL, "buffer holds %lld CTAs, need %d", (long long)cap_ctas, idx->cta_clock_n);
     if (idx->have_last_stream) CU(cudaStreamSynchronize(idx->last_stream));
     CU(cudaMemcpy(out_host, idx->cta_clock, (size_t)idx->cta_clock_n * 16, cudaMemcpyDeviceToHost));
+    if (cap_ctas >= idx->cta_clock_n + 4)  // then the last CTA's own stamps: after its epilogue / after the finalise (+ merge)
+        CU(cudaMemcpy(out_host + 2 * (size_t)idx->cta_clock_n, idx->cta_clock + 2 * (size_t)idx->cta_clock_n, 64, cudaMemcpyDeviceToHost));
     return EVS_OK;
 }
 

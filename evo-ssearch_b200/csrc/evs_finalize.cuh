@@ -86,8 +86,14 @@ __device__ __forceinline__ void canon32_dot_pair(const float* __restrict__ xa, c
 //   T0 = kp-th largest list HEAD is a lower bound of the kp-th best key (kp heads are >= it), only the
 //   <= kp lists whose head is >= T0 can hold survivors, and only their prefix >= T0 does.  The
 //   survivors (about kp + a few for unordered data, kp*kp at most) are sorted in shared memory.
-// shared memory (finalize_smem_bytes): FinalizeShared | surv[finalize_surv_slots(L, kp)] u64 | heads[L] u64 | sc[kp] f64 |
-//   id[kp] i64 | ok[kp] u64 | qs[d] f64
+// Latency shape (the single-query search runs this in ONE 256-thread CTA at the end of the scan kernel):
+//   * one round of independent loads brings the first two keys (16 bytes) of EVERY list: the heads for T0 and, for
+//     unordered data, almost all survivors (a list contributes 0.2 keys on average); only lists whose second key also
+//     survives are read in full ("deep" lists, a warp each, all loads of a list in flight together);
+//   * the rows of the survivors are prefetched into L2 while they are being ranked, so that the canonical re-score
+//     (two candidates per warp at a time) waits on L2, not on HBM.
+// shared memory (finalize_smem_bytes): FinalizeShared | surv[finalize_surv_slots(L, kp)] u64 | pre[2 L] u64 | deep[L] int
+//   (padded to 8 bytes) | sc[kp] f64 | id[kp] i64 | ok[kp] u64 | qs[d] f64
 // (survivor capacity scap = min(L, kp) * kp: with one list per query -- the tensor-core scans -- the kernel needs
 // 7 KB instead of 38 KB of shared memory and eight 256-thread CTAs fit an SM)
 __host__ __device__ inline int finalize_surv_cap(int L, int kp) { return (L < kp ? L : kp) * kp; }
@@ -100,12 +106,15 @@ __host__ __device__ inline int finalize_surv_slots(int L, int kp) {
 struct FinalizeShared {
     int nsurv, nvalid;
     unsigned maxerr;  // ordered-uint of the largest (canonical - scan) score difference among the candidates
-    int pad0;
+    int ndeep;
     u64 T0;
     double qnorm2;    // |q|^2
+    int fail;         // fused exchange merge: 1 = a rank never arrived, 2 = a rank reported failure
+    int pad0;
 };
+__host__ __device__ inline size_t finalize_deep_slots(int L) { return (size_t)((L + 1) / 2); }  // ints, in 8-byte units
 __host__ __device__ inline size_t finalize_smem_bytes(int L, int kp, int d) {
-    return sizeof(FinalizeShared) + (size_t)finalize_surv_slots(L, kp) * 8 + (size_t)L * 8 + (size_t)kp * 24 + (size_t)d * 8;
+    return sizeof(FinalizeShared) + ((size_t)finalize_surv_slots(L, kp) + 2 * (size_t)L + finalize_deep_slots(L) + 3 * (size_t)kp + (size_t)d) * 8;
 }
 
 // the part that does not depend on the scan's output: the query widened to fp64 (may run before griddepcontrol.wait)
@@ -113,15 +122,98 @@ __device__ __forceinline__ void finalize_prologue(const FinalizeParams& p, long 
     const int t = threadIdx.x, nt = blockDim.x;
     FinalizeShared* sh = reinterpret_cast<FinalizeShared*>(smem_raw);
     double* qs = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) +
-                                           ((size_t)finalize_surv_slots(p.L, p.kp) + p.L + 3 * (size_t)p.kp) * 8);
+                                           ((size_t)finalize_surv_slots(p.L, p.kp) + 2 * (size_t)p.L + finalize_deep_slots(p.L) + 3 * (size_t)p.kp) * 8);
     const float* q = p.xq + (size_t)qi * p.d;
     for (int i = t; i < p.d; i += nt) qs[i] = (double)q[i];
     if (t == 0) {
         sh->nsurv = 0;
         sh->nvalid = 0;
         sh->maxerr = 0u;
+        sh->ndeep = 0;
         sh->T0 = 0ull;
         sh->qnorm2 = 0.0;
+        sh->fail = 0;
+    }
+}
+
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Merge after the peer-store exchange: wait until every shard's flag for search x.seq has arrived in the LOCAL gather
+// buffer, then rank the world*k partials of query `qi` into (D, I).  A rank that never arrives (~10 s watchdog) or that
+// reported failure (poisoned flag) makes the result padding and sets *x.status (host-mapped): stale slots are never merged.
+// Called by all threads of the CTA; smem_raw holds world*k*24 bytes (+ 8); `fail` is a shared int set to 0 before.
+__device__ __forceinline__ void exchange_merge(const Exchange& x, long long qi, long long nq, int k, float* __restrict__ D,
+                                               long long* __restrict__ I, unsigned char* smem_raw, int* fail, int* nvalid) {
+    const int m = x.world * k;
+    double* sc = reinterpret_cast<double*>(smem_raw);
+    long long* id = reinterpret_cast<long long*>(sc + m);
+    u64* ok = reinterpret_cast<u64*>(id + m);
+    unsigned char* local = x.peer[x.rank];
+    if (threadIdx.x < x.world) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(local + 2 * (size_t)x.world * x.slot_bytes) +
+                                         (size_t)x.parity * x.world + threadIdx.x;
+        const long long t0 = clock64();
+        for (;;) {
+            const unsigned long long v = ld_relaxed_sys_u64(flag);
+            const unsigned long long vs = v & ~kExchangePoison;
+            if (vs >= x.seq) {
+                if (vs == x.seq && (v & kExchangePoison)) atomicMax(fail, 2);  // that rank failed this search
+                break;
+            }
+            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a rank never arrived
+                atomicMax(fail, 1);
+                break;
+            }
+            __nanosleep(32);
+        }
+        __threadfence_system();  // acquire side: the slots written before the flags are visible to the loads below
+    }
+    __syncthreads();
+    if (*fail) {  // CTA-uniform: report, never merge what sits in the slots (it is an older search's partial)
+        for (int r = threadIdx.x; r < k; r += blockDim.x) {
+            D[(size_t)qi * k + r] = -FLT_MAX;
+            I[(size_t)qi * k + r] = -1;
+        }
+        if (threadIdx.x == 0 && x.status) {
+            *reinterpret_cast<volatile int*>(x.status) = *fail;
+            __threadfence_system();
+        }
+        return;
+    }
+    for (int e = threadIdx.x; e < m; e += blockDim.x) {
+        const int part = e / k, r = e % k;
+        const unsigned char* slot = local + ((size_t)x.parity * x.world + part) * x.slot_bytes;
+        const double sv = __ldcv(reinterpret_cast<const double*>(slot) + (size_t)qi * k + r);
+        const long long iv = __ldcv(reinterpret_cast<const long long*>(slot + (size_t)nq * k * 8) + (size_t)qi * k + r);
+        sc[e] = sv;
+        id[e] = iv;
+        ok[e] = iv >= 0 ? score_rank_key(sv) : 0ull;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < m; e += blockDim.x) {
+        if (id[e] < 0) continue;
+        atomicAdd(nvalid, 1);
+        const double st = sc[e];
+        const long long it = id[e];
+        const u64 ot = ok[e];
+        int rank = 0;
+        for (int j = 0; j < m; j++) rank += better_i(ok[j], id[j], ot, it) & (int)(id[j] >= 0);
+        if (rank < k) {
+            D[(size_t)qi * k + rank] = (float)st;
+            I[(size_t)qi * k + rank] = it;
+        }
+    }
+    __syncthreads();
+    for (int r = *nvalid + threadIdx.x; r < k; r += blockDim.x) {
+        D[(size_t)qi * k + r] = -FLT_MAX;
+        I[(size_t)qi * k + r] = -1;
     }
 }
 
@@ -135,14 +227,20 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
     const int scap = finalize_surv_cap(L, kp);
     FinalizeShared* sh = reinterpret_cast<FinalizeShared*>(smem_raw);
     u64* surv = reinterpret_cast<u64*>(smem_raw + sizeof(FinalizeShared));  // [finalize_surv_slots(L, kp)]
-    u64* heads = surv + finalize_surv_slots(L, kp);         // [L]
-    double* sc = reinterpret_cast<double*>(heads + L);      // [kp]
+    u64* pre = surv + finalize_surv_slots(L, kp);           // [L][2]: the first two keys of every list
+    int* deep = reinterpret_cast<int*>(pre + 2 * (size_t)L);  // [L]: lists that must be read in full
+    double* sc = reinterpret_cast<double*>(pre + 2 * (size_t)L + finalize_deep_slots(L));  // [kp]
     long long* id = reinterpret_cast<long long*>(sc + kp);  // [kp]
     u64* ok = reinterpret_cast<u64*>(id + kp);              // [kp] integer rank keys of the scores
     double* qs = reinterpret_cast<double*>(ok + kp);        // [d] the query widened once
 
-    // lists were written by other SMs (possibly during this very kernel): read them past L1
-    for (int l = t; l < L; l += nt) heads[l] = __ldcg(lists + (size_t)l * kp);
+    // 0. the first two keys of every list, all loads independent.  Lists were written by other SMs (possibly during this
+    //    very kernel): read them past L1.
+    for (int l = t; l < L; l += nt) {
+        const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(lists + (size_t)l * kp));
+        pre[2 * l] = v.x;
+        pre[2 * l + 1] = v.y;
+    }
     if (qi == 0 && t == 0 && p.guard_count_next) *p.guard_count_next = 0;  // ready for the next guarded search of this handle
     __syncthreads();
     if (p.err_coef > 0.f && warp == 0) {  // |q|^2 for the certification bound (qs is complete: barrier above)
@@ -165,6 +263,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
             __syncthreads();
             if (t == 0) {
                 sh->nsurv = 0;
+                sh->ndeep = 0;
                 sh->T0 = 0ull;
             }
             hs = 1;
@@ -177,24 +276,40 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
             const int part = t & (nper - 1);
             for (int l0 = 0; l0 < Ls; l0 += nt / nper) {
                 const int l = l0 + t / nper;
-                const u64 h = l < Ls ? heads[l * hs] : 0ull;
+                const u64 h = l < Ls ? pre[2 * (l * hs)] : 0ull;
                 int r = 0;
                 if (h != 0ull)
-                    for (int j = part; j < Ls; j += nper) r += heads[j * hs] > h ? 1 : 0;
+                    for (int j = part; j < Ls; j += nper) r += pre[2 * (j * hs)] > h ? 1 : 0;
                 for (int off = 1; off < nper; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
                 if (h != 0ull && part == 0 && r == kp - 1) sh->T0 = h;
             }
         }
         __syncthreads();
         const u64 T0 = sh->T0;  // 0: fewer than kp non-empty lists -> every key survives (at most kp*kp)
-        // 2. survivors: one warp per qualifying list, prefix >= T0
-        for (int l = warp; l < L; l += nwarps) {
-            const u64 h = heads[l];
-            if (h == 0ull || h < T0) continue;  // warp-uniform
-            const u64* src = lists + (size_t)l * kp;
+        // 2a. survivors among the first two keys of every list (a thread per list); a list whose second key survives too
+        //     goes to the deep queue
+        for (int l = t; l < L; l += nt) {
+            const u64 k0 = pre[2 * l], k1 = pre[2 * l + 1];
+            if (k0 == 0ull || k0 < T0) continue;
+            const int both = (k1 != 0ull && k1 >= T0) ? 1 : 0;
+            const int pos = atomicAdd(&sh->nsurv, 1 + both);
+            if (pos < scap) surv[pos] = k0;
+            if (both) {
+                if (pos + 1 < scap) surv[pos + 1] = k1;
+                deep[atomicAdd(&sh->ndeep, 1)] = l;
+            }
+        }
+        __syncthreads();
+        // 2b. deep lists: one warp per list, keys 2 .. kp-1, prefix >= T0
+        const int ndeep = sh->ndeep;
+        for (int di = warp; di < ndeep; di += nwarps) {
+            const u64* src = lists + (size_t)deep[di] * kp;
             u64 keys[4];  // kp <= 128: all loads of the list issued before the first use
 #pragma unroll
-            for (int u = 0; u < 4; u++) keys[u] = (32 * u + lane < kp) ? __ldcg(src + 32 * u + lane) : 0ull;
+            for (int u = 0; u < 4; u++) {
+                const int i = 32 * u + lane;
+                keys[u] = (i >= 2 && i < kp) ? __ldcg(src + i) : 0ull;
+            }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const bool keep = keys[u] != 0ull && keys[u] >= T0;
@@ -211,6 +326,17 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
     }  // attempt
     // 3. the kp best survivors in descending order -> A[0..kp)
     const int nsurv = sh->nsurv;
+    // the re-score below reads the survivors' rows: start them on their way from HBM to L2 now (fp32 master rows)
+    if (!p.xb_is_bf16 && nsurv <= 4 * kp) {
+        const int lines = (p.d * 4 + 127) / 128;
+        for (int i = t; i < nsurv * lines; i += nt) {
+            const u64 key = surv[i / lines];
+            if (key != 0ull) {
+                const char* row = reinterpret_cast<const char*>(p.xb) + (size_t)key_row(key) * p.d * 4 + (size_t)(i % lines) * 128;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+            }
+        }
+    }
     const u64* A;
     if (nsurv <= nt) {
         // usual case (a few more than kp survivors): rank by counting, one barrier instead of a sort
@@ -251,7 +377,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
             const __nv_bfloat16* xb16 = reinterpret_cast<const __nv_bfloat16*>(p.xb);
             if (ka) sa = canon32_dot_bf16(xb16 + (size_t)rowa * p.d, qs, p.d, lane);
             if (kb) sb = canon32_dot_bf16(xb16 + (size_t)rowb * p.d, qs, p.d, lane);
-        } else {
+        } else if (ka || kb) {
             const float* xb32 = reinterpret_cast<const float*>(p.xb);
             canon32_dot_pair(ka ? xb32 + (size_t)rowa * p.d : nullptr, kb ? xb32 + (size_t)rowb * p.d : nullptr, qs, p.d, lane,
                              sa, sb);
@@ -305,7 +431,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
                 // true score is at most that plus the scan's error.  margin = canonical score of rank k minus (worst
                 // retained scan score + the largest under-estimate observed on the retained candidates); the result is
                 // CERTIFIED exact when margin > E = err_coef * |q| * max|x|, E being the error bound of the scan that
-                // produced the lists (fp32 GEMV / 3xTF32: a few 1e-6; single tf32 / bf16: the caller's statistical eps).
+                // produced the lists (fp32 GEMV / 3xTF32: a few 1e-6 .. 1e-5; single tf32: the caller's statistical eps).
                 const float worst = key_score(A[kp - 1]);
                 const float under = fmaxf(ordered_to_score(sh->maxerr), 0.f);
                 const float margin = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) - under : INFINITY;
@@ -353,19 +479,28 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
     }
     if (t == 0 && p.margins && nvalid < p.k) p.margins[qi] = INFINITY;  // every row was a candidate
     if (p.x.world > 0 && p.D == nullptr) {
-        // publish: when the last query's CTA has written its part, raise this shard's flag on every rank
+        // publish: when the last query's CTA has written its part, raise this shard's flag on every rank.  ONE system fence
+        // orders the slot stores of the whole CTA (barrier above it) before the flags, which are then plain relaxed stores
+        // (eight st.release.sys in a row would each pay their own fence round trip over NVLink).
         __syncthreads();
         if (t == 0) {
             __threadfence_system();
             const unsigned prev = atomicAdd(p.x.done, 1u);
             if (prev == (unsigned)p.x.nq_total - 1u) {  // counts across the launches of one search
                 *p.x.done = 0u;
-                __threadfence_system();
+                if (p.x.nq_total > 1) __threadfence_system();  // the other CTAs' slot stores (they fenced before their count)
                 for (int g = 0; g < p.x.world; g++) {
                     unsigned long long* flags = reinterpret_cast<unsigned long long*>(p.x.peer[g] + 2 * (size_t)p.x.world * p.x.slot_bytes);
-                    st_release_sys_u64(flags + (size_t)p.x.parity * p.x.world + p.x.rank, p.x.seq);
+                    st_relaxed_sys_u64(flags + (size_t)p.x.parity * p.x.world + p.x.rank, p.x.seq);
                 }
             }
+            sh->nvalid = 0;
+        }
+        if (p.x.merge_D != nullptr) {
+            // single-query search fused into the scan kernel: the same CTA waits for the peers' partials and merges
+            __syncthreads();
+            exchange_merge(p.x, p.x.q_off + qi, p.x.nq_total, p.k, p.x.merge_D, p.x.merge_I, reinterpret_cast<unsigned char*>(surv),
+                           &sh->fail, &sh->nvalid);
         }
     }
 }

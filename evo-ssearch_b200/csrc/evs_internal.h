@@ -21,8 +21,10 @@ struct ScanTuning {
                            // (scripts/small_nq_sweep.py): from 2 queries on it beats the CUDA-core GEMV for fp32 and bf16 rows
     int tc_pair_min_nq = 129;  // ... and of at least this many the CTA-pair kernel (evs_tc2.cu); 0 = never
     int fuse_finalize = 1;     // single-query GEMV searches: the scan's last CTA finalises (no second launch)
-    int scan_dynamic = 1;      // ... and rows are dealt dynamically, `scan_chunk_groups` row groups per grab
-    int scan_chunk_groups = 2;
+    int scan_dynamic = 0;      // ... and rows are dealt dynamically, `scan_chunk_groups` row groups per grab.  Off: measured
+                               // (scripts/scan_tail_probe.py) the spread of the CTAs' end times halves, but the last CTA
+                               // ends only ~3 us earlier and grabs of fewer than 4 groups choke on the one counter
+    int scan_chunk_groups = 4;
     int scan_clock = 0;        // diagnostics: record per-CTA start / end-of-scan-loop times of fused single-query scans
     int x3 = 1;                // fp32 rows, batches up to x3_max_nq queries: 3xTF32 split scan (fp32-class scan error)
     int x3_max_nq = 32;
@@ -51,6 +53,8 @@ struct Exchange {
     long long nq_total = 0;    // queries of the whole search (a search may be finalised in several launches)
     long long q_off = 0;       // first query of this launch
     int* status = nullptr;     // host-mapped: 1 = a merge gave up waiting for a rank (~10 s), 2 = a rank reported failure
+    float* merge_D = nullptr;  // non-null (single-query searches finalised inside the scan kernel): the same CTA also waits
+    long long* merge_I = nullptr;  //   for the peers' partials and merges them into (D, I): one launch per search at N > 1 too
 };
 
 // everything the finalise step needs (evs_finalize.cuh: finalize_query).  Plain data, filled by evs_api.cu.

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) publish_partials_kernel(Exchange x, long 
             __threadfence_system();
             for (int g = 0; g < x.world; g++) {
                 unsigned long long* flags = reinterpret_cast<unsigned long long*>(x.peer[g] + 2 * (size_t)x.world * x.slot_bytes);
-                st_release_sys_u64(flags + (size_t)x.parity * x.world + x.rank, x.seq);
+                st_relaxed_sys_u64(flags + (size_t)x.parity * x.world + x.rank, x.seq);
             }
         }
     }
@@ -104,13 +104,7 @@ __global__ void publish_poison_kernel(Exchange x) {
 __global__ void __launch_bounds__(256) merge_exchange_kernel(Exchange x, long long nq, int k, float* __restrict__ D,
                                                             long long* __restrict__ I) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int m = x.world * k;
-    double* sc = reinterpret_cast<double*>(smem_raw);
-    long long* id = reinterpret_cast<long long*>(sc + m);
-    u64* ok = reinterpret_cast<u64*>(id + m);
     __shared__ int s_nvalid, s_fail;
-    const long long qi = blockIdx.x;
-    unsigned char* local = x.peer[x.rank];
     if (threadIdx.x == 0) {
         s_nvalid = 0;
         s_fail = 0;
@@ -118,64 +112,7 @@ __global__ void __launch_bounds__(256) merge_exchange_kernel(Exchange x, long lo
     asm volatile("griddepcontrol.wait;" ::: "memory");  // launched programmatically behind this rank's finalise / publish kernel
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x < x.world) {
-        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(local + 2 * (size_t)x.world * x.slot_bytes) +
-                                         (size_t)x.parity * x.world + threadIdx.x;
-        const long long t0 = clock64();
-        for (;;) {
-            const unsigned long long v = ld_acquire_sys_u64(flag);
-            const unsigned long long vs = v & ~kExchangePoison;
-            if (vs >= x.seq) {
-                if (vs == x.seq && (v & kExchangePoison)) atomicMax(&s_fail, 2);  // that rank failed this search
-                break;
-            }
-            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a rank never arrived
-                atomicMax(&s_fail, 1);
-                break;
-            }
-            __nanosleep(64);
-        }
-    }
-    __syncthreads();
-    if (s_fail) {  // CTA-uniform: report, never merge what sits in the slots (it is an older search's partial)
-        for (int r = threadIdx.x; r < k; r += blockDim.x) {
-            D[(size_t)qi * k + r] = -FLT_MAX;
-            I[(size_t)qi * k + r] = -1;
-        }
-        if (threadIdx.x == 0 && x.status) {
-            *reinterpret_cast<volatile int*>(x.status) = s_fail;
-            __threadfence_system();
-        }
-        return;
-    }
-    for (int e = threadIdx.x; e < m; e += blockDim.x) {
-        const int part = e / k, r = e % k;
-        const unsigned char* slot = local + ((size_t)x.parity * x.world + part) * x.slot_bytes;
-        const double sv = __ldcv(reinterpret_cast<const double*>(slot) + (size_t)qi * k + r);
-        const long long iv = __ldcv(reinterpret_cast<const long long*>(slot + (size_t)nq * k * 8) + (size_t)qi * k + r);
-        sc[e] = sv;
-        id[e] = iv;
-        ok[e] = iv >= 0 ? score_rank_key(sv) : 0ull;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < m; e += blockDim.x) {
-        if (id[e] < 0) continue;
-        atomicAdd(&s_nvalid, 1);
-        const double st = sc[e];
-        const long long it = id[e];
-        const u64 ot = ok[e];
-        int rank = 0;
-        for (int j = 0; j < m; j++) rank += better_i(ok[j], id[j], ot, it) & (int)(id[j] >= 0);
-        if (rank < k) {
-            D[(size_t)qi * k + rank] = (float)st;
-            I[(size_t)qi * k + rank] = it;
-        }
-    }
-    __syncthreads();
-    for (int r = s_nvalid + threadIdx.x; r < k; r += blockDim.x) {
-        D[(size_t)qi * k + r] = -FLT_MAX;
-        I[(size_t)qi * k + r] = -1;
-    }
+    exchange_merge(x, blockIdx.x, nq, k, D, I, smem_raw, &s_fail, &s_nvalid);
 }
 
 // =============================================================================================

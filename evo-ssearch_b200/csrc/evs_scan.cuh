@@ -320,9 +320,11 @@ __global__ void __launch_bounds__(256, ScanOcc<T, NQ, NV>::value) scan_direct_ke
                     if (p.next_chunk) *p.next_chunk = 0u;
                 }
                 __threadfence();
+                if (p.cta_clock && threadIdx.x == 0) p.cta_clock[2 * gridDim.x] = globaltimer_ns();
                 finalize_prologue(f, p.q0, smem_raw);
                 __syncthreads();
                 finalize_query(f, p.q0, f.lists + (size_t)p.q0 * f.L * f.kp, smem_raw);
+                if (p.cta_clock && threadIdx.x == 0) p.cta_clock[2 * gridDim.x + 1] = globaltimer_ns();
             }
         }
     }

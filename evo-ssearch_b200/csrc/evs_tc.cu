@@ -76,18 +76,23 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------------
 
 // X3 (fp32 rows only): 3xTF32 split scan.  tf32 keeps 11 significant bits of each operand, a ~1e-3 relative error that
-// is far above fp32 noise; here every operand is split  v = hi + lo  (hi = the tf32 part, lo = v - hi exactly) and each
-// K step issues  D += A_hi*Q_hi + A_hi*Q_lo + A_lo*Q_hi : the dropped terms are ~2^-20 relative, i.e. fp32-class scores
-// from the tensor cores.  The queries are split once (tc_split_queries, both halves resident in shared memory); the
-// database tile is split on the fly by four converter warps (8-11): hi overwrites the staged tile in place, lo goes to
-// a two-deep side ring; the MMA issuer waits for the converted stage instead of the raw one.  The tensor pipe is a few
-// percent busy at these batch sizes, so the three MMAs per K step hide under the HBM stream.
+// is far above fp32 noise; here every operand is split  v = hi + lo  (hi = the tf32 part, lo = v - hi exactly) and the
+// products A_hi*Q_hi + A_hi*Q_lo + A_lo*Q_hi are accumulated: the dropped terms are ~2^-20 relative, i.e. fp32-class
+// scores from the tensor cores.  The queries are split once (tc_split_queries); the resident query block holds, per K
+// chunk, the NP hi rows followed by the NP lo rows, so that ONE MMA with N = 2 NP multiplies the staged tile by both halves
+// (accumulator columns [0, NP) = A_hi*Q_hi, [NP, 2 NP) = A_hi*Q_lo; the tensor core narrows the raw fp32 tile to its tf32
+// part by itself: kind::tf32 ignores the low 13 mantissa bits) and a second MMA with N = NP adds A_lo*Q_hi into columns
+// [0, NP); the epilogue adds the two column halves.  A_lo is produced on the fly by four converter warps (8-11) into a
+// two-deep side ring.  What bounds this kernel is shared-memory bandwidth, not the tensor pipe (12 % busy): per 16 KB stage
+// the TMA writes 16 KB, the converters read 16 and write 16, the MMAs read 2 x 16 KB of A -- 80 KB against the 82 KB the SM
+// can move in the time HBM delivers the stage; the first version (three MMAs, hi rewritten in place) moved 118 KB and
+// ran at 0.53x of the HBM roofline.
 template <typename T, int MODE, bool X3>
 __global__ void __launch_bounds__(X3 ? 384 : 256, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant__ CUtensorMap tm_q, TcParams p) {
     static_assert(!X3 || sizeof(T) == 4, "the 3xTF32 split applies to fp32 rows");
     constexpr bool TF32 = sizeof(T) == 4;
-    constexpr int QH = X3 ? 2 : 1;             // resident query copies (hi, lo)
+    constexpr int QH = X3 ? 2 : 1;             // resident query copies (hi, lo): chunk c holds [hi: NP rows][lo: NP rows]
     constexpr int LO_STAGES = 2;
     constexpr int EC = 128 / sizeof(T);        // elements per 128-byte chunk
     constexpr int KSTEP_BYTES = 32;            // one MMA consumes 32 bytes of K per row (16 bf16 / 8 tf32)
@@ -113,8 +118,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
     int* cnt_s = reinterpret_cast<int*>(tau_s + NP);
     u64* heap_s = reinterpret_cast<u64*>(cnt_s + NP);  // MODE_HEAP: [NP][TC_HEAP_SLOTS]; 16-byte aligned (NP % 16 == 0)
 
+    const int ACC = QH * NP;  // accumulator columns per buffer
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)(2 * NP)) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)(2 * ACC)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tm_db);
@@ -158,10 +164,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
             for (int b = 0; b < p.nblocks; b++) {
                 if (b > 0) mbar_wait(q_empty, (uint32_t)((b - 1) & 1));  // previous block's MMAs are done with it
                 mbar_arrive_expect_tx(q_full, (uint32_t)(QH * NK * NP * 128));
-                for (int c = 0; c < NK; c++) tma_load_2d(q_smem + (size_t)c * NP * 128, &tm_q, c * EC, b * NP, q_full);
+                for (int c = 0; c < NK; c++) tma_load_2d(q_smem + (size_t)c * QH * NP * 128, &tm_q, c * EC, b * NP, q_full);
                 if (X3)  // the lo halves of the queries are rows [nqp, 2 nqp) of the split query matrix
                     for (int c = 0; c < NK; c++)
-                        tma_load_2d(q_smem + (size_t)(NK + c) * NP * 128, &tm_q, c * EC, p.nqp + b * NP, q_full);
+                        tma_load_2d(q_smem + ((size_t)c * QH + 1) * NP * 128, &tm_q, c * EC, p.nqp + b * NP, q_full);
                 for (long long i = 0; i < my_tiles; i++) {
                     const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
                     const int row0 = (int)(tile * TC_BM);
@@ -182,6 +188,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         // ================= MMA issuer =================
         if (lane == 0 && my_tiles > 0) {
             const uint32_t idesc = make_idesc(TF32, TC_BM, NP);
+            const uint32_t idesc2 = make_idesc(TF32, TC_BM, 2 * NP);  // X3: both query halves in one MMA
             int stage = 0, lo_stage = 0;
             uint32_t phase = 0, lo_phase = 0;
             long long it = 0;  // tile counter across blocks: accumulator buffer and its phase
@@ -193,24 +200,25 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                     const uint32_t aphase = (uint32_t)((it >> 1) & 1);
                     mbar_wait(&acc_empty[a], aphase ^ 1u);  // epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * NP);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * ACC);
                     for (int c = 0; c < NK; c++) {
                         mbar_wait(&full[stage], phase);
-                        if (X3) mbar_wait(&lo_full[lo_stage], lo_phase);  // hi written in place, lo in the side ring
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(ring + (size_t)stage * TC_STAGE_BYTES);
-                        const uint32_t b_addr = smem_u32(q_smem + (size_t)c * NP * 128);
+                        const uint32_t b_addr = smem_u32(q_smem + (size_t)c * QH * NP * 128);
                         if (X3) {
-                            const uint32_t al_addr = smem_u32(lo_ring + (size_t)lo_stage * TC_STAGE_BYTES);
-                            const uint32_t bl_addr = smem_u32(q_smem + (size_t)(NK + c) * NP * 128);
+                            // raw tile x [Q_hi; Q_lo] (N = 2 NP): does not need the converters, issue it first
 #pragma unroll
-                            for (int k = 0; k < 128 / KSTEP_BYTES; k++) {
-                                const uint64_t ah = smem_desc_sw128(a_addr + k * KSTEP_BYTES), al = smem_desc_sw128(al_addr + k * KSTEP_BYTES);
-                                const uint64_t bh = smem_desc_sw128(b_addr + k * KSTEP_BYTES), bl = smem_desc_sw128(bl_addr + k * KSTEP_BYTES);
-                                umma<TF32>(d_tmem, ah, bh, idesc, (uint32_t)((c | k) != 0));
-                                umma<TF32>(d_tmem, ah, bl, idesc, 1u);
-                                umma<TF32>(d_tmem, al, bh, idesc, 1u);
-                            }
+                            for (int k = 0; k < 128 / KSTEP_BYTES; k++)
+                                umma<TF32>(d_tmem, smem_desc_sw128(a_addr + k * KSTEP_BYTES), smem_desc_sw128(b_addr + k * KSTEP_BYTES),
+                                           idesc2, (uint32_t)((c | k) != 0));
+                            mbar_wait(&lo_full[lo_stage], lo_phase);  // A_lo of this stage is in the side ring
+                            tc_fence_after();
+                            const uint32_t al_addr = smem_u32(lo_ring + (size_t)lo_stage * TC_STAGE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 128 / KSTEP_BYTES; k++)
+                                umma<TF32>(d_tmem, smem_desc_sw128(al_addr + k * KSTEP_BYTES), smem_desc_sw128(b_addr + k * KSTEP_BYTES),
+                                           idesc, 1u);
                             umma_commit(&lo_empty[lo_stage]);
                             if (++lo_stage == LO_STAGES) {
                                 lo_stage = 0;
@@ -250,17 +258,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
 #pragma unroll
                     for (int u = 0; u < TC_STAGE_BYTES / 16 / 128; u++) {  // 8 vectors per thread, element-wise: any swizzle
                         const float4 v = raw4[ct + 128 * u];
-                        float4 h, l;
-                        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                        // exact: the low 13 mantissa bits.  (inf - inf would turn an infinite element into NaN: keep hi only)
-                        l.x = fabsf(v.x) <= FLT_MAX ? v.x - h.x : 0.f;
-                        l.y = fabsf(v.y) <= FLT_MAX ? v.y - h.y : 0.f;
-                        l.z = fabsf(v.z) <= FLT_MAX ? v.z - h.z : 0.f;
-                        l.w = fabsf(v.w) <= FLT_MAX ? v.w - h.w : 0.f;
-                        raw4[ct + 128 * u] = h;  // explicit: the result does not depend on how the MMA narrows fp32 bits
+                        float4 l;
+                        // lo = v - (v with the low 13 mantissa bits cleared): exact.  (inf - inf would turn an infinite element
+                        // into NaN: keep hi only.)  hi is NOT written back: kind::tf32 reads exactly those upper 19 bits of the raw
+                        // tile (tests/test_gpu_tensorcore.py checks the 3xTF32 scores to 2e-6, which a rounding MMA would miss).
+                        l.x = fabsf(v.x) <= FLT_MAX ? v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u) : 0.f;
+                        l.y = fabsf(v.y) <= FLT_MAX ? v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u) : 0.f;
+                        l.z = fabsf(v.z) <= FLT_MAX ? v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u) : 0.f;
+                        l.w = fabsf(v.w) <= FLT_MAX ? v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u) : 0.f;
                         lo4[ct + 128 * u] = l;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> the MMA's async-proxy reads
@@ -310,10 +315,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                 const bool row_ok = row < p.n;
                 mbar_wait(&acc_full[a], aphase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(a * NP);
+                const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(a * ACC);
                 for (int c0 = 0; c0 < NP; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c0, v);
+                    if (X3) {  // score = (A_hi Q_hi + A_lo Q_hi) + A_hi Q_lo
+                        uint32_t w[16];
+                        tmem_ld16(taddr + NP + c0, w);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+                    }
                     if (MODE == MODE_DUMP) {
                         if (row_ok) {
 #pragma unroll

@@ -136,10 +136,11 @@ class IndexFlatIP:
         the last fused single-query scan."""
         n = ctypes.c_int64(0)
         check(lib().evs_index_scan_clocks(self._h, None, 0, ctypes.byref(n)))
-        out = np.zeros((n.value, 2), np.uint64)
+        out = np.zeros((n.value + 4, 2), np.uint64)
         if n.value:
-            check(lib().evs_index_scan_clocks(self._h, out.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n)))
-        return out
+            check(lib().evs_index_scan_clocks(self._h, out.ctypes.data_as(ctypes.c_void_p), n.value + 4, ctypes.byref(n)))
+        self.last_cta_stamps = out[n.value]  # (the last CTA's time after its epilogue, after the finalise [+ merge])
+        return out[:n.value]
 
     def reset(self) -> None:
         """faiss ``Index.reset``: drop all vectors."""

@@ -31,11 +31,11 @@ del qi
 SETS = [
     ("unfused static (round-1 path: scan + finalize)", dict(fuse_finalize=0, scan_dynamic=0)),
     ("fused static", dict(fuse_finalize=1, scan_dynamic=0)),
-    ("fused dynamic c=1", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=1)),
-    ("fused dynamic c=2", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=2)),
     ("fused dynamic c=4", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=4)),
-    ("fused dynamic c=8", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=8)),
+    ("fused dynamic c=6", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=6)),
 ]
+if os.environ.get("EVS_PROBE_ALL"):
+    SETS += [("fused dynamic c=%d" % c, dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=c)) for c in (1, 2, 8)]
 for rows in [int(r) for r in a.rows.split(",")]:
     idx = evs.IndexFlatIP(a.dim, storage=a.storage)
     idx.reserve(rows)
@@ -58,20 +58,48 @@ for rows in [int(r) for r in a.rows.split(",")]:
                "GBps_whole_search": round(rows * a.dim * esz / ms / 1e6, 1)}
         if opts.get("fuse_finalize"):
             evs.set_option("scan_clock", 1)
-            spans, spreads, tails = [], [], []
+            spans, spreads, tails, epi, fin = [], [], [], [], []
             for i in range(8):
                 idx.search(q[i:i + 1], 48)
                 c = idx.scan_clocks().astype(np.int64)
+                st = idx.last_cta_stamps.astype(np.int64)
                 t0 = c[:, 0].min()
                 end = c[:, 1] - t0
                 spans.append(end.max() / 1e3)
                 spreads.append((end.max() - end.min()) / 1e3)
                 tails.append((end.max() - np.median(end)) / 1e3)
+                epi.append((st[0] - t0 - end.max()) / 1e3)  # last scan-loop end -> the last CTA has its ticket
+                fin.append((st[1] - st[0]) / 1e3)           # the fused finalise
             evs.set_option("scan_clock", 0)
             rec.update(scan_loop_us=round(float(np.median(spans)), 1), cta_end_spread_us=round(float(np.median(spreads)), 1),
                        last_cta_after_median_us=round(float(np.median(tails)), 1),
-                       start_skew_us=round(float((c[:, 0].max() - c[:, 0].min()) / 1e3), 1))
+                       start_skew_us=round(float((c[:, 0].max() - c[:, 0].min()) / 1e3), 1),
+                       epilogue_us=round(float(np.median(epi)), 1), fused_finalize_us=round(float(np.median(fin)), 1))
         print(json.dumps(rec), flush=True)
     del idx
-for k_, v_ in dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=2).items():
+for k_, v_ in dict(fuse_finalize=1, scan_dynamic=0, scan_chunk_groups=4).items():
     evs.set_option(k_, v_)
+
+# small fp32 batches: 3xTF32 vs single tf32 vs the fp32 GEMV (1M x 512, the C2 shape)
+idx = evs.IndexFlatIP(a.dim)
+idx.add_synthetic(1_000_000, seed=0)
+q16 = q[:16].contiguous()
+for name, opts in (("3xTF32 + device guard", dict(x3=1, guard=1)), ("3xTF32, guard off", dict(x3=1, guard=0)),
+                   ("single tf32 + device guard", dict(x3=0, guard=1)), ("single tf32, guard off", dict(x3=0, guard=0))):
+    for k_, v_ in opts.items():
+        evs.set_option(k_, v_)
+    for nq in (2, 8, 16, 32):
+        qq = q[:nq].contiguous()
+        for i in range(5):
+            idx.search(qq, 48)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(50):
+            idx.search(qq, 48)
+        e1.record()
+        torch.cuda.synchronize()
+        print(json.dumps({"rows": 1_000_000, "nq": nq, "options": name, "ms_per_search": round(e0.elapsed_time(e1) / 50, 4),
+                          "scan_ms": round(idx.time_scan(qq, 48, iters=20), 4)}), flush=True)
+evs.set_option("x3", 1)
+evs.set_option("guard", 1)
