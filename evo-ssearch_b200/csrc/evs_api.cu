@@ -906,9 +906,10 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
                     a.chunk_groups = tune.scan_chunk_groups > 0 ? tune.scan_chunk_groups : 2;
                 }
                 if (tune.scan_clock) {
-                    if ((rc = ensure_dev(&idx->cta_clock, &idx->cta_clock_cap, (size_t)plan.grid * 2 + 8))) return rc;
+                    if ((rc = ensure_dev(&idx->cta_clock, &idx->cta_clock_cap, (size_t)plan.grid * 2 + 16))) return rc;
                     idx->cta_clock_n = plan.grid;
                     a.cta_clock = idx->cta_clock;
+                    f.dbg = idx->cta_clock + (size_t)plan.grid * 2 + 8;
                 }
             }
             // the plan's shared-memory size was computed for qpp queries per pass: large enough for fewer
@@ -1401,8 +1402,8 @@ extern "C" int evs_index_scan_clocks(evs_index* idx, uint64_t* out_host, int64_t
     if (cap_ctas < idx->cta_clock_n) return fail(EVS_EINVAL, "buffer holds %lld CTAs, need %d", (long long)cap_ctas, idx->cta_clock_n);
     if (idx->have_last_stream) CU(cudaStreamSynchronize(idx->last_stream));
     CU(cudaMemcpy(out_host, idx->cta_clock, (size_t)idx->cta_clock_n * 16, cudaMemcpyDeviceToHost));
-    if (cap_ctas >= idx->cta_clock_n + 4)  // then the last CTA's own stamps: after its epilogue / after the finalise (+ merge)
-        CU(cudaMemcpy(out_host + 2 * (size_t)idx->cta_clock_n, idx->cta_clock + 2 * (size_t)idx->cta_clock_n, 64, cudaMemcpyDeviceToHost));
+    if (cap_ctas >= idx->cta_clock_n + 8)  // then the last CTA's own stamps (8) and the phases of its finalise (8)
+        CU(cudaMemcpy(out_host + 2 * (size_t)idx->cta_clock_n, idx->cta_clock + 2 * (size_t)idx->cta_clock_n, 128, cudaMemcpyDeviceToHost));
     return EVS_OK;
 }
 

@@ -56,16 +56,17 @@ __device__ __forceinline__ void cmpx_desc(u64* a, int i, int j, bool desc) {
     }
 }
 
+// index of the lower element of compare-exchange pair t at distance `stride` (a power of two): insert a 0 bit at log2(stride)
+__device__ __forceinline__ int bitonic_low(int t, int stride) { return ((t & ~(stride - 1)) << 1) | (t & (stride - 1)); }
+
 // full sort: after the call a[0] >= a[1] >= ... >= a[n-1]
 __device__ __forceinline__ void warp_bitonic_sort_desc(u64* a, int n, int lane) {
     for (int size = 2; size <= n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncwarp();
             for (int t = lane; t < (n >> 1); t += 32) {
-                int i = ((t / stride) * (stride << 1)) + (t % stride);
-                int j = i + stride;
-                bool desc = ((i & size) == 0);
-                cmpx_desc(a, i, j, desc);
+                const int i = bitonic_low(t, stride);
+                cmpx_desc(a, i, i + stride, (i & size) == 0);
             }
         }
     }
@@ -77,7 +78,7 @@ __device__ __forceinline__ void warp_bitonic_merge_desc(u64* a, int n, int lane)
     for (int stride = n >> 1; stride > 0; stride >>= 1) {
         __syncwarp();
         for (int t = lane; t < (n >> 1); t += 32) {
-            int i = ((t / stride) * (stride << 1)) + (t % stride);
+            const int i = bitonic_low(t, stride);
             cmpx_desc(a, i, i + stride, true);
         }
     }

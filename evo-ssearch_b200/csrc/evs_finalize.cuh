@@ -136,6 +136,14 @@ __device__ __forceinline__ void finalize_prologue(const FinalizeParams& p, long 
     }
 }
 
+__device__ __forceinline__ void fin_stamp(const FinalizeParams& p, int slot) {
+    if (p.dbg != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg[slot] = t;
+    }
+}
+
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -243,6 +251,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
     }
     if (qi == 0 && t == 0 && p.guard_count_next) *p.guard_count_next = 0;  // ready for the next guarded search of this handle
     __syncthreads();
+    fin_stamp(p, 0);  // head blocks loaded
     if (p.err_coef > 0.f && warp == 0) {  // |q|^2 for the certification bound (qs is complete: barrier above)
         double s2 = 0.0;
         for (int i = lane; i < p.d; i += 32) s2 = fma(qs[i], qs[i], s2);
@@ -324,6 +333,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
         }
         __syncthreads();
     }  // attempt
+    fin_stamp(p, 1);  // T0 + survivors
     // 3. the kp best survivors in descending order -> A[0..kp)
     const int nsurv = sh->nsurv;
     // the re-score below reads the survivors' rows: start them on their way from HBM to L2 now (fp32 master rows)
@@ -359,7 +369,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 __syncthreads();
                 for (int e = t; e < (pow2 >> 1); e += nt) {
-                    int i = ((e / stride) * (stride << 1)) + (e % stride);
+                    const int i = bitonic_low(e, stride);
                     cmpx_desc(surv, i, i + stride, (i & size) == 0);
                 }
             }
@@ -368,6 +378,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
         A = surv;  // A[0..kp) = the kp best scan keys
     }
 
+    fin_stamp(p, 2);  // the kp best survivors ranked
     // 4. canonical re-score of the kp candidates (a warp takes two candidates at a time)
     for (int c = 2 * warp; c < kp; c += 2 * nwarps) {
         const u64 ka = A[c], kb = (c + 1 < kp) ? A[c + 1] : 0ull;
@@ -394,6 +405,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
         }
     }
     __syncthreads();
+    fin_stamp(p, 3);  // re-scored
     // how far the scan under-estimated its own candidates at most (tf32 truncates towards zero: a bias of ~1e-3 relative;
     // bf16 and fp32 scans scatter around zero)
     const bool want_margin = p.margins != nullptr || p.guard_count != nullptr || p.pred_slot != nullptr;
@@ -478,6 +490,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
         }
     }
     if (t == 0 && p.margins && nvalid < p.k) p.margins[qi] = INFINITY;  // every row was a candidate
+    fin_stamp(p, 4);  // ranked, results written
     if (p.x.world > 0 && p.D == nullptr) {
         // publish: when the last query's CTA has written its part, raise this shard's flag on every rank.  ONE system fence
         // orders the slot stores of the whole CTA (barrier above it) before the flags, which are then plain relaxed stores

@@ -90,6 +90,7 @@ struct FinalizeParams {
     const int* pred_slot = nullptr;
     unsigned long long* uncertified = nullptr;  // device counter: results that stayed uncertified
     unsigned long long* reruns = nullptr;       // device counter: queries finalised again from the exact re-run
+    unsigned long long* dbg = nullptr;          // diagnostics (option "scan_clock"): %globaltimer stamps of the finalise's phases
 };
 
 struct ScanArgs {

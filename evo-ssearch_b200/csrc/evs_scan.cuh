@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256, ScanOcc<T, NQ, NV>::value) scan_direct_ke
     // only now may the next kernel of the stream (finalise / merge / the next search's scan) become resident: its own
     // prologue may read the queries too, and they are complete from here on
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    unsigned long long t_start = 0;
+    unsigned long long t_start = 0, t_fin = 0, t_merged = 0;
     if (p.cta_clock && threadIdx.x == 0) t_start = globaltimer_ns();
 
     int nact = NQ;
@@ -303,9 +303,12 @@ __global__ void __launch_bounds__(256, ScanOcc<T, NQ, NV>::value) scan_direct_ke
             p.cta_clock[2 * blockIdx.x + 1] = globaltimer_ns();
         }
         sel.finish(lane);
+        __syncwarp();
+        if (p.cta_clock && threadIdx.x == 0) t_fin = globaltimer_ns();
         const int left = nact - g0;
         cta_merge_and_store<NQ>(sel_base, nwarps, p.kp, p, p.nactive ? g0 : p.q0, left < NQ ? left : NQ);
         __syncthreads();  // the selection buffers are reused by the next group / by the finalise below
+        if (p.cta_clock && threadIdx.x == 0) t_merged = globaltimer_ns();
     }
 
     if constexpr (NQ == 1) {
@@ -320,7 +323,13 @@ __global__ void __launch_bounds__(256, ScanOcc<T, NQ, NV>::value) scan_direct_ke
                     if (p.next_chunk) *p.next_chunk = 0u;
                 }
                 __threadfence();
-                if (p.cta_clock && threadIdx.x == 0) p.cta_clock[2 * gridDim.x] = globaltimer_ns();
+                if (p.cta_clock && threadIdx.x == 0) {
+                    unsigned long long* x = p.cta_clock + 2 * gridDim.x;
+                    x[0] = globaltimer_ns();  // this (the last) CTA holds its ticket
+                    x[2] = t_fin;             // ... had sorted its warps' buffers
+                    x[3] = t_merged;          // ... had merged them and stored its list
+                    x[4] = p.cta_clock[2 * blockIdx.x + 1];  // ... had left its scan loop (warp 0)
+                }
                 finalize_prologue(f, p.q0, smem_raw);
                 __syncthreads();
                 finalize_query(f, p.q0, f.lists + (size_t)p.q0 * f.L * f.kp, smem_raw);

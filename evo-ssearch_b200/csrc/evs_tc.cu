@@ -255,17 +255,22 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                     mbar_wait(&lo_empty[lo_stage], lo_phase ^ 1u);  // the MMAs that read this lo slot are done
                     float4* raw4 = reinterpret_cast<float4*>(ring + (size_t)stage * TC_STAGE_BYTES);
                     float4* lo4 = reinterpret_cast<float4*>(lo_ring + (size_t)lo_stage * TC_STAGE_BYTES);
+                    // lo = v - (v with the low 13 mantissa bits cleared): exact.  (inf - inf would turn an infinite element into
+                    // NaN: keep hi only.)  hi is NOT written back: kind::tf32 reads exactly those upper 19 bits of the raw tile
+                    // (tests/test_gpu_tensorcore.py checks the 3xTF32 scores to 2e-6, which a rounding MMA would miss).
+                    // All eight loads first: a store between them would serialise the loop on shared-memory latency (the
+                    // compiler cannot prove that the two rings do not alias).
+                    constexpr int NV8 = TC_STAGE_BYTES / 16 / 128;  // 8 vectors per thread; element-wise, so any swizzle
+                    float4 v[NV8];
 #pragma unroll
-                    for (int u = 0; u < TC_STAGE_BYTES / 16 / 128; u++) {  // 8 vectors per thread, element-wise: any swizzle
-                        const float4 v = raw4[ct + 128 * u];
+                    for (int u = 0; u < NV8; u++) v[u] = raw4[ct + 128 * u];
+#pragma unroll
+                    for (int u = 0; u < NV8; u++) {
                         float4 l;
-                        // lo = v - (v with the low 13 mantissa bits cleared): exact.  (inf - inf would turn an infinite element
-                        // into NaN: keep hi only.)  hi is NOT written back: kind::tf32 reads exactly those upper 19 bits of the raw
-                        // tile (tests/test_gpu_tensorcore.py checks the 3xTF32 scores to 2e-6, which a rounding MMA would miss).
-                        l.x = fabsf(v.x) <= FLT_MAX ? v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u) : 0.f;
-                        l.y = fabsf(v.y) <= FLT_MAX ? v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u) : 0.f;
-                        l.z = fabsf(v.z) <= FLT_MAX ? v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u) : 0.f;
-                        l.w = fabsf(v.w) <= FLT_MAX ? v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u) : 0.f;
+                        l.x = fabsf(v[u].x) <= FLT_MAX ? v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u) : 0.f;
+                        l.y = fabsf(v[u].y) <= FLT_MAX ? v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u) : 0.f;
+                        l.z = fabsf(v[u].z) <= FLT_MAX ? v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u) : 0.f;
+                        l.w = fabsf(v[u].w) <= FLT_MAX ? v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u) : 0.f;
                         lo4[ct + 128 * u] = l;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> the MMA's async-proxy reads
@@ -701,7 +706,7 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ 
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 __syncthreads();
                 for (int t = threadIdx.x; t < (pow2 >> 1); t += nt) {
-                    int i = ((t / stride) * (stride << 1)) + (t % stride);
+                    const int i = bitonic_low(t, stride);
                     cmpx_desc(all, i, i + stride, (i & size) == 0);
                 }
             }

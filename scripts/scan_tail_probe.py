@@ -71,6 +71,11 @@ for rows in [int(r) for r in a.rows.split(",")]:
                 epi.append((st[0] - t0 - end.max()) / 1e3)  # last scan-loop end -> the last CTA has its ticket
                 fin.append((st[1] - st[0]) / 1e3)           # the fused finalise
             evs.set_option("scan_clock", 0)
+            fs = idx.finalize_stamps.astype(np.int64)
+            rec["last_cta_us"] = {"loop_end_to_sorted": round((st[2] - st[4]) / 1e3, 1), "sorted_to_stored": round((st[3] - st[2]) / 1e3, 1),
+                                  "stored_to_ticket": round((st[0] - st[3]) / 1e3, 1), "ticket_to_heads": round((fs[0] - st[0]) / 1e3, 1),
+                                  "heads_to_survivors": round((fs[1] - fs[0]) / 1e3, 1), "survivors_to_ranked": round((fs[2] - fs[1]) / 1e3, 1),
+                                  "ranked_to_rescored": round((fs[3] - fs[2]) / 1e3, 1), "rescored_to_written": round((fs[4] - fs[3]) / 1e3, 1)}
             rec.update(scan_loop_us=round(float(np.median(spans)), 1), cta_end_spread_us=round(float(np.median(spreads)), 1),
                        last_cta_after_median_us=round(float(np.median(tails)), 1),
                        start_skew_us=round(float((c[:, 0].max() - c[:, 0].min()) / 1e3), 1),
