@@ -202,7 +202,8 @@ def scan_arithmetic(evs, storage: str, nq: int, rows_per_gpu: int, dim: int) -> 
         return "bf16 tensor-core scan (tcgen05.mma kind::f16), fp32 accumulate"
     if evs.get_option("x3") and nq <= evs.get_option("x3_max_nq") and dim * 4 % 128 == 0 and dim <= 768:
         return "3xTF32 tensor-core scan (tcgen05.mma kind::tf32, hi/lo split operands, 3 MMAs per K step), fp32 accumulate"
-    return "single-tf32 tensor-core scan (tcgen05.mma kind::tf32) + statistical certification + fp32 GEMV re-run of uncertified queries"
+    return ("single-tf32 tensor-core scan (tcgen05.mma kind::tf32) + on-device certification against the rigorous truncation bound "
+            "+ fp32 GEMV re-run of uncertified queries")
 
 
 def device_timed(torch, dev, fn, reps, warmup=3):
@@ -279,6 +280,14 @@ def config_legs_single(evs, torch, dev, k):
                     rec["fp32_gemv_ms_per_search"] = gms
                     rec["fp32_gemv_queries_per_s"] = nq / gms * 1e3
                     rec["guard"] = dict(zip(("device_reruns", "uncertified"), idx.guard_stats()))
+                    rec["guard"]["searches"] = 50 + 3 + 21
+                    # ... and on the 3xTF32 split scan (fp32-class scan scores from the tensor cores, option "x3")
+                    oldx = evs.get_option("x3")
+                    evs.set_option("x3", 1)
+                    if idx.tc_x3_max_queries() >= nq:
+                        rec["x3_ms_per_search"] = device_timed(torch, dev, lambda: idx.search(xq, k), 20)
+                        rec["x3_scan_ms"] = idx.time_scan(xq, k, iters=20)
+                    evs.set_option("x3", oldx)
             else:
                 flops = 2.0 * nq * rows * d
                 ach = flops / (scan_ms * 1e-3) / 1e12

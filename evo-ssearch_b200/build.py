@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libevs.so")
 SOURCES = ["evs_kernels.cu", "evs_api.cu", "evs_tc.cu", "evs_tc2.cu"]
-HEADERS = ["evs_common.cuh", "evs_scan.cuh", "evs_tc_common.cuh", "evs_internal.h", os.path.join("..", "..", "include", "evs.h")]
+HEADERS = ["evs_common.cuh", "evs_scan.cuh", "evs_finalize.cuh", "evs_tc_common.cuh", "evs_internal.h", os.path.join("..", "..", "include", "evs.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -48,8 +48,9 @@ static int g_profile_scans = 0;                    // record CUDA events around 
 static std::atomic<long long> g_tc_fallbacks{0};   // queries re-run through the GEMV scan after a tensor-core buffer overflow
 static std::atomic<long long> g_exact_reruns{0};   // queries the HOST re-ran with the fp32 GEMV scan because the finalise could not
                                                    // certify them (the device-side re-runs are counted per handle: evs_index_guard_stats)
-static int g_tf32_guard_eps_e6 = 150;              // option "tf32_guard_eps_e6": STATISTICAL error bound (x 1e-6, relative to |q| max|x|)
-                                                   // of the single-tf32 scans (fp32 rows, batches beyond the 3xTF32 range); 0 = off
+static int g_tf32_guard_eps_e6 = 0;                // option "tf32_guard_eps_e6": 0 (default) = the single-tf32 scans are certified against
+                                                   // their RIGOROUS truncation bound (tf32_trunc_coef); > 0 = a statistical bound instead
+                                                   // (x 1e-6, relative to |q| max|x|; round 1 used 150) -- experiments only
 
 // ---------------------------------------------------------------------------------------------
 // the handle
@@ -514,6 +515,7 @@ struct PathInfo {
     bool guard = false;  // results are certified on the device and uncertified queries re-run exactly (fp32 storage, batches)
     int blk = 0;         // PATH_TC_HEAP: queries per launch set
     float err_coef = 0.f;  // scan error bound relative to |q| * max|x| (0 = not certified: bf16 storage)
+    float err_trunc = 0.f; // single tf32: the truncation part of the bound, relative to (|q| max|x| + |worst retained score|)
     bool fused = false;  // PATH_GEMV, one query: the scan's last CTA finalises (and, in exchange mode, merges): ONE launch
 };
 
@@ -521,6 +523,14 @@ struct PathInfo {
 // additions to combine: (d/128 + 9) roundings of 2^-24, stated generously.  3xTF32: three dropped terms of 2^-20 each plus
 // one fp32 accumulation per MMA (3 per 8 elements of K), each taken as a full 2^-23 truncation of the running sum.
 static float gemv_err_coef(int d) { return (float)((d / 32 + 8) * ldexp(1.0, -24)); }
+// single tf32 (kind::tf32 on raw fp32 operands: the low 13 mantissa bits of BOTH operands are ignored, i.e. truncation
+// towards zero -- tests/test_gpu_tensorcore.py::test_tf32_scan_truncates_its_operands pins that): each product is scaled
+// by (1 - a)(1 - b), a, b in [0, 2^-10), so a row is under-estimated by at most (2^-9) * (sum of its positive products)
+// <= 2^-10 * (|q||x| + score).  Solving  s <= w + 2^-10 (B + s) + acc  for s gives the coefficient below (the 1/(1 - 2^-10)
+// factor folded in).  The products themselves are exact in fp32 (11 x 11 significant bits); what is left is the fp32
+// accumulation: one rounding of the running sum per MMA (d/8 of them) and one per product, taken as full 2^-23 truncations.
+static float tf32_trunc_coef() { return (float)(ldexp(1.0, -10) * (1.0 + ldexp(1.0, -9))); }
+static float tf32_acc_coef(int d) { return (float)((d / 8.0 + 16.0) * ldexp(1.0, -22)); }
 static float x3_err_coef(int d) { return (float)(3.0 * ldexp(1.0, -20) + (3.0 * d / 8.0 + 8.0) * ldexp(1.0, -23)); }
 
 static bool takes_tc_path(const evs_index* idx, int64_t nq, const ScanTuning& tune) {
@@ -557,8 +567,17 @@ static PathInfo plan_path(const evs_index* idx, int64_t nq, int64_t k, const Sca
         pi.err_coef = x3_err_coef(idx->d);
         return pi;
     }
-    pi.err_coef = bf16 ? 0.f : (float)g_tf32_guard_eps_e6 * 1e-6f;  // single tf32: statistical bound (option), not a proof
-    if (pi.err_coef <= 0.f) pi.guard = false;
+    if (!bf16) {
+        if (g_tf32_guard_eps_e6 > 0) {
+            pi.err_coef = (float)g_tf32_guard_eps_e6 * 1e-6f;  // statistical override (option), not a proof
+        } else {
+            pi.err_coef = tf32_acc_coef(idx->d);
+            pi.err_trunc = tf32_trunc_coef();
+        }
+    } else {
+        pi.err_coef = 0.f;
+        pi.guard = false;
+    }
     pi.kind = PATH_TC_SYNC;
     if (nq <= kTcQueryChunk) {
         const bool pair = tune.tc_pair_min_nq > 0 && (nq >= tune.tc_pair_min_nq || nq > tc_max_queries(idx->d, bf16)) &&
@@ -595,7 +614,7 @@ static int ws_acquire(evs_index* idx, cudaStream_t st) {
 }
 
 static FinalizeParams make_finalize(evs_index* idx, const void* lists, int L, int kp, const float* xq, int64_t k, const SearchOut& out,
-                                    int64_t c0, int64_t nq_total, float err_coef) {
+                                    int64_t c0, int64_t nq_total, float err_coef, float err_trunc = 0.f) {
     FinalizeParams f;
     f.lists = reinterpret_cast<const unsigned long long*>(lists);
     f.L = L;
@@ -617,6 +636,7 @@ static FinalizeParams make_finalize(evs_index* idx, const void* lists, int L, in
         f.x.q_off = c0;
     }
     f.err_coef = err_coef;
+    f.err_trunc = err_trunc;
     f.max_norm = reinterpret_cast<const float*>(idx->words + W_MAX_NORM);
     f.uncertified = reinterpret_cast<unsigned long long*>(idx->words + W_UNCERT);
     return f;
@@ -704,7 +724,7 @@ static int search_tc_heap_locked(evs_index* idx, int64_t nq, const float* q_dev,
     }
     if ((rc = prof.end(st))) return rc;
     if (scan_only) return EVS_OK;
-    FinalizeParams f = make_finalize(idx, idx->lists, grid, kp, q_dev, k, out, 0, nq, pi.err_coef);
+    FinalizeParams f = make_finalize(idx, idx->lists, grid, kp, q_dev, k, out, 0, nq, pi.err_coef, pi.err_trunc);
     int* gslot = idx->guard_slot;
     int* gqueue = idx->guard_slot ? idx->guard_slot + (nq > kGuardCap ? nq : kGuardCap) : nullptr;
     int* gcount = nullptr;
@@ -812,7 +832,7 @@ static int search_tc_sync_locked(evs_index* idx, int64_t nq, const float* q_dev,
         }
         if ((rc = prof.end(st))) return rc;
         if (scan_only) continue;
-        FinalizeParams f = make_finalize(idx, idx->lists, lists_per_query, kp, q_dev + (size_t)c0 * idx->d, k, out, c0, nq, pi.err_coef);
+        FinalizeParams f = make_finalize(idx, idx->lists, lists_per_query, kp, q_dev + (size_t)c0 * idx->d, k, out, c0, nq, pi.err_coef, pi.err_trunc);
         if (guard) {  // certification only: the queue is read by the host below, nothing is re-run on the device
             f.guard_count = gcount;
             f.guard_count_next = gcount_next;

@@ -442,16 +442,22 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
                 // All kp slots taken -> every row outside the list has a scan score <= the worst retained one, so its
                 // true score is at most that plus the scan's error.  margin = canonical score of rank k minus (worst
                 // retained scan score + the largest under-estimate observed on the retained candidates); the result is
-                // CERTIFIED exact when margin > E = err_coef * |q| * max|x|, E being the error bound of the scan that
-                // produced the lists (fp32 GEMV / 3xTF32: a few 1e-6 .. 1e-5; single tf32: the caller's statistical eps).
+                // CERTIFIED exact when it clears the error bound of the scan that produced the lists (below).
                 const float worst = key_score(A[kp - 1]);
                 const float under = fmaxf(ordered_to_score(sh->maxerr), 0.f);
-                const float margin = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) - under : INFINITY;
+                const float gap = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) : INFINITY;
+                const float margin = gap - under;
                 if (p.margins) p.margins[qi] = margin;
                 if (p.err_coef > 0.f) {
                     const float mx = p.max_norm ? *p.max_norm : 1.f;
-                    const float E = p.err_coef * (float)sqrt(sh->qnorm2) * mx;
-                    const bool certified = margin > E;  // false for NaN
+                    const float B = (float)sqrt(sh->qnorm2) * mx;  // >= sum |x_i q_i| of any row (Cauchy-Schwarz)
+                    // Symmetric scan error (fp32 GEMV, 3xTF32): |scan - true| <= err_coef * B.
+                    // Truncating scan (single tf32: both operands lose their low 13 mantissa bits, towards zero): every product
+                    // shrinks by a factor in (1 - 2^-9, 1], so a row is UNDER-estimated by at most 2^-9 * (sum of its positive
+                    // products) <= 2^-10 * (B + true score): a row the scan dropped (scan score <= w) has a true score
+                    // <= w + err_trunc * (B + |w|) + accumulation error.  A bound, not a statistic.
+                    const bool certified = p.err_trunc > 0.f ? gap > p.err_trunc * (B + fabsf(worst)) + p.err_coef * B  // false for NaN
+                                                             : margin > p.err_coef * B;
                     if (!certified) {
                         if (p.guard_count) {  // first phase: queue the query for the exact re-run
                             const int slot = atomicAdd(p.guard_count, 1);

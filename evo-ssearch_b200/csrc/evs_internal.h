@@ -26,8 +26,12 @@ struct ScanTuning {
                                // ends only ~3 us earlier and grabs of fewer than 4 groups choke on the one counter
     int scan_chunk_groups = 4;
     int scan_clock = 0;        // diagnostics: record per-CTA start / end-of-scan-loop times of fused single-query scans
-    int x3 = 1;                // fp32 rows, batches up to x3_max_nq queries: 3xTF32 split scan (fp32-class scan error)
-    int x3_max_nq = 32;
+    int x3 = 0;                // fp32 rows, batches up to x3_max_nq queries: 3xTF32 split scan (fp32-class scan error, so the
+                               // guard practically never re-runs) instead of the single-tf32 scan + guard.  Off by default:
+                               // measured at 1M x 512, 16 queries: 0.417 ms against 0.343 ms (the split doubles the MMAs per
+                               // staged byte and MMAs this small cost ~100 cycles each: 5.3 TB/s instead of 6.4); worth it for
+                               // data whose near-duplicates would make the tf32 guard re-run most queries
+    int x3_max_nq = 16;
     int guard = 1;             // certify fp32-storage batch results on the device and re-run uncertified queries exactly
 };
 
@@ -79,6 +83,8 @@ struct FinalizeParams {
     Exchange x;
     // certification: the result of a query is certified when  margin > err_coef * |q| * max|x|  (see finalize_query)
     float err_coef = 0.f;             // error bound of the scan that produced the lists, relative to |q|*|x|; 0 = do not certify
+    float err_trunc = 0.f;            // > 0: the scan TRUNCATES its operands (single tf32): the result is certified when
+                                      //   (score of rank k) - (worst retained scan score w) > err_trunc * (|q| max|x| + |w|) + err_coef * |q| max|x|
     const float* max_norm = nullptr;  // device: largest row norm of the index (null -> 1)
     // guard, first phase: uncertified queries are queued for the exact re-run
     int* guard_count = nullptr;       // device counter (null -> no guard)

@@ -79,21 +79,25 @@ struct TcParams {
 // is far above fp32 noise; here every operand is split  v = hi + lo  (hi = the tf32 part, lo = v - hi exactly) and the
 // products A_hi*Q_hi + A_hi*Q_lo + A_lo*Q_hi are accumulated: the dropped terms are ~2^-20 relative, i.e. fp32-class
 // scores from the tensor cores.  The queries are split once (tc_split_queries); the resident query block holds, per K
-// chunk, the NP hi rows followed by the NP lo rows, so that ONE MMA with N = 2 NP multiplies the staged tile by both halves
-// (accumulator columns [0, NP) = A_hi*Q_hi, [NP, 2 NP) = A_hi*Q_lo; the tensor core narrows the raw fp32 tile to its tf32
-// part by itself: kind::tf32 ignores the low 13 mantissa bits) and a second MMA with N = NP adds A_lo*Q_hi into columns
-// [0, NP); the epilogue adds the two column halves.  A_lo is produced on the fly by four converter warps (8-11) into a
-// two-deep side ring.  What bounds this kernel is shared-memory bandwidth, not the tensor pipe (12 % busy): per 16 KB stage
-// the TMA writes 16 KB, the converters read 16 and write 16, the MMAs read 2 x 16 KB of A -- 80 KB against the 82 KB the SM
-// can move in the time HBM delivers the stage; the first version (three MMAs, hi rewritten in place) moved 118 KB and
-// ran at 0.53x of the HBM roofline.
+// chunk, the NP hi rows followed by the NP lo rows, so that ONE MMA with N = 2 NP multiplies the tile by both halves
+// (accumulator columns [0, NP) = A_hi*Q_hi, [NP, 2 NP) = A_hi*Q_lo; the tensor core narrows the raw fp32 values to their
+// tf32 part by itself: kind::tf32 ignores the low 13 mantissa bits) and a second MMA with N = NP adds A_lo*Q_hi into
+// columns [0, NP); the epilogue adds the two column halves.
+// The A operands of both MMAs come from TENSOR MEMORY (tcgen05.mma with [a_tmem]): eight converter warps (8-15, two per
+// TMEM lane quarter, alternating stages) read each staged tile once from shared memory -- a thread owns a row, its eight
+// 16-byte reads undo the 128-byte swizzle -- and write the raw values and their lo parts into a six-deep ring of TMEM
+// columns with tcgen05.st.  Shared memory then carries, per 16 KB stage, the TMA write (16 KB), the converters' read
+// (16 KB) and the MMAs' reads of the query block (12 KB): 44 KB.  The first two versions kept A_lo in a shared-memory
+// side ring (TMA write 16 + converter read 16 + write 16 + two A reads of 16 each + 12 = 92 KB per stage against the
+// ~82 KB the SM can move while HBM delivers the stage): they ran at 0.53x and 0.64x of the HBM roofline.
 template <typename T, int MODE, bool X3>
-__global__ void __launch_bounds__(X3 ? 384 : 256, 1)
+__global__ void __launch_bounds__(X3 ? 512 : 256, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant__ CUtensorMap tm_q, TcParams p) {
     static_assert(!X3 || sizeof(T) == 4, "the 3xTF32 split applies to fp32 rows");
     constexpr bool TF32 = sizeof(T) == 4;
     constexpr int QH = X3 ? 2 : 1;             // resident query copies (hi, lo): chunk c holds [hi: NP rows][lo: NP rows]
-    constexpr int LO_STAGES = 2;
+    constexpr int AS = TC_X3_TMEM_STAGES;      // X3: TMEM ring of A operands, 64 columns per stage (raw | lo)
+    constexpr uint32_t A_COL0 = 128;           // X3: the ring starts behind the two accumulator buffers (2 x 3 NP <= 96)
     constexpr int EC = 128 / sizeof(T);        // elements per 128-byte chunk
     constexpr int KSTEP_BYTES = 32;            // one MMA consumes 32 bytes of K per row (16 bf16 / 8 tf32)
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -103,24 +107,24 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
     // 128B-swizzled operands need 1024-byte aligned bases: align by hand (1 KiB of slack is allocated)
     unsigned char* q_smem = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);  // X3: [hi: NK chunks][lo: NK chunks]
     unsigned char* ring = q_smem + (size_t)QH * NK * NP * 128;
-    unsigned char* lo_ring = ring + (size_t)S * TC_STAGE_BYTES;  // X3: LO_STAGES x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? (size_t)LO_STAGES * TC_STAGE_BYTES : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * TC_STAGE_BYTES);
     uint64_t* q_full = bars;             // 1: the query block has landed
     uint64_t* q_empty = bars + 1;        // 1: every MMA that reads the query block has completed
     uint64_t* full = bars + 2;           // S
     uint64_t* empty = full + S;          // S
     uint64_t* acc_full = empty + S;      // 2
     uint64_t* acc_empty = acc_full + 2;  // 2
-    uint64_t* lo_full = acc_empty + 2;   // LO_STAGES (X3): the converter warps have split the stage
-    uint64_t* lo_empty = lo_full + LO_STAGES;  // LO_STAGES (X3): the MMAs that read the lo tile have completed
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(lo_empty + LO_STAGES);
+    uint64_t* a_full = acc_empty + 2;    // AS (X3): the converter warps have filled the TMEM stage
+    uint64_t* a_empty = a_full + AS;     // AS (X3): the MMAs that read the TMEM stage have completed
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(a_empty + AS);
     float* tau_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_smem + 4) + 15) & ~(uintptr_t)15);  // float4 reads
     int* cnt_s = reinterpret_cast<int*>(tau_s + NP);
     u64* heap_s = reinterpret_cast<u64*>(cnt_s + NP);  // MODE_HEAP: [NP][TC_HEAP_SLOTS]; 16-byte aligned (NP % 16 == 0)
 
-    const int ACC = QH * NP;  // accumulator columns per buffer
+    const int ACC = (X3 ? 3 : 1) * NP;  // accumulator columns per buffer (X3: A_hi*Q_hi | A_hi*Q_lo | A_lo*Q_hi)
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(2 * ACC)) tmem_cols <<= 1;
+    if (X3) tmem_cols = 512;  // accumulators [0, 128) + AS x 64 columns of A operands
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tm_db);
@@ -129,15 +133,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         mbar_init(q_empty, 1);
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], X3 ? 4 : 1);  // X3: released by the four converter warps that read the stage
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], 4);
         }
-        for (int a = 0; a < LO_STAGES; a++) {
-            mbar_init(&lo_full[a], 4);  // one arrival per converter warp
-            mbar_init(&lo_empty[a], 1);
+        for (int a = 0; a < AS; a++) {
+            mbar_init(&a_full[a], 4);  // one arrival per converter warp of the stage's group
+            mbar_init(&a_empty[a], 1);
         }
         mbar_fence_init();
     }
@@ -189,8 +193,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         if (lane == 0 && my_tiles > 0) {
             const uint32_t idesc = make_idesc(TF32, TC_BM, NP);
             const uint32_t idesc2 = make_idesc(TF32, TC_BM, 2 * NP);  // X3: both query halves in one MMA
-            int stage = 0, lo_stage = 0;
-            uint32_t phase = 0, lo_phase = 0;
+            int stage = 0, ts = 0;
+            uint32_t phase = 0, tphase = 0;
             long long it = 0;  // tile counter across blocks: accumulator buffer and its phase
             for (int b = 0; b < p.nblocks; b++) {
                 mbar_wait(q_full, (uint32_t)(b & 1));
@@ -202,39 +206,41 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(a * ACC);
                     for (int c = 0; c < NK; c++) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(ring + (size_t)stage * TC_STAGE_BYTES);
                         const uint32_t b_addr = smem_u32(q_smem + (size_t)c * QH * NP * 128);
                         if (X3) {
-                            // raw tile x [Q_hi; Q_lo] (N = 2 NP): does not need the converters, issue it first
-#pragma unroll
-                            for (int k = 0; k < 128 / KSTEP_BYTES; k++)
-                                umma<TF32>(d_tmem, smem_desc_sw128(a_addr + k * KSTEP_BYTES), smem_desc_sw128(b_addr + k * KSTEP_BYTES),
-                                           idesc2, (uint32_t)((c | k) != 0));
-                            mbar_wait(&lo_full[lo_stage], lo_phase);  // A_lo of this stage is in the side ring
+                            mbar_wait(&a_full[ts], tphase);  // the converters have put this K chunk (raw | lo) into TMEM
                             tc_fence_after();
-                            const uint32_t al_addr = smem_u32(lo_ring + (size_t)lo_stage * TC_STAGE_BYTES);
+                            const uint32_t a_raw = tmem_base + A_COL0 + (uint32_t)(ts * 64);
+                            // raw tile x [Q_hi; Q_lo] (N = 2 NP) into columns [0, 2 NP), lo tile x Q_hi (N = NP) into columns
+                            // [2 NP, 3 NP): two INDEPENDENT accumulation chains issued alternately.  MMAs this small are bound
+                            // by their latency (~100 cycles each when every one waits for the previous one's accumulator:
+                            // ncu had the converters waiting for the TMEM ring half of the time with both products chained
+                            // through the same columns)
 #pragma unroll
-                            for (int k = 0; k < 128 / KSTEP_BYTES; k++)
-                                umma<TF32>(d_tmem, smem_desc_sw128(al_addr + k * KSTEP_BYTES), smem_desc_sw128(b_addr + k * KSTEP_BYTES),
-                                           idesc, 1u);
-                            umma_commit(&lo_empty[lo_stage]);
-                            if (++lo_stage == LO_STAGES) {
-                                lo_stage = 0;
-                                lo_phase ^= 1u;
+                            for (int k = 0; k < 128 / KSTEP_BYTES; k++) {
+                                const uint64_t bd = smem_desc_sw128(b_addr + k * KSTEP_BYTES);
+                                umma_ts_tf32(d_tmem, a_raw + 8 * k, bd, idesc2, (uint32_t)((c | k) != 0));
+                                umma_ts_tf32(d_tmem + 2 * NP, a_raw + 32 + 8 * k, bd, idesc, (uint32_t)((c | k) != 0));
+                            }
+                            umma_commit(&a_empty[ts]);  // frees the TMEM stage when these MMAs have read it
+                            if (++ts == AS) {
+                                ts = 0;
+                                tphase ^= 1u;
                             }
                         } else {
+                            mbar_wait(&full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t a_addr = smem_u32(ring + (size_t)stage * TC_STAGE_BYTES);
 #pragma unroll
                             for (int k = 0; k < 128 / KSTEP_BYTES; k++) {
                                 umma<TF32>(d_tmem, smem_desc_sw128(a_addr + k * KSTEP_BYTES),
                                            smem_desc_sw128(b_addr + k * KSTEP_BYTES), idesc, (uint32_t)((c | k) != 0));
                             }
-                        }
-                        umma_commit(&empty[stage]);  // frees the ring slot when these MMAs have read it
-                        if (++stage == S) {
-                            stage = 0;
-                            phase ^= 1u;
+                            umma_commit(&empty[stage]);  // frees the ring slot when these MMAs have read it
+                            if (++stage == S) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
                         }
                     }
                     umma_commit(&acc_full[a]);  // accumulator complete -> epilogue
@@ -244,45 +250,60 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         }
         __syncwarp();
     } else if (X3 && warp >= 8) {
-        // ================= converter warps (3xTF32): split every staged tile into hi (in place) + lo =================
-        const int ct = threadIdx.x - 256;  // 0..127
-        int stage = 0, lo_stage = 0;
-        uint32_t phase = 0, lo_phase = 0;
+        // ================= converter warps (3xTF32): staged tile -> TMEM as the two A operands (raw | lo) =================
+        const int cw = warp - 8;        // 0..7
+        const int quarter = cw & 3;     // = warp % 4: the TMEM lanes this warp may access
+        const int grp = cw >> 2;        // the two groups of four warps take alternate stages
+        const int r = quarter * 32 + lane;  // this thread's row of the tile = its TMEM lane
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + A_COL0;
+        int stage = 0, ts = 0;
+        uint32_t phase = 0, tphase = 0;
+        long long itc = 0;
         for (int b = 0; b < p.nblocks; b++) {
             for (long long i = 0; i < my_tiles; i++) {
-                for (int c = 0; c < NK; c++) {
-                    mbar_wait(&full[stage], phase);                 // the raw fp32 tile has landed (TMA)
-                    mbar_wait(&lo_empty[lo_stage], lo_phase ^ 1u);  // the MMAs that read this lo slot are done
-                    float4* raw4 = reinterpret_cast<float4*>(ring + (size_t)stage * TC_STAGE_BYTES);
-                    float4* lo4 = reinterpret_cast<float4*>(lo_ring + (size_t)lo_stage * TC_STAGE_BYTES);
-                    // lo = v - (v with the low 13 mantissa bits cleared): exact.  (inf - inf would turn an infinite element into
-                    // NaN: keep hi only.)  hi is NOT written back: kind::tf32 reads exactly those upper 19 bits of the raw tile
-                    // (tests/test_gpu_tensorcore.py checks the 3xTF32 scores to 2e-6, which a rounding MMA would miss).
-                    // All eight loads first: a store between them would serialise the loop on shared-memory latency (the
-                    // compiler cannot prove that the two rings do not alias).
-                    constexpr int NV8 = TC_STAGE_BYTES / 16 / 128;  // 8 vectors per thread; element-wise, so any swizzle
-                    float4 v[NV8];
+                for (int c = 0; c < NK; c++, itc++) {
+                    if ((int)(itc & 1) == grp) {
+                        mbar_wait(&full[stage], phase);           // the raw fp32 tile has landed (TMA)
+                        mbar_wait(&a_empty[ts], tphase ^ 1u);     // the MMAs that read this TMEM stage are done
+                        tc_fence_after();
+                        // row r of the 128-byte-swizzled tile: logical 16-byte chunk u sits at chunk u ^ (r & 7); a quarter warp
+                        // (8 consecutive rows) covers all 32 banks once per load: conflict-free
+                        const float4* row = reinterpret_cast<const float4*>(ring + (size_t)stage * TC_STAGE_BYTES + (size_t)r * 128);
+                        uint32_t v[32];
 #pragma unroll
-                    for (int u = 0; u < NV8; u++) v[u] = raw4[ct + 128 * u];
+                        for (int u = 0; u < 8; u++) {
+                            const float4 t = row[u ^ (r & 7)];
+                            v[4 * u + 0] = __float_as_uint(t.x);
+                            v[4 * u + 1] = __float_as_uint(t.y);
+                            v[4 * u + 2] = __float_as_uint(t.z);
+                            v[4 * u + 3] = __float_as_uint(t.w);
+                        }
+                        // raw values as they are: kind::tf32 reads exactly their upper 19 bits (tests/test_gpu_tensorcore.py
+                        // checks the 3xTF32 scores to 2e-6, which a rounding MMA would miss)
+                        tmem_st32(t_lane + (uint32_t)(ts * 64), v);
+                        // lo = v - (v with the low 13 mantissa bits cleared): exact.  (inf - inf would turn an infinite element
+                        // into NaN: keep hi only.)
 #pragma unroll
-                    for (int u = 0; u < NV8; u++) {
-                        float4 l;
-                        l.x = fabsf(v[u].x) <= FLT_MAX ? v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u) : 0.f;
-                        l.y = fabsf(v[u].y) <= FLT_MAX ? v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u) : 0.f;
-                        l.z = fabsf(v[u].z) <= FLT_MAX ? v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u) : 0.f;
-                        l.w = fabsf(v[u].w) <= FLT_MAX ? v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u) : 0.f;
-                        lo4[ct + 128 * u] = l;
+                        for (int j = 0; j < 32; j++) {
+                            const float f = __uint_as_float(v[j]);
+                            v[j] = fabsf(f) <= FLT_MAX ? __float_as_uint(f - __uint_as_float(v[j] & 0xFFFFE000u)) : 0u;
+                        }
+                        tmem_st32(t_lane + (uint32_t)(ts * 64 + 32), v);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(&empty[stage]);  // every lane has its row in registers: the ring slot may be refilled
+                            mbar_arrive(&a_full[ts]);
+                        }
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> the MMA's async-proxy reads
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&lo_full[lo_stage]);
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1u;
                     }
-                    if (++lo_stage == LO_STAGES) {
-                        lo_stage = 0;
-                        lo_phase ^= 1u;
+                    if (++ts == AS) {
+                        ts = 0;
+                        tphase ^= 1u;
                     }
                 }
             }
@@ -323,12 +344,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                 const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(a * ACC);
                 for (int c0 = 0; c0 < NP; c0 += 16) {
                     uint32_t v[16];
-                    tmem_ld16(taddr + c0, v);
-                    if (X3) {  // score = (A_hi Q_hi + A_lo Q_hi) + A_hi Q_lo
-                        uint32_t w[16];
-                        tmem_ld16(taddr + NP + c0, w);
+                    if (X3) {  // score = A_hi Q_hi + (A_lo Q_hi + A_hi Q_lo)
+                        uint32_t w[16], z[16];
+                        tmem_ld16_nowait(taddr + c0, v);
+                        tmem_ld16_nowait(taddr + NP + c0, w);
+                        tmem_ld16_nowait(taddr + 2 * NP + c0, z);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+                        for (int j = 0; j < 16; j++)
+                            v[j] = __float_as_uint(__uint_as_float(v[j]) + (__uint_as_float(w[j]) + __uint_as_float(z[j])));
+                    } else {
+                        tmem_ld16(taddr + c0, v);
                     }
                     if (MODE == MODE_DUMP) {
                         if (row_ok) {
@@ -852,15 +878,14 @@ int tc_max_queries(int d, int is_bf16) {
 }
 
 static size_t tc_smem_bytes(int nk, int npad, int stages) {
-    return (size_t)nk * npad * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4 + 4) * 8 + 32 + (size_t)npad * 8 + 1024;
+    return (size_t)nk * npad * 128 + (size_t)stages * TC_STAGE_BYTES + (size_t)(2 + 2 * stages + 4 + 2 * TC_X3_TMEM_STAGES) * 8 + 32 + (size_t)npad * 8 + 1024;
 }
 static size_t tc_smem_bytes_heap(int nk, int npad, int stages) {
     return tc_smem_bytes(nk, npad, stages) + (size_t)npad * TC_HEAP_SLOTS * 8;
 }
-// 3xTF32: two resident query copies (hi, lo) and the two-deep lo ring of the converter warps
+// 3xTF32: two resident query copies (hi, lo); the A operands live in tensor memory
 static size_t tc_smem_bytes_x3(int nk, int npad, int stages, bool heap) {
-    return tc_smem_bytes(nk, npad, stages) + (size_t)nk * npad * 128 + 2 * (size_t)TC_STAGE_BYTES +
-           (heap ? (size_t)npad * TC_HEAP_SLOTS * 8 : 0);
+    return tc_smem_bytes(nk, npad, stages) + (size_t)nk * npad * 128 + (heap ? (size_t)npad * TC_HEAP_SLOTS * 8 : 0);
 }
 
 template <typename T, int MODE, bool X3>
@@ -869,7 +894,7 @@ static cudaError_t launch_tc_mode(const CUtensorMap& tdb, const CUtensorMap& tq,
     auto kern = tc_scan_kernel<T, MODE, X3>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = launch_pdl(kern, dim3((unsigned)grid), dim3(X3 ? 384 : 256), smem, st, tdb, tq, p);
+    e = launch_pdl(kern, dim3((unsigned)grid), dim3(X3 ? 512 : 256), smem, st, tdb, tq, p);
     g_kernel_launches.fetch_add(1);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
@@ -902,7 +927,7 @@ static size_t tc_smem_bytes_plain(const TcPlan& pl) {
     return pl.x3 ? tc_smem_bytes_x3(pl.nk, pl.npad, pl.stages, false) : tc_smem_bytes(pl.nk, pl.npad, pl.stages);
 }
 
-// queries one 3xTF32 pass serves: both query halves, the on-chip heaps, the lo ring and >= 4 raw stages must fit
+// queries one 3xTF32 pass serves: both query halves, the on-chip heaps and >= 4 raw stages must fit
 int tc_x3_max_queries(int d) {
     if (((size_t)d * 4) % 128) return 0;
     const int nk = (int)((size_t)d * 4 / 128);

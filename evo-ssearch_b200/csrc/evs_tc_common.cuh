@@ -50,6 +50,14 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
             : "memory");
     }
 }
+// the same with the A operand in tensor memory (lane = row of the M x K tile, one 32-bit column per tf32 element)
+__device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier when all MMAs issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -65,6 +73,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same without the wait (pair with tmem_ld_wait): several loads in flight
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
 // K-major, 128-byte-swizzled shared-memory operand descriptor (what TMA SWIZZLE_128B writes):
 // rows are 128 bytes apart, 8-row groups 1024 bytes apart (SBO), descriptor version 1 (sm_100).
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
@@ -78,6 +96,7 @@ __host__ __device__ constexpr uint32_t make_idesc(bool tf32, int M, int N) {
 
 constexpr int TC_BM = 128;           // database rows per CTA tile = TMEM lanes
 constexpr int TC_STAGE_BYTES = TC_BM * 128;
+constexpr int TC_X3_TMEM_STAGES = 6;  // 3xTF32 scan: TMEM ring of A operands (64 columns each) behind 128 accumulator columns
 
 // ---- CTA-pair (cta_group::2) forms ------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -167,6 +186,19 @@ __device__ __forceinline__ float warp_max_f32(float v) {
 }
 // group maximum -> the ordered-uint the threshold kernel ranks; 0 = "no usable value" (every row out of range, or NaN only)
 __device__ __forceinline__ uint32_t group_max_to_ordered(float m) { return m == -INFINITY ? 0u : score_to_ordered(m); }
+// 32 registers per thread -> 32 lanes x 32 consecutive columns (the warp's own lane quarter)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(
+            taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- host helpers shared by the two scans (defined in evs_tc.cu) --------------------------------

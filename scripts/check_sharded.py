@@ -96,7 +96,7 @@ for exchange in ("nccl", "peer"):
         ok = ok and good and uncert == 0
         say(f"guard: planted near-ties, 6 fp32 queries, exchange={exchange} x3={x3} world={world}: {'OK' if good else 'MISMATCH'} "
             f"(rank 0: {reruns} device re-runs, {uncert} uncertified)")
-evs.set_option("x3", 1)
+evs.set_option("x3", 0)
 
 # ---- shard loader: rank 0 writes a single-GPU index.faiss; every rank streams only its own block ---------------------------
 n, d, k = 600_011, 512, 48

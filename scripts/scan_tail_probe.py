@@ -36,7 +36,7 @@ SETS = [
 ]
 if os.environ.get("EVS_PROBE_ALL"):
     SETS += [("fused dynamic c=%d" % c, dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=c)) for c in (1, 2, 8)]
-for rows in [int(r) for r in a.rows.split(",")]:
+for rows in [int(r) for r in a.rows.split(",") if r]:
     idx = evs.IndexFlatIP(a.dim, storage=a.storage)
     idx.reserve(rows)
     idx.add_synthetic(rows, seed=0)

@@ -476,6 +476,30 @@ def test_normalize_bitexact_vs_oracle_and_close_to_torch():
     z = np.zeros((2, 8), np.float32)
     evs.normalize_L2(z)
     assert np.isnan(z).all()  # no epsilon
+    # The tuned fp32 kernel (rows of 128 .. 1024 values) divides with a shared reciprocal + two FMA correction steps and
+    # falls back to IEEE division for rows outside [2^-60, 2^60]: bit-identical to the oracle's division either way --
+    # many random mantissas, odd row counts (the kernel takes rows in pairs), signed zeros, huge / tiny / subnormal /
+    # inf / NaN elements, zero rows.
+    for d in (128, 256, 384, 512, 640, 768, 1024):
+        n = 4001
+        x = (rng.standard_normal((n, d)) * np.exp2(rng.integers(-40, 40, (n, 1)))).astype(np.float32)
+        x[rng.random((n, d)) < 0.02] = 0.0
+        x[rng.random((n, d)) < 0.01] = -0.0
+        x[7] *= np.float32(2.0 ** 70)          # row beyond the fast range
+        x[8] *= np.float32(2.0 ** -75)
+        x[9, ::5] = np.float32(1e-41)          # subnormal elements
+        x[10, 3] = np.float32(3e38)            # the sum of squares overflows fp32 but not fp64
+        x[11, 0] = np.inf
+        x[12, 1] = np.nan
+        x[13] = 0.0
+        x[14, 5] = np.float32(1e-30)           # one tiny element in an ordinary row
+        with np.errstate(all="ignore"):
+            want = oracle.l2_normalize(x)
+        t = torch.from_numpy(x).cuda()
+        evs.normalize_L2(t)
+        got = t.cpu().numpy()
+        assert np.array_equal(got.view(np.uint32)[~np.isnan(want)], want.view(np.uint32)[~np.isnan(want)]), d
+        assert np.array_equal(np.isnan(got), np.isnan(want)), d
 
 
 def test_bf16_layout_kernel_is_rne():

@@ -18,10 +18,10 @@ def _reset_options():
     evs.set_option("tc_heap_pure_max_nq", 0)
     evs.set_option("tc2_slice_tiles", 0)
     evs.set_option("scan_variant", 0)
-    evs.set_option("x3", 1)
-    evs.set_option("x3_max_nq", 32)
+    evs.set_option("x3", 0)
+    evs.set_option("x3_max_nq", 16)
     evs.set_option("guard", 1)
-    evs.set_option("tf32_guard_eps_e6", 150)
+    evs.set_option("tf32_guard_eps_e6", 0)
 
 
 @pytest.mark.parametrize("storage,d", [("bf16", 512), ("f32", 512), ("bf16", 768), ("f32", 768), ("bf16", 1024), ("bf16", 64)])
@@ -33,6 +33,7 @@ def test_tc_raw_scores_match_torch(storage, d):
     xb = torch.from_numpy(idx.reconstruct_n(0, n)).cuda()
     nmax = idx.tc_max_queries()
     assert nmax >= 16
+    evs.set_option("x3", 1)  # fp32 rows: batches up to tc_x3_max_queries() through the 3xTF32 split scan
     for nq in sorted({1, 16, 17, nmax}):
         xq = torch.from_numpy(oracle.synth_fill(nq, d, 4)).cuda()
         got = idx.tc_scores(xq)
@@ -56,6 +57,40 @@ def test_tc_raw_scores_match_torch(storage, d):
         evs.set_option("x3", 1)
         err3 = (idx.tc_scores(xq) - (xb.double() @ xq.double().T).float()).abs().max().item()
         assert err3 <= 2e-6 and err1 > 20 * err3, (d, err1, err3)
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+def test_tf32_scan_truncates_its_operands(pair):
+    """The certification bound of the single-tf32 scans (evs_api.cu: tf32_trunc_coef) rests on ONE hardware fact: kind::tf32
+    ignores the low 13 mantissa bits of both operands (truncation towards zero, not rounding).  Pin it: the raw scores equal
+    the fp64 product of the TRUNCATED inputs to fp32-accumulation accuracy -- a rounding tensor core would be ~1e-4 away --
+    and every score lies inside the rigorous interval [true - 2^-9 P+, true + 2^-9 P-] the bound is derived from."""
+    import torch
+    d, n, nq = 512, 40_003, 48
+    idx = evs.IndexFlatIP(d)
+    idx.add_synthetic(n, seed=13)
+    xb = idx.reconstruct_n(0, n)
+    xq = oracle.synth_fill(nq, d, 14)
+    evs.set_option("x3", 0)
+    evs.set_option("tc_pair_min_nq", 1 if pair else 129)
+    got = idx.tc_scores(torch.from_numpy(xq).cuda()).cpu().numpy().astype(np.float64)
+
+    def trunc(a):
+        return (a.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
+    emu = trunc(xb) @ trunc(xq).T
+    assert np.abs(got - emu).max() <= 3e-6, np.abs(got - emu).max()
+    rounded = (xb.view(np.uint32) + np.uint32(0x1000) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64) @ \
+              (xq.view(np.uint32) + np.uint32(0x1000) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64).T
+    assert np.abs(got - rounded).max() > 1e-4  # the test can tell the two apart
+    x64, q64 = xb.astype(np.float64), xq.astype(np.float64)
+    true = x64 @ q64.T
+    pos = np.maximum(x64, 0) @ np.maximum(q64, 0).T + np.maximum(-x64, 0) @ np.maximum(-q64, 0).T  # sum of the positive products
+    neg = pos - true                                                                                  # |sum of the negative ones|
+    acc = (d / 8 + 16) * 2.0 ** -22
+    assert (got >= true - 2.0 ** -9 * pos - acc).all() and (got <= true + 2.0 ** -9 * neg + acc).all()
+    # ... and inside the simplified form the finalise kernel uses: under-estimate <= 2^-10 (|q||x| + score)
+    B = np.linalg.norm(x64, axis=1)[:, None] * np.linalg.norm(q64, axis=1)[None, :]
+    assert (true - got <= 2.0 ** -10 * (1 + 2.0 ** -9) * (B + np.abs(got)) + acc * B).all()
 
 
 @pytest.mark.parametrize("storage,d", [("bf16", 512), ("f32", 512), ("bf16", 768), ("bf16", 64)])
@@ -212,7 +247,7 @@ def _planted(spacing, d=512, n=120_000, nq=6):
 def test_device_guard_reruns_near_tie_queries_exactly_on_every_entry_point(x3):
     """fp32 storage, small batches.  The finalise kernel certifies every result against the error bound of the scan that
     produced the candidates (3xTF32: a few 1e-5 relative to |q| max|x| as a bound, ~1e-6 in fact; single tf32 with
-    x3 = 0: the statistical 1.5e-4); a query whose margin is inside the bound -- 80 planted rows closer together than the
+    x3 = 0: the rigorous truncation bound, ~1.2e-3 on unit vectors); a query whose margin is inside the bound -- 80 planted rows closer together than the
     scan can resolve straddle rank 48 -- is queued, re-run ON THE DEVICE with the fp32 GEMV scan (k' = 128) and finalised
     again.  Same answer, bit for bit the oracle's, through the host API, the CUDA-tensor API, the shard-partial API and the
     exchange API; no host synchronisation is involved; ordinary queries of the batch are not re-run."""
@@ -273,10 +308,12 @@ def test_host_side_guard_for_batches_beyond_the_heap_range():
     assert evs.get_option("exact_reruns") - e1 == e1 - e0
 
 
-def test_certification_scales_with_the_norms():
+@pytest.mark.parametrize("x3", [0, 1])
+def test_certification_scales_with_the_norms(x3):
     """IndexFlatIP.add accepts any scale: the bound is relative to |q| * max|x|, so un-normalised data neither triggers
     spurious re-runs nor escapes the guard."""
     k = 48
+    evs.set_option("x3", x3)
     xb, q = _planted(2e-7)
     idx = evs.IndexFlatIP(512)
     idx.add(xb * np.float32(8.0))
@@ -295,6 +332,8 @@ def test_x3_blocks_equal_oracle(nq):
     """fp32 storage, 2..32 queries = one or two 3xTF32 blocks of 16: results are the oracle's, the margins are far above
     the scan's error bound on ordinary data (nothing is re-run), and no buffer can overflow."""
     d, n, k = 512, 150_001, 48
+    evs.set_option("x3", 1)
+    evs.set_option("x3_max_nq", 32)
     idx = evs.IndexFlatIP(d)
     idx.add_synthetic(n, seed=5)
     xb = idx.reconstruct_n(0, n)
