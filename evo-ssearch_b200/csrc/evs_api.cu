@@ -60,7 +60,7 @@ static const int kTcQueryChunk = 4096;  // tensor-core path: queries per launch 
 
 // per-handle device words (idx->words): counters the kernels share across searches
 enum { W_TICKET = 0, W_NEXT_CHUNK = 1, W_GUARD_COUNT0 = 2, W_GUARD_COUNT1 = 3, W_UNCERT = 4 /* u64 */, W_RERUNS = 6 /* u64 */,
-       W_MAX_NORM = 8 /* float */, W_WORDS = 16 };
+       W_MAX_NORM = 8 /* float */, W_SPECIAL = 9, W_WORDS = 16 };
 
 struct evs_index {
     int d = 0, device = 0, storage = EVS_STORE_F32;
@@ -85,6 +85,8 @@ struct evs_index {
     int* guard_slot = nullptr; size_t guard_slot_cap = 0;   // [max(nq, 32)] slot per query, then [max(nq, 32)] the re-run queue
     unsigned long long* guard_lists = nullptr; size_t guard_lists_cap = 0;  // lists of the device-side exact re-run
     unsigned long long guard_seq = 0;                       // guarded searches so far (parity of the counter in use)
+    unsigned long long* pool = nullptr; size_t pool_cap = 0;  // single-query pool selection (slot maxima, counters, survivors); zeroed
+                                                              // at allocation, left zeroed by every search's last CTA
     unsigned long long* cta_clock = nullptr; size_t cta_clock_cap = 0; int cta_clock_n = 0;  // option "scan_clock"
     cudaStream_t last_stream = nullptr; bool have_last_stream = false;  // the stream the workspace was last used on
     TmapCache tmaps;
@@ -196,6 +198,8 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "scan_chunk_groups")) {
         if (value < 1 || value > 64) return fail(EVS_EINVAL, "scan_chunk_groups must be in [1, 64]");
         g_tune.scan_chunk_groups = (int)value;
+    } else if (!strcmp(name, "pool_select")) {
+        g_tune.pool_select = value ? 1 : 0;
     } else if (!strcmp(name, "scan_clock")) {
         g_tune.scan_clock = value ? 1 : 0;
     } else if (!strcmp(name, "x3")) {
@@ -232,6 +236,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "fuse_finalize")) *value = g_tune.fuse_finalize;
     else if (!strcmp(name, "scan_dynamic")) *value = g_tune.scan_dynamic;
     else if (!strcmp(name, "scan_chunk_groups")) *value = g_tune.scan_chunk_groups;
+    else if (!strcmp(name, "pool_select")) *value = g_tune.pool_select;
     else if (!strcmp(name, "scan_clock")) *value = g_tune.scan_clock;
     else if (!strcmp(name, "x3")) *value = g_tune.x3;
     else if (!strcmp(name, "x3_max_nq")) *value = g_tune.x3_max_nq;
@@ -294,6 +299,7 @@ extern "C" int evs_index_free(evs_index* idx) {
     cudaFree(idx->guard_slot);
     cudaFree(idx->guard_lists);
     cudaFree(idx->cta_clock);
+    cudaFree(idx->pool);
     cudaFreeHost(idx->tc_overflow_pin);
     cudaFreeHost(idx->q_pin);
     cudaFreeHost(idx->I_pin);  // D_pin points into the same allocation
@@ -380,7 +386,7 @@ static int finish_add_locked(evs_index* idx, int64_t n) {
     }
     // the largest row norm scales the certification bound of the searches (finalize_query)
     CU(launch_row_norm_max(idx->xb32 + (size_t)idx->ntotal * d, (long long)n, idx->d, reinterpret_cast<float*>(idx->words + W_MAX_NORM),
-                           idx->sm_count, idx->stream));
+                           idx->words + W_SPECIAL, idx->sm_count, idx->stream));
     CU(cudaStreamSynchronize(idx->stream));
     idx->ntotal += n;
     return EVS_OK;
@@ -638,6 +644,7 @@ static FinalizeParams make_finalize(evs_index* idx, const void* lists, int L, in
     f.err_coef = err_coef;
     f.err_trunc = err_trunc;
     f.max_norm = reinterpret_cast<const float*>(idx->words + W_MAX_NORM);
+    f.special = idx->words + W_SPECIAL;
     f.uncertified = reinterpret_cast<unsigned long long*>(idx->words + W_UNCERT);
     return f;
 }
@@ -921,6 +928,18 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
             if (fused) {
                 a.fuse = &f;
                 a.ticket = idx->words + W_TICKET;
+                if (tune.pool_select && kp == 64) {
+                    const size_t need = scan_pool_words(plan);
+                    if (idx->pool_cap < need) {  // (re)allocated zeroed; every search's last CTA leaves it zeroed
+                        if (idx->pool) CU(cudaFree(idx->pool));
+                        idx->pool = nullptr;
+                        idx->pool_cap = 0;
+                        CU(cudaMalloc(reinterpret_cast<void**>(&idx->pool), need * 8));
+                        CU(cudaMemsetAsync(idx->pool, 0, need * 8, st));
+                        idx->pool_cap = need;
+                    }
+                    a.pool = idx->pool;
+                }
                 if (tune.scan_dynamic) {
                     a.next_chunk = idx->words + W_NEXT_CHUNK;
                     a.chunk_groups = tune.scan_chunk_groups > 0 ? tune.scan_chunk_groups : 2;

@@ -10,6 +10,8 @@
 #pragma once
 #include <float.h>
 
+#include <type_traits>
+
 #include "evs_common.cuh"
 #include "evs_internal.h"
 
@@ -50,36 +52,52 @@ __device__ __forceinline__ double canon32_dot_bf16(const __nv_bfloat16* __restri
     return acc;
 }
 
-// CANON-32 of TWO rows at once with the row loads batched (same accumulation order per row; the two
-// rows' load latencies and fp64 chains overlap).  A null row pointer yields -DBL_MAX.
-__device__ __forceinline__ void canon32_dot_pair(const float* __restrict__ xa, const float* __restrict__ xb,
-                                                 const double* __restrict__ qs, int d, int lane, double& ra, double& rb) {
-    double acca = 0.0, accb = 0.0;
-    for (int base = 0; base < d; base += 512) {
-        float va[16], vb[16];
+// fp32 -> fp64, exact for zero and normal numbers, branch-free (5 + 2 integer instructions).  F2F.F64.F32 is very slow on
+// B200: re-scoring 64 rows of 512 values through it took 32 us instead of 10 (scripts/scan_tail_probe.py); the general
+// widen_f32 above pays ~19 instructions for its special-case branch.  Used when the index is known to hold no subnormal,
+// infinite or NaN element (row_norm_max_kernel records that at add time).
+__device__ __forceinline__ double widen_f32_normal(float f) {
+    const uint32_t u = __float_as_uint(f);
+    const uint32_t t = u & 0x7FFFFFFFu;
+    uint32_t hi = (t >> 3) + 0x38000000u;
+    hi = t ? hi : 0u;
+    return __hiloint2double((int)(hi | (u & 0x80000000u)), (int)(u << 29));
+}
+
+// CANON-32 of R rows at once with the row loads batched (the same accumulation order per row; the rows' load latencies
+// and fp64 chains overlap).  A null row pointer yields -DBL_MAX.
+template <int R, bool FAST>
+__device__ __forceinline__ void canon32_dot_multi(const float* const (&x)[R], const double* __restrict__ qs, int d, int lane,
+                                                  double (&res)[R]) {
+    double acc[R];
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-            int i = base + lane + 32 * u;
-            va[u] = (xa && i < d) ? __ldg(xa + i) : 0.f;
-            vb[u] = (xb && i < d) ? __ldg(xb + i) : 0.f;
+    for (int r = 0; r < R; r++) acc[r] = 0.0;
+    constexpr int U = R <= 2 ? 16 : 8;  // values per row held at a time: R * U loads in flight per lane
+    for (int base = 0; base < d; base += 32 * U) {
+        float v[R][U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + lane + 32 * u;
+#pragma unroll
+            for (int r = 0; r < R; r++) v[r][u] = (x[r] && i < d) ? __ldg(x[r] + i) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-            int i = base + lane + 32 * u;
+        for (int u = 0; u < U; u++) {
+            const int i = base + lane + 32 * u;
             if (i < d) {
                 const double qv = qs[i];
-                acca = fma(widen_f32(va[u]), qv, acca);
-                accb = fma(widen_f32(vb[u]), qv, accb);
+#pragma unroll
+                for (int r = 0; r < R; r++) acc[r] = fma(FAST ? widen_f32_normal(v[r][u]) : widen_f32(v[r][u]), qv, acc[r]);
             }
         }
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
-        acca = acca + __shfl_xor_sync(0xffffffffu, acca, off);
-        accb = accb + __shfl_xor_sync(0xffffffffu, accb, off);
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = acc[r] + __shfl_xor_sync(0xffffffffu, acc[r], off);
     }
-    ra = xa ? acca : -DBL_MAX;
-    rb = xb ? accb : -DBL_MAX;
+#pragma unroll
+    for (int r = 0; r < R; r++) res[r] = x[r] ? acc[r] : -DBL_MAX;
 }
 
 // The L per-CTA lists are sorted, so the global top-kp is found without merging them all:
@@ -118,11 +136,8 @@ __host__ __device__ inline size_t finalize_smem_bytes(int L, int kp, int d) {
 }
 
 // the part that does not depend on the scan's output: the query widened to fp64 (may run before griddepcontrol.wait)
-__device__ __forceinline__ void finalize_prologue(const FinalizeParams& p, long long qi, unsigned char* smem_raw) {
+__device__ __forceinline__ void finalize_prologue_at(const FinalizeParams& p, long long qi, FinalizeShared* sh, double* qs) {
     const int t = threadIdx.x, nt = blockDim.x;
-    FinalizeShared* sh = reinterpret_cast<FinalizeShared*>(smem_raw);
-    double* qs = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) +
-                                           ((size_t)finalize_surv_slots(p.L, p.kp) + 2 * (size_t)p.L + finalize_deep_slots(p.L) + 3 * (size_t)p.kp) * 8);
     const float* q = p.xq + (size_t)qi * p.d;
     for (int i = t; i < p.d; i += nt) qs[i] = (double)q[i];
     if (t == 0) {
@@ -134,6 +149,12 @@ __device__ __forceinline__ void finalize_prologue(const FinalizeParams& p, long 
         sh->qnorm2 = 0.0;
         sh->fail = 0;
     }
+}
+__device__ __forceinline__ void finalize_prologue(const FinalizeParams& p, long long qi, unsigned char* smem_raw) {
+    FinalizeShared* sh = reinterpret_cast<FinalizeShared*>(smem_raw);
+    double* qs = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) +
+                                           ((size_t)finalize_surv_slots(p.L, p.kp) + 2 * (size_t)p.L + finalize_deep_slots(p.L) + 3 * (size_t)p.kp) * 8);
+    finalize_prologue_at(p, qi, sh, qs);
 }
 
 __device__ __forceinline__ void fin_stamp(const FinalizeParams& p, int slot) {
@@ -224,6 +245,181 @@ __device__ __forceinline__ void exchange_merge(const Exchange& x, long long qi, 
         I[(size_t)qi * k + r] = -1;
     }
 }
+
+// Second half of the finalise, shared by every candidate source (per-CTA lists: finalize_query; the survivor pool of the
+// single-query scan: evs_scan.cuh).  A[0..kp) = the kp best scan keys in descending order (0 = empty); every row outside A
+// has a smaller scan key.  Canonical re-score, ranking, output (final / shard partial / peer stores + fused merge), margin
+// and certification.  Called by every thread of the CTA; `scratch` holds at least max(world * k * 24 + 8, 0) bytes that
+// no longer hold anything needed (the exchange merge ranks the gathered partials there).
+template <int MAXR = 4>  // candidates a warp re-scores at a time at most (kernels held to 64 registers pass 2)
+__device__ __forceinline__ void finalize_rank_emit(const FinalizeParams& p, long long qi, const u64* A, FinalizeShared* sh, double* sc,
+                                                   long long* id, u64* ok, const double* qs, unsigned char* scratch) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int warp = t >> 5, lane = t & 31, nwarps = nt >> 5;
+    const int kp = p.kp;
+    // 4. canonical re-score of the kp candidates: a warp takes two candidates at a time, or four when the CTA has fewer than
+    //    kp / 2 warps (the 256-thread CTA of the single-query scan: two rounds instead of four)
+    const float* xb32 = reinterpret_cast<const float*>(p.xb);
+    const bool fastw = p.special != nullptr && __ldg(p.special) == 0u;  // CTA-uniform
+    auto rescore = [&](auto rtag, auto ftag) {
+        constexpr int R = decltype(rtag)::value;
+        constexpr bool FAST = decltype(ftag)::value;
+        for (int c = R * warp; c < kp; c += R * nwarps) {
+            u64 key[R];
+            long long row[R];
+            const float* xr[R];
+            double sv[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                key[r] = (c + r < kp) ? A[c + r] : 0ull;
+                row[r] = key[r] ? (long long)key_row(key[r]) : -1;
+                xr[r] = (key[r] && !p.xb_is_bf16) ? xb32 + (size_t)row[r] * p.d : nullptr;
+            }
+            canon32_dot_multi<R, FAST>(xr, qs, p.d, lane, sv);
+            if (p.xb_is_bf16) {
+                const __nv_bfloat16* xb16 = reinterpret_cast<const __nv_bfloat16*>(p.xb);
+#pragma unroll
+                for (int r = 0; r < R; r++) sv[r] = key[r] ? canon32_dot_bf16(xb16 + (size_t)row[r] * p.d, qs, p.d, lane) : -DBL_MAX;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (c + r < kp) {
+                        sc[c + r] = sv[r];
+                        id[c + r] = row[r];
+                        ok[c + r] = row[r] >= 0 ? score_rank_key(sv[r]) : 0ull;
+                    }
+            }
+        }
+    };
+    if (MAXR < 4 || 2 * nwarps >= kp) {
+        if (fastw) rescore(std::integral_constant<int, 2>{}, std::true_type{});
+        else rescore(std::integral_constant<int, 2>{}, std::false_type{});
+    } else {
+        if (fastw) rescore(std::integral_constant<int, MAXR < 4 ? 2 : 4>{}, std::true_type{});
+        else rescore(std::integral_constant<int, MAXR < 4 ? 2 : 4>{}, std::false_type{});
+    }
+    __syncthreads();
+    fin_stamp(p, 3);  // re-scored
+    // how far the scan under-estimated its own candidates at most (tf32 truncates towards zero: a bias of ~1e-3 relative;
+    // bf16 and fp32 scans scatter around zero)
+    const bool want_margin = p.margins != nullptr || p.guard_count != nullptr || p.pred_slot != nullptr;
+    for (int c = t; c < kp; c += nt)
+        if (id[c] >= 0 && want_margin) atomicMax(&sh->maxerr, score_to_ordered((float)(sc[c] - (double)key_score(A[c]))));
+    __syncthreads();
+
+    // 5. rank by counting under (score desc, id asc); ids are unique so ranks are a permutation
+    for (int c = t; c < kp; c += nt) {
+        if (id[c] < 0) continue;
+        atomicAdd(&sh->nvalid, 1);
+        const double st = sc[c];
+        const long long it = id[c];
+        const u64 ot = ok[c];
+        int rank = 0;
+        // empty slots have id -1 and key 0: a real candidate never loses to them -> mask by id >= 0 arithmetically
+        for (int j = 0; j < kp; j++) rank += better_i(ok[j], id[j], ot, it) & (int)(id[j] >= 0);
+        if (rank < p.k) {
+            if (p.D) {
+                p.D[(size_t)qi * p.k + rank] = (float)st;
+                p.I[(size_t)qi * p.k + rank] = it + p.id_base;
+            } else if (p.x.world > 0) {
+                const size_t e = (size_t)(p.x.q_off + qi) * p.k + rank;
+                for (int g = 0; g < p.x.world; g++) {  // the same 16 bytes to every rank's slot for this shard
+                    unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
+                    reinterpret_cast<double*>(slot)[e] = st;
+                    reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = it + p.id_base;
+                }
+            } else {
+                p.P_scores[(size_t)qi * p.k + rank] = st;
+                p.P_ids[(size_t)qi * p.k + rank] = it + p.id_base;
+            }
+            if (rank == p.k - 1 && want_margin) {
+                // All kp slots taken -> every row outside the list has a scan score <= the worst retained one, so its
+                // true score is at most that plus the scan's error.  margin = canonical score of rank k minus (worst
+                // retained scan score + the largest under-estimate observed on the retained candidates); the result is
+                // CERTIFIED exact when it clears the error bound of the scan that produced the lists (below).
+                const float worst = key_score(A[kp - 1]);
+                const float under = fmaxf(ordered_to_score(sh->maxerr), 0.f);
+                const float gap = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) : INFINITY;
+                const float margin = gap - under;
+                if (p.margins) p.margins[qi] = margin;
+                if (p.err_coef > 0.f) {
+                    const float mx = p.max_norm ? *p.max_norm : 1.f;
+                    const float B = (float)sqrt(sh->qnorm2) * mx;  // >= sum |x_i q_i| of any row (Cauchy-Schwarz)
+                    // Symmetric scan error (fp32 GEMV, 3xTF32): |scan - true| <= err_coef * B.
+                    // Truncating scan (single tf32: both operands lose their low 13 mantissa bits, towards zero): every product
+                    // shrinks by a factor in (1 - 2^-9, 1], so a row is UNDER-estimated by at most 2^-9 * (sum of its positive
+                    // products) <= 2^-10 * (B + true score): a row the scan dropped (scan score <= w) has a true score
+                    // <= w + err_trunc * (B + |w|) + accumulation error.  A bound, not a statistic.
+                    const bool certified = p.err_trunc > 0.f ? gap > p.err_trunc * (B + fabsf(worst)) + p.err_coef * B  // false for NaN
+                                                             : margin > p.err_coef * B;
+                    if (!certified) {
+                        if (p.guard_count) {  // first phase: queue the query for the exact re-run
+                            const int slot = atomicAdd(p.guard_count, 1);
+                            if (slot < p.guard_cap) {
+                                p.guard_slot[qi] = slot;
+                                p.guard_q[slot] = (int)qi;
+                            } else {
+                                p.guard_slot[qi] = -2;  // flagged only: the host re-runs it (guard_cap = 0), or the queue is full
+                                if (p.guard_cap > 0 && p.uncertified) atomicAdd(p.uncertified, 1ull);
+                            }
+                        } else if (p.uncertified) {  // second phase (or no re-run available): best effort, counted
+                            atomicAdd(p.uncertified, 1ull);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // 6. padding (-FLT_MAX,-1) / (-DBL_MAX,-1) for the slots no candidate ranked into
+    const int nvalid = sh->nvalid;
+    for (int r = nvalid + t; r < p.k; r += nt) {
+        if (p.D) {
+            p.D[(size_t)qi * p.k + r] = -FLT_MAX;
+            p.I[(size_t)qi * p.k + r] = -1;
+        } else if (p.x.world > 0) {
+            const size_t e = (size_t)(p.x.q_off + qi) * p.k + r;
+            for (int g = 0; g < p.x.world; g++) {
+                unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
+                reinterpret_cast<double*>(slot)[e] = -DBL_MAX;
+                reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = -1;
+            }
+        } else {
+            p.P_scores[(size_t)qi * p.k + r] = -DBL_MAX;
+            p.P_ids[(size_t)qi * p.k + r] = -1;
+        }
+    }
+    if (t == 0 && p.margins && nvalid < p.k) p.margins[qi] = INFINITY;  // every row was a candidate
+    fin_stamp(p, 4);  // ranked, results written
+    if (p.x.world > 0 && p.D == nullptr) {
+        // publish: when the last query's CTA has written its part, raise this shard's flag on every rank.  ONE system fence
+        // orders the slot stores of the whole CTA (barrier above it) before the flags, which are then plain relaxed stores
+        // (eight st.release.sys in a row would each pay their own fence round trip over NVLink).
+        __syncthreads();
+        if (t == 0) {
+            __threadfence_system();
+            const unsigned prev = atomicAdd(p.x.done, 1u);
+            if (prev == (unsigned)p.x.nq_total - 1u) {  // counts across the launches of one search
+                *p.x.done = 0u;
+                if (p.x.nq_total > 1) __threadfence_system();  // the other CTAs' slot stores (they fenced before their count)
+                for (int g = 0; g < p.x.world; g++) {
+                    unsigned long long* flags = reinterpret_cast<unsigned long long*>(p.x.peer[g] + 2 * (size_t)p.x.world * p.x.slot_bytes);
+                    st_relaxed_sys_u64(flags + (size_t)p.x.parity * p.x.world + p.x.rank, p.x.seq);
+                }
+            }
+            sh->nvalid = 0;
+        }
+        if (p.x.merge_D != nullptr) {
+            // single-query search fused into the scan kernel: the same CTA waits for the peers' partials and merges
+            __syncthreads();
+            exchange_merge(p.x, p.x.q_off + qi, p.x.nq_total, p.k, p.x.merge_D, p.x.merge_I, scratch,
+                           &sh->fail, &sh->nvalid);
+        }
+    }
+}
+
+
 
 // Finalise query `qi` (index into xq / the outputs) from the lists at `lists` ([L][kp]).  Called by every thread of the
 // CTA (a multiple of 32 threads, at least 64) after finalize_prologue and a point where the lists are visible.
@@ -379,149 +575,7 @@ __device__ __forceinline__ void finalize_query(const FinalizeParams& p, long lon
     }
 
     fin_stamp(p, 2);  // the kp best survivors ranked
-    // 4. canonical re-score of the kp candidates (a warp takes two candidates at a time)
-    for (int c = 2 * warp; c < kp; c += 2 * nwarps) {
-        const u64 ka = A[c], kb = (c + 1 < kp) ? A[c + 1] : 0ull;
-        const long long rowa = ka ? (long long)key_row(ka) : -1, rowb = kb ? (long long)key_row(kb) : -1;
-        double sa = -DBL_MAX, sb = -DBL_MAX;
-        if (p.xb_is_bf16) {
-            const __nv_bfloat16* xb16 = reinterpret_cast<const __nv_bfloat16*>(p.xb);
-            if (ka) sa = canon32_dot_bf16(xb16 + (size_t)rowa * p.d, qs, p.d, lane);
-            if (kb) sb = canon32_dot_bf16(xb16 + (size_t)rowb * p.d, qs, p.d, lane);
-        } else if (ka || kb) {
-            const float* xb32 = reinterpret_cast<const float*>(p.xb);
-            canon32_dot_pair(ka ? xb32 + (size_t)rowa * p.d : nullptr, kb ? xb32 + (size_t)rowb * p.d : nullptr, qs, p.d, lane,
-                             sa, sb);
-        }
-        if (lane == 0) {
-            sc[c] = sa;
-            id[c] = rowa;
-            ok[c] = rowa >= 0 ? score_rank_key(sa) : 0ull;
-            if (c + 1 < kp) {
-                sc[c + 1] = sb;
-                id[c + 1] = rowb;
-                ok[c + 1] = rowb >= 0 ? score_rank_key(sb) : 0ull;
-            }
-        }
-    }
-    __syncthreads();
-    fin_stamp(p, 3);  // re-scored
-    // how far the scan under-estimated its own candidates at most (tf32 truncates towards zero: a bias of ~1e-3 relative;
-    // bf16 and fp32 scans scatter around zero)
-    const bool want_margin = p.margins != nullptr || p.guard_count != nullptr || p.pred_slot != nullptr;
-    for (int c = t; c < kp; c += nt)
-        if (id[c] >= 0 && want_margin) atomicMax(&sh->maxerr, score_to_ordered((float)(sc[c] - (double)key_score(A[c]))));
-    __syncthreads();
-
-    // 5. rank by counting under (score desc, id asc); ids are unique so ranks are a permutation
-    for (int c = t; c < kp; c += nt) {
-        if (id[c] < 0) continue;
-        atomicAdd(&sh->nvalid, 1);
-        const double st = sc[c];
-        const long long it = id[c];
-        const u64 ot = ok[c];
-        int rank = 0;
-        // empty slots have id -1 and key 0: a real candidate never loses to them -> mask by id >= 0 arithmetically
-        for (int j = 0; j < kp; j++) rank += better_i(ok[j], id[j], ot, it) & (int)(id[j] >= 0);
-        if (rank < p.k) {
-            if (p.D) {
-                p.D[(size_t)qi * p.k + rank] = (float)st;
-                p.I[(size_t)qi * p.k + rank] = it + p.id_base;
-            } else if (p.x.world > 0) {
-                const size_t e = (size_t)(p.x.q_off + qi) * p.k + rank;
-                for (int g = 0; g < p.x.world; g++) {  // the same 16 bytes to every rank's slot for this shard
-                    unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
-                    reinterpret_cast<double*>(slot)[e] = st;
-                    reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = it + p.id_base;
-                }
-            } else {
-                p.P_scores[(size_t)qi * p.k + rank] = st;
-                p.P_ids[(size_t)qi * p.k + rank] = it + p.id_base;
-            }
-            if (rank == p.k - 1 && want_margin) {
-                // All kp slots taken -> every row outside the list has a scan score <= the worst retained one, so its
-                // true score is at most that plus the scan's error.  margin = canonical score of rank k minus (worst
-                // retained scan score + the largest under-estimate observed on the retained candidates); the result is
-                // CERTIFIED exact when it clears the error bound of the scan that produced the lists (below).
-                const float worst = key_score(A[kp - 1]);
-                const float under = fmaxf(ordered_to_score(sh->maxerr), 0.f);
-                const float gap = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) : INFINITY;
-                const float margin = gap - under;
-                if (p.margins) p.margins[qi] = margin;
-                if (p.err_coef > 0.f) {
-                    const float mx = p.max_norm ? *p.max_norm : 1.f;
-                    const float B = (float)sqrt(sh->qnorm2) * mx;  // >= sum |x_i q_i| of any row (Cauchy-Schwarz)
-                    // Symmetric scan error (fp32 GEMV, 3xTF32): |scan - true| <= err_coef * B.
-                    // Truncating scan (single tf32: both operands lose their low 13 mantissa bits, towards zero): every product
-                    // shrinks by a factor in (1 - 2^-9, 1], so a row is UNDER-estimated by at most 2^-9 * (sum of its positive
-                    // products) <= 2^-10 * (B + true score): a row the scan dropped (scan score <= w) has a true score
-                    // <= w + err_trunc * (B + |w|) + accumulation error.  A bound, not a statistic.
-                    const bool certified = p.err_trunc > 0.f ? gap > p.err_trunc * (B + fabsf(worst)) + p.err_coef * B  // false for NaN
-                                                             : margin > p.err_coef * B;
-                    if (!certified) {
-                        if (p.guard_count) {  // first phase: queue the query for the exact re-run
-                            const int slot = atomicAdd(p.guard_count, 1);
-                            if (slot < p.guard_cap) {
-                                p.guard_slot[qi] = slot;
-                                p.guard_q[slot] = (int)qi;
-                            } else {
-                                p.guard_slot[qi] = -2;  // flagged only: the host re-runs it (guard_cap = 0), or the queue is full
-                                if (p.guard_cap > 0 && p.uncertified) atomicAdd(p.uncertified, 1ull);
-                            }
-                        } else if (p.uncertified) {  // second phase (or no re-run available): best effort, counted
-                            atomicAdd(p.uncertified, 1ull);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // 6. padding (-FLT_MAX,-1) / (-DBL_MAX,-1) for the slots no candidate ranked into
-    const int nvalid = sh->nvalid;
-    for (int r = nvalid + t; r < p.k; r += nt) {
-        if (p.D) {
-            p.D[(size_t)qi * p.k + r] = -FLT_MAX;
-            p.I[(size_t)qi * p.k + r] = -1;
-        } else if (p.x.world > 0) {
-            const size_t e = (size_t)(p.x.q_off + qi) * p.k + r;
-            for (int g = 0; g < p.x.world; g++) {
-                unsigned char* slot = p.x.peer[g] + ((size_t)p.x.parity * p.x.world + p.x.rank) * p.x.slot_bytes;
-                reinterpret_cast<double*>(slot)[e] = -DBL_MAX;
-                reinterpret_cast<long long*>(slot + (size_t)p.x.nq_total * p.k * 8)[e] = -1;
-            }
-        } else {
-            p.P_scores[(size_t)qi * p.k + r] = -DBL_MAX;
-            p.P_ids[(size_t)qi * p.k + r] = -1;
-        }
-    }
-    if (t == 0 && p.margins && nvalid < p.k) p.margins[qi] = INFINITY;  // every row was a candidate
-    fin_stamp(p, 4);  // ranked, results written
-    if (p.x.world > 0 && p.D == nullptr) {
-        // publish: when the last query's CTA has written its part, raise this shard's flag on every rank.  ONE system fence
-        // orders the slot stores of the whole CTA (barrier above it) before the flags, which are then plain relaxed stores
-        // (eight st.release.sys in a row would each pay their own fence round trip over NVLink).
-        __syncthreads();
-        if (t == 0) {
-            __threadfence_system();
-            const unsigned prev = atomicAdd(p.x.done, 1u);
-            if (prev == (unsigned)p.x.nq_total - 1u) {  // counts across the launches of one search
-                *p.x.done = 0u;
-                if (p.x.nq_total > 1) __threadfence_system();  // the other CTAs' slot stores (they fenced before their count)
-                for (int g = 0; g < p.x.world; g++) {
-                    unsigned long long* flags = reinterpret_cast<unsigned long long*>(p.x.peer[g] + 2 * (size_t)p.x.world * p.x.slot_bytes);
-                    st_relaxed_sys_u64(flags + (size_t)p.x.parity * p.x.world + p.x.rank, p.x.seq);
-                }
-            }
-            sh->nvalid = 0;
-        }
-        if (p.x.merge_D != nullptr) {
-            // single-query search fused into the scan kernel: the same CTA waits for the peers' partials and merges
-            __syncthreads();
-            exchange_merge(p.x, p.x.q_off + qi, p.x.nq_total, p.k, p.x.merge_D, p.x.merge_I, reinterpret_cast<unsigned char*>(surv),
-                           &sh->fail, &sh->nvalid);
-        }
-    }
+    finalize_rank_emit(p, qi, A, sh, sc, id, ok, qs, reinterpret_cast<unsigned char*>(surv));
 }
 
 }  // namespace evs

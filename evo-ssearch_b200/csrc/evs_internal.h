@@ -25,6 +25,9 @@ struct ScanTuning {
                                // (scripts/scan_tail_probe.py) the spread of the CTAs' end times halves, but the last CTA
                                // ends only ~3 us earlier and grabs of fewer than 4 groups choke on the one counter
     int scan_chunk_groups = 4;
+    int pool_select = 1;       // ... and (k <= 48) candidates meet in one survivor pool under a global running threshold instead of
+                               // per-CTA sorted lists (evs_scan.cuh: scan_pool_kernel): no per-warp final sort, no CTA merge tree,
+                               // no head ranking in the last CTA
     int scan_clock = 0;        // diagnostics: record per-CTA start / end-of-scan-loop times of fused single-query scans
     int x3 = 0;                // fp32 rows, batches up to x3_max_nq queries: 3xTF32 split scan (fp32-class scan error, so the
                                // guard practically never re-runs) instead of the single-tf32 scan + guard.  Off by default:
@@ -86,6 +89,7 @@ struct FinalizeParams {
     float err_trunc = 0.f;            // > 0: the scan TRUNCATES its operands (single tf32): the result is certified when
                                       //   (score of rank k) - (worst retained scan score w) > err_trunc * (|q| max|x| + |w|) + err_coef * |q| max|x|
     const float* max_norm = nullptr;  // device: largest row norm of the index (null -> 1)
+    const unsigned* special = nullptr;  // device: non-zero when the index holds subnormal / inf / NaN elements (null -> assume so)
     // guard, first phase: uncertified queries are queued for the exact re-run
     int* guard_count = nullptr;       // device counter (null -> no guard)
     int* guard_count_next = nullptr;  // the counter the NEXT guarded search will use: zeroed here (no memset node in the chain)
@@ -110,8 +114,9 @@ struct ScanArgs {
     void* lists = nullptr;  // u64 [nq_chunk][grid][kp]
     int kp = 64;
     // direct variant only (all optional):
-    const FinalizeParams* fuse = nullptr;  // single-query launch: the last CTA finalises the query (needs `ticket`)
+    const FinalizeParams* fuse = nullptr;  // single-query launch: the last CTA finalises the query (needs `ticket` or `pool`)
     unsigned* ticket = nullptr;
+    unsigned long long* pool = nullptr;    // kp = 64: pool selection (slot maxima, counters, survivor pool of pool_words(grid) words)
     unsigned* next_chunk = nullptr;        // dynamic row dealing (with `ticket` only: the last CTA resets the counter)
     int chunk_groups = 0;
     const int* qmap = nullptr;             // guard re-run: queries qmap[0 .. *nactive), nq_pass at a time
@@ -202,6 +207,7 @@ cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int 
                       ScanPlan* plan);
 int max_queries_per_pass(int d, int is_bf16);
 cudaError_t launch_scan(const ScanArgs& a, ScanPlan* plan, cudaStream_t st);
+size_t scan_pool_words(const ScanPlan& plan);  // u64 words of the pool a fused single-query launch of this plan needs (zeroed once)
 cudaError_t launch_finalize(const FinalizeParams& p, long long nq, cudaStream_t st);
 size_t finalize_smem_bytes_host(int L, int kp, int d);
 cudaError_t launch_publish_partials(const Exchange& x, long long nq, int k, const double* scores, const long long* ids,
@@ -219,8 +225,8 @@ cudaError_t launch_gather_rows(const float* src, const long long* ids_dev, float
 cudaError_t launch_synth_fill(float* out, long long n, int d, unsigned long long seed, long long row_base, int sm_count,
                               cudaStream_t st);
 // max_norm[0] = max(max_norm[0], largest |row|) over rows [0, n): float bits compared as unsigned (norms are >= 0);
-// NaN rows are ignored
-cudaError_t launch_row_norm_max(const float* rows, long long n, int d, float* max_norm, int sm_count, cudaStream_t st);
+// NaN rows are ignored.  *special |= 1 when a row holds a subnormal, infinite or NaN element.
+cudaError_t launch_row_norm_max(const float* rows, long long n, int d, float* max_norm, unsigned* special, int sm_count, cudaStream_t st);
 // small device fills used on the search path instead of memset nodes
 cudaError_t launch_fill_i32(int* p, long long count, int value, cudaStream_t st);
 

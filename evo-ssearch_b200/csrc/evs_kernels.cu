@@ -382,10 +382,17 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 // certification needs: it is inflated by 1e-6 relative on use), atomicMax on the float bits (norms are >= 0, so the
 // unsigned order of the bits is the numeric order).  NaN rows are ignored.
 // =============================================================================================
-__global__ void __launch_bounds__(256) row_norm_max_kernel(const float* __restrict__ rows, long long n, int d, float* __restrict__ max_norm) {
+// 1 when |x| is subnormal, infinite or NaN (zero and normal numbers: 0)
+__device__ __forceinline__ unsigned is_special_f32(float x) {
+    const unsigned t = __float_as_uint(x) & 0x7FFFFFFFu;
+    return (t != 0u && (t - 0x00800000u) >= 0x7F000000u) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) row_norm_max_kernel(const float* __restrict__ rows, long long n, int d, float* __restrict__ max_norm,
+                                                          unsigned* __restrict__ special) {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     float best = 0.f;
+    unsigned spec = 0u;
     for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
         const float* x = rows + (size_t)r * d;
         float s = 0.f;
@@ -396,15 +403,20 @@ __global__ void __launch_bounds__(256) row_norm_max_kernel(const float* __restri
                 s = fmaf(v.y, v.y, s);
                 s = fmaf(v.z, v.z, s);
                 s = fmaf(v.w, v.w, s);
+                spec |= is_special_f32(v.x) | is_special_f32(v.y) | is_special_f32(v.z) | is_special_f32(v.w);
             }
         } else {
-            for (int i = lane; i < d; i += 32) s = fmaf(x[i], x[i], s);
+            for (int i = lane; i < d; i += 32) {
+                s = fmaf(x[i], x[i], s);
+                spec |= is_special_f32(x[i]);
+            }
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (s == s) best = fmaxf(best, s);
     }
     if (lane == 0 && best > 0.f) atomicMax(reinterpret_cast<unsigned*>(max_norm), __float_as_uint(sqrtf(best) * 1.000001f));
+    if (spec && special) atomicOr(special, 1u);  // the index holds a subnormal / inf / NaN element: the finalise widens fp32 -> fp64 the slow exact way
 }
 
 __global__ void fill_i32_kernel(int* __restrict__ p, long long count, int value) {
@@ -610,10 +622,10 @@ cudaError_t launch_merge_exchange(const Exchange& x, long long nq, int k, float*
     return cudaGetLastError();
 }
 
-cudaError_t launch_row_norm_max(const float* rows, long long n, int d, float* max_norm, int sm_count, cudaStream_t st) {
+cudaError_t launch_row_norm_max(const float* rows, long long n, int d, float* max_norm, unsigned* special, int sm_count, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     int grid = clamp_grid((n * 32 + 255) / 256, sm_count * 8);
-    row_norm_max_kernel<<<grid, 256, 0, st>>>(rows, n, d, max_norm);
+    row_norm_max_kernel<<<grid, 256, 0, st>>>(rows, n, d, max_norm, special);
     EVS_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -677,6 +689,27 @@ static cudaError_t launch_scan_t(const ScanArgs& a, ScanPlan* plan, cudaStream_t
     }
     FinalizeParams f;
     size_t smem = plan->smem_bytes;
+    if constexpr (NQ == 1) {
+        if (a.fuse != nullptr && a.pool != nullptr && a.kp == 64 && a.nactive == nullptr) {
+            f = *a.fuse;
+            p.cta_clock = a.cta_clock;
+            if (a.next_chunk != nullptr && a.chunk_groups > 0) {
+                p.next_chunk = a.next_chunk;
+                p.chunk_groups = a.chunk_groups;
+            }
+            const size_t fs = pool_finalize_smem_bytes(64, f.d, f.x.world * f.k);
+            smem = (size_t)(plan->threads / 32) * 128 * 8;
+            if (fs > smem) smem = fs;
+            auto pk = scan_pool_kernel<T, NV>;
+            static size_t optin_p[16] = {};
+            cudaError_t oe = ensure_smem_optin(pk, smem, optin_p);
+            if (oe != cudaSuccess) return oe;
+            cudaError_t le = launch_pdl(pk, dim3((unsigned)plan->grid), dim3((unsigned)plan->threads), smem, st, p, f, reinterpret_cast<u64*>(a.pool));
+            g_kernel_launches.fetch_add(1);
+            if (le != cudaSuccess) return le;
+            return cudaGetLastError();
+        }
+    }
     if (a.fuse != nullptr && NQ == 1 && a.ticket != nullptr) {
         f = *a.fuse;
         p.ticket = a.ticket;
@@ -797,6 +830,8 @@ cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int 
     plan->grid = clamp_grid((groups + 7) / 8, sm_count * per_sm);
     return cudaSuccess;
 }
+
+size_t scan_pool_words(const ScanPlan& plan) { return (size_t)POOL_HDR + (size_t)plan.grid * (plan.threads / 32) * 128; }
 
 cudaError_t launch_scan(const ScanArgs& a, ScanPlan* plan, cudaStream_t st) {
     if (a.n <= 0) return cudaErrorInvalidValue;

@@ -340,6 +340,364 @@ __global__ void __launch_bounds__(256, ScanOcc<T, NQ, NV>::value) scan_direct_ke
 }
 
 // ---------------------------------------------------------------------------------------------
+// Variant 1p: the single-query search in ONE launch with a GLOBAL running threshold ("pool" selection).
+//
+// What index.search(q.reshape(1,-1), k) (/root/reference/oldapp.py:2005, :2112) issues, and the metric's step.  The streaming
+// loop is scan_direct's; what differs is everything after the last byte, which at 1.25M rows per GPU (the metric over 8
+// GPUs) was 10 % of the kernel: every warp bitonic-sorted its 128-key buffer, the CTA tree-merged eight lists and stored
+// one, and the last CTA ranked 296 list heads before it could pick the survivors (scripts/scan_tail_probe.py: 7 + 9 + 27 us).
+//   * 64 slot maxima G[s] live in global memory (L2): a warp publishes the best keys of a compaction with
+//     atomicMax(G[row mod 64], key).  tau_g = min_s G[s] is a lower bound of the 64th best key of the whole shard (the 64
+//     maxima belong to 64 different rows), so a warp may raise its own threshold to it: after the first compactions
+//     hardly anything is admitted any more, anywhere.
+//   * At the end a warp does NOT sort: it re-reads tau_g, appends the few buffered keys >= tau_g (0.2 per warp on
+//     unordered data) to one survivor pool S and publishes them to G.  The last CTA (ticket) filters S by the final
+//     tau_g -- some hundreds of keys -- ranks them by counting and continues with the canonical re-score
+//     (finalize_rank_emit).  No lists, no merge tree, no head ranking.
+// Exactness does not depend on the data: a key is dropped only below a threshold that 64 other rows are known to beat, the
+// pool holds every warp's whole buffer in the worst case (capacity = warps x 128), and the last CTA streams a pool of any
+// size through a 2048-key bitonic top-k' (ascending-score data: tests/test_gpu_parity.py).
+// The slot maxima sit 128 bytes apart: atomics on one L2 line serialise, and all warps publish their first compaction at
+// about the same time (with the 64 slots packed into four lines that storm stalled the scan for ~30 us: 385 instead of
+// 357 us at 1.25M rows); a key is published only if it beats the slot value the warp has just read.
+// pool layout (u64 words): G[s] at 16 s, s < 64 | [1024] survivor count (low word) | [1040] ticket (low word) | [1056, 1056 + cap) S
+// ---------------------------------------------------------------------------------------------
+constexpr int POOL_SLOTS = 64;          // slot maxima; must be >= the largest kp served (64): one row per slot
+constexpr int POOL_GSTRIDE = 16;        // u64 words between slot maxima (one 128-byte line each)
+constexpr int POOL_COUNT = POOL_SLOTS * POOL_GSTRIDE;   // word of the survivor counter
+constexpr int POOL_TICKET = POOL_COUNT + 16;            // ... of the ticket counter
+constexpr int POOL_HDR = POOL_TICKET + 16;              // u64 words before S
+constexpr int POOL_SURV = 2048;         // survivors the last CTA holds in shared memory at a time
+__host__ __device__ inline size_t pool_finalize_smem_bytes(int kp, int d, int world_k) {
+    size_t surv = (size_t)(POOL_SURV + kp) * 8;
+    const size_t merge = (size_t)world_k * 24 + 8;  // the fused exchange merge ranks world * k partials in the same place
+    if (merge > surv) surv = (merge + 7) & ~(size_t)7;
+    return sizeof(FinalizeShared) + surv + (3 * (size_t)kp + (size_t)d) * 8 + 16;
+}
+
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+// tau_g: the smallest slot maximum (0 while a slot is still empty).  Read past L1: other SMs raise the slots.
+// Lane l leaves with G[l] in ga and G[l + 32] in gb.
+__device__ __forceinline__ u64 pool_tau(const u64* G, int lane, u64& ga, u64& gb) {
+    ga = __ldcg(G + (size_t)lane * POOL_GSTRIDE);
+    gb = __ldcg(G + (size_t)(lane + 32) * POOL_GSTRIDE);
+    return warp_min_u64(ga < gb ? ga : gb);
+}
+// every lane passes its key (or 0): published where it beats the slot value read by pool_tau.  Warp-synchronous.
+__device__ __forceinline__ void pool_publish(u64* G, u64 key, u64 ga, u64 gb) {
+    const int slot = (int)((~(uint32_t)key) & (POOL_SLOTS - 1));
+    const u64 va = __shfl_sync(0xffffffffu, ga, slot & 31), vb = __shfl_sync(0xffffffffu, gb, slot & 31);
+    const u64 cur = slot < 32 ? va : vb;
+    if (key != 0ull && key > cur) atomicMax(reinterpret_cast<unsigned long long*>(G + (size_t)slot * POOL_GSTRIDE), (unsigned long long)key);
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kernel(ScanParams p, FinalizeParams f, u64* pool) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_last, s_ns;
+    __shared__ u64 s_tau;
+    typedef typename RawVec<T>::type raw_t;
+    constexpr int QREGS = NV * Elem<T>::VEC;
+    constexpr int RPG_RAW = (100 - QREGS) / (NV * 4);
+    constexpr int RPG = RPG_RAW < 1 ? 1 : (RPG_RAW > 4 ? 4 : RPG_RAW);
+    constexpr int KP = 64, CAPW = 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    u64* G = pool;
+    unsigned* count = reinterpret_cast<unsigned*>(pool + POOL_COUNT);
+    unsigned* ticket = reinterpret_cast<unsigned*>(pool + POOL_TICKET);
+    u64* S = pool + POOL_HDR;
+    u64* buf = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * CAPW;
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // the query may be the preceding kernel's output
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next search's prologue may overlap our tail
+    unsigned long long t_start = 0, t_loop = 0, t_app = 0;
+    if (p.cta_clock && threadIdx.x == 0) t_start = globaltimer_ns();
+
+    const long long total_warps = (long long)gridDim.x * nwarps;
+    const long long gw = (long long)blockIdx.x * nwarps + warp;
+    const long long ngroups = (p.n + RPG - 1) / RPG;
+    const size_t row_vecs = (size_t)p.d / Elem<T>::VEC;
+    const raw_t* base = reinterpret_cast<const raw_t*>(p.xb);
+    QueryRegs<T, 1, NV> q;
+    q.load(p.xq, p.q0, p.d, lane);
+    int cnt = 0;
+    u64 tau = 0ull;
+    // the last CTA's re-score wants the query in fp64: every CTA widens it now, off the critical path (the area lies behind
+    // the warps' buffers and is not touched in between)
+    double* qs;
+    {
+        size_t surv_bytes = (size_t)(POOL_SURV + KP) * 8;
+        const size_t merge = (size_t)f.x.world * f.k * 24 + 8;
+        if (merge > surv_bytes) surv_bytes = (merge + 7) & ~(size_t)7;
+        qs = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) + surv_bytes + 3 * (size_t)KP * 8);
+        const float* qf = p.xq + (size_t)p.q0 * p.d;
+        for (int i = threadIdx.x; i < p.d; i += blockDim.x) qs[i] = (double)qf[i];
+    }
+
+    // buffer full: sort, keep the best 64, publish the best 8 where they raise their slot (a warp sees ~n / warps rows: whatever it holds of the shard's
+    // best few hundred is among its own best 8), raise the threshold to max(own 64th best, tau_g)
+    auto compact = [&]() {
+        __syncwarp();
+        for (int i = cnt + lane; i < CAPW; i += 32) buf[i] = 0ull;
+        warp_bitonic_sort_desc(buf, CAPW, lane);
+        u64 ga, gb;
+        const u64 tg = pool_tau(G, lane, ga, gb);
+        pool_publish(G, lane < 8 ? buf[lane] : 0ull, ga, gb);
+        tau = umax64(tau, umax64(buf[KP - 1], tg));
+        const u64 k0 = buf[lane], k1 = buf[lane + 32];  // sorted: the keys >= tau are a prefix
+        cnt = __popc(__ballot_sync(0xffffffffu, k0 != 0ull && k0 >= tau)) + __popc(__ballot_sync(0xffffffffu, k1 != 0ull && k1 >= tau));
+    };
+
+    auto do_group = [&](long long g) {
+        const long long r0 = g * RPG;
+        raw_t raw[RPG][NV];
+#pragma unroll
+        for (int r = 0; r < RPG; r++) {
+            long long row = r0 + r < p.n ? r0 + r : p.n - 1;  // clamp: tail rows are re-read, not offered
+            const raw_t* src = base + (size_t)row * row_vecs + lane;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                if constexpr (sizeof(T) == 4) raw[r][j] = ldg_stream_f4(src + 32 * j);
+                else raw[r][j] = ldg_stream_u4(src + 32 * j);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RPG; r++) {
+            float s[1];
+            row_scores<T, 1, NV>(raw[r], q, s);
+            if (r0 + r < p.n) {
+                const u64 key = make_key(s[0], (uint32_t)(r0 + r));  // warp-uniform
+                if (key > tau) {
+                    if (lane == 0) buf[cnt] = key;
+                    if (++cnt == CAPW) compact();
+                }
+            }
+        }
+    };
+    // Rows are dealt statically (group g to warp g mod W: the whole machine walks one window of the database, DRAM-friendly,
+    // no counter traffic) for the first part of the shard and dynamically -- `chunk_groups` groups per grab from a global
+    // counter, the next grab always in flight -- for the last `dyn_groups` groups: the SMs that the memory system served
+    // more slowly would otherwise still be streaming while the others idle (scripts/scan_tail_probe.py: the last CTA left
+    // its loop 10-14 us after the median one with a purely static deal at 1.25M rows).
+    const long long dyn_groups = p.next_chunk ? (ngroups / 8 > 64 * total_warps ? 64 * total_warps : ngroups / 8) : 0;
+    const long long static_end = ngroups - dyn_groups;
+    long long next = -1;
+    if (dyn_groups > 0 && lane == 0) next = (long long)atomicAdd(p.next_chunk, 1u);  // the first grab: needed only after the static part
+    for (long long g = gw; g < static_end; g += total_warps) do_group(g);
+    if (dyn_groups > 0) {
+        const long long C = p.chunk_groups;
+        const long long nchunks = (dyn_groups + C - 1) / C;
+        long long chunk = __shfl_sync(0xffffffffu, next, 0);
+        while (chunk < nchunks) {
+            if (lane == 0) next = (long long)atomicAdd(p.next_chunk, 1u);  // consumed after this chunk
+            const long long g0 = static_end + chunk * C;
+            const long long gend = g0 + C < ngroups ? g0 + C : ngroups;
+            for (long long g = g0; g < gend; g++) do_group(g);
+            chunk = __shfl_sync(0xffffffffu, next, 0);
+        }
+    }
+    if (p.cta_clock && threadIdx.x == 0) t_loop = globaltimer_ns();
+
+    // end of this warp's rows: no sort.  Survivors = buffered keys >= the current tau_g; append them to S, publish them.
+    {
+        __syncwarp();
+        u64 ga, gb;
+        tau = umax64(tau, pool_tau(G, lane, ga, gb));
+        for (int i0 = 0; i0 < cnt; i0 += 32) {  // warp-uniform
+            const u64 key = (i0 + lane < cnt) ? buf[i0 + lane] : 0ull;
+            const bool keep = key != 0ull && key >= tau;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m == 0u) continue;
+            unsigned pos = 0;
+            if (lane == 0) pos = atomicAdd(count, (unsigned)__popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (keep) S[pos + __popc(m & ((1u << lane) - 1u))] = key;
+            pool_publish(G, keep ? key : 0ull, ga, gb);
+        }
+    }
+    if (p.cta_clock && threadIdx.x == 0) {
+        t_app = globaltimer_ns();
+        p.cta_clock[2 * blockIdx.x] = t_start;
+        p.cta_clock[2 * blockIdx.x + 1] = t_loop;
+    }
+
+    __threadfence();  // this thread's pool stores / slot updates are visible device-wide before the CTA takes its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;  // CTA-uniform
+
+    // ---------------- the last CTA: every other CTA's survivors are in S ----------------
+    __threadfence();
+    const int t = threadIdx.x, nt = blockDim.x;
+    FinalizeShared* sh = reinterpret_cast<FinalizeShared*>(smem_raw);
+    u64* surv = reinterpret_cast<u64*>(smem_raw + sizeof(FinalizeShared));  // [POOL_SURV + KP] (or the merge scratch, if larger)
+    size_t surv_bytes = (size_t)(POOL_SURV + KP) * 8;
+    {
+        const size_t merge = (size_t)f.x.world * f.k * 24 + 8;
+        if (merge > surv_bytes) surv_bytes = (merge + 7) & ~(size_t)7;
+    }
+    double* sc = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) + surv_bytes);
+    long long* id = reinterpret_cast<long long*>(sc + KP);
+    u64* ok = reinterpret_cast<u64*>(id + KP);  // qs (filled at kernel start) follows
+    if (p.cta_clock && t == 0) {
+        unsigned long long* x = p.cta_clock + 2 * gridDim.x;
+        x[0] = globaltimer_ns();  // this (the last) CTA holds its ticket
+        x[2] = t_app;             // ... its warp 0 had appended its survivors
+        x[3] = t_app;
+        x[4] = t_loop;            // ... had left its scan loop
+    }
+    // one round of loads: the survivor count, the slot maxima and -- speculatively -- the first keys of the pool
+    const unsigned m = __ldcg(count);
+    u64 spec[POOL_SURV / 2 / 256];
+#pragma unroll
+    for (int u = 0; u < POOL_SURV / 2 / 256; u++) spec[u] = __ldcg(S + t + 256 * u);  // blockDim.x = 256; stale beyond m: masked below
+    if (warp == 0) {
+        u64 ga, gb;
+        const u64 tg = pool_tau(G, lane, ga, gb);
+        if (lane == 0) s_tau = tg;
+    }
+    if (t == 0) {
+        s_ns = 0;
+        sh->nsurv = 0;
+        sh->nvalid = 0;
+        sh->maxerr = 0u;
+        sh->ndeep = 0;
+        sh->T0 = 0ull;
+        sh->qnorm2 = 0.0;
+        sh->fail = 0;
+    }
+    __syncthreads();
+    if (f.err_coef > 0.f && warp == 0) {  // |q|^2 for the certification bound
+        double s2 = 0.0;
+        for (int i = lane; i < f.d; i += 32) s2 = fma(qs[i], qs[i], s2);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        if (lane == 0) sh->qnorm2 = s2;
+    }
+    // stream the pool through the shared-memory buffer: keys >= thr are kept; when more than half of the buffer is taken
+    // it is sorted, cut to the best KP and thr rises to the KP-th best (at most POOL_SURV / 2 new keys per round: no overflow)
+    u64 thr = s_tau;
+    for (unsigned b0 = 0; b0 < m; b0 += POOL_SURV / 2) {
+        const unsigned bend = b0 + POOL_SURV / 2 < m ? b0 + POOL_SURV / 2 : m;
+        if (b0 == 0) {
+#pragma unroll
+            for (int u = 0; u < POOL_SURV / 2 / 256; u++)
+                if ((unsigned)(t + 256 * u) < bend && spec[u] != 0ull && spec[u] >= thr) surv[atomicAdd(&s_ns, 1)] = spec[u];
+        } else {
+            for (unsigned i = b0 + t; i < bend; i += nt) {
+                const u64 key = __ldcg(S + i);
+                if (key != 0ull && key >= thr) surv[atomicAdd(&s_ns, 1)] = key;
+            }
+        }
+        __syncthreads();
+        if (s_ns > POOL_SURV / 2 && bend < m) {  // CTA-uniform
+            const int ns = s_ns;
+            for (int i = ns + t; i < POOL_SURV; i += nt) surv[i] = 0ull;
+            for (int size = 2; size <= POOL_SURV; size <<= 1)
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    __syncthreads();
+                    for (int e = t; e < (POOL_SURV >> 1); e += nt) {
+                        const int i = bitonic_low(e, stride);
+                        cmpx_desc(surv, i, i + stride, (i & size) == 0);
+                    }
+                }
+            __syncthreads();
+            if (surv[KP - 1] > thr) thr = surv[KP - 1];
+            if (t == 0) s_ns = KP;
+            __syncthreads();
+        }
+    }
+    const int ns = s_ns;
+    __syncthreads();  // s_ns is reused as a counter below
+    fin_stamp(f, 0);  // pool read
+    // reset the pool for the next search of this handle (its CTAs touch it only after this kernel has completed)
+    if (t < POOL_SLOTS) G[(size_t)t * POOL_GSTRIDE] = 0ull;
+    if (t == 0) {
+        *count = 0u;
+        *ticket = 0u;
+        if (p.next_chunk) *p.next_chunk = 0u;
+    }
+    fin_stamp(f, 1);
+    const u64* A;
+    if (ns <= POOL_SURV / 2) {
+        const u64* src = surv;
+        int nsrc = ns;
+        if (ns > 3 * KP) {
+            // a few hundred survivors of which KP are wanted: cut them into 2 KP strided chunks, T = KP-th largest chunk maximum
+            // (at least KP keys are >= T, typically ~1.5 KP), keep the keys >= T in the upper half of the buffer
+            u64* cmax = reinterpret_cast<u64*>(sc);  // 2 KP words: sc | id are free until the re-score
+            if (t < 2 * KP) {
+                u64 mx = 0ull;
+                for (int i = t; i < ns; i += 2 * KP) mx = umax64(mx, surv[i]);
+                cmax[t] = mx;
+            }
+            if (t == 0) s_ns = 0;
+            __syncthreads();
+            if (t < 2 * KP) {
+                const u64 mine = cmax[t];
+                int r = 0;
+                for (int j = 0; j < 2 * KP; j++) r += cmax[j] > mine ? 1 : 0;
+                if (r == KP - 1) s_tau = mine;  // keys are unique and every chunk is non-empty: exactly one chunk has this rank
+            }
+            __syncthreads();
+            const u64 T = s_tau;
+            u64* dst = surv + POOL_SURV / 2;
+            for (int i = t; i < ns; i += nt) {
+                const u64 key = surv[i];
+                if (key >= T) dst[atomicAdd(&s_ns, 1)] = key;
+            }
+            __syncthreads();
+            src = dst;
+            nsrc = s_ns;
+        }
+        // the re-score reads the candidates' rows: start them on their way from HBM to L2 now (fp32 master rows)
+        if (!f.xb_is_bf16 && nsrc <= 4 * KP) {
+            const int lines = (f.d * 4 + 127) / 128;
+            for (int i = t; i < nsrc * lines; i += nt) {
+                const char* row = reinterpret_cast<const char*>(f.xb) + (size_t)key_row(src[i / lines]) * f.d * 4 + (size_t)(i % lines) * 128;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+            }
+        }
+        // rank by counting (keys are unique)
+        u64* top = surv + POOL_SURV;  // KP slots behind the buffer
+        for (int i = t; i < KP; i += nt) top[i] = 0ull;
+        __syncthreads();
+        for (int i = t; i < nsrc; i += nt) {
+            const u64 key = src[i];
+            int r = 0;
+            for (int j = 0; j < nsrc; j++) r += src[j] > key ? 1 : 0;
+            if (r < KP) top[r] = key;
+        }
+        __syncthreads();
+        A = top;
+    } else {
+        for (int i = ns + t; i < POOL_SURV; i += nt) surv[i] = 0ull;
+        for (int size = 2; size <= POOL_SURV; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int e = t; e < (POOL_SURV >> 1); e += nt) {
+                    const int i = bitonic_low(e, stride);
+                    cmpx_desc(surv, i, i + stride, (i & size) == 0);
+                }
+            }
+        __syncthreads();
+        A = surv;
+    }
+    fin_stamp(f, 2);  // the KP best ranked
+    finalize_rank_emit<(ScanOcc<T, 1, NV>::value >= 4 ? 2 : 4)>(f, p.q0, A, sh, sc, id, ok, qs, reinterpret_cast<unsigned char*>(surv));
+    if (p.cta_clock && t == 0) p.cta_clock[2 * gridDim.x + 1] = globaltimer_ns();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Variant 2: bulk-async ring.  block = 32 * (consumer warps + 1) <= 288; the LAST warp is the producer.
 // dynamic smem layout (bytes):
 //   [0, stages*stage_bytes)                       ring, stage_bytes = tile_rows * d * sizeof(T) (mult. of 128)

@@ -29,10 +29,12 @@ q = torch.from_numpy(qi.reconstruct_n(0, 64)).to(dev)
 del qi
 
 SETS = [
-    ("unfused static (round-1 path: scan + finalize)", dict(fuse_finalize=0, scan_dynamic=0)),
-    ("fused static", dict(fuse_finalize=1, scan_dynamic=0)),
-    ("fused dynamic c=4", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=4)),
-    ("fused dynamic c=6", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=6)),
+    ("unfused static (round-1 path: scan + finalize)", dict(fuse_finalize=0, scan_dynamic=0, pool_select=0)),
+    ("fused lists static", dict(fuse_finalize=1, scan_dynamic=0, pool_select=0)),
+    ("fused lists dynamic c=6", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=6, pool_select=0)),
+    ("fused pool static", dict(fuse_finalize=1, scan_dynamic=0, pool_select=1)),
+    ("fused pool, dynamic tail c=2", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=2, pool_select=1)),
+    ("fused pool, dynamic tail c=4", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=4, pool_select=1)),
 ]
 if os.environ.get("EVS_PROBE_ALL"):
     SETS += [("fused dynamic c=%d" % c, dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=c)) for c in (1, 2, 8)]
@@ -82,7 +84,7 @@ for rows in [int(r) for r in a.rows.split(",") if r]:
                        epilogue_us=round(float(np.median(epi)), 1), fused_finalize_us=round(float(np.median(fin)), 1))
         print(json.dumps(rec), flush=True)
     del idx
-for k_, v_ in dict(fuse_finalize=1, scan_dynamic=0, scan_chunk_groups=4).items():
+for k_, v_ in dict(fuse_finalize=1, scan_dynamic=0, scan_chunk_groups=4, pool_select=1).items():
     evs.set_option(k_, v_)
 
 # small fp32 batches: 3xTF32 vs single tf32 vs the fp32 GEMV (1M x 512, the C2 shape)

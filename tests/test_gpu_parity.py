@@ -33,6 +33,7 @@ def _reset_options():
     for name in ("scan_variant", "tile_rows", "stages", "ctas_per_sm", "scan_clock"):
         evs.set_option(name, 0)
     evs.set_option("fuse_finalize", 1)
+    evs.set_option("pool_select", 1)
     evs.set_option("scan_dynamic", 1)
     evs.set_option("scan_chunk_groups", 2)
 
@@ -329,15 +330,17 @@ def test_single_query_search_is_one_launch_whatever_the_scan_options():
         idx.add_synthetic(n, seed=11)
         xb = idx.reconstruct_n(0, n)
         Dr, Ir = oracle.canon_search(q, xb, k)
-        for fuse, dyn, chunk in ((1, 1, 2), (1, 1, 1), (1, 1, 7), (1, 0, 2), (0, 0, 2)):
+        for fuse, pool, dyn, chunk in ((1, 1, 0, 2), (1, 0, 1, 2), (1, 0, 1, 1), (1, 0, 1, 7), (1, 0, 0, 2), (0, 0, 0, 2)):
             evs.set_option("fuse_finalize", fuse)
+            evs.set_option("pool_select", pool)  # 1: survivor pool under a global threshold (the default); 0: per-CTA lists
             evs.set_option("scan_dynamic", dyn)
             evs.set_option("scan_chunk_groups", chunk)
             for qi in range(3):
                 l0 = evs.kernel_launches()
                 D, I = idx.search(q[qi:qi + 1], k)
-                assert evs.kernel_launches() - l0 == (1 if fuse else 2), (storage, fuse, dyn, chunk)
-                assert np.array_equal(I, Ir[qi:qi + 1]) and np.array_equal(D, Dr[qi:qi + 1]), (storage, fuse, dyn, chunk, qi)
+                assert evs.kernel_launches() - l0 == (1 if fuse else 2), (storage, fuse, pool, dyn, chunk)
+                assert np.array_equal(I, Ir[qi:qi + 1]) and np.array_equal(D, Dr[qi:qi + 1]), (storage, fuse, pool, dyn, chunk, qi)
+        evs.set_option("pool_select", 1)
         # per-CTA scan clocks (diagnostics): one record per CTA, ends after starts
         evs.set_option("fuse_finalize", 1)
         evs.set_option("scan_clock", 1)
@@ -345,6 +348,47 @@ def test_single_query_search_is_one_launch_whatever_the_scan_options():
         clk = idx.scan_clocks()
         evs.set_option("scan_clock", 0)
         assert clk.shape[0] >= 148 and (clk[:, 1] >= clk[:, 0]).all()
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_pool_selection_does_not_depend_on_the_data(storage):
+    """The single-query search keeps its candidates in one survivor pool under a global running threshold (scan_pool_kernel).
+    Worst cases for it: rows in ASCENDING score order (every row beats everything before it: every warp keeps re-filling
+    its buffer and the pool ends up holding the warps' whole buffers, far more than the last CTA holds in shared memory at a
+    time, so its streaming bitonic rounds run); all high rows in ONE slot of the 64 slot maxima (rows = 0 mod 64: the
+    global threshold stays low); descending order; fewer rows than slots; k' = 128 (the per-CTA-list path); consecutive
+    searches (the last CTA must leave the pool zeroed).  Always the oracle's bits, and the same as the list-based paths."""
+    d, k = 512, 48
+    rng = np.random.default_rng(17)
+    q = oracle.synth_fill(2, d, 7)
+    for n in (200_003, 40_000, 63, 1):
+        xb = oracle.synth_fill(n, d, 21)
+        order = np.argsort(xb @ q[0])
+        cases = {"ascending": xb[order], "descending": xb[order[::-1]]}
+        if n > 1000:
+            hot = xb.copy()  # the 500 best rows of query 0 moved to rows that are multiples of 64
+            best = order[-500:]
+            dst = np.arange(500) * 64
+            tmp = hot[dst].copy()
+            hot[dst] = xb[best]
+            hot[best] = tmp
+            cases["one hot slot"] = hot
+        for name, x in cases.items():
+            x = np.ascontiguousarray(x)
+            idx = evs.IndexFlatIP(d, storage=storage)
+            idx.add(x)
+            for kk in (k, 1, 100):
+                Dr, Ir = oracle.canon_search(q, x, kk)
+                for rep in range(2):  # pool left clean by the previous search
+                    for qi in range(2):
+                        D, I = idx.search(q[qi:qi + 1], kk)
+                        assert np.array_equal(I, Ir[qi:qi + 1]) and np.array_equal(D, Dr[qi:qi + 1]), (n, name, kk, rep, qi)
+                evs.set_option("pool_select", 0)
+                D0, I0 = idx.search(q[:1], kk)
+                evs.set_option("pool_select", 1)
+                assert np.array_equal(I0, Ir[:1]) and np.array_equal(D0, Dr[:1]), (n, name, kk)
+            m = idx.last_margins(1)
+            assert m[0] >= 0 or n <= 100
 
 
 def test_back_to_back_device_searches_overlap_safely():
