@@ -598,6 +598,8 @@ static PathInfo plan_path(const evs_index* idx, int64_t nq, int64_t k, const Sca
 }
 
 static const int kGuardCap = 32;  // queries one device-side guard re-run can take (the on-chip-heap batches are <= 32 queries)
+static const int kRepairCap = 256;  // threshold-scan batches up to this size repair overflowed / uncertified queries on the device
+                                    // too (no host synchronisation); larger batches read the flags on the host
 
 template <typename T>
 static int ensure_pinned(T** ptr, size_t* cap, size_t need_elems);
@@ -805,10 +807,21 @@ static int search_tc_sync_locked(evs_index* idx, int64_t nq, const float* q_dev,
     if ((rc = ensure_dev(reinterpret_cast<unsigned long long**>(&idx->lists), &idx->lists_cap, lists_need))) return rc;
     if ((rc = ensure_dev(&idx->margins_dev, &idx->margins_cap, (size_t)nq))) return rc;
     const bool guard = pi.guard && !scan_only;
-    if (guard && (rc = ensure_dev(&idx->guard_slot, &idx->guard_slot_cap, (size_t)(nq > kGuardCap ? nq : kGuardCap) * 2))) return rc;
+    // Batches of up to kRepairCap queries repair themselves on the device: the finalise queues every query whose candidate
+    // buffers overflowed (adversarial data) or -- fp32 storage -- whose result did not clear the scan's error bound, an fp32
+    // GEMV re-run (k' = 128) walks the queue in one launch that returns at once when the queue is empty, and a predicated
+    // second finalise overwrites those results.  The search never touches the host: the device API stays asynchronous.
+    ScanPlan gp;
+    ScanTuning gt = tune;
+    gt.scan_variant = 1;
+    const int gq = max_queries_per_pass(idx->d, 0);
+    const bool dev_repair = !scan_only && nq <= kRepairCap &&
+                            plan_scan(idx->ntotal, idx->d, 0, 128, gq, idx->sm_count, gt, &gp) == cudaSuccess && gp.variant == 1;
+    if ((guard || dev_repair) && (rc = ensure_dev(&idx->guard_slot, &idx->guard_slot_cap, (size_t)(nq > kGuardCap ? nq : kGuardCap) * 2))) return rc;
+    if (dev_repair && (rc = ensure_dev(&idx->guard_lists, &idx->guard_lists_cap, (size_t)nq * gp.grid * 128))) return rc;
     int* gcount = nullptr;
     int* gcount_next = nullptr;
-    if (guard) {
+    if (guard || dev_repair) {
         const int par = (int)(++idx->guard_seq & 1ull);
         gcount = reinterpret_cast<int*>(idx->words) + W_GUARD_COUNT0 + par;
         gcount_next = reinterpret_cast<int*>(idx->words) + W_GUARD_COUNT0 + (par ^ 1);
@@ -819,12 +832,34 @@ static int search_tc_sync_locked(evs_index* idx, int64_t nq, const float* q_dev,
         ProfileScope prof;
         if ((rc = prof.begin(idx, profile, st))) return rc;
         int lists_per_query = 1;
+        // the finalise parameters first: the threshold scans end in a gather kernel that finalises the query itself
+        FinalizeParams f = make_finalize(idx, idx->lists, 1, kp, q_dev + (size_t)c0 * idx->d, k, out, c0, nq, pi.err_coef, pi.err_trunc);
+        int* gqueue = idx->guard_slot ? idx->guard_slot + (nq > kGuardCap ? nq : kGuardCap) : nullptr;
+        if (dev_repair) {  // one chunk (nq <= kRepairCap): queue on the device, re-run below
+            f.guard_count = gcount;
+            f.guard_count_next = gcount_next;
+            f.guard_slot = idx->guard_slot;
+            f.guard_q = gqueue;
+            f.guard_cap = (int)nq;
+            f.overflow = idx->tc_overflow;  // the fused gather reads the scan's own flags instead
+        } else if (guard) {  // certification only: the flags are read by the host below, nothing is re-run on the device
+            f.guard_count = gcount;
+            f.guard_count_next = gcount_next;
+            f.guard_slot = idx->guard_slot + c0;
+            f.guard_q = gqueue;
+            f.guard_cap = 0;  // slots are not used: every uncertified query gets guard_slot = -2
+        }
+        bool fused_finalize = false;
         {
             TcArgs a = make_tc_args(idx, q_dev + (size_t)c0 * idx->d, cn, idx->lists, idx->tc_overflow + c0);
             if (use_pair(cn)) {
                 Tc2Plan plb;
                 CU(tc2_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, &plb));
                 if (tc2_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
+                if (!scan_only) {
+                    a.fin = &f;
+                    fused_finalize = true;
+                }
                 CU(tc2_scan(a, plb, idx->tc_ws, st));
             } else {
                 TcPlan plb;  // same workspace bound: cn <= the chunk the workspace was sized for
@@ -832,22 +867,43 @@ static int search_tc_sync_locked(evs_index* idx, int64_t nq, const float* q_dev,
                 if (tc_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
                 if (plb.heap) {
                     lists_per_query = plb.grid;
+                    f.L = plb.grid;
                     if ((size_t)cn * plb.grid * kp > idx->lists_cap) return fail(EVS_ECUDA, "internal: list workspace too small");
+                } else if (!scan_only) {
+                    a.fin = &f;
+                    fused_finalize = true;
                 }
                 CU(tc_scan_block(a, plb, idx->tc_ws, st));
             }
         }
         if ((rc = prof.end(st))) return rc;
         if (scan_only) continue;
-        FinalizeParams f = make_finalize(idx, idx->lists, lists_per_query, kp, q_dev + (size_t)c0 * idx->d, k, out, c0, nq, pi.err_coef, pi.err_trunc);
-        if (guard) {  // certification only: the queue is read by the host below, nothing is re-run on the device
-            f.guard_count = gcount;
-            f.guard_count_next = gcount_next;
-            f.guard_slot = idx->guard_slot + c0;
-            f.guard_q = idx->guard_slot + (nq > kGuardCap ? nq : kGuardCap);
-            f.guard_cap = 0;  // slots are not used: every uncertified query gets guard_slot = -2
+        (void)lists_per_query;
+        if (!fused_finalize) {
+            CU(launch_finalize(f, cn, st));
         }
-        CU(launch_finalize(f, cn, st));
+        if (dev_repair) {
+            ScanArgs ga;
+            ga.xb = idx->xb32;
+            ga.is_bf16 = 0;
+            ga.n = idx->ntotal;
+            ga.d = idx->d;
+            ga.xq = q_dev;
+            ga.q0 = 0;
+            ga.nq_pass = gq;
+            ga.lists = idx->guard_lists;
+            ga.kp = 128;
+            ga.qmap = gqueue;
+            ga.nactive = gcount;
+            ga.qcap = (int)nq;
+            CU(launch_scan(ga, &gp, st));
+            FinalizeParams f2 = make_finalize(idx, idx->guard_lists, gp.grid, 128, q_dev, k, out, 0, nq, gemv_err_coef(idx->d));
+            f2.pred_slot = idx->guard_slot;
+            f2.guard_cap = (int)nq;
+            f2.reruns = reinterpret_cast<unsigned long long*>(idx->words + W_RERUNS);
+            CU(launch_finalize(f2, nq, st));
+            return EVS_OK;
+        }
     }
     if (scan_only) return EVS_OK;
     // exactness guards: re-run overflowed and uncertified queries with the fp32 GEMV scan

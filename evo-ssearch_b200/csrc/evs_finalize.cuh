@@ -128,7 +128,7 @@ struct FinalizeShared {
     u64 T0;
     double qnorm2;    // |q|^2
     int fail;         // fused exchange merge: 1 = a rank never arrived, 2 = a rank reported failure
-    int pad0;
+    int uncert;       // the result did not clear the scan's error bound (set by the thread that ranks k-th)
 };
 __host__ __device__ inline size_t finalize_deep_slots(int L) { return (size_t)((L + 1) / 2); }  // ints, in 8-byte units
 __host__ __device__ inline size_t finalize_smem_bytes(int L, int kp, int d) {
@@ -148,6 +148,7 @@ __device__ __forceinline__ void finalize_prologue_at(const FinalizeParams& p, lo
         sh->T0 = 0ull;
         sh->qnorm2 = 0.0;
         sh->fail = 0;
+        sh->uncert = 0;
     }
 }
 __device__ __forceinline__ void finalize_prologue(const FinalizeParams& p, long long qi, unsigned char* smem_raw) {
@@ -155,6 +156,18 @@ __device__ __forceinline__ void finalize_prologue(const FinalizeParams& p, long 
     double* qs = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) +
                                            ((size_t)finalize_surv_slots(p.L, p.kp) + 2 * (size_t)p.L + finalize_deep_slots(p.L) + 3 * (size_t)p.kp) * 8);
     finalize_prologue_at(p, qi, sh, qs);
+}
+
+// |q|^2 for the certification bound, by warp 0 (qs complete and visible: call after a barrier; visible after the next one)
+__device__ __forceinline__ void finalize_qnorm2(const FinalizeParams& p, FinalizeShared* sh, const double* qs) {
+    if (p.err_coef > 0.f && (threadIdx.x >> 5) == 0) {
+        const int lane = threadIdx.x & 31;
+        double s2 = 0.0;
+        for (int i = lane; i < p.d; i += 32) s2 = fma(qs[i], qs[i], s2);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        if (lane == 0) sh->qnorm2 = s2;
+    }
 }
 
 __device__ __forceinline__ void fin_stamp(const FinalizeParams& p, int slot) {
@@ -353,20 +366,7 @@ __device__ __forceinline__ void finalize_rank_emit(const FinalizeParams& p, long
                     // <= w + err_trunc * (B + |w|) + accumulation error.  A bound, not a statistic.
                     const bool certified = p.err_trunc > 0.f ? gap > p.err_trunc * (B + fabsf(worst)) + p.err_coef * B  // false for NaN
                                                              : margin > p.err_coef * B;
-                    if (!certified) {
-                        if (p.guard_count) {  // first phase: queue the query for the exact re-run
-                            const int slot = atomicAdd(p.guard_count, 1);
-                            if (slot < p.guard_cap) {
-                                p.guard_slot[qi] = slot;
-                                p.guard_q[slot] = (int)qi;
-                            } else {
-                                p.guard_slot[qi] = -2;  // flagged only: the host re-runs it (guard_cap = 0), or the queue is full
-                                if (p.guard_cap > 0 && p.uncertified) atomicAdd(p.uncertified, 1ull);
-                            }
-                        } else if (p.uncertified) {  // second phase (or no re-run available): best effort, counted
-                            atomicAdd(p.uncertified, 1ull);
-                        }
-                    }
+                    if (!certified) sh->uncert = 1;  // acted on by thread 0 below (after the barrier)
                 }
             }
         }
@@ -391,6 +391,25 @@ __device__ __forceinline__ void finalize_rank_emit(const FinalizeParams& p, long
         }
     }
     if (t == 0 && p.margins && nvalid < p.k) p.margins[qi] = INFINITY;  // every row was a candidate
+    if (t == 0) {
+        // the guard: a result that did not clear its scan's error bound, or whose candidate buffers overflowed in the
+        // threshold scan, is queued for the exact re-run (first phase), flagged for the host (guard_cap = 0), or counted
+        const bool over = p.overflow != nullptr && p.overflow[qi] != 0;
+        if (sh->uncert || over) {
+            if (p.guard_count) {
+                const int slot = atomicAdd(p.guard_count, 1);
+                if (slot < p.guard_cap) {
+                    p.guard_slot[qi] = slot;
+                    p.guard_q[slot] = (int)qi;
+                } else {
+                    p.guard_slot[qi] = -2;  // flagged only: the host re-runs it (guard_cap = 0), or the queue is full
+                    if (p.guard_cap > 0 && p.uncertified) atomicAdd(p.uncertified, 1ull);
+                }
+            } else if (p.uncertified) {  // second phase (or no re-run available): best effort, counted
+                atomicAdd(p.uncertified, 1ull);
+            }
+        }
+    }
     fin_stamp(p, 4);  // ranked, results written
     if (p.x.world > 0 && p.D == nullptr) {
         // publish: when the last query's CTA has written its part, raise this shard's flag on every rank.  ONE system fence

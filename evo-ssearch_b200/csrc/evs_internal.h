@@ -96,6 +96,9 @@ struct FinalizeParams {
     int* guard_slot = nullptr;        // [nq]: slot of the query in the re-run queue, -1 = certified, -2 = uncertified but not queued
     int* guard_q = nullptr;           // [guard_cap]: query of each slot
     int guard_cap = 0;                // 0: flag only (the host re-runs)
+    const int* overflow = nullptr;    // [nq] (optional): non-zero = a candidate buffer of the threshold scan overflowed for this
+                                      // query: its result is not to be trusted whatever the margin says -> queued like an
+                                      // uncertified one
     // guard, second phase: only the queries with pred_slot[q] >= 0 are finalised again, from the re-run's lists
     const int* pred_slot = nullptr;
     unsigned long long* uncertified = nullptr;  // device counter: results that stayed uncertified
@@ -156,6 +159,8 @@ struct TcArgs {
     void* lists;      // out: u64 [nq][kp]
     int* overflow_out;  // out (optional): int [nq]
     TmapCache* tmaps = nullptr;
+    const FinalizeParams* fin = nullptr;  // threshold scans: the gather kernel finalises the query itself (no list, no second
+                                          // launch); fin->overflow != null -> it is pointed at the scan's own overflow flags
 };
 // CTA-pair tensor-core scan for large batches (evs_tc2.cu)
 struct Tc2Plan {

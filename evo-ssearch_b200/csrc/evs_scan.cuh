@@ -401,7 +401,8 @@ __device__ __forceinline__ void pool_publish(u64* G, u64 key, u64 ga, u64 gb) {
 template <typename T, int NV>
 __global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kernel(ScanParams p, FinalizeParams f, u64* pool) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int s_last, s_ns;
+    __shared__ int s_last, s_ns, s_wcnt[9];
+    __shared__ unsigned s_base;
     __shared__ u64 s_tau;
     typedef typename RawVec<T>::type raw_t;
     constexpr int QREGS = NV * Elem<T>::VEC;
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kerne
     q.load(p.xq, p.q0, p.d, lane);
     int cnt = 0;
     u64 tau = 0ull;
+    bool early = false;
     // the last CTA's re-score wants the query in fp64: every CTA widens it now, off the critical path (the area lies behind
     // the warps' buffers and is not touched in between)
     double* qs;
@@ -478,6 +480,17 @@ __global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kerne
                 if (key > tau) {
                     if (lane == 0) buf[cnt] = key;
                     if (++cnt == CAPW) compact();
+                    else if (cnt == 16 && !early) {
+                        // the best of the first 16 keys goes to its slot right away: on shards where a warp sees fewer than
+                        // 128 rows (100k-row indexes) nobody ever compacts, and without this the slot maxima would stay
+                        // empty and the pool would receive every key of the shard
+                        early = true;
+                        __syncwarp();
+                        u64 mx = lane < 16 ? buf[lane] : 0ull;
+#pragma unroll
+                        for (int off = 8; off >= 1; off >>= 1) mx = umax64(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                        if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(G + (size_t)((~(uint32_t)mx) & (POOL_SLOTS - 1)) * POOL_GSTRIDE), (unsigned long long)mx);
+                    }
                 }
             }
         }
@@ -506,27 +519,47 @@ __global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kerne
     }
     if (p.cta_clock && threadIdx.x == 0) t_loop = globaltimer_ns();
 
-    // end of this warp's rows: no sort.  Survivors = buffered keys >= the current tau_g; append them to S, publish them.
+    // end of this warp's rows: no sort.  Survivors = buffered keys >= the current tau_g: compacted to the front of the warp's
+    // buffer and published to the slot maxima; the CTA then reserves room in the pool with ONE atomic for all of its warps
+    // (with one atomic per warp a 10k-row index -- every warp ends at once, every key survives -- spent ~25 us queueing
+    // on the counter) and copies them out.
     {
         __syncwarp();
         u64 ga, gb;
         tau = umax64(tau, pool_tau(G, lane, ga, gb));
+        int kept = 0;
         for (int i0 = 0; i0 < cnt; i0 += 32) {  // warp-uniform
             const u64 key = (i0 + lane < cnt) ? buf[i0 + lane] : 0ull;
             const bool keep = key != 0ull && key >= tau;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m == 0u) continue;
-            unsigned pos = 0;
-            if (lane == 0) pos = atomicAdd(count, (unsigned)__popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (keep) S[pos + __popc(m & ((1u << lane) - 1u))] = key;
+            __syncwarp();
+            if (keep) buf[kept + __popc(m & ((1u << lane) - 1u))] = key;  // kept <= i0: never ahead of the reads
             pool_publish(G, keep ? key : 0ull, ga, gb);
+            kept += __popc(m);
+            __syncwarp();
         }
+        if (lane == 0) s_wcnt[warp] = kept;
     }
     if (p.cta_clock && threadIdx.x == 0) {
         t_app = globaltimer_ns();
         p.cta_clock[2 * blockIdx.x] = t_start;
         p.cta_clock[2 * blockIdx.x + 1] = t_loop;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int w = 0; w < nwarps; w++) {
+            const int c = s_wcnt[w];
+            s_wcnt[w] = total;  // exclusive prefix
+            total += c;
+        }
+        s_wcnt[nwarps] = total;
+        s_base = total ? atomicAdd(count, (unsigned)total) : 0u;
+    }
+    __syncthreads();
+    {
+        const int off = s_wcnt[warp], end = warp + 1 < nwarps ? s_wcnt[warp + 1] : s_wcnt[nwarps];
+        for (int i = lane; i < end - off; i += 32) S[s_base + off + i] = buf[i];
     }
 
     __threadfence();  // this thread's pool stores / slot updates are visible device-wide before the CTA takes its ticket
@@ -574,6 +607,7 @@ __global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kerne
         sh->T0 = 0ull;
         sh->qnorm2 = 0.0;
         sh->fail = 0;
+        sh->uncert = 0;
     }
     __syncthreads();
     if (f.err_coef > 0.f && warp == 0) {  // |q|^2 for the certification bound
@@ -586,17 +620,40 @@ __global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kerne
     // stream the pool through the shared-memory buffer: keys >= thr are kept; when more than half of the buffer is taken
     // it is sorted, cut to the best KP and thr rises to the KP-th best (at most POOL_SURV / 2 new keys per round: no overflow)
     u64 thr = s_tau;
+    if (m > POOL_SURV / 2) {
+        // A large pool (a small index: no warp ever filled its buffer, so the slot maxima are empty; or adversarial order):
+        // first a threshold from the pool's first 1024 keys -- KP-th largest of 2 KP strided chunk maxima: at least KP keys
+        // are >= it -- so that the rounds below keep about KP * m / 1024 keys instead of sorting everything.
+        u64* cmax = reinterpret_cast<u64*>(sc);  // 2 KP words: sc | id are free until the re-score
+        u64 mine = 0ull;
+#pragma unroll
+        for (int u = 0; u < POOL_SURV / 2 / 256; u++) mine = umax64(mine, spec[u]);  // thread t: keys t, t + 256, ... = chunk t mod 128
+        mine = umax64(mine, __shfl_xor_sync(0xffffffffu, mine, 0));  // (keeps the warp converged)
+        if (t >= 2 * KP) cmax[t - 2 * KP] = mine;
+        __syncthreads();
+        if (t < 2 * KP) cmax[t] = umax64(cmax[t], mine);
+        __syncthreads();
+        if (t < 2 * KP) {
+            const u64 v = cmax[t];
+            int r = 0;
+            for (int j = 0; j < 2 * KP; j++) r += cmax[j] > v ? 1 : 0;
+            if (r == KP - 1 && v > s_tau) s_tau = v;  // keys are unique: exactly one chunk maximum has this rank
+        }
+        __syncthreads();
+        thr = s_tau;
+    }
     for (unsigned b0 = 0; b0 < m; b0 += POOL_SURV / 2) {
         const unsigned bend = b0 + POOL_SURV / 2 < m ? b0 + POOL_SURV / 2 : m;
-        if (b0 == 0) {
+        u64 nxt[POOL_SURV / 2 / 256];  // the next round's keys are on their way while this round is filtered
 #pragma unroll
-            for (int u = 0; u < POOL_SURV / 2 / 256; u++)
-                if ((unsigned)(t + 256 * u) < bend && spec[u] != 0ull && spec[u] >= thr) surv[atomicAdd(&s_ns, 1)] = spec[u];
-        } else {
-            for (unsigned i = b0 + t; i < bend; i += nt) {
-                const u64 key = __ldcg(S + i);
-                if (key != 0ull && key >= thr) surv[atomicAdd(&s_ns, 1)] = key;
-            }
+        for (int u = 0; u < POOL_SURV / 2 / 256; u++) {
+            const unsigned i = bend + t + 256 * u;
+            nxt[u] = i < m ? __ldcg(S + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < POOL_SURV / 2 / 256; u++) {
+            if (b0 + t + 256 * u < bend && spec[u] != 0ull && spec[u] >= thr) surv[atomicAdd(&s_ns, 1)] = spec[u];
+            spec[u] = nxt[u];
         }
         __syncthreads();
         if (s_ns > POOL_SURV / 2 && bend < m) {  // CTA-uniform

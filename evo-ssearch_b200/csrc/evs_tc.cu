@@ -38,6 +38,7 @@
 #include "evs_internal.h"
 #include "evs_common.cuh"
 #include "evs_tc_common.cuh"
+#include "evs_finalize.cuh"
 
 namespace evs {
 
@@ -503,8 +504,21 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // gmax is the pre-pass kernel's output
     if (staged) {
+        // eight loads in flight per thread (one at a time this loop was 32 dependent L2 round trips: 10 of the kernel's 15 us)
         const int q = threadIdx.x & 7;
-        for (int i = threadIdx.x >> 3; i < groups; i += 32) tile[q * pitch + i] = __ldg(gmax + (size_t)i * npad + blockIdx.x * 8 + q);
+        for (int i0 = threadIdx.x >> 3; i0 < groups; i0 += 32 * 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + 32 * u;
+                v[u] = i < groups ? __ldg(gmax + (size_t)i * npad + blockIdx.x * 8 + q) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + 32 * u;
+                if (i < groups) tile[q * pitch + i] = v[u];
+            }
+        }
         __syncthreads();
     }
     const uint32_t* mine_vals = tile + warp * pitch;
@@ -579,18 +593,38 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
 constexpr int GATHER_ALL = 4096;   // keys of one query held in shared memory; more -> overflow (GEMV re-run)
 constexpr int GATHER_SURV = 1024;  // also holds the buffer maxima: nctas + 1 <= GATHER_SURV
 
-__global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int nctas,
+// FUSE: the kernel goes on to finalise the query itself (canonical re-score, ranking, output, margin / guard:
+// finalize_rank_emit) from the list it has just built in shared memory: one launch and one list round trip less per search
+// (the 4096-query batch spent 83 + 175 us in gather + finalise, a 64-query batch 16 + 17 us of its 395).
+__host__ __device__ inline size_t gather_smem_bytes(int nctas, int kp) {
+    return ((size_t)(GATHER_ALL + GATHER_SURV + 2 * kp) * 8 + (size_t)(nctas + 1) * 4 + 15) & ~(size_t)15;
+}
+template <bool FUSE>
+__global__ void __launch_bounds__(FUSE ? 1024 : 256) tc_gather_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int nctas,
                                                         int cap, int kp, u64* __restrict__ lists, int* __restrict__ overflow,
-                                                        const int* __restrict__ spill_cnt, const u64* __restrict__ spill) {
+                                                        const int* __restrict__ spill_cnt, const u64* __restrict__ spill,
+                                                        FinalizeParams f) {
     extern __shared__ __align__(16) unsigned char sraw[];
     u64* all = reinterpret_cast<u64*>(sraw);       // GATHER_ALL
     u64* surv = all + GATHER_ALL;                  // GATHER_SURV
     u64* cmax = surv + GATHER_SURV;                // 2 * kp
     int* cnt = reinterpret_cast<int*>(cmax + 2 * kp);  // nctas + 1
+    // FUSE: FinalizeShared | A[kp] | sc[kp] | id[kp] | ok[kp] | qs[d] behind the gather's own arrays
+    FinalizeShared* fsh = reinterpret_cast<FinalizeShared*>(sraw + gather_smem_bytes(nctas, kp));
+    u64* fA = reinterpret_cast<u64*>(fsh + 1);
+    double* fsc = reinterpret_cast<double*>(fA + kp);
+    long long* fid = reinterpret_cast<long long*>(fsc + kp);
+    u64* fok = reinterpret_cast<u64*>(fid + kp);
+    double* fqs = reinterpret_cast<double*>(fok + kp);
     __shared__ int s_n, s_m;
     __shared__ u64 s_T;
     const int c = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nt = blockDim.x, nwarps = nt >> 5;
+    if (FUSE) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        finalize_prologue_at(f, c, fsh, fqs);  // the query does not come from the scan: widened while the scan drains
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     const u64* base = cand + (size_t)c * nctas * cap;
     for (int b = threadIdx.x; b < nctas; b += nt) cnt[b] = counts[(size_t)c * nctas + b];
     // the query's spill list is one more buffer (index nctas): normally empty
@@ -677,7 +711,7 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ 
         if (threadIdx.x == 0) overflow[c] = 1;  // the caller re-runs this query through the GEMV scan
         total = GATHER_ALL;
     }
-    u64* out = lists + (size_t)c * kp;
+    u64* out = FUSE ? fA : lists + (size_t)c * kp;
     // 2. threshold from strided chunk maxima (only worth it when there are clearly more than kp keys)
     const int nch = 2 * kp;
     const u64* src = all;
@@ -739,6 +773,15 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const u64* __restrict__ 
         }
         __syncthreads();
         for (int i = threadIdx.x; i < kp; i += nt) out[i] = all[i];
+    }
+    if (FUSE) {
+        if (threadIdx.x == 0) {
+            if (f.guard_slot) f.guard_slot[c] = -1;  // overwritten by the guard (barriers in between) if the query is queued
+            if (c == 0 && f.guard_count_next) *f.guard_count_next = 0;  // ready for the next guarded search of this handle
+        }
+        finalize_qnorm2(f, fsh, fqs);
+        __syncthreads();  // the list and |q|^2 are complete
+        finalize_rank_emit<2>(f, c, fA, fsh, fsc, fid, fok, fqs, reinterpret_cast<unsigned char*>(all));
     }
 }
 
@@ -856,13 +899,35 @@ cudaError_t tc_launch_tau0(const uint32_t* gmax, int groups, int gpow2, int nqp,
 }
 
 cudaError_t tc_launch_gather(const u64* cand, const int* counts, int nctas, int nqp, int cap, int kp, int cap_total, int nq,
-                             u64* lists, int* overflow, const int* spill_cnt, const u64* spill, cudaStream_t st) {
+                             u64* lists, int* overflow, const int* spill_cnt, const u64* spill, const FinalizeParams* fin, cudaStream_t st) {
     (void)cap_total;
     (void)nqp;
-    const size_t gs = (size_t)(GATHER_ALL + GATHER_SURV + 2 * kp) * 8 + (size_t)(nctas + 1) * 4;
-    if (gs > 200 * 1024 || nctas + 1 > GATHER_SURV) return cudaErrorInvalidValue;
-    if (gs > 40 * 1024) cudaFuncSetAttribute(tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
-    tc_gather_kernel<<<nq, 256, gs, st>>>(cand, counts, nctas, cap, kp, lists, overflow, spill_cnt, spill);
+    size_t gs = gather_smem_bytes(nctas, kp);
+    if (nctas + 1 > GATHER_SURV) return cudaErrorInvalidValue;
+    if (fin != nullptr) {
+        FinalizeParams f = *fin;
+        if (f.overflow) f.overflow = overflow;  // the scan's own flags (set by the select pass or by this very CTA)
+        gs += sizeof(FinalizeShared) + (4 * (size_t)kp + (size_t)f.d) * 8 + 16;
+        if (gs > 200 * 1024) return cudaErrorInvalidValue;
+        static size_t have[16] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (gs > have[dev & 15]) {
+            cudaError_t ae = cudaFuncSetAttribute(tc_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
+            if (ae != cudaSuccess) return ae;
+            have[dev & 15] = gs;
+        }
+        // small batches: 1024 threads shorten the single CTA's critical path (one re-score round); large ones: 256 threads so
+        // that several queries share an SM
+        cudaError_t le = launch_pdl(tc_gather_kernel<true>, dim3((unsigned)nq), dim3(nq <= 296 ? 1024 : 256), gs, st, cand, counts, nctas, cap, kp,
+                                    lists, overflow, spill_cnt, spill, f);
+        g_kernel_launches.fetch_add(1);
+        if (le != cudaSuccess) return le;
+        return cudaGetLastError();
+    }
+    if (gs > 200 * 1024) return cudaErrorInvalidValue;
+    if (gs > 40 * 1024) cudaFuncSetAttribute(tc_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
+    tc_gather_kernel<false><<<nq, 256, gs, st>>>(cand, counts, nctas, cap, kp, lists, overflow, spill_cnt, spill, FinalizeParams{});
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -981,6 +1046,10 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     // pre-pass sample: every `stride`-th tile, at least 512 tiles (or all of them)
     long long want = pl->ntiles / 128;
     if (want < tc_sample_rows(nq) / TC_BM) want = tc_sample_rows(nq) / TC_BM;
+    // one-CTA kernel (<= 128 queries per block): the pre-pass is latency-bound (~10 us per tile per CTA), so up to 1.2 million
+    // rows it takes one tile per SM (18 944 rows on 148 SMs) instead of a second round for a few CTAs; the select pass
+    // absorbs the 1.7x admissions unnoticed at these batch sizes
+    if (g_tc_sample_rows == 0 && nq > 32 && want > sm_count && pl->ntiles / 128 <= sm_count) want = sm_count;
     if (want > pl->ntiles) want = pl->ntiles;
     pl->pre_stride = pl->ntiles / want;
     pl->pre_tiles = (pl->ntiles + pl->pre_stride - 1) / pl->pre_stride;
@@ -1097,7 +1166,7 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     if (e != cudaSuccess) return e;
     // 3. per query: gather + sort -> top-kp list
     if ((e = tc_launch_gather(p.cand, p.counts, pl.grid, pl.nqp, pl.cap, pl.kp, pl.cap_total, a.nq,
-                              reinterpret_cast<u64*>(a.lists), p.overflow, p.spill_cnt, p.spill, st)) != cudaSuccess)
+                              reinterpret_cast<u64*>(a.lists), p.overflow, p.spill_cnt, p.spill, a.fin, st)) != cudaSuccess)
         return e;
     if (a.overflow_out)
         e = cudaMemcpyAsync(a.overflow_out, ws + pl.off_overflow, (size_t)a.nq * 4, cudaMemcpyDeviceToDevice, st);

@@ -575,7 +575,7 @@ cudaError_t tc2_scan(const TcArgs& a, const Tc2Plan& pl, unsigned char* ws, cuda
     if ((e = launch_tc2<MODE_SELECT>(a.is_bf16, tdb, tq, p, pl.grid, pl.smem, st)) != cudaSuccess) return e;
     // 3. per query: gather + sort -> top-kp list
     if ((e = tc_launch_gather(p.cand, p.counts, pl.grid, pl.nqp, pl.cap, pl.kp, pl.cap_total, a.nq,
-                              reinterpret_cast<u64*>(a.lists), p.overflow, p.spill_cnt, p.spill, st)) != cudaSuccess)
+                              reinterpret_cast<u64*>(a.lists), p.overflow, p.spill_cnt, p.spill, a.fin, st)) != cudaSuccess)
         return e;
     if (a.overflow_out)
         e = cudaMemcpyAsync(a.overflow_out, ws + pl.off_overflow, (size_t)a.nq * 4, cudaMemcpyDeviceToDevice, st);

@@ -4,6 +4,7 @@
 #include <cuda.h>
 
 #include "evs_common.cuh"
+#include "evs_internal.h"
 
 namespace evs {
 
@@ -207,6 +208,6 @@ cudaError_t tc_make_tmap(CUtensorMap* map, const void* base, long long rows, int
 cudaError_t tc_queries_to_bf16(const float* xq, void* dst, long long count, cudaStream_t st);
 cudaError_t tc_launch_tau0(const uint32_t* gmax, int groups, int gpow2, int nqp, int nq, int kp, float* tau0, cudaStream_t st);
 cudaError_t tc_launch_gather(const u64* cand, const int* counts, int nctas, int nqp, int cap, int kp, int cap_total, int nq,
-                             u64* lists, int* overflow, const int* spill_cnt, const u64* spill, cudaStream_t st);
+                             u64* lists, int* overflow, const int* spill_cnt, const u64* spill, const FinalizeParams* fin, cudaStream_t st);
 
 }  // namespace evs
