@@ -1182,7 +1182,7 @@ struct evs_exchange {
     int device = 0, rank = 0, world = 0;
     int64_t max_nq = 0, max_k = 0;
     size_t slot_bytes = 0, total_bytes = 0;
-    unsigned char* local = nullptr;     // [2][world][slot_bytes] slots, [2][world] u64 flags, done counter
+    unsigned char* local = nullptr;     // [2][world][slot_bytes] slots of flagged 32-byte entries
     unsigned char* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool opened[8] = {false, false, false, false, false, false, false, false};
     bool connected = false;
@@ -1192,8 +1192,6 @@ struct evs_exchange {
     volatile int* status_host = nullptr;  // host-mapped word the merge kernel writes on failure (1 timeout, 2 peer failed)
     int* status_dev = nullptr;
     std::mutex mu;
-    size_t flags_off() const { return 2 * (size_t)world * slot_bytes; }
-    unsigned* done() const { return reinterpret_cast<unsigned*>(local + flags_off() + 2 * (size_t)world * 8); }
 };
 
 extern "C" int evs_exchange_create(int device, int rank, int world, int64_t max_nq, int64_t max_k, evs_exchange** out) {
@@ -1215,8 +1213,8 @@ extern "C" int evs_exchange_create(int device, int rank, int world, int64_t max_
     ex->world = world;
     ex->max_nq = max_nq;
     ex->max_k = max_k;
-    ex->slot_bytes = ((size_t)max_nq * max_k * 16 + 255) & ~(size_t)255;
-    ex->total_bytes = ex->flags_off() + 2 * (size_t)world * 8 + 16;
+    ex->slot_bytes = ((size_t)max_nq * max_k * kExchangeEntryBytes + 255) & ~(size_t)255;
+    ex->total_bytes = 2 * (size_t)world * ex->slot_bytes;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ex->local), ex->total_bytes);
     if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->total_bytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ex->stage_scores), (size_t)max_nq * max_k * 8);
@@ -1318,8 +1316,8 @@ static int search_exchange_enqueue_locked(evs_index* idx, evs_exchange* ex, int6
     x.seq = ex->seq + 1;             // every rank calls in the same order: the sequence numbers agree
     x.parity = (int)(x.seq & 1ull);  // two generations of slots: a fast rank may start search s+1 while a slow one merges s
     x.slot_bytes = ex->slot_bytes;
-    x.done = ex->done();
     x.nq_total = nq;
+    x.k = (int)k;
     x.status = ex->status_dev;
     const ScanTuning tune = tune_snapshot();  // ONE snapshot decides the path here and inside the search
     const PathInfo pi = plan_path(idx, nq, k, tune, true);

@@ -47,18 +47,25 @@ struct ScanPlan {
 };
 
 // Peer-store exchange of shard partials (row sharding): every rank owns a symmetric buffer
-//   [2 parities][world shards][slot_bytes]  gather slots (float64 scores [nq*k] then int64 ids [nq*k])
-//   [2 parities][world shards] uint64       arrival flags: the search sequence number; bit 63 = that rank FAILED the search
-// and sees all ranks' buffers through peer-mapped pointers.
-constexpr unsigned long long kExchangePoison = 1ull << 63;
+//   [2 parities][world shards][slot_bytes]  gather slots, one 32-byte ENTRY per (query, rank-in-partial):
+//       { score bits 31..0, flag, score bits 63..32, flag, id bits 31..0, flag, id bits 63..32, flag }   (eight u32)
+// and sees all ranks' buffers through peer-mapped pointers.  The flag travels WITH the data (the protocol NCCL calls LL):
+// an entry is written with two 16-byte stores whose 8-byte halves (4 bytes of payload + the flag) are each atomic, and a
+// reader polls an entry until all four flags carry the sequence number of the search it is merging.  No fence, no separate
+// arrival flag: one NVLink traversal instead of three (data, fence round trip, flag) -- at 8 ranks the fenced protocol
+// spent 32 us between "partial stored" and "merged" on every rank (scripts/exchange_probe.py).
+// flag = low 31 bits of the search sequence number (never 0: buffers start zeroed, sequence numbers at 1); bit 31 set = that
+// rank FAILED this search.  Two parities: a fast rank may start search s+1 while a slow one still merges s.
+constexpr unsigned kExchangePoison = 1u << 31;
+constexpr int kExchangeEntryBytes = 32;
 struct Exchange {
     unsigned char* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int rank = 0, world = 0, parity = 0;
     unsigned long long seq = 0;
     size_t slot_bytes = 0;
-    unsigned* done = nullptr;  // local counter of finished finalize CTAs
     long long nq_total = 0;    // queries of the whole search (a search may be finalised in several launches)
     long long q_off = 0;       // first query of this launch
+    int k = 0;                 // results per query of this search (entry index = query * k + rank)
     int* status = nullptr;     // host-mapped: 1 = a merge gave up waiting for a rank (~10 s), 2 = a rank reported failure
     float* merge_D = nullptr;  // non-null (single-query searches finalised inside the scan kernel): the same CTA also waits
     long long* merge_I = nullptr;  //   for the peers' partials and merges them into (D, I): one launch per search at N > 1 too

@@ -48,56 +48,33 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeParams p) {
 
 // =============================================================================================
 // publish: copy this shard's partial (scores[nq*k], ids[nq*k]) into its slot on EVERY rank over NVLink
-// (peer stores), then raise the arrival flag on every rank.  Used when the partial was produced by a
-// path that cannot write the slots itself (tensor-core scan with its host-side overflow repair, empty
+// (peer stores, one flagged 32-byte entry per result: evs_internal.h).  Used when the partial was produced by a
+// path that cannot write the slots itself (scans whose result the device guard may still overwrite, empty
 // shard).  grid = any, block = 256.
 // =============================================================================================
 __global__ void __launch_bounds__(256) publish_partials_kernel(Exchange x, long long count, const double* __restrict__ scores,
                                                               const long long* __restrict__ ids) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
-        const double sv = scores[e];
-        const long long iv = ids[e];
-        for (int g = 0; g < x.world; g++) {
-            unsigned char* slot = x.peer[g] + ((size_t)x.parity * x.world + x.rank) * x.slot_bytes;
-            reinterpret_cast<double*>(slot)[e] = sv;
-            reinterpret_cast<long long*>(slot + (size_t)count * 8)[e] = iv;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const unsigned prev = atomicAdd(x.done, 1u);
-        if (prev == gridDim.x - 1) {
-            *x.done = 0u;
-            __threadfence_system();
-            for (int g = 0; g < x.world; g++) {
-                unsigned long long* flags = reinterpret_cast<unsigned long long*>(x.peer[g] + 2 * (size_t)x.world * x.slot_bytes);
-                st_relaxed_sys_u64(flags + (size_t)x.parity * x.world + x.rank, x.seq);
-            }
-        }
-    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the partial is the preceding kernels' output
+    const uint32_t flag = exchange_flag(x.seq);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x)
+        exchange_store_entry(x, (size_t)e, scores[e], ids[e], flag);
 }
 
 // =============================================================================================
 // poison: this rank could not run search `x.seq` (an allocation or a launch failed after its peers may already be waiting):
-// raise its flag with bit 63 set on every rank, so that the peers' merges report the failure instead of waiting ~10 s or
-// returning a result that silently misses this shard.  grid = 1, block = 32.
+// every entry of its slot on every rank gets the sequence flag with bit 31 set, so that the peers' merges report the failure
+// instead of waiting ~10 s or returning a result that silently misses this shard.  grid = any, block = 256.
 // =============================================================================================
-__global__ void publish_poison_kernel(Exchange x) {
-    if (threadIdx.x == 0) {
-        *x.done = 0u;
-        __threadfence_system();
-        for (int g = 0; g < x.world; g++) {
-            unsigned long long* flags = reinterpret_cast<unsigned long long*>(x.peer[g] + 2 * (size_t)x.world * x.slot_bytes);
-            st_release_sys_u64(flags + (size_t)x.parity * x.world + x.rank, x.seq | kExchangePoison);
-        }
-    }
+__global__ void publish_poison_kernel(Exchange x, long long count) {
+    const uint32_t flag = exchange_flag(x.seq) | kExchangePoison;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x)
+        exchange_store_entry(x, (size_t)e, 0.0, -1, flag);
 }
 
 // =============================================================================================
-// merge after the peer-store exchange: wait until every shard's flag for this search has arrived in the
-// LOCAL gather buffer, then rank the world*k partials of each query.  grid = nq, block = 256.
-// Every rank runs this kernel on its own GPU; the flags are written by the other GPUs' finalize kernels.
+// merge after the peer-store exchange: poll the entries of this search in the LOCAL gather buffer until every
+// shard's have arrived, then rank the world*k partials of each query.  grid = nq, block = 256.
+// Every rank runs this kernel on its own GPU; the entries are written by the other GPUs' finalise / publish kernels.
 // A rank that never arrives (~10 s watchdog) or that reported failure (poisoned flag) makes the whole result
 // padding (-FLT_MAX, -1) and sets *x.status (host-mapped): stale slots are never merged.
 // =============================================================================================
@@ -605,7 +582,10 @@ cudaError_t launch_publish_partials(const Exchange& x, long long nq, int k, cons
 }
 
 cudaError_t launch_publish_poison(const Exchange& x, cudaStream_t st) {
-    publish_poison_kernel<<<1, 32, 0, st>>>(x);
+    const long long count = x.nq_total * x.k;
+    if (count <= 0) return cudaSuccess;
+    int grid = (int)((count + 255) / 256 < 64 ? (count + 255) / 256 : 64);
+    publish_poison_kernel<<<grid, 256, 0, st>>>(x, count);
     EVS_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -590,27 +590,30 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
 // kp are among the keys >= T, typically ~1.5 kp of them -- (3) rank those survivors by counting.  Many survivors
 // (clustered candidates) fall back to a bitonic sort.  grid = nq, block = 256.
 // ---------------------------------------------------------------------------------------------
-constexpr int GATHER_ALL = 4096;   // keys of one query held in shared memory; more -> overflow (GEMV re-run)
+constexpr int GATHER_ALL_MAX = 4096;  // keys of one query held in shared memory at most; more -> overflow (exact re-run).  The launch
+                                      // sizes the array (`gall`, a power of two in [1024, 4096]) from the expected candidate
+                                      // count: a 4096-query batch expects ~1100 keys per query, and 2048 slots instead of
+                                      // 4096 let eight CTAs share an SM instead of four
 constexpr int GATHER_SURV = 1024;  // also holds the buffer maxima: nctas + 1 <= GATHER_SURV
 
 // FUSE: the kernel goes on to finalise the query itself (canonical re-score, ranking, output, margin / guard:
 // finalize_rank_emit) from the list it has just built in shared memory: one launch and one list round trip less per search
 // (the 4096-query batch spent 83 + 175 us in gather + finalise, a 64-query batch 16 + 17 us of its 395).
-__host__ __device__ inline size_t gather_smem_bytes(int nctas, int kp) {
-    return ((size_t)(GATHER_ALL + GATHER_SURV + 2 * kp) * 8 + (size_t)(nctas + 1) * 4 + 15) & ~(size_t)15;
+__host__ __device__ inline size_t gather_smem_bytes(int nctas, int kp, int gall) {
+    return ((size_t)(gall + GATHER_SURV + 2 * kp) * 8 + (size_t)(nctas + 1) * 4 + 15) & ~(size_t)15;
 }
 template <bool FUSE>
 __global__ void __launch_bounds__(FUSE ? 1024 : 256) tc_gather_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int nctas,
                                                         int cap, int kp, u64* __restrict__ lists, int* __restrict__ overflow,
-                                                        const int* __restrict__ spill_cnt, const u64* __restrict__ spill,
+                                                        const int* __restrict__ spill_cnt, const u64* __restrict__ spill, int gall,
                                                         FinalizeParams f) {
     extern __shared__ __align__(16) unsigned char sraw[];
-    u64* all = reinterpret_cast<u64*>(sraw);       // GATHER_ALL
-    u64* surv = all + GATHER_ALL;                  // GATHER_SURV
+    u64* all = reinterpret_cast<u64*>(sraw);       // gall
+    u64* surv = all + gall;                        // GATHER_SURV
     u64* cmax = surv + GATHER_SURV;                // 2 * kp
     int* cnt = reinterpret_cast<int*>(cmax + 2 * kp);  // nctas + 1
     // FUSE: FinalizeShared | A[kp] | sc[kp] | id[kp] | ok[kp] | qs[d] behind the gather's own arrays
-    FinalizeShared* fsh = reinterpret_cast<FinalizeShared*>(sraw + gather_smem_bytes(nctas, kp));
+    FinalizeShared* fsh = reinterpret_cast<FinalizeShared*>(sraw + gather_smem_bytes(nctas, kp, gall));
     u64* fA = reinterpret_cast<u64*>(fsh + 1);
     double* fsc = reinterpret_cast<double*>(fA + kp);
     long long* fid = reinterpret_cast<long long*>(fsc + kp);
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(FUSE ? 1024 : 256) tc_gather_kernel(const u64*
     __syncthreads();
     if (threadIdx.x == 0) s_m = 0;
     u64 T1 = 0ull;
-    if (grand > GATHER_ALL) {
+    if (grand > gall) {
         // 0. too many keys for shared memory (large shards: the pre-pass samples n/128 rows, so ~140 kp keys pass):
         //    first a threshold from the buffer maxima -- T1 = kp-th largest head, at least kp keys are >= T1 and
         //    only ~1.5 % of the keys are -- then the compaction below keeps the keys >= T1 only.
@@ -701,15 +704,15 @@ __global__ void __launch_bounds__(FUSE ? 1024 : 256) tc_gather_kernel(const u64*
                 if (lane == 0) pos = atomicAdd(&s_n, __popc(m));
                 pos = __shfl_sync(0xffffffffu, pos, 0);
                 const int dst = pos + __popc(m & ((1u << lane) - 1u));
-                if (valid && dst < GATHER_ALL) all[dst] = k;
+                if (valid && dst < gall) all[dst] = k;
             }
         }
     }
     __syncthreads();
     int total = s_n;
-    if (total > GATHER_ALL) {
+    if (total > gall) {
         if (threadIdx.x == 0) overflow[c] = 1;  // the caller re-runs this query through the GEMV scan
-        total = GATHER_ALL;
+        total = gall;
     }
     u64* out = FUSE ? fA : lists + (size_t)c * kp;
     // 2. threshold from strided chunk maxima (only worth it when there are clearly more than kp keys)
@@ -759,8 +762,8 @@ __global__ void __launch_bounds__(FUSE ? 1024 : 256) tc_gather_kernel(const u64*
         }
     } else {
         // 3b. bitonic sort of everything, descending
-        int pow2 = 2048;
-        while (pow2 < total) pow2 <<= 1;
+        int pow2 = 1024;
+        while (pow2 < total) pow2 <<= 1;  // <= gall (a power of two)
         for (int i = total + threadIdx.x; i < pow2; i += nt) all[i] = 0ull;
         for (int size = 2; size <= pow2; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -900,9 +903,10 @@ cudaError_t tc_launch_tau0(const uint32_t* gmax, int groups, int gpow2, int nqp,
 
 cudaError_t tc_launch_gather(const u64* cand, const int* counts, int nctas, int nqp, int cap, int kp, int cap_total, int nq,
                              u64* lists, int* overflow, const int* spill_cnt, const u64* spill, const FinalizeParams* fin, cudaStream_t st) {
-    (void)cap_total;
     (void)nqp;
-    size_t gs = gather_smem_bytes(nctas, kp);
+    int gall = 1024;
+    while (gall < cap_total && gall < GATHER_ALL_MAX) gall <<= 1;  // cap_total: what the plan expects per query, with slack
+    size_t gs = gather_smem_bytes(nctas, kp, gall);
     if (nctas + 1 > GATHER_SURV) return cudaErrorInvalidValue;
     if (fin != nullptr) {
         FinalizeParams f = *fin;
@@ -920,14 +924,14 @@ cudaError_t tc_launch_gather(const u64* cand, const int* counts, int nctas, int 
         // small batches: 1024 threads shorten the single CTA's critical path (one re-score round); large ones: 256 threads so
         // that several queries share an SM
         cudaError_t le = launch_pdl(tc_gather_kernel<true>, dim3((unsigned)nq), dim3(nq <= 296 ? 1024 : 256), gs, st, cand, counts, nctas, cap, kp,
-                                    lists, overflow, spill_cnt, spill, f);
+                                    lists, overflow, spill_cnt, spill, gall, f);
         g_kernel_launches.fetch_add(1);
         if (le != cudaSuccess) return le;
         return cudaGetLastError();
     }
     if (gs > 200 * 1024) return cudaErrorInvalidValue;
     if (gs > 40 * 1024) cudaFuncSetAttribute(tc_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
-    tc_gather_kernel<false><<<nq, 256, gs, st>>>(cand, counts, nctas, cap, kp, lists, overflow, spill_cnt, spill, FinalizeParams{});
+    tc_gather_kernel<false><<<nq, 256, gs, st>>>(cand, counts, nctas, cap, kp, lists, overflow, spill_cnt, spill, gall, FinalizeParams{});
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -1065,7 +1069,7 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     int cap = 32;
     while (cap < 4.0 * expect + 24.0 && cap < 1024) cap <<= 1;
     pl->cap = cap;
-    pl->cap_total = 16384;
+    pl->cap_total = (int)(3.0 * expect * pl->grid) + 256;  // keys per query the gather should hold in shared memory (3x the expectation)
     // workspace layout
     size_t off = 0;
     auto take = [&](size_t bytes) {

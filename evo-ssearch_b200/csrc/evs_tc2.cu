@@ -476,7 +476,7 @@ cudaError_t tc2_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_cou
     int cap = 32;
     while (cap < 4.0 * expect + 24.0 && cap < 1024) cap <<= 1;
     pl->cap = cap;
-    pl->cap_total = 16384;
+    pl->cap_total = (int)(3.0 * 1.1 * kp / ((double)pl->groups * 32.0) * (double)n) + 256;  // keys per query the gather should hold
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;

@@ -161,9 +161,10 @@ EVS_API int evs_merge_partials_dev(int device, int nparts, int64_t nq, int64_t k
  * Replaces the all-gather + merge of SURVEY.md section 8(e) -- (fp64 score, id)[nq][k] per rank -- by
  * stores over NVLink: every rank owns one symmetric buffer of `world` slots (two generations) that all
  * ranks map (CUDA IPC).  evs_index_search_exchange_dev scans the local shard, and its finalise kernel
- * writes the shard's k best into slot `rank` of EVERY rank's buffer, then raises a flag there
- * (st.release.sys); a merge kernel on each rank waits for the `world` flags of this search
- * (ld.acquire.sys) and ranks the world*k partials into the final (D, I).  No NCCL call, no host
+ * writes the shard's k best into slot `rank` of EVERY rank's buffer as 32-byte entries that carry the
+ * search's sequence number beside the payload (two 16-byte stores per entry; no fence, no separate
+ * flag); the merge on each rank polls the world*k entries of a query until all carry this search's
+ * number and ranks them into the final (D, I).  No NCCL call, no host
  * synchronisation; all ranks must call it in the same order with the same nq and k.
  *   evs_exchange_create   allocate the local buffer for at most max_nq queries x max_k results.
  *   evs_exchange_handle   64-byte IPC handle of the local buffer (all-gather these out of band).
