@@ -355,6 +355,21 @@ def config_legs_sharded(evs, torch, dist, dev, world, rank, a, barrier, max_over
             ach = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
             rec["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst,
                                "frac_whole_search": flops / (ms * 1e-3) / 1e12 / tf_burst, "per": "GPU (rank 0)"}
+        # answers at full size (no single GPU holds these databases): a query equal to database row r -- regenerated from its
+        # global id -- must return r first with score ~1, scores descending; probes fall into different shards
+        ok_self = True
+        probes = [0, rows // 7, rows // 2 + 3, (rows * 6) // 7, rows - 1]
+        for r in probes:
+            pi = evs.IndexFlatIP(d, device=dev.index)
+            pi.id_base = r
+            pi.add_synthetic(1, seed=0)
+            qrow = np.repeat(pi.reconstruct_n(0, 1), min(nq, 16), axis=0)
+            del pi
+            Dp, Ip = index.search(qrow, a.k)
+            tol = 1e-5 if storage == "f32" else 1e-2  # the re-score is fp64 over the fp32 master rows either way
+            ok_self = ok_self and bool((Ip[:, 0] == r).all()) and abs(float(Dp[0, 0]) - 1.0) < tol and bool((np.diff(Dp.astype(np.float64), axis=1) <= 0).all())
+        rec["self_match_at_full_size"] = bool(ok_self)
+        rec["self_match_rows"] = probes
         out.append(rec)
     del index
     torch.cuda.empty_cache()

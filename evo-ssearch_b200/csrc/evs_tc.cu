@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
         for (int i = lane; i < groups; i += 32) {
             const uint32_t v = staged ? mine_vals[i] : __ldg(gmax + (size_t)i * npad + c);
             const bool in = pass == 0 || (v >> (shift + 8)) == prefix;
-            if (in) atomicAdd(&hist[(v >> shift) & 255u], 1);
+            if (in) atomicAdd(&hist[(v >> shift) & 255u], 1);  // (electing one lane per bin with match.any was 5x slower)
         }
         __syncwarp();
         // lane l owns bins [8l, 8l+8); walk from the top bin down until krem values are covered
@@ -784,6 +784,16 @@ __global__ void __launch_bounds__(FUSE ? 1024 : 256) tc_gather_kernel(const u64*
         }
         finalize_qnorm2(f, fsh, fqs);
         __syncthreads();  // the list and |q|^2 are complete
+        if (!f.xb_is_bf16) {  // the re-score reads the candidates' rows (fp32 master copy): all their lines on the way to L2 at once
+            const int lines = (f.d * 4 + 127) / 128;
+            for (int i = threadIdx.x; i < kp * lines; i += nt) {
+                const u64 key = fA[i / lines];
+                if (key != 0ull) {
+                    const char* row = reinterpret_cast<const char*>(f.xb) + (size_t)key_row(key) * f.d * 4 + (size_t)(i % lines) * 128;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                }
+            }
+        }
         finalize_rank_emit<2>(f, c, fA, fsh, fsc, fid, fok, fqs, reinterpret_cast<unsigned char*>(all));
     }
 }
