@@ -525,6 +525,8 @@ __global__ void __launch_bounds__(256) tc_tau0_kernel(const uint32_t* __restrict
     uint32_t prefix = 0;  // the high bits of the answer found so far
     int krem = kp;        // rank of the answer among the values that share `prefix`
     bool found = groups >= kp;
+    // (a bit-by-bit counting search without shared-memory atomics was tried instead of the radix passes: 92 vs 66 us for
+    // 4096 queries, 17.7 vs 11.5 us for 64)
     for (int pass = 0; pass < 4 && found; pass++) {
         const int shift = 24 - 8 * pass;
 #pragma unroll
