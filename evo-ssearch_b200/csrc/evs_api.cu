@@ -196,7 +196,8 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "fuse_finalize")) {
         g_tune.fuse_finalize = value ? 1 : 0;
     } else if (!strcmp(name, "scan_dynamic")) {
-        g_tune.scan_dynamic = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail(EVS_EINVAL, "scan_dynamic must be 0, 1 or 2");
+        g_tune.scan_dynamic = (int)value;  // 1: dynamic tail in the pool kernel; 2: also fully dynamic dealing in the list-based fused scan
     } else if (!strcmp(name, "scan_chunk_groups")) {
         if (value < 1 || value > 64) return fail(EVS_EINVAL, "scan_chunk_groups must be in [1, 64]");
         g_tune.scan_chunk_groups = (int)value;
@@ -998,7 +999,7 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
                     }
                     a.pool = idx->pool;
                 }
-                if (tune.scan_dynamic) {
+                if (tune.scan_dynamic > 1 || (tune.scan_dynamic == 1 && a.pool != nullptr)) {
                     a.next_chunk = idx->words + W_NEXT_CHUNK;
                     a.chunk_groups = tune.scan_chunk_groups > 0 ? tune.scan_chunk_groups : 2;
                 }

@@ -342,7 +342,7 @@ __device__ __forceinline__ void finalize_rank_emit(const FinalizeParams& p, long
     // bf16 and fp32 scans scatter around zero)
     const bool want_margin = p.margins != nullptr || p.guard_count != nullptr || p.pred_slot != nullptr;
     for (int c = t; c < kp; c += nt)
-        if (id[c] >= 0 && want_margin) atomicMax(&sh->maxerr, score_to_ordered((float)(sc[c] - (double)key_score(A[c]))));
+        if (id[c] >= 0 && want_margin) atomicMax(&sh->maxerr, score_to_ordered((float)(sc[c] - widen_f32(key_score(A[c])))));
     __syncthreads();
 
     // 5. rank by counting under (score desc, id asc); ids are unique so ranks are a permutation
@@ -372,12 +372,12 @@ __device__ __forceinline__ void finalize_rank_emit(const FinalizeParams& p, long
                 // CERTIFIED exact when it clears the error bound of the scan that produced the lists (below).
                 const float worst = key_score(A[kp - 1]);
                 const float under = fmaxf(ordered_to_score(sh->maxerr), 0.f);
-                const float gap = (A[kp - 1] != 0ull) ? (float)(st - (double)worst) : INFINITY;
+                const float gap = (A[kp - 1] != 0ull) ? (float)(st - widen_f32(worst)) : INFINITY;
                 const float margin = gap - under;
                 if (p.margins) p.margins[qi] = margin;
                 if (p.err_coef > 0.f) {
                     const float mx = p.max_norm ? *p.max_norm : 1.f;
-                    const float B = (float)sqrt(sh->qnorm2) * mx;  // >= sum |x_i q_i| of any row (Cauchy-Schwarz)
+                    const float B = sqrtf((float)sh->qnorm2) * 1.000001f * mx;  // >= sum |x_i q_i| of any row (Cauchy-Schwarz); fp32 sqrt, inflated
                     // Symmetric scan error (fp32 GEMV, 3xTF32): |scan - true| <= err_coef * B.
                     // Truncating scan (single tf32: both operands lose their low 13 mantissa bits, towards zero): every product
                     // shrinks by a factor in (1 - 2^-9, 1], so a row is UNDER-estimated by at most 2^-9 * (sum of its positive

@@ -21,9 +21,9 @@ struct ScanTuning {
                            // (scripts/small_nq_sweep.py): from 2 queries on it beats the CUDA-core GEMV for fp32 and bf16 rows
     int tc_pair_min_nq = 129;  // ... and of at least this many the CTA-pair kernel (evs_tc2.cu); 0 = never
     int fuse_finalize = 1;     // single-query GEMV searches: the scan's last CTA finalises (no second launch)
-    int scan_dynamic = 0;      // ... and rows are dealt dynamically, `scan_chunk_groups` row groups per grab.  Off: measured
-                               // (scripts/scan_tail_probe.py) the spread of the CTAs' end times halves, but the last CTA
-                               // ends only ~3 us earlier and grabs of fewer than 4 groups choke on the one counter
+    int scan_dynamic = 1;      // ... rows are dealt statically for the first 7/8 of the shard and dynamically (`scan_chunk_groups` row
+                               // groups per grab) for the tail: neutral on one GPU (scripts/scan_tail_probe.py), but it halves the
+                               // spread of the CTAs' end times, and a sharded search waits for the slowest of G ranks (+1.3 % at 8)
     int scan_chunk_groups = 4;
     int pool_select = 1;       // ... and (k <= 48) candidates meet in one survivor pool under a global running threshold instead of
                                // per-CTA sorted lists (evs_scan.cuh: scan_pool_kernel): no per-warp final sort, no CTA merge tree,

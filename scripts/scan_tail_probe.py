@@ -31,7 +31,7 @@ del qi
 SETS = [
     ("unfused static (round-1 path: scan + finalize)", dict(fuse_finalize=0, scan_dynamic=0, pool_select=0)),
     ("fused lists static", dict(fuse_finalize=1, scan_dynamic=0, pool_select=0)),
-    ("fused lists dynamic c=6", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=6, pool_select=0)),
+    ("fused lists dynamic c=6", dict(fuse_finalize=1, scan_dynamic=2, scan_chunk_groups=6, pool_select=0)),
     ("fused pool static", dict(fuse_finalize=1, scan_dynamic=0, pool_select=1)),
     ("fused pool, dynamic tail c=2", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=2, pool_select=1)),
     ("fused pool, dynamic tail c=4", dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=4, pool_select=1)),
@@ -84,7 +84,7 @@ for rows in [int(r) for r in a.rows.split(",") if r]:
                        epilogue_us=round(float(np.median(epi)), 1), fused_finalize_us=round(float(np.median(fin)), 1))
         print(json.dumps(rec), flush=True)
     del idx
-for k_, v_ in dict(fuse_finalize=1, scan_dynamic=0, scan_chunk_groups=4, pool_select=1).items():
+for k_, v_ in dict(fuse_finalize=1, scan_dynamic=1, scan_chunk_groups=4, pool_select=1).items():
     evs.set_option(k_, v_)
 
 # small fp32 batches: 3xTF32 vs single tf32 vs the fp32 GEMV (1M x 512, the C2 shape)

@@ -35,7 +35,7 @@ def _reset_options():
     evs.set_option("fuse_finalize", 1)
     evs.set_option("pool_select", 1)
     evs.set_option("scan_dynamic", 1)
-    evs.set_option("scan_chunk_groups", 2)
+    evs.set_option("scan_chunk_groups", 4)
 
 
 def _index(xb, storage="f32", variant=0):
@@ -330,7 +330,7 @@ def test_single_query_search_is_one_launch_whatever_the_scan_options():
         idx.add_synthetic(n, seed=11)
         xb = idx.reconstruct_n(0, n)
         Dr, Ir = oracle.canon_search(q, xb, k)
-        for fuse, pool, dyn, chunk in ((1, 1, 0, 2), (1, 0, 1, 2), (1, 0, 1, 1), (1, 0, 1, 7), (1, 0, 0, 2), (0, 0, 0, 2)):
+        for fuse, pool, dyn, chunk in ((1, 1, 0, 2), (1, 1, 1, 4), (1, 1, 1, 1), (1, 0, 2, 2), (1, 0, 2, 1), (1, 0, 2, 7), (1, 0, 0, 2), (0, 0, 0, 2)):
             evs.set_option("fuse_finalize", fuse)
             evs.set_option("pool_select", pool)  # 1: survivor pool under a global threshold (the default); 0: per-CTA lists
             evs.set_option("scan_dynamic", dyn)
