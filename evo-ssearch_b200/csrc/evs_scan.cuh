@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kerne
     // counter, the next grab always in flight -- for the last `dyn_groups` groups: the SMs that the memory system served
     // more slowly would otherwise still be streaming while the others idle (scripts/scan_tail_probe.py: the last CTA left
     // its loop 10-14 us after the median one with a purely static deal at 1.25M rows).
-    const long long dyn_groups = p.next_chunk ? (ngroups / 8 > 64 * total_warps ? 64 * total_warps : ngroups / 8) : 0;
+    // (small shards -- fewer than 32 groups per warp -- stay static: the first grab is on every warp's critical path there)
+    const long long dyn_groups = (p.next_chunk && ngroups >= 32 * total_warps) ? (ngroups / 8 > 64 * total_warps ? 64 * total_warps : ngroups / 8) : 0;
     const long long static_end = ngroups - dyn_groups;
     long long next = -1;
     if (dyn_groups > 0 && lane == 0) next = (long long)atomicAdd(p.next_chunk, 1u);  // the first grab: needed only after the static part
