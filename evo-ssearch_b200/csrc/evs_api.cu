@@ -48,6 +48,8 @@ static int g_profile_scans = 0;                    // record CUDA events around 
 static std::atomic<long long> g_tc_fallbacks{0};   // queries re-run through the GEMV scan after a tensor-core buffer overflow
 static std::atomic<long long> g_exact_reruns{0};   // queries the HOST re-ran with the fp32 GEMV scan because the finalise could not
                                                    // certify them (the device-side re-runs are counted per handle: evs_index_guard_stats)
+static std::atomic<int> g_exchange_fail_next{0};   // option "exchange_fail_next" (tests): the next exchange-mode search of this process
+                                                   // fails after it has taken its sequence number, as an allocation failure would
 static int g_tf32_guard_eps_e6 = 0;                // option "tf32_guard_eps_e6": 0 (default) = the single-tf32 scans are certified against
                                                    // their RIGOROUS truncation bound (tf32_trunc_coef); > 0 = a statistical bound instead
                                                    // (x 1e-6, relative to |q| max|x|; round 1 used 150) -- experiments only
@@ -201,6 +203,8 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "scan_chunk_groups")) {
         if (value < 1 || value > 64) return fail(EVS_EINVAL, "scan_chunk_groups must be in [1, 64]");
         g_tune.scan_chunk_groups = (int)value;
+    } else if (!strcmp(name, "exchange_fail_next")) {
+        g_exchange_fail_next.store(value ? 1 : 0);
     } else if (!strcmp(name, "pool_select")) {
         g_tune.pool_select = value ? 1 : 0;
     } else if (!strcmp(name, "scan_clock")) {
@@ -239,6 +243,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "fuse_finalize")) *value = g_tune.fuse_finalize;
     else if (!strcmp(name, "scan_dynamic")) *value = g_tune.scan_dynamic;
     else if (!strcmp(name, "scan_chunk_groups")) *value = g_tune.scan_chunk_groups;
+    else if (!strcmp(name, "exchange_fail_next")) *value = g_exchange_fail_next.load();
     else if (!strcmp(name, "pool_select")) *value = g_tune.pool_select;
     else if (!strcmp(name, "scan_clock")) *value = g_tune.scan_clock;
     else if (!strcmp(name, "x3")) *value = g_tune.x3;
@@ -1359,7 +1364,8 @@ static int search_exchange_enqueue_locked(evs_index* idx, evs_exchange* ex, int6
         }
         out.x = &x;
     }
-    int rc = search_dev_common(idx, nq, q_dev, k, out, st, tune, pi);
+    int rc = g_exchange_fail_next.exchange(0) ? fail(EVS_ECUDA, "injected failure (option exchange_fail_next)")
+                                              : search_dev_common(idx, nq, q_dev, k, out, st, tune, pi);
     cudaError_t e = cudaSuccess;
     if (!rc && staged) e = launch_publish_partials(x, nq, (int)k, ex->stage_scores, reinterpret_cast<const long long*>(ex->stage_ids), st);
     if (!rc && e == cudaSuccess && !one_launch) e = launch_merge_exchange(x, nq, (int)k, D_dev, reinterpret_cast<long long*>(I_dev), st);

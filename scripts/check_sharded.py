@@ -98,6 +98,50 @@ for exchange in ("nccl", "peer"):
             f"(rank 0: {reruns} device re-runs, {uncert} uncertified)")
 evs.set_option("x3", 0)
 
+# ---- a rank that fails a collective search: its peers must report it, never merge without that shard ---------------------
+if world >= 2:
+    n, d, k = 200_003, 512, 48
+    xb = oracle.synth_fill(n, d, 33)
+    xq = oracle.synth_fill(2, d, 34)
+    Dr, Ir = oracle.canon_search(xq, xb, k)
+    sh = evs.ShardedIndexFlatIP(d, device=local, storage="f32", exchange="peer", exchange_max_nq=64)
+    sh.add(xb)
+    D, I = sh.search(xq[:1], k)
+    good = bool(np.array_equal(I, Ir[:1]))
+    for api in ("host", "device"):
+        if rank == world - 1:
+            evs.set_option("exchange_fail_next", 1)  # this rank's next exchange search fails after taking its sequence number
+        raised = False
+        try:
+            if api == "host":
+                D, I = sh.search(xq[:1], k)  # host entry point: the failure of THIS search is reported by THIS call on every rank
+            else:
+                Dt, It = sh.search_tensor(torch.from_numpy(xq[:1]).cuda(), k)  # asynchronous: the failing rank raises now ...
+                torch.cuda.synchronize()
+                D, I = Dt.cpu().numpy(), It.cpu().numpy()
+        except evs.EvsError:
+            raised = True
+        if api == "host":
+            good = good and raised
+        else:
+            # ... its peers got padding (never a merge of stale entries) and raise on their next call
+            good = good and (raised if rank == world - 1 else bool((I == -1).all()))
+            raised2 = False
+            try:
+                sh.search_tensor(torch.from_numpy(xq[:1]).cuda(), k)
+                torch.cuda.synchronize()
+            except evs.EvsError:
+                raised2 = True
+            good = good and (raised2 if rank != world - 1 else True)
+        # the ranks are still in step: the following searches are right again
+        D, I = sh.search(xq, k)
+        good = good and bool(np.array_equal(I, Ir) and np.array_equal(D, Dr))
+    flags = [None] * world
+    dist.all_gather_object(flags, good)
+    ok = ok and all(flags)
+    say(f"failure injection (rank {world - 1} fails one host and one device search): peers report it, later searches correct: "
+        f"{'OK' if all(flags) else 'MISMATCH ' + str(flags)}")
+
 # ---- shard loader: rank 0 writes a single-GPU index.faiss; every rank streams only its own block ---------------------------
 n, d, k = 600_011, 512, 48
 tmp = bcast_obj(tempfile.mkdtemp(prefix="evs_shard_") if rank == 0 else None)
