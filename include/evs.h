@@ -232,16 +232,23 @@ EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev,
  *                 least this many the CTA-pair kernel; 0 = never), "tc_stages", "tc2_slice_tiles", "tc_sample_rows", "tc_heap_max_nq" (batches up to
  *                 this size keep a running top-k' per CTA in shared memory: no gather, no overflow case, no host sync),
  *                 "tc_heap_pure_max_nq" (... and up to this size also without the threshold pre-pass).
- *                 "x3" (default 1) / "x3_max_nq" (default 32): fp32 rows, batches up to that many queries use the 3xTF32
- *                 split scan; "guard" (default 1): certify fp32-storage batch results and re-run uncertified queries;
- *                 "tf32_guard_eps_e6": the statistical error bound, in millionths relative to |q| max|x|, that the
- *                 single-tf32 scans (fp32 rows, batches beyond the 3xTF32 range) are certified against (default 150,
- *                 0 = off); "exact_reruns" counts the queries the host re-ran (evs_index_guard_stats: the device's).
- *                 "fuse_finalize" (default 1): single-query searches finalise inside the scan's last CTA;
- *                 "scan_dynamic" / "scan_chunk_groups": dynamic row dealing of that scan; "scan_clock": record per-CTA
- *                 scan times (evs_index_scan_clocks).
- *                 evs_get_option also reads "tc_fallbacks": queries re-run through the GEMV scan so far because a
- *                 tensor-core candidate buffer overflowed (exactness guard; should stay 0 on ordinary data).
+ *                 fp32 rows, batches: scanned in single tf32 and certified on the device against the rigorous truncation
+ *                 bound of that scan; "guard" (default 1): uncertified queries are re-run exactly in
+ *                 the same call (0: only certified and counted); "x3" (default 0) / "x3_max_nq" (default 16): batches up to
+ *                 that many queries use the 3xTF32 split scan instead (fp32-class scan scores, ~20 % slower);
+ *                 "tf32_guard_eps_e6" (default 0 = the rigorous bound): a statistical bound instead, in millionths relative
+ *                 to |q| max|x| (experiments); "exact_reruns" counts the queries the HOST re-ran (batches beyond 256
+ *                 queries; evs_index_guard_stats counts the device's re-runs and the results that stayed uncertified).
+ *                 "fuse_finalize" (default 1): single-query searches are ONE launch (the scan's last CTA finalises);
+ *                 "pool_select" (default 1): ... with the candidates in one survivor pool under a global running threshold
+ *                 (k <= 48) instead of per-CTA sorted lists; "scan_dynamic" (0 static, 1 = default: dynamic tail in the pool
+ *                 kernel, 2: also fully dynamic dealing in the list-based scan) / "scan_chunk_groups" (row groups per grab);
+ *                 "scan_clock": record per-CTA scan times and the last CTA's phase stamps (evs_index_scan_clocks);
+ *                 "exchange_fail_next" (tests): the next exchange-mode search of this process fails after taking its
+ *                 sequence number, so that the peers' failure reporting can be exercised.
+ *                 evs_get_option also reads "tc_fallbacks": queries the HOST re-ran through the GEMV scan because a
+ *                 tensor-core candidate buffer overflowed (batches beyond 256 queries; smaller batches repair on the device
+ *                 and count in evs_index_guard_stats; should stay 0 on ordinary data).
  *                 Unknown names -> EVS_EINVAL.
  * evs_kernel_launches: number of kernels this library has launched in this process.
  * evs_index_time_scan: runs the scan stage alone `iters` times on the index's stream for queries
