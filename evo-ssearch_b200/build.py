@@ -14,8 +14,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libevs.so")
-SOURCES = ["evs_kernels.cu", "evs_api.cu", "evs_tc.cu", "evs_tc2.cu"]
-HEADERS = ["evs_common.cuh", "evs_scan.cuh", "evs_finalize.cuh", "evs_tc_common.cuh", "evs_internal.h", os.path.join("..", "..", "include", "evs.h")]
+SOURCES = ["evs_scan_f32_512.cu", "evs_scan_f32_narrow.cu", "evs_scan_f32_wide.cu", "evs_scan_bf16_narrow.cu", "evs_scan_bf16_wide.cu",
+           "evs_scan_generic.cu", "evs_kernels.cu", "evs_api.cu", "evs_tc.cu", "evs_tc2.cu"]
+HEADERS = ["evs_common.cuh", "evs_scan.cuh", "evs_scan_launch.cuh", "evs_finalize.cuh", "evs_tc_common.cuh", "evs_internal.h", os.path.join("..", "..", "include", "evs.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

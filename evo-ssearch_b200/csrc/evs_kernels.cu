@@ -13,6 +13,7 @@
 
 #include "evs_internal.h"
 #include "evs_scan.cuh"
+#include "evs_scan_launch.cuh"
 
 namespace evs {
 
@@ -444,29 +445,9 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(float* __restrict__ out
 // =============================================================================================
 // launch wrappers
 // =============================================================================================
-#define EVS_LAUNCH_CHECK()                                  \
-    do {                                                    \
-        g_kernel_launches.fetch_add(1);                     \
-        cudaError_t e__ = cudaGetLastError();               \
-        if (e__ != cudaSuccess) return e__;                 \
-    } while (0)
-
 static int clamp_grid(long long want, int cap) {
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
-}
-
-// opt a kernel in to more than 48 KB of dynamic shared memory once per (kernel, device): `table` is a per-kernel array
-template <typename K>
-static cudaError_t ensure_smem_optin(K kern, size_t smem, size_t (&table)[16]) {
-    if (smem <= 48 * 1024) return cudaSuccess;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    size_t& have = table[dev & 15];
-    if (smem <= have) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) have = smem;
-    return e;
 }
 
 template <int NV>
@@ -636,122 +617,6 @@ cudaError_t launch_finalize(const FinalizeParams& p, long long nq, cudaStream_t 
     return cudaGetLastError();
 }
 
-// ---------------------------------------------------------------------------------------------
-// scan dispatch
-// ---------------------------------------------------------------------------------------------
-template <typename T, int NQ, int NV>
-static cudaError_t launch_scan_t(const ScanArgs& a, ScanPlan* plan, cudaStream_t st) {
-    ScanParams p;
-    p.xb = a.xb;
-    p.n = a.n;
-    p.d = a.d;
-    p.xq = a.xq;
-    p.q0 = a.q0;
-    p.lists = reinterpret_cast<u64*>(a.lists);
-    p.kp = a.kp;
-    p.tile_rows = plan->tile_rows;
-    p.stages = plan->stages;
-    p.lists_stride_q = plan->grid * a.kp;
-    p.ticket = nullptr;
-    p.next_chunk = nullptr;
-    p.chunk_groups = 1;
-    p.qmap = a.qmap;
-    p.nactive = a.nactive;
-    p.qcap = a.qcap;
-    p.cta_clock = nullptr;
-    if (plan->variant == 2) {
-        if (a.fuse || a.nactive) return cudaErrorInvalidValue;  // the ring variant neither fuses nor re-runs
-        auto kern = scan_ring_kernel<T, NQ, NV>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-        kern<<<plan->grid, plan->threads, plan->smem_bytes, st>>>(p);
-        EVS_LAUNCH_CHECK();
-        return cudaSuccess;
-    }
-    FinalizeParams f;
-    size_t smem = plan->smem_bytes;
-    if constexpr (NQ == 1) {
-        if (a.fuse != nullptr && a.pool != nullptr && a.kp == 64 && a.nactive == nullptr) {
-            f = *a.fuse;
-            p.cta_clock = a.cta_clock;
-            if (a.next_chunk != nullptr && a.chunk_groups > 0) {
-                p.next_chunk = a.next_chunk;
-                p.chunk_groups = a.chunk_groups;
-            }
-            const size_t fs = pool_finalize_smem_bytes(64, f.d, f.x.world * f.k);
-            smem = (size_t)(plan->threads / 32) * 128 * 8;
-            if (fs > smem) smem = fs;
-            auto pk = scan_pool_kernel<T, NV>;
-            static size_t optin_p[16] = {};
-            cudaError_t oe = ensure_smem_optin(pk, smem, optin_p);
-            if (oe != cudaSuccess) return oe;
-            cudaError_t le = launch_pdl(pk, dim3((unsigned)plan->grid), dim3((unsigned)plan->threads), smem, st, p, f, reinterpret_cast<u64*>(a.pool));
-            g_kernel_launches.fetch_add(1);
-            if (le != cudaSuccess) return le;
-            return cudaGetLastError();
-        }
-    }
-    if (a.fuse != nullptr && NQ == 1 && a.ticket != nullptr) {
-        f = *a.fuse;
-        p.ticket = a.ticket;
-        p.cta_clock = a.cta_clock;
-        if (a.next_chunk != nullptr && a.chunk_groups > 0) {
-            p.next_chunk = a.next_chunk;
-            p.chunk_groups = a.chunk_groups;
-        }
-        const size_t fs = finalize_smem_bytes_host(f.L, f.kp, f.d);
-        if (fs > smem) smem = fs;
-    } else if (a.fuse != nullptr) {
-        return cudaErrorInvalidValue;
-    }
-    auto kern = scan_direct_kernel<T, NQ, NV>;
-    static size_t optin[16] = {};  // per instantiation
-    cudaError_t oe = ensure_smem_optin(kern, smem, optin);
-    if (oe != cudaSuccess) return oe;
-    cudaError_t le = launch_pdl(kern, dim3((unsigned)plan->grid), dim3((unsigned)plan->threads), smem, st, p, f);
-    g_kernel_launches.fetch_add(1);
-    if (le != cudaSuccess) return le;
-    return cudaGetLastError();
-}
-
-template <typename T, int NV>
-static cudaError_t launch_scan_nq(const ScanArgs& a, ScanPlan* plan, cudaStream_t st) {
-    switch (a.nq_pass) {
-        case 1: return launch_scan_t<T, 1, NV>(a, plan, st);
-        case 2: return launch_scan_t<T, 2, NV>(a, plan, st);
-        case 3: return launch_scan_t<T, 3, NV>(a, plan, st);
-        case 4: return launch_scan_t<T, 4, NV>(a, plan, st);
-        default: return cudaErrorInvalidValue;
-    }
-}
-
-template <typename T>
-static cudaError_t launch_scan_generic(const ScanArgs& a, ScanPlan* plan, cudaStream_t st) {
-    ScanParams p;
-    p.xb = a.xb;
-    p.n = a.n;
-    p.d = a.d;
-    p.xq = a.xq;
-    p.lists = reinterpret_cast<u64*>(a.lists);
-    p.kp = a.kp;
-    p.tile_rows = 0;
-    p.stages = 0;
-    p.lists_stride_q = plan->grid * a.kp;
-    p.ticket = nullptr;
-    p.next_chunk = nullptr;
-    p.chunk_groups = 1;
-    p.qmap = nullptr;
-    p.nactive = nullptr;
-    p.qcap = 0;
-    p.cta_clock = nullptr;
-    if (a.fuse || a.nactive) return cudaErrorInvalidValue;
-    for (int qi = 0; qi < a.nq_pass; qi++) {
-        p.q0 = a.q0 + qi;
-        scan_generic_kernel<T><<<plan->grid, plan->threads, plan->smem_bytes, st>>>(p);
-        EVS_LAUNCH_CHECK();
-    }
-    return cudaSuccess;
-}
-
 // number of 16-byte vectors per lane per row for the vectorised kernels, 0 = use the generic kernel
 static int vectors_per_lane(int d, int is_bf16) {
     int unit = is_bf16 ? 256 : 128;
@@ -815,25 +680,11 @@ size_t scan_pool_words(const ScanPlan& plan) { return (size_t)POOL_HDR + (size_t
 
 cudaError_t launch_scan(const ScanArgs& a, ScanPlan* plan, cudaStream_t st) {
     if (a.n <= 0) return cudaErrorInvalidValue;
-    if (plan->nv == 0) return a.is_bf16 ? launch_scan_generic<__nv_bfloat16>(a, plan, st) : launch_scan_generic<float>(a, plan, st);
-    if (a.is_bf16) {
-        switch (plan->nv) {
-            case 1: return launch_scan_nq<__nv_bfloat16, 1>(a, plan, st);
-            case 2: return launch_scan_nq<__nv_bfloat16, 2>(a, plan, st);
-            case 3: return launch_scan_nq<__nv_bfloat16, 3>(a, plan, st);
-            case 4: return launch_scan_nq<__nv_bfloat16, 4>(a, plan, st);
-        }
-    } else {
-        switch (plan->nv) {
-            case 1: return launch_scan_nq<float, 1>(a, plan, st);
-            case 2: return launch_scan_nq<float, 2>(a, plan, st);
-            case 3: return launch_scan_nq<float, 3>(a, plan, st);
-            case 4: return launch_scan_nq<float, 4>(a, plan, st);
-            case 6: return launch_scan_nq<float, 6>(a, plan, st);
-            case 8: return launch_scan_nq<float, 8>(a, plan, st);
-        }
-    }
-    return cudaErrorInvalidValue;
+    if (plan->nv == 0) return launch_scan_generic_any(a, plan, st);
+    if (a.is_bf16) return plan->nv <= 2 ? launch_scan_bf16_narrow(a, plan, st) : launch_scan_bf16_wide(a, plan, st);
+    if (plan->nv <= 3) return launch_scan_f32_narrow(a, plan, st);
+    if (plan->nv == 4) return launch_scan_f32_512(a, plan, st);
+    return launch_scan_f32_wide(a, plan, st);
 }
 
 }  // namespace evs
