@@ -180,3 +180,29 @@ def test_resident_cache_is_an_lru_with_a_byte_budget(tmp_path, monkeypatch):
     s1 = lifecycle._signature(ip)
     assert s1 != s0 and s1[0] == s0[0]
     assert lifecycle._want_sharded(False) is False and lifecycle._want_sharded(None) is False  # no process group here
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the CUDA arm) on a small workload: ONE JSON line with the
+    contract's keys, `impl: reference`, a cpu_baseline block describing the run and an e2e block equal to the line's value;
+    ranks other than 0 print nothing and exit 0."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--rows", "20000", "--steps", "2", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "0"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "20000" in d["cpu_baseline"]["sample"]
+    assert d["config"]["workload"].startswith("20000x512 f32 flat-IP")
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
+    assert other.returncode == 0 and other.stdout.strip() == ""
