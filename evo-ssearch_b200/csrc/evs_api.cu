@@ -62,7 +62,7 @@ static const int kTcQueryChunk = 4096;  // tensor-core path: queries per launch 
 
 // per-handle device words (idx->words): counters the kernels share across searches
 enum { W_TICKET = 0, W_NEXT_CHUNK = 1, W_GUARD_COUNT0 = 2, W_GUARD_COUNT1 = 3, W_UNCERT = 4 /* u64 */, W_RERUNS = 6 /* u64 */,
-       W_MAX_NORM = 8 /* float */, W_SPECIAL = 9, W_WORDS = 16 };
+       W_MAX_NORM = 8 /* float */, W_SPECIAL = 9, W_BAR = 10 /* 3 words: grid barrier of the in-launch pre-pass */, W_WORDS = 16 };
 
 struct evs_index {
     int d = 0, device = 0, storage = EVS_STORE_F32;
@@ -92,6 +92,7 @@ struct evs_index {
     unsigned long long* cta_clock = nullptr; size_t cta_clock_cap = 0; int cta_clock_n = 0;  // option "scan_clock"
     cudaStream_t last_stream = nullptr; bool have_last_stream = false;  // the stream the workspace was last used on
     TmapCache tmaps;
+    bool bar_used = false;            // the search being enqueued contains a launch with a grid barrier (in-launch pre-pass)
     // optional per-search timing of the scan stage (option "profile_scans")
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
@@ -187,6 +188,8 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "tf32_guard_eps_e6")) {
         if (value < 0 || value > 100000) return fail(EVS_EINVAL, "tf32_guard_eps_e6 must be in [0, 100000]");
         g_tf32_guard_eps_e6 = (int)value;
+    } else if (!strcmp(name, "tc_inline_pre")) {
+        g_tc_inline_pre = value ? 1 : 0;
     } else if (!strcmp(name, "tc_sample_rows")) {
         if (value != 0 && (value < 1024 || value > (1 << 24))) return fail(EVS_EINVAL, "tc_sample_rows must be 0 (auto) or in [1024, 2^24]");
         g_tc_sample_rows = (int)value;
@@ -234,6 +237,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "tc2_slice_tiles")) *value = g_tc2_slice_tiles;
     else if (!strcmp(name, "tc_heap_max_nq")) *value = g_tc_heap_max_nq;
     else if (!strcmp(name, "tc_heap_pure_max_nq")) *value = g_tc_heap_pure_max_nq;
+    else if (!strcmp(name, "tc_inline_pre")) *value = g_tc_inline_pre;
     else if (!strcmp(name, "tc_sample_rows")) *value = g_tc_sample_rows;
     else if (!strcmp(name, "tc_stages")) *value = g_tc_max_stages;
     else if (!strcmp(name, "profile_scans")) *value = g_profile_scans;
@@ -605,6 +609,31 @@ static PathInfo plan_path(const evs_index* idx, int64_t nq, int64_t k, const Sca
     return pi;
 }
 
+// Scan launches that synchronise their own grid (the in-launch threshold pre-pass) need every CTA resident: two of them from
+// different streams (two handles searched concurrently) could each hold part of the SMs and wait forever.  They are therefore
+// ordered one after the other per device: every such search records an event behind its last launch, and a search on
+// another stream than the previous one first waits for that event.  (The event, not the previous stream, is what is kept:
+// a stream may have been destroyed by its owner in the meantime.)
+static std::mutex g_bar_mu;
+static cudaStream_t g_bar_stream[16];
+static bool g_bar_has[16];
+static cudaEvent_t g_bar_event[16];
+static int barrier_scan_order(int device, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_bar_mu);
+    const int dv = device & 15;
+    if (g_bar_has[dv] && g_bar_stream[dv] != st) CU(cudaStreamWaitEvent(st, g_bar_event[dv], 0));
+    return EVS_OK;
+}
+static int barrier_scan_done(int device, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_bar_mu);
+    const int dv = device & 15;
+    if (!g_bar_event[dv]) CU(cudaEventCreateWithFlags(&g_bar_event[dv], cudaEventDisableTiming));
+    CU(cudaEventRecord(g_bar_event[dv], st));
+    g_bar_stream[dv] = st;
+    g_bar_has[dv] = true;
+    return EVS_OK;
+}
+
 static const int kGuardCap = 32;  // queries one device-side guard re-run can take (the on-chip-heap batches are <= 32 queries)
 static const int kRepairCap = 256;  // threshold-scan batches up to this size repair overflowed / uncertified queries on the device
                                     // too (no host synchronisation); larger batches read the flags on the host
@@ -694,6 +723,7 @@ static TcArgs make_tc_args(evs_index* idx, const float* xq, int64_t nq, void* li
     a.lists = lists;
     a.overflow_out = overflow_out;
     a.tmaps = &idx->tmaps;
+    a.bar = idx->words + W_BAR;
     return a;
 }
 
@@ -726,6 +756,10 @@ static int search_tc_heap_locked(evs_index* idx, int64_t nq, const float* q_dev,
         if (gp.variant != 1) return fail(EVS_ECUDA, "internal: no vectorised GEMV scan for the guard at d = %d", idx->d);
         if ((rc = ensure_dev(&idx->guard_slot, &idx->guard_slot_cap, (size_t)(nq > kGuardCap ? nq : kGuardCap) * 2))) return rc;
         if ((rc = ensure_dev(&idx->guard_lists, &idx->guard_lists_cap, (size_t)kGuardCap * gp.grid * 128))) return rc;
+    }
+    if (pl0.inline_pre) {
+        if ((rc = barrier_scan_order(idx->device, st))) return rc;
+        idx->bar_used = true;
     }
     ProfileScope prof;
     if ((rc = prof.begin(idx, profile, st))) return rc;
@@ -873,6 +907,10 @@ static int search_tc_sync_locked(evs_index* idx, int64_t nq, const float* q_dev,
                 TcPlan plb;  // same workspace bound: cn <= the chunk the workspace was sized for
                 CU(tc_plan(idx->ntotal, idx->d, bf16, (int)cn, kp, idx->sm_count, 0, &plb));
                 if (tc_workspace_bytes(plb) > idx->tc_ws_cap) return fail(EVS_ECUDA, "internal: tensor-core workspace too small");
+                if (plb.inline_pre) {
+                    if ((rc = barrier_scan_order(idx->device, st))) return rc;
+                    idx->bar_used = true;
+                }
                 if (plb.heap) {
                     lists_per_query = plb.grid;
                     f.L = plb.grid;
@@ -951,8 +989,16 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
         std::lock_guard<std::mutex> lk(g_tune_mu);
         profile = g_profile_scans && !scan_only;
     }
-    if (pi.kind == PATH_TC_HEAP) return search_tc_heap_locked(idx, nq, q_dev, k, out, st, tune, pi, scan_only, profile);
-    if (pi.kind == PATH_TC_SYNC) return search_tc_sync_locked(idx, nq, q_dev, k, out, st, tune, pi, scan_only, profile);
+    if (pi.kind == PATH_TC_HEAP || pi.kind == PATH_TC_SYNC) {
+        idx->bar_used = false;
+        int rc = pi.kind == PATH_TC_HEAP ? search_tc_heap_locked(idx, nq, q_dev, k, out, st, tune, pi, scan_only, profile)
+                                         : search_tc_sync_locked(idx, nq, q_dev, k, out, st, tune, pi, scan_only, profile);
+        if (idx->bar_used) {  // also on failure: whatever was launched is ordered before the next such search
+            const int rc2 = barrier_scan_done(idx->device, st);
+            if (!rc) rc = rc2;
+        }
+        return rc;
+    }
     const int kp = kp_override ? kp_override : pi.kp;
     const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
     const bool scan_bf16 = bf16 && kp_override == 0;  // an exact re-run always scans the fp32 rows

@@ -150,6 +150,7 @@ struct TmapCache {
 // tensor-core scan (evs_tc.cu)
 struct TcPlan {
     int npad, nblocks, nqp, nk, stages, grid, pre_grid, groups, gpow2, cap, cap_total, kp;
+    int inline_pre;  // the threshold pre-pass runs inside the scan launch (one sample tile per CTA, two grid barriers)
     int heap;  // 1: MODE_HEAP (small batch, lists [nq][grid][64] come straight out of the scan, L = grid for finalize); 2: ... seeded by a pre-pass
     int x3;    // 3xTF32: fp32 rows split hi + lo on the fly, queries split once; scan error ~1e-6 instead of ~1e-3
     size_t smem;
@@ -166,6 +167,7 @@ struct TcArgs {
     void* lists;      // out: u64 [nq][kp]
     int* overflow_out;  // out (optional): int [nq]
     TmapCache* tmaps = nullptr;
+    unsigned* bar = nullptr;  // three zero-initialised device words for the in-launch pre-pass's grid barrier (null: separate launches)
     const FinalizeParams* fin = nullptr;  // threshold scans: the gather kernel finalises the query itself (no list, no second
                                           // launch); fin->overflow != null -> it is pointed at the scan's own overflow flags
 };
@@ -188,6 +190,7 @@ extern int g_tc_max_stages;
 extern int g_tc_sample_rows;
 extern int g_tc_heap_max_nq;
 extern int g_tc_heap_pure_max_nq;
+extern int g_tc_inline_pre;
 int tc_sample_rows(int nq);
 int tc_max_queries(int d, int is_bf16);
 int tc_x3_max_queries(int d);  // queries one 3xTF32 pass serves (0 = dimension not supported)

@@ -63,10 +63,19 @@ struct TcParams {
     int* overflow;        // [nqp] set to 1 when a buffer AND the query's spill list overflowed
     int* spill_cnt;       // [nqp] keys offered to the spill list of the query
     u64* spill;           // [nqp][TC_SPILL_CAP]: where a full (CTA, query) buffer sends its extra keys (clustered rows)
+    int kp_sel;           // k' the thresholds are taken for (in-launch pre-pass)
     // MODE_HEAP
     u64* lists;           // [nq][gridDim.x][64] sorted descending, 0 = empty
     // MODE_DUMP
     float* dump;          // [n][nqp]
+    // MODE_HEAP / MODE_SELECT with the threshold pre-pass INSIDE the launch (inline_pre = 1): every CTA first scores one sampled
+    // tile (tile blockIdx.x * pre_stride) per query block and writes its group maxima, a grid barrier makes them visible,
+    // the CTAs that own a query compute its tau0, a second barrier publishes the thresholds -- two launches and ~15 us less
+    // per search than the MODE_MAX launch + tc_tau0_kernel
+    int inline_pre;
+    long long pre_stride;
+    float* tau0_w;        // the tau0 array, writable
+    unsigned* bar;        // [0] arrivals, [1] generation, [2] sticky failure flag (a barrier timed out once: never used again)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -75,6 +84,30 @@ struct TcParams {
 //   [.., + stages*16384)              ring of database tiles (128 rows x 128 B)
 //   then barriers, TMEM base address, tau0[npad], cnt[npad]
 // ---------------------------------------------------------------------------------------------
+
+// Grid barrier for the persistent scan (one CTA per SM, all resident): sense-reversing on two global words, called by ONE
+// thread per CTA.  A watchdog (~2 s) sets the sticky failure flag instead of hanging the GPU; the caller then falls back to
+// thresholds that are valid without the pre-pass (and the host never uses the in-launch pre-pass on this handle again).
+__device__ __forceinline__ void tc_grid_barrier(unsigned* bar, unsigned nctas) {
+    volatile unsigned* gen = bar + 1;
+    __threadfence();
+    const unsigned g = *gen;
+    if (atomicAdd(bar, 1u) == nctas - 1u) {
+        bar[0] = 0u;
+        __threadfence();
+        atomicAdd(bar + 1, 1u);
+    } else {
+        const long long t0 = clock64();
+        while (*gen == g) {
+            if (clock64() - t0 > 4000000000ll) {
+                *reinterpret_cast<volatile unsigned*>(bar + 2) = 1u;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __threadfence();
+}
 
 // X3 (fp32 rows only): 3xTF32 split scan.  tf32 keeps 11 significant bits of each operand, a ~1e-3 relative error that
 // is far above fp32 noise; here every operand is split  v = hi + lo  (hi = the tf32 part, lo = v - hi exactly) and the
@@ -160,10 +193,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
 
     // tiles of this CTA (the same list for every query block)
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // in-launch pre-pass: one leading sample tile per query block (decided once, grid-uniformly: the sticky failure flag is
+    // only ever set by a launch that is already past this point)
+    const int pre = ((MODE == MODE_HEAP || MODE == MODE_SELECT) && p.inline_pre && *reinterpret_cast<volatile unsigned*>(p.bar + 2) == 0u) ? 1 : 0;
+    const long long n_iter = my_tiles + pre;
+    auto tile_of = [&](long long i) -> long long {
+        return i < pre ? (long long)blockIdx.x * p.pre_stride : (blockIdx.x + (i - pre) * gridDim.x) * p.tile_stride;
+    };
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0 && my_tiles > 0) {
+        if (lane == 0 && n_iter > 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int b = 0; b < p.nblocks; b++) {
@@ -173,8 +213,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                 if (X3)  // the lo halves of the queries are rows [nqp, 2 nqp) of the split query matrix
                     for (int c = 0; c < NK; c++)
                         tma_load_2d(q_smem + ((size_t)c * QH + 1) * NP * 128, &tm_q, c * EC, p.nqp + b * NP, q_full);
-                for (long long i = 0; i < my_tiles; i++) {
-                    const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
+                for (long long i = 0; i < n_iter; i++) {
+                    const long long tile = tile_of(i);
                     const int row0 = (int)(tile * TC_BM);
                     for (int c = 0; c < NK; c++) {
                         mbar_wait(&empty[stage], phase ^ 1u);
@@ -191,7 +231,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && my_tiles > 0) {
+        if (lane == 0 && n_iter > 0) {
             const uint32_t idesc = make_idesc(TF32, TC_BM, NP);
             const uint32_t idesc2 = make_idesc(TF32, TC_BM, 2 * NP);  // X3: both query halves in one MMA
             int stage = 0, ts = 0;
@@ -200,7 +240,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
             for (int b = 0; b < p.nblocks; b++) {
                 mbar_wait(q_full, (uint32_t)(b & 1));
                 tc_fence_after();
-                for (long long i = 0; i < my_tiles; i++, it++) {
+                for (long long i = 0; i < n_iter; i++, it++) {
                     const int a = (int)(it & 1);
                     const uint32_t aphase = (uint32_t)((it >> 1) & 1);
                     mbar_wait(&acc_empty[a], aphase ^ 1u);  // epilogue has drained this accumulator
@@ -261,7 +301,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
         uint32_t phase = 0, tphase = 0;
         long long itc = 0;
         for (int b = 0; b < p.nblocks; b++) {
-            for (long long i = 0; i < my_tiles; i++) {
+            for (long long i = 0; i < n_iter; i++) {
                 for (int c = 0; c < NK; c++, itc++) {
                     if ((int)(itc & 1) == grp) {
                         mbar_wait(&full[stage], phase);           // the raw fp32 tile has landed (TMA)
@@ -320,7 +360,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
             if (MODE == MODE_SELECT) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // all epilogue warps have left the previous block
                 for (int c = et; c < NP; c += 128) {
-                    tau_s[c] = (qb + c < p.nq) ? p.tau0[qb + c] : INFINITY;
+                    tau_s[c] = (!pre && qb + c < p.nq) ? p.tau0[qb + c] : INFINITY;  // pre: set behind the sample tile below
                     cnt_s[c] = 0;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -329,15 +369,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                 for (int c = et; c < NP; c += 128) {
                     // start from the pre-pass bound when there is one (it spares the early sorts: with it a CTA sees
                     // ~10 admissions per query in all); padded queries never admit anything
-                    tau_s[c] = (qb + c < p.nq) ? (p.tau0 ? p.tau0[qb + c] : -INFINITY) : INFINITY;
+                    tau_s[c] = (!pre && qb + c < p.nq) ? (p.tau0 ? p.tau0[qb + c] : -INFINITY) : INFINITY;
                     cnt_s[c] = 0;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            for (long long i = 0; i < my_tiles; i++, it++) {
+            for (long long i = 0; i < n_iter; i++, it++) {
                 const int a = (int)(it & 1);
                 const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-                const long long tile = (blockIdx.x + i * gridDim.x) * p.tile_stride;
+                const bool sample = i < pre;  // the leading sample tile: group maxima only, then the thresholds
+                const long long tile = tile_of(i);
                 const long long row = tile * TC_BM + row_in_tile;
                 const bool row_ok = row < p.n;
                 mbar_wait(&acc_full[a], aphase);
@@ -362,8 +403,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
 #pragma unroll
                             for (int j = 0; j < 16; j++) p.dump[(size_t)row * p.nqp + qb + c0 + j] = __uint_as_float(v[j]);
                         }
-                    } else if (MODE == MODE_MAX) {
-                        const long long g = ((blockIdx.x + i * gridDim.x) * 4 + e);  // 32-row group index of this launch
+                    } else if (MODE == MODE_MAX || sample) {
+                        const long long g = sample ? ((long long)blockIdx.x * 4 + e) : ((blockIdx.x + i * gridDim.x) * 4 + e);  // 32-row group index
                         float mine = -INFINITY;  // lane j keeps column j's maximum, then one coalesced 64-byte store
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
@@ -438,7 +479,53 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tm_db, const __grid_constant_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
-                if (MODE == MODE_HEAP) {
+                if (sample) {
+                    // ---- thresholds from the sample tiles of all CTAs (in-launch pre-pass) ----
+                    __threadfence();  // this thread's group maxima are visible device-wide
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) tc_grid_barrier(p.bar, gridDim.x);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (e == 0) {  // tau0 of the queries of this block that this CTA owns: k'-th largest of the 4 * grid group maxima
+                        const int G = (int)gridDim.x * 4;  // <= 1024 (checked by the host)
+                        for (int c = (int)blockIdx.x; c < NP; c += (int)gridDim.x) {
+                            const int qq = qb + c;
+                            if (qq >= p.nq) continue;  // warp-uniform
+                            uint32_t vals[32];
+#pragma unroll
+                            for (int u = 0; u < 32; u++) {
+                                const int g = lane + 32 * u;
+                                vals[u] = g < G ? __ldcg(p.gmax + (size_t)g * p.nqp + qq) : 0u;
+                            }
+                            uint32_t prefix = 0u;  // bit by bit: the largest v with count(values >= v) >= k'
+                            for (int bit = 31; bit >= 0; bit--) {
+                                const uint32_t cand = prefix | (1u << bit);
+                                int cnt = 0;
+#pragma unroll
+                                for (int u = 0; u < 32; u++) cnt += vals[u] >= cand ? 1 : 0;
+                                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                                if (cnt >= p.kp_sel) prefix = cand;
+                            }
+                            if (lane == 0) p.tau0_w[qq] = prefix != 0u ? ordered_to_score(prefix) : -INFINITY;
+                        }
+                    }
+                    __threadfence();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) tc_grid_barrier(p.bar, gridDim.x);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const bool failed = *reinterpret_cast<volatile unsigned*>(p.bar + 2) != 0u;
+                    for (int c = et; c < NP; c += 128) {
+                        float t = (qb + c < p.nq) ? __ldcg(p.tau0_w + qb + c) : INFINITY;
+                        if (failed) {  // a barrier timed out: thresholds that need no pre-pass
+                            if (MODE == MODE_HEAP) t = (qb + c < p.nq) ? -INFINITY : INFINITY;
+                            else {
+                                t = INFINITY;  // admit nothing; every query of the block is re-run exactly by the repair
+                                if (qb + c < p.nq) p.overflow[qb + c] = 1;
+                            }
+                        }
+                        tau_s[c] = t;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                } else if (MODE == MODE_HEAP) {
                     // every warp has appended this tile's admissions (at most 128 per query: room is guaranteed because a
                     // query never starts a tile with more than 128 keys); warp e now tidies the queries c = e, e+4, ...
                     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -998,6 +1085,7 @@ int g_tc_heap_max_nq = 32;  // option "tc_heap_max_nq": batches up to this size 
 int g_tc_heap_pure_max_nq = 0;  // option "tc_heap_pure_max_nq": ... and up to this size without the threshold pre-pass.  Off by
                                 // default: with the 16384-row sample the seeded heaps win at 1M rows for every batch size
                                 // (bf16, 2 queries: 0.195 vs 0.229 ms) and lose 1-2 % at 10M rows for <= 3 queries
+int g_tc_inline_pre = 1;   // option "tc_inline_pre": one-CTA kernel, <= 2 query blocks: thresholds from a sample tile per CTA INSIDE the scan launch
 int g_tc_sample_rows = 0;  // option "tc_sample_rows": rows the threshold pre-pass scores at least (0 = auto)
 
 // auto: 65536 rows for large batches (the select pass pays for every admitted candidate: 1.1 k' n / sample per query),
@@ -1071,6 +1159,18 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     pl->pre_tiles = (pl->ntiles + pl->pre_stride - 1) / pl->pre_stride;
     pl->pre_grid = (int)(pl->pre_tiles < sm_count ? pl->pre_tiles : sm_count);
     pl->groups = (int)(pl->pre_tiles * 4);
+    // In-launch pre-pass (tc_scan_kernel, inline_pre): every CTA of the persistent grid scores ONE sampled tile first and the
+    // thresholds are agreed through two grid barriers -- needs the full grid resident (one CTA per SM), k' <= 4 * grid group
+    // maxima held in registers by one warp (<= 1024), and a CTA per query of a block.
+    pl->inline_pre = 0;
+    if (g_tc_inline_pre && g_tc_sample_rows == 0 && (pl->heap == 2 || (!pl->heap && pl->nblocks <= 2)) && pl->grid == sm_count &&
+        pl->grid * 4 <= 1024 && pl->grid * 4 >= 2 * kp && pl->grid >= pl->npad && pl->ntiles >= 2 * (long long)pl->grid) {
+        pl->inline_pre = 1;
+        pl->pre_tiles = pl->grid;
+        pl->pre_stride = pl->ntiles / pl->grid;
+        pl->pre_grid = pl->grid;
+        pl->groups = pl->grid * 4;
+    }
     int g2 = 1;
     while (g2 < pl->groups) g2 <<= 1;
     pl->gpow2 = g2;
@@ -1146,9 +1246,19 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
     TcParams p;
     cudaError_t e = tc_prepare(a, pl, ws, &tdb, &tq, &p, st);
     if (e != cudaSuccess) return e;
+    const bool inline_pre = pl.inline_pre && a.bar != nullptr;
+    if (inline_pre) {
+        p.inline_pre = 1;
+        p.pre_stride = pl.pre_stride;
+        p.tau0_w = reinterpret_cast<float*>(ws + pl.off_tau0);
+        p.bar = a.bar;
+        p.kp_sel = pl.kp;
+    }
     if (pl.heap) {
         // small batch: the CTAs keep their own top-k' per query on chip and write [nq][grid][64] lists
-        if (pl.heap == 2) {  // pre-pass thresholds first: the running top-k' then hardly ever needs a sort
+        if (pl.heap == 2 && inline_pre) {
+            // thresholds from inside the scan launch
+        } else if (pl.heap == 2) {  // pre-pass thresholds first: the running top-k' then hardly ever needs a sort
             p.ntiles = pl.pre_tiles;
             p.tile_stride = pl.pre_stride;
             if ((e = launch_tc<MODE_MAX>(a.is_bf16, pl.x3, tdb, tq, p, pl.pre_grid, tc_smem_bytes_plain(pl), st)) != cudaSuccess) return e;
@@ -1165,14 +1275,16 @@ cudaError_t tc_scan_block(const TcArgs& a, const TcPlan& pl, unsigned char* ws, 
         if (a.overflow_out) e = cudaMemsetAsync(a.overflow_out, 0, (size_t)a.nq * 4, st);  // this mode cannot overflow
         return e;
     }
-    // 1. threshold pre-pass over the sampled tiles
-    p.ntiles = pl.pre_tiles;
-    p.tile_stride = pl.pre_stride;
-    e = launch_tc<MODE_MAX>(a.is_bf16, 0, tdb, tq, p, pl.pre_grid, pl.smem, st);
-    if (e != cudaSuccess) return e;
-    if ((e = tc_launch_tau0(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp, reinterpret_cast<float*>(ws + pl.off_tau0), st)) !=
-        cudaSuccess)
-        return e;
+    // 1. threshold pre-pass over the sampled tiles (separate launches unless it runs inside the select launch)
+    if (!inline_pre) {
+        p.ntiles = pl.pre_tiles;
+        p.tile_stride = pl.pre_stride;
+        e = launch_tc<MODE_MAX>(a.is_bf16, 0, tdb, tq, p, pl.pre_grid, pl.smem, st);
+        if (e != cudaSuccess) return e;
+        if ((e = tc_launch_tau0(p.gmax, pl.groups, pl.gpow2, pl.nqp, a.nq, pl.kp, reinterpret_cast<float*>(ws + pl.off_tau0), st)) !=
+            cudaSuccess)
+            return e;
+    }
     // overflow flags and spill counters start at zero (adjacent in the workspace)
     if ((e = cudaMemsetAsync(ws + pl.off_overflow, 0, pl.off_cand - pl.off_overflow, st)) != cudaSuccess) return e;
     // 2. selection pass over every tile, all query blocks in one persistent launch

@@ -22,6 +22,7 @@ def _reset_options():
     evs.set_option("x3_max_nq", 16)
     evs.set_option("guard", 1)
     evs.set_option("tf32_guard_eps_e6", 0)
+    evs.set_option("tc_inline_pre", 1)
 
 
 @pytest.mark.parametrize("storage,d", [("bf16", 512), ("f32", 512), ("bf16", 768), ("f32", 768), ("bf16", 1024), ("bf16", 64)])
@@ -228,6 +229,49 @@ def test_tc_paths_across_dims_and_batch_sizes(d):
             Dr, Ir = oracle.canon_search(xq[sample], xb, k)
             assert np.array_equal(I[sample], Ir) and np.array_equal(D[sample], Dr), (d, storage, nq, k)
         assert evs.get_option("tc_fallbacks") == fb0, (d, storage)
+
+
+def test_inline_prepass_equals_separate_launches_and_concurrent_handles_do_not_deadlock():
+    """Batches of 2..128 queries take their thresholds from a sample tile per CTA INSIDE the scan launch (two grid barriers)
+    instead of a pre-pass launch + tau0 launch: same bits either way.  Kernels that synchronise their own grid need every CTA
+    resident, so two handles searched concurrently from two threads (each on its own stream) must be ordered by the library:
+    the test would hang (and hit the barrier's 2 s watchdog) otherwise."""
+    import threading
+    d, n, k = 512, 150_011, 48
+    xb = oracle.synth_fill(n, d, 91)
+    xq = oracle.synth_fill(64, d, 92)
+    Dr, Ir = oracle.canon_search(xq, xb, k)
+    for storage in ("f32", "bf16"):
+        idx = evs.IndexFlatIP(d, storage=storage)
+        idx.add(xb)
+        for nq in (2, 16, 33, 64):
+            l0 = evs.kernel_launches()
+            D1, I1 = idx.search(xq[:nq], k)
+            n_inline = evs.kernel_launches() - l0
+            evs.set_option("tc_inline_pre", 0)
+            l0 = evs.kernel_launches()
+            D0, I0 = idx.search(xq[:nq], k)
+            n_separate = evs.kernel_launches() - l0
+            evs.set_option("tc_inline_pre", 1)
+            assert n_inline == n_separate - 2, (storage, nq, n_inline, n_separate)  # pre-pass and tau0 launches are gone
+            assert np.array_equal(I1, I0) and np.array_equal(D1, D0), (storage, nq)
+            assert np.array_equal(I1, Ir[:nq]) and np.array_equal(D1, Dr[:nq]), (storage, nq)
+    handles = [evs.IndexFlatIP(d), evs.IndexFlatIP(d, storage="bf16"), evs.IndexFlatIP(d)]
+    for h in handles:
+        h.add(xb)
+    errs = []
+
+    def work(t):
+        nq = (16, 40, 64)[t]
+        for _ in range(40):
+            D, I = handles[t].search(xq[:nq], k)  # host API: each handle on its own stream
+            if not (np.array_equal(I, Ir[:nq]) and np.array_equal(D, Dr[:nq])):
+                errs.append(t)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(3)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
 
 
 def _planted(spacing, d=512, n=120_000, nq=6):
