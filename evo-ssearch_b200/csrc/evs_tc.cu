@@ -1164,7 +1164,9 @@ cudaError_t tc_plan(long long n, int d, int is_bf16, int nq, int kp, int sm_coun
     // maxima held in registers by one warp (<= 1024), and a CTA per query of a block.
     pl->inline_pre = 0;
     if (g_tc_inline_pre && g_tc_sample_rows == 0 && (pl->heap == 2 || (!pl->heap && pl->nblocks <= 2)) && pl->grid == sm_count &&
-        pl->grid * 4 <= 1024 && pl->grid * 4 >= 2 * kp && pl->grid >= pl->npad && pl->ntiles >= 2 * (long long)pl->grid) {
+        pl->grid * 4 <= 1024 && pl->grid * 4 >= 2 * kp && pl->grid >= pl->npad && pl->ntiles >= 2 * (long long)pl->grid &&
+        pl->ntiles / 128 <= pl->grid) {  // larger shards want a larger sample than one tile per CTA (the separate pre-pass scores
+                                         // n / 128 rows: at 10M rows the 18 944-row sample cost more in admissions than it saved)
         pl->inline_pre = 1;
         pl->pre_tiles = pl->grid;
         pl->pre_stride = pl->ntiles / pl->grid;
