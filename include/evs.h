@@ -244,6 +244,9 @@ EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev,
  *                 (k <= 48) instead of per-CTA sorted lists; "scan_dynamic" (0 static, 1 = default: dynamic tail in the pool
  *                 kernel, 2: also fully dynamic dealing in the list-based scan) / "scan_chunk_groups" (row groups per grab);
  *                 "scan_clock": record per-CTA scan times and the last CTA's phase stamps (evs_index_scan_clocks);
+ *                 "tc_inline_pre" (default 1): batches on the one-CTA tensor-core kernel over shards of up to ~2.4M rows take
+ *                 their thresholds from one sampled tile per CTA inside the scan launch (two grid barriers) instead of a
+ *                 pre-pass launch and a threshold launch;
  *                 "exchange_fail_next" (tests): the next exchange-mode search of this process fails after taking its
  *                 sequence number, so that the peers' failure reporting can be exercised.
  *                 evs_get_option also reads "tc_fallbacks": queries the HOST re-ran through the GEMV scan because a
