@@ -103,6 +103,18 @@ def check(rc: int) -> None:
         raise EvsError(rc, msg.decode("utf-8", "replace") if msg else "")
 
 
+_c_char = ctypes.c_char
+
+
+def host_ptr(a) -> int:
+    """Address of a C-contiguous numpy array's data.  ``a.ctypes.data_as(...)`` builds a helper object per call (~5 us, three
+    of them per search: a third of the 10k-row search's end-to-end time); the buffer protocol is ~6 times cheaper."""
+    try:
+        return ctypes.addressof(_c_char.from_buffer(a))
+    except (TypeError, ValueError, BufferError):  # read-only or empty arrays
+        return a.ctypes.data
+
+
 def device_count() -> int:
     n = ctypes.c_int(0)
     check(lib().evs_device_count(ctypes.byref(n)))

@@ -47,9 +47,13 @@ def build_libevs(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    hdr_t = max(os.path.getmtime(p) for p in [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)] if os.path.exists(p))
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
         objs.append(o)
+        # an object newer than its source, every header and this script is kept
+        if not force and not verbose and os.path.exists(o) and os.path.getmtime(o) > max(hdr_t, os.path.getmtime(os.path.join(CSRC, s))):
+            continue
         cmd = [_nvcc(), *NVCC_FLAGS[:-2], "-DEVS_BUILDING", "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -6,12 +6,15 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -48,6 +51,7 @@ static int g_profile_scans = 0;                    // record CUDA events around 
 static std::atomic<long long> g_tc_fallbacks{0};   // queries re-run through the GEMV scan after a tensor-core buffer overflow
 static std::atomic<long long> g_exact_reruns{0};   // queries the HOST re-ran with the fp32 GEMV scan because the finalise could not
                                                    // certify them (the device-side re-runs are counted per handle: evs_index_guard_stats)
+static std::atomic<int> g_io_threads{0};           // option "io_threads": reader / writer threads per index.faiss chunk (0 = auto)
 static std::atomic<int> g_exchange_fail_next{0};   // option "exchange_fail_next" (tests): the next exchange-mode search of this process
                                                    // fails after it has taken its sequence number, as an allocation failure would
 static int g_tf32_guard_eps_e6 = 0;                // option "tf32_guard_eps_e6": 0 (default) = the single-tf32 scans are certified against
@@ -219,6 +223,9 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
         g_tune.x3_max_nq = (int)value;
     } else if (!strcmp(name, "guard")) {
         g_tune.guard = value ? 1 : 0;
+    } else if (!strcmp(name, "io_threads")) {
+        if (value < 0 || value > 64) return fail(EVS_EINVAL, "io_threads must be in [0, 64]");
+        g_io_threads.store((int)value);
     } else {
         return fail(EVS_EINVAL, "unknown option '%s'", name);
     }
@@ -253,6 +260,7 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "x3")) *value = g_tune.x3;
     else if (!strcmp(name, "x3_max_nq")) *value = g_tune.x3_max_nq;
     else if (!strcmp(name, "guard")) *value = g_tune.guard;
+    else if (!strcmp(name, "io_threads")) *value = g_io_threads.load();
     else return fail(EVS_EINVAL, "unknown option '%s'", name);
     return EVS_OK;
 }
@@ -1718,13 +1726,117 @@ static_assert(sizeof(FlatHeader) == 45, "index.faiss flat header is 45 bytes");
 
 static const size_t kIoChunk = (size_t)64 << 20;
 
+// One chunk of the file is read (or written) by several threads at once, each with its own pread / pwrite over a disjoint
+// 4 KiB-aligned slice: a single thread copies out of the page cache at 2-3 GB/s, far below what the host-to-device copy
+// behind it takes (PCIe 5 x16), and a cold file wants several requests in flight anyway.
+static int io_threads_for(size_t nb) {
+    int t = g_io_threads.load();
+    if (t <= 0) {
+        // measured on the pool's 16-thread B200 hosts, page cache -> pinned -> HBM: 6.5 GB/s with 1 thread, 23 with 4, 35 with 16
+        unsigned hc = std::thread::hardware_concurrency();
+        t = hc >= 16 ? 16 : hc >= 2 ? (int)hc : 1;
+    }
+    size_t most = nb / ((size_t)4 << 20);  // at least 4 MiB per thread
+    if ((size_t)t > most) t = (int)most;
+    return t < 1 ? 1 : t;
+}
+
+static bool rw_full(int fd, unsigned char* buf, size_t nb, off_t off, bool write) {
+    while (nb) {
+        ssize_t r = write ? pwrite(fd, buf, nb, off) : pread(fd, buf, nb, off);
+        if (r < 0 && errno == EINTR) continue;
+        if (r <= 0) return false;  // error, or end of file inside the payload
+        buf += r;
+        off += r;
+        nb -= (size_t)r;
+    }
+    return true;
+}
+
+static bool rw_parallel(int fd, void* buf, size_t nb, off_t off, bool write) {
+    const int t = io_threads_for(nb);
+    unsigned char* p = static_cast<unsigned char*>(buf);
+    if (t == 1) return rw_full(fd, p, nb, off, write);
+    size_t slice = ((nb + t - 1) / t + 4095) & ~(size_t)4095;
+    std::atomic<int> bad{0};
+    std::vector<std::thread> th;
+    th.reserve(t - 1);
+    auto job = [&](size_t lo) {
+        size_t n = nb - lo < slice ? nb - lo : slice;
+        if (!rw_full(fd, p + lo, n, off + (off_t)lo, write)) bad.store(1);
+    };
+    size_t lo = slice;
+    try {
+        for (; lo < nb; lo += slice) th.emplace_back(job, lo);
+    } catch (...) {  // no more threads: this one takes the rest
+        for (; lo < nb; lo += slice) job(lo);
+    }
+    job(0);
+    for (auto& x : th) x.join();
+    return bad.load() == 0;
+}
+
+// The two pinned staging chunks are kept for the life of the process (cudaMallocHost of 64 MiB costs tens of milliseconds,
+// the application loads an index per request until the resident cache holds it); a second concurrent load or save
+// allocates its own pair.
+struct IoStage {
+    void* pin[2] = {nullptr, nullptr};
+    size_t bytes = 0;
+    bool cached = false;
+};
+static std::mutex g_io_stage_mu;
+static IoStage g_io_stage;
+
+static int io_stage_acquire(size_t chunk, IoStage* st) {
+    if (g_io_stage_mu.try_lock()) {
+        if (g_io_stage.bytes < chunk) {
+            cudaFreeHost(g_io_stage.pin[0]);
+            cudaFreeHost(g_io_stage.pin[1]);
+            g_io_stage.pin[0] = g_io_stage.pin[1] = nullptr;
+            g_io_stage.bytes = 0;
+            if (cudaMallocHost(&g_io_stage.pin[0], chunk) != cudaSuccess || cudaMallocHost(&g_io_stage.pin[1], chunk) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFreeHost(g_io_stage.pin[0]);
+                cudaFreeHost(g_io_stage.pin[1]);
+                g_io_stage.pin[0] = g_io_stage.pin[1] = nullptr;
+                g_io_stage_mu.unlock();
+                return fail(EVS_ENOMEM, "cudaMallocHost of the staging chunks failed");
+            }
+            g_io_stage.bytes = chunk;
+        }
+        *st = g_io_stage;
+        st->cached = true;
+        return EVS_OK;
+    }
+    st->cached = false;
+    st->bytes = chunk;
+    if (cudaMallocHost(&st->pin[0], chunk) != cudaSuccess || cudaMallocHost(&st->pin[1], chunk) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFreeHost(st->pin[0]);
+        cudaFreeHost(st->pin[1]);
+        st->pin[0] = st->pin[1] = nullptr;
+        return fail(EVS_ENOMEM, "cudaMallocHost of the staging chunks failed");
+    }
+    return EVS_OK;
+}
+
+static void io_stage_release(IoStage* st) {
+    if (st->cached) {
+        g_io_stage_mu.unlock();
+    } else {
+        cudaFreeHost(st->pin[0]);
+        cudaFreeHost(st->pin[1]);
+    }
+    st->pin[0] = st->pin[1] = nullptr;
+}
+
 extern "C" int evs_index_write(const evs_index* idx, const char* path) {
     if (!idx || !path) return fail(EVS_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(idx->mu);  // save_index may race a re-index on another Flask thread
     int rc = use_device(idx->device);
     if (rc) return rc;
-    FILE* f = fopen(path, "wb");
-    if (!f) return fail(EVS_EIO, "cannot open '%s' for writing: %s", path, strerror(errno));
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0666);
+    if (fd < 0) return fail(EVS_EIO, "cannot open '%s' for writing: %s", path, strerror(errno));
     FlatHeader h;
     memcpy(h.fourcc, "IxFI", 4);
     h.d = idx->d;
@@ -1733,30 +1845,48 @@ extern "C" int evs_index_write(const evs_index* idx, const char* path) {
     h.is_trained = 1;
     h.metric_type = 0;
     h.count = (uint64_t)idx->ntotal * (uint64_t)idx->d;
-    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
-    size_t total = (size_t)h.count * sizeof(float);
-    void* pin = nullptr;
+    bool ok = rw_full(fd, reinterpret_cast<unsigned char*>(&h), sizeof(h), 0, true);
+    const size_t total = (size_t)h.count * sizeof(float);
     if (ok && total) {
-        size_t chunk = total < kIoChunk ? total : kIoChunk;
-        cudaError_t e = cudaMallocHost(&pin, chunk);
-        if (e != cudaSuccess) {
-            fclose(f);
-            return fail(EVS_ENOMEM, "cudaMallocHost failed: %s", cudaGetErrorString(e));
+        const size_t chunk = total < kIoChunk ? total : kIoChunk;
+        IoStage st;
+        rc = io_stage_acquire(chunk, &st);
+        if (rc) {
+            close(fd);
+            return rc;
         }
-        for (size_t off = 0; ok && off < total; off += chunk) {
+        // double-buffered: the device-to-host copy of chunk i+1 runs while the threads write chunk i
+        cudaEvent_t ready[2] = {nullptr, nullptr};
+        cudaEventCreateWithFlags(&ready[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ready[1], cudaEventDisableTiming);
+        cudaError_t e = cudaSuccess;
+        auto fetch = [&](size_t off, int b) {
             size_t nb = total - off < chunk ? total - off : chunk;
-            e = cudaMemcpy(pin, reinterpret_cast<const unsigned char*>(idx->xb32) + off, nb, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) {
-                cudaFreeHost(pin);
-                fclose(f);
-                return fail(EVS_ECUDA, "device read failed: %s", cudaGetErrorString(e));
-            }
-            ok = fwrite(pin, 1, nb, f) == nb;
+            cudaError_t r = cudaMemcpyAsync(st.pin[b], reinterpret_cast<const unsigned char*>(idx->xb32) + off, nb, cudaMemcpyDeviceToHost,
+                                            idx->stream);
+            if (r == cudaSuccess) r = cudaEventRecord(ready[b], idx->stream);
+            return r;
+        };
+        e = fetch(0, 0);
+        int b = 0;
+        for (size_t off = 0; ok && e == cudaSuccess && off < total; off += chunk, b ^= 1) {
+            size_t nb = total - off < chunk ? total - off : chunk;
+            if (off + chunk < total) e = fetch(off + chunk, b ^ 1);
+            if (e == cudaSuccess) e = cudaEventSynchronize(ready[b]);
+            // one writer: concurrent pwrites to one file serialise on the inode lock (8 threads measured slower than 1)
+            if (e == cudaSuccess) ok = rw_full(fd, static_cast<unsigned char*>(st.pin[b]), nb, (off_t)(sizeof(h) + off), true);
         }
-        cudaFreeHost(pin);
+        cudaStreamSynchronize(idx->stream);
+        cudaEventDestroy(ready[0]);
+        cudaEventDestroy(ready[1]);
+        io_stage_release(&st);
+        if (e != cudaSuccess) {
+            close(fd);
+            return fail(EVS_ECUDA, "device read failed: %s", cudaGetErrorString(e));
+        }
     }
-    if (fclose(f) != 0) ok = false;
-    if (!ok) return fail(EVS_EIO, "short write to '%s'", path);
+    if (close(fd) != 0) ok = false;
+    if (!ok) return fail(EVS_EIO, "short write to '%s': %s", path, strerror(errno));
     return EVS_OK;
 }
 
@@ -1765,36 +1895,36 @@ extern "C" int evs_index_write(const evs_index* idx, const char* path) {
 static int read_rows(const char* path, int device, int storage, int64_t row_lo, int64_t row_hi, evs_index** out, int64_t* ntotal_file) {
     if (!path || !out) return fail(EVS_EINVAL, "NULL argument");
     *out = nullptr;
-    FILE* f = fopen(path, "rb");
-    if (!f) return fail(EVS_EIO, "cannot open '%s': %s", path, strerror(errno));
+    int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return fail(EVS_EIO, "cannot open '%s': %s", path, strerror(errno));
     FlatHeader h;
-    if (fread(&h, sizeof(h), 1, f) != 1) {
-        fclose(f);
+    if (!rw_full(fd, reinterpret_cast<unsigned char*>(&h), sizeof(h), 0, false)) {
+        close(fd);
         return fail(EVS_EFORMAT, "'%s': truncated header", path);
     }
     const bool ip = !memcmp(h.fourcc, "IxFI", 4);
     if (!ip && memcmp(h.fourcc, "IxF2", 4) && memcmp(h.fourcc, "IxFl", 4)) {
-        fclose(f);
+        close(fd);
         return fail(EVS_EFORMAT, "'%s': not a flat index (fourcc %.4s)", path, h.fourcc);
     }
     if (h.metric_type != 0) {
-        fclose(f);
+        close(fd);
         return fail(EVS_EFORMAT, "'%s': metric %d is not inner product", path, h.metric_type);
     }
     if (h.d <= 0 || h.ntotal < 0 || h.count >= ((uint64_t)1 << 40) || h.count != (uint64_t)h.ntotal * (uint64_t)h.d) {
-        fclose(f);
+        close(fd);
         return fail(EVS_EFORMAT, "'%s': inconsistent header (d=%d ntotal=%lld count=%llu)", path, h.d, (long long)h.ntotal,
                     (unsigned long long)h.count);
     }
     struct stat sb;
-    if (fstat(fileno(f), &sb) == 0 && (uint64_t)sb.st_size < sizeof(h) + h.count * 4) {
-        fclose(f);
+    if (fstat(fd, &sb) == 0 && (uint64_t)sb.st_size < sizeof(h) + h.count * 4) {
+        close(fd);
         return fail(EVS_EFORMAT, "'%s': truncated payload", path);
     }
     if (ntotal_file) *ntotal_file = h.ntotal;
     if (row_hi < 0 || row_hi > h.ntotal) row_hi = h.ntotal;
     if (row_lo < 0 || row_lo > row_hi) {
-        fclose(f);
+        close(fd);
         return fail(EVS_EINVAL, "rows [%lld, %lld) out of range for '%s' (%lld rows)", (long long)row_lo, (long long)row_hi, path,
                     (long long)h.ntotal);
     }
@@ -1802,23 +1932,28 @@ static int read_rows(const char* path, int device, int storage, int64_t row_lo, 
     evs_index* idx = nullptr;
     int rc = evs_index_create(h.d, device, storage, &idx);
     if (rc) {
-        fclose(f);
+        close(fd);
         return rc;
     }
     idx->id_base = row_lo;
-    size_t total = (size_t)nrows * (size_t)h.d * sizeof(float);
+    const size_t total = (size_t)nrows * (size_t)h.d * sizeof(float);
     if (total) {
-        if (fseeko(f, (off_t)(sizeof(h) + (size_t)row_lo * (size_t)h.d * sizeof(float)), SEEK_SET) != 0)
-            rc = fail(EVS_EIO, "'%s': seek failed: %s", path, strerror(errno));
-        if (!rc) {
+        const off_t base = (off_t)(sizeof(h) + (size_t)row_lo * (size_t)h.d * sizeof(float));
+#ifdef POSIX_FADV_SEQUENTIAL
+        posix_fadvise(fd, base, (off_t)total, POSIX_FADV_SEQUENTIAL);
+#endif
+        {
             std::lock_guard<std::mutex> lk(idx->mu);
             rc = grow_locked(idx, nrows);
         }
-        void* pin[2] = {nullptr, nullptr};
-        size_t chunk = total < kIoChunk ? total : kIoChunk;
-        if (!rc && (cudaMallocHost(&pin[0], chunk) != cudaSuccess || cudaMallocHost(&pin[1], chunk) != cudaSuccess))
-            rc = fail(EVS_ENOMEM, "cudaMallocHost failed");
-        // double-buffered: fread into one pinned buffer while the other is in flight to the device
+        const size_t chunk = total < kIoChunk ? total : kIoChunk;
+        IoStage st;
+        bool staged = false;
+        if (!rc) {
+            rc = io_stage_acquire(chunk, &st);
+            staged = !rc;
+        }
+        // double-buffered: the threads fill one pinned chunk while the other is in flight to the device
         cudaEvent_t done[2] = {nullptr, nullptr};
         if (!rc) {
             cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming);
@@ -1828,11 +1963,11 @@ static int read_rows(const char* path, int device, int storage, int64_t row_lo, 
         for (size_t off = 0; !rc && off < total; off += chunk, b ^= 1) {
             size_t nb = total - off < chunk ? total - off : chunk;
             cudaEventSynchronize(done[b]);
-            if (fread(pin[b], 1, nb, f) != nb) {
+            if (!rw_parallel(fd, st.pin[b], nb, base + (off_t)off, false)) {
                 rc = fail(EVS_EFORMAT, "'%s': short read", path);
                 break;
             }
-            cudaError_t e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(idx->xb32) + off, pin[b], nb, cudaMemcpyHostToDevice,
+            cudaError_t e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(idx->xb32) + off, st.pin[b], nb, cudaMemcpyHostToDevice,
                                             idx->stream);
             if (e == cudaSuccess) e = cudaEventRecord(done[b], idx->stream);
             if (e != cudaSuccess) rc = fail(EVS_ECUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -1840,15 +1975,14 @@ static int read_rows(const char* path, int device, int storage, int64_t row_lo, 
         if (!rc) {
             std::lock_guard<std::mutex> lk(idx->mu);
             rc = finish_add_locked(idx, nrows);
-        } else {
-            cudaStreamSynchronize(idx->stream);
         }
+        // the staging chunks go back to the next load: nothing of this one may still be reading them
+        if (staged) cudaStreamSynchronize(idx->stream);
         if (done[0]) cudaEventDestroy(done[0]);
         if (done[1]) cudaEventDestroy(done[1]);
-        cudaFreeHost(pin[0]);
-        cudaFreeHost(pin[1]);
+        if (staged) io_stage_release(&st);
     }
-    fclose(f);
+    close(fd);
     if (rc) {
         evs_index_free(idx);
         return rc;

@@ -26,7 +26,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import EVS_BF16, EVS_F16, EVS_F32, EVS_STORE_BF16_F32, EVS_STORE_F32, check, lib
+from ._lib import EVS_BF16, EVS_F16, EVS_F32, EVS_STORE_BF16_F32, EVS_STORE_F32, check, host_ptr, lib
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
@@ -204,8 +204,7 @@ class IndexFlatIP:
             I = np.empty((n, k), dtype=np.int64)
         else:
             assert I.shape == (n, k) and I.dtype == np.int64 and I.flags.c_contiguous
-        check(lib().evs_index_search(self._h, n, x.ctypes.data_as(ctypes.c_void_p), int(k),
-                                     D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p)))
+        check(lib().evs_index_search(self._h, n, host_ptr(x), int(k), host_ptr(D), host_ptr(I)))
         return D, I
 
     def _search_torch(self, x, k: int, D=None, I=None):
@@ -266,8 +265,7 @@ class IndexFlatIP:
         assert d == self.d and k > 0
         D = np.empty((n, k), dtype=np.float32)
         I = np.empty((n, k), dtype=np.int64)
-        check(lib().evs_index_search_exchange(self._h, exchange._h, n, x.ctypes.data_as(ctypes.c_void_p), int(k),
-                                              D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p)))
+        check(lib().evs_index_search_exchange(self._h, exchange._h, n, host_ptr(x), int(k), host_ptr(D), host_ptr(I)))
         return D, I
 
     def last_margins(self, nq: int) -> np.ndarray:
@@ -416,7 +414,7 @@ def normalize_L2(x) -> None:
                                          _torch_dtype_code(x), ctypes.c_void_p(st)))
         return
     assert isinstance(x, np.ndarray) and x.dtype == np.float32 and x.ndim == 2 and x.flags.c_contiguous
-    check(lib().evs_l2_normalize(default_device(), x.ctypes.data_as(ctypes.c_void_p), x.shape[0], x.shape[1]))
+    check(lib().evs_l2_normalize(default_device(), host_ptr(x), x.shape[0], x.shape[1]))
 
 
 def merge_partials(scores, ids, k: int):
