@@ -223,6 +223,12 @@ extern "C" int evs_set_option(const char* name, int64_t value) {
         g_tune.x3_max_nq = (int)value;
     } else if (!strcmp(name, "guard")) {
         g_tune.guard = value ? 1 : 0;
+    } else if (!strcmp(name, "small_max_rows")) {
+        if (value < 0 || value > (1 << 20)) return fail(EVS_EINVAL, "small_max_rows must be in [0, 2^20]");
+        g_tune.small_max_rows = (int)value;
+    } else if (!strcmp(name, "small_fast_cap")) {
+        if (value < 1 || value > 2048) return fail(EVS_EINVAL, "small_fast_cap must be in [1, 2048]");
+        g_tune.small_fast_cap = (int)value;
     } else if (!strcmp(name, "io_threads")) {
         if (value < 0 || value > 64) return fail(EVS_EINVAL, "io_threads must be in [0, 64]");
         g_io_threads.store((int)value);
@@ -261,6 +267,8 @@ extern "C" int evs_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "x3_max_nq")) *value = g_tune.x3_max_nq;
     else if (!strcmp(name, "guard")) *value = g_tune.guard;
     else if (!strcmp(name, "io_threads")) *value = g_io_threads.load();
+    else if (!strcmp(name, "small_max_rows")) *value = g_tune.small_max_rows;
+    else if (!strcmp(name, "small_fast_cap")) *value = g_tune.small_fast_cap;
     else return fail(EVS_EINVAL, "unknown option '%s'", name);
     return EVS_OK;
 }
@@ -1057,6 +1065,10 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
                         idx->pool_cap = need;
                     }
                     a.pool = idx->pool;
+                    // small shards (the application's 10k-row indexes): one key slot per row instead of the survivor pool
+                    if (tune.small_max_rows > 0 && idx->ntotal <= tune.small_max_rows && plan.threads == 256 &&
+                        (size_t)idx->ntotal <= scan_pool_key_slots(idx->pool_cap))
+                        a.small_fast_cap = tune.small_fast_cap > 0 ? tune.small_fast_cap : 1;
                 }
                 if (tune.scan_dynamic > 1 || (tune.scan_dynamic == 1 && a.pool != nullptr)) {
                     a.next_chunk = idx->words + W_NEXT_CHUNK;

@@ -66,13 +66,15 @@ __device__ __forceinline__ double widen_f32_normal(float f) {
 
 // CANON-32 of R rows at once with the row loads batched (the same accumulation order per row; the rows' load latencies
 // and fp64 chains overlap).  A null row pointer yields -DBL_MAX.
-template <int R, bool FAST>
+template <int R, bool FAST, int UW = 0>
 __device__ __forceinline__ void canon32_dot_multi(const float* const (&x)[R], const double* __restrict__ qs, int d, int lane,
                                                   double (&res)[R]) {
     double acc[R];
 #pragma unroll
     for (int r = 0; r < R; r++) acc[r] = 0.0;
-    constexpr int U = R <= 2 ? 16 : 8;  // values per row held at a time: R * U loads in flight per lane
+    // values per row held at a time: R * U loads in flight per lane (UW: a kernel with registers to spare asks for more; the
+    // order of a lane's additions does not depend on it)
+    constexpr int U = UW > 0 ? UW : (R <= 2 ? 16 : 8);
     for (int base = 0; base < d; base += 32 * U) {
         float v[R][U];
 #pragma unroll
@@ -288,12 +290,12 @@ __device__ __forceinline__ void exchange_merge(const Exchange& x, long long qi, 
 // has a smaller scan key.  Canonical re-score, ranking, output (final / shard partial / peer stores + fused merge), margin
 // and certification.  Called by every thread of the CTA; `scratch` holds at least max(world * k * 24 + 8, 0) bytes that
 // no longer hold anything needed (the exchange merge ranks the gathered partials there).
-template <int MAXR = 4>  // candidates a warp re-scores at a time at most (kernels held to 64 registers pass 2)
+template <int MAXR = 4, int UW = 0>  // candidates a warp re-scores at a time at most (kernels held to 64 registers pass 2)
 __device__ __forceinline__ void finalize_rank_emit(const FinalizeParams& p, long long qi, const u64* A, FinalizeShared* sh, double* sc,
-                                                   long long* id, u64* ok, const double* qs, unsigned char* scratch) {
+                                                   long long* id, u64* ok, const double* qs, unsigned char* scratch, int kp_use = 0) {
     const int t = threadIdx.x, nt = blockDim.x;
     const int warp = t >> 5, lane = t & 31, nwarps = nt >> 5;
-    const int kp = p.kp;
+    const int kp = kp_use > 0 ? kp_use : p.kp;  // kp_use: only the best kp_use (<= p.kp) entries of A are candidates
     // 4. canonical re-score of the kp candidates: a warp takes two candidates at a time, or four when the CTA has fewer than
     //    kp / 2 warps (the 256-thread CTA of the single-query scan: two rounds instead of four)
     const float* xb32 = reinterpret_cast<const float*>(p.xb);
@@ -312,7 +314,7 @@ __device__ __forceinline__ void finalize_rank_emit(const FinalizeParams& p, long
                 row[r] = key[r] ? (long long)key_row(key[r]) : -1;
                 xr[r] = (key[r] && !p.xb_is_bf16) ? xb32 + (size_t)row[r] * p.d : nullptr;
             }
-            canon32_dot_multi<R, FAST>(xr, qs, p.d, lane, sv);
+            canon32_dot_multi<R, FAST, UW>(xr, qs, p.d, lane, sv);
             if (p.xb_is_bf16) {
                 const __nv_bfloat16* xb16 = reinterpret_cast<const __nv_bfloat16*>(p.xb);
 #pragma unroll

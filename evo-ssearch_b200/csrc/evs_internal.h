@@ -36,6 +36,10 @@ struct ScanTuning {
                                // data whose near-duplicates would make the tf32 guard re-run most queries
     int x3_max_nq = 16;
     int guard = 1;             // certify fp32-storage batch results on the device and re-run uncertified queries exactly
+    int small_max_rows = 32768;  // single-query searches of shards up to this many rows take scan_small_kernel (evs_scan.cuh: keys
+                                 // stored by row, threshold from 128 chunk maxima; 10k x 512: 27 -> ~20 us); 0 = never
+    int small_fast_cap = 2048;   // ... whose last CTA takes the register fast path up to this many keys above the threshold (tests
+                                 // lower it to drive the general path)
 };
 
 struct ScanPlan {
@@ -126,6 +130,7 @@ struct ScanArgs {
     // direct variant only (all optional):
     const FinalizeParams* fuse = nullptr;  // single-query launch: the last CTA finalises the query (needs `ticket` or `pool`)
     unsigned* ticket = nullptr;
+    int small_fast_cap = 0;                // > 0 (with `pool`): the small-shard kernel (scan_small_kernel), fast path up to this many keys
     unsigned long long* pool = nullptr;    // kp = 64: pool selection (slot maxima, counters, survivor pool of pool_words(grid) words)
     unsigned* next_chunk = nullptr;        // dynamic row dealing (with `ticket` only: the last CTA resets the counter)
     int chunk_groups = 0;
@@ -222,6 +227,7 @@ cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int 
                       ScanPlan* plan);
 int max_queries_per_pass(int d, int is_bf16);
 cudaError_t launch_scan(const ScanArgs& a, ScanPlan* plan, cudaStream_t st);
+size_t scan_pool_key_slots(size_t pool_words);  // key slots behind the header of a pool of that many words
 size_t scan_pool_words(const ScanPlan& plan);  // u64 words of the pool a fused single-query launch of this plan needs (zeroed once)
 cudaError_t launch_finalize(const FinalizeParams& p, long long nq, cudaStream_t st);
 size_t finalize_smem_bytes_host(int L, int kp, int d);

@@ -676,6 +676,7 @@ cudaError_t plan_scan(long long n, int d, int is_bf16, int kp, int nq_pass, int 
     return cudaSuccess;
 }
 
+size_t scan_pool_key_slots(size_t pool_words) { return pool_words > (size_t)POOL_HDR ? pool_words - (size_t)POOL_HDR : 0; }
 size_t scan_pool_words(const ScanPlan& plan) { return (size_t)POOL_HDR + (size_t)plan.grid * (plan.threads / 32) * 128; }
 
 cudaError_t launch_scan(const ScanArgs& a, ScanPlan* plan, cudaStream_t st) {

@@ -756,6 +756,310 @@ __global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kerne
     if (p.cta_clock && t == 0) p.cta_clock[2 * gridDim.x + 1] = globaltimer_ns();
 }
 
+// ns survivors in surv[0 .. ns), ns <= POOL_SURV: returns the KP best in descending order (0 = empty) -- in the KP slots behind
+// the buffer (counting rank; more than 3 KP survivors are first cut by 2 KP strided chunk maxima) or, for more than
+// POOL_SURV / 2 survivors, at the front of the sorted buffer.  Starts the candidates' rows on their way to L2.  Called by all
+// 256 threads; cmax = 2 KP scratch words; *s_ns / *s_tau = shared scratch.
+__device__ __forceinline__ const u64* pool_rank_survivors(const FinalizeParams& f, u64* surv, int ns, int* s_ns, u64* s_tau, u64* cmax) {
+    constexpr int KP = 64;
+    const int t = threadIdx.x, nt = blockDim.x;
+    if (ns <= POOL_SURV / 2) {
+        const u64* src = surv;
+        int nsrc = ns;
+        if (ns > 3 * KP) {
+            if (t < 2 * KP) {
+                u64 mx = 0ull;
+                for (int i = t; i < ns; i += 2 * KP) mx = umax64(mx, surv[i]);
+                cmax[t] = mx;
+            }
+            if (t == 0) *s_ns = 0;
+            __syncthreads();
+            if (t < 2 * KP) {
+                const u64 mine = cmax[t];
+                int r = 0;
+                for (int j = 0; j < 2 * KP; j++) r += cmax[j] > mine ? 1 : 0;
+                if (r == KP - 1) *s_tau = mine;  // keys are unique and every chunk is non-empty: exactly one chunk has this rank
+            }
+            __syncthreads();
+            const u64 T = *s_tau;
+            u64* dst = surv + POOL_SURV / 2;
+            for (int i = t; i < ns; i += nt) {
+                const u64 key = surv[i];
+                if (key >= T) dst[atomicAdd(s_ns, 1)] = key;
+            }
+            __syncthreads();
+            src = dst;
+            nsrc = *s_ns;
+        }
+        if (!f.xb_is_bf16 && nsrc <= 4 * KP) {
+            const int lines = (f.d * 4 + 127) / 128;
+            for (int i = t; i < nsrc * lines; i += nt) {
+                const char* row = reinterpret_cast<const char*>(f.xb) + (size_t)key_row(src[i / lines]) * f.d * 4 + (size_t)(i % lines) * 128;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+            }
+        }
+        u64* top = surv + POOL_SURV;  // KP slots behind the buffer
+        for (int i = t; i < KP; i += nt) top[i] = 0ull;
+        __syncthreads();
+        for (int i = t; i < nsrc; i += nt) {
+            const u64 key = src[i];
+            int r = 0;
+            for (int j = 0; j < nsrc; j++) r += src[j] > key ? 1 : 0;
+            if (r < KP) top[r] = key;
+        }
+        __syncthreads();
+        return top;
+    }
+    for (int i = ns + t; i < POOL_SURV; i += nt) surv[i] = 0ull;
+    for (int size = 2; size <= POOL_SURV; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int e = t; e < (POOL_SURV >> 1); e += nt) {
+                const int i = bitonic_low(e, stride);
+                cmpx_desc(surv, i, i + stride, (i & size) == 0);
+            }
+        }
+    __syncthreads();
+    return surv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variant 1s: the single-query search of a SMALL shard in one launch (n <= SMALL_MAX_ROWS: the 10k-row indexes the
+// application really holds -- BASELINE config 1, /root/reference/oldapp.py:2005 with MAX_RESULTS <= 48).
+//
+// Such a shard is L2-resident and the scan loop is over after ~3 us; what the search costs is the chain of dependent
+// memory round trips behind it.  With the pool selection above no warp of a small shard ever fills a buffer, so the slot
+// maxima stay empty, EVERY key goes to the pool (a counter reservation per CTA) and the last CTA streams them all in
+// rounds of 1024 (scripts/scan_tail_probe.py at 10k rows: 2.4 + 2.2 us from the end of the loop to the ticket, 6.9 us for
+// the pool read).  Here instead
+//   * a warp stores the key of row r straight to S[r] (fire and forget, inside the loop) and raises the maximum of its
+//     CHUNK (warp index mod 128) with one reduction at the end: no buffer, no tau_g read, no reservation;
+//   * the chunks partition the rows, so T = the 64th largest of the 128 chunk maxima has at least 64 keys >= it: it is a
+//     lower bound of the 64th best key, and on unordered data ~90 keys pass it;
+//   * the last CTA has its first 40 keys per thread (10 240 rows) in flight before it knows T, counts the keys >= T in
+//     registers and appends them in one step.  More than 2048 of them (ordered / tied data) -> the general rounds with
+//     sort-and-cut, from global memory.
+// The tail (ranking, canonical re-score, certification, output, fused exchange merge) is the pool kernel's.
+// pool layout: chunk maxima M[c] at word 8 c, c < 128 (the pool kernel's 64 slots are the even ones; both kernels leave the
+// header zeroed) | [1040] ticket | [1056, 1056 + n) S
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_CHUNKS = 2 * 64;    // chunk maxima (2 KP)
+constexpr int SMALL_MSTRIDE = 8;        // u64 words between them (64 bytes)
+constexpr int SMALL_PF = 40;            // keys per thread of the last CTA in flight at once (256 threads: 10 240 rows)
+static_assert(SMALL_CHUNKS * SMALL_MSTRIDE <= POOL_COUNT, "chunk maxima overlap the pool counters");
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256, 2) scan_small_kernel(ScanParams p, FinalizeParams f, u64* pool, int fast_cap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_last, s_ns, s_cnt;
+    __shared__ u64 s_tau;
+    typedef typename RawVec<T>::type raw_t;
+    constexpr int QREGS = NV * Elem<T>::VEC;
+    constexpr int RPG_RAW = (100 - QREGS) / (NV * 4);
+    constexpr int RPG = RPG_RAW < 1 ? 1 : (RPG_RAW > 4 ? 4 : RPG_RAW);
+    constexpr int KP = 64;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    u64* M = pool;
+    unsigned* ticket = reinterpret_cast<unsigned*>(pool + POOL_TICKET);
+    u64* S = pool + POOL_HDR;
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // the query may be the preceding kernel's output
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next search's prologue may overlap our tail
+    unsigned long long t_start = 0, t_loop = 0;
+    if (p.cta_clock && threadIdx.x == 0) t_start = globaltimer_ns();
+
+    const long long total_warps = (long long)gridDim.x * nwarps;
+    const long long gw = (long long)blockIdx.x * nwarps + warp;
+    const long long ngroups = (p.n + RPG - 1) / RPG;
+    const size_t row_vecs = (size_t)p.d / Elem<T>::VEC;
+    const raw_t* base = reinterpret_cast<const raw_t*>(p.xb);
+    QueryRegs<T, 1, NV> q;
+    q.load(p.xq, p.q0, p.d, lane);
+    // shared memory as in the pool kernel: FinalizeShared | surv | sc | id | ok | qs (the query in fp64, widened by every CTA now)
+    size_t surv_bytes = (size_t)(POOL_SURV + KP) * 8;
+    {
+        const size_t merge = (size_t)f.x.world * f.k * 24 + 8;
+        if (merge > surv_bytes) surv_bytes = (merge + 7) & ~(size_t)7;
+    }
+    double* qs = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) + surv_bytes + 3 * (size_t)KP * 8);
+    {
+        const float* qf = p.xq + (size_t)p.q0 * p.d;
+        for (int i = threadIdx.x; i < p.d; i += blockDim.x) qs[i] = (double)qf[i];
+    }
+
+    u64 wmax = 0ull;  // warp-uniform
+    for (long long g = gw; g < ngroups; g += total_warps) {
+        const long long r0 = g * RPG;
+        raw_t raw[RPG][NV];
+#pragma unroll
+        for (int r = 0; r < RPG; r++) {
+            long long row = r0 + r < p.n ? r0 + r : p.n - 1;  // clamp: tail rows are re-read, not stored
+            const raw_t* src = base + (size_t)row * row_vecs + lane;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                if constexpr (sizeof(T) == 4) raw[r][j] = ldg_stream_f4(src + 32 * j);
+                else raw[r][j] = ldg_stream_u4(src + 32 * j);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RPG; r++) {
+            float s[1];
+            row_scores<T, 1, NV>(raw[r], q, s);
+            if (r0 + r < p.n) {
+                const u64 key = make_key(s[0], (uint32_t)(r0 + r));  // warp-uniform; 0 for a NaN score: never a candidate
+                if (lane == r) S[r0 + r] = key;
+                wmax = umax64(wmax, key);
+            }
+        }
+    }
+    if (lane == 0 && wmax != 0ull)
+        atomicMax(reinterpret_cast<unsigned long long*>(M + (size_t)(gw & (SMALL_CHUNKS - 1)) * SMALL_MSTRIDE), (unsigned long long)wmax);
+    if (p.cta_clock && threadIdx.x == 0) {
+        t_loop = globaltimer_ns();
+        p.cta_clock[2 * blockIdx.x] = t_start;
+        p.cta_clock[2 * blockIdx.x + 1] = t_loop;
+    }
+
+    __threadfence();  // this thread's key stores / chunk maximum are visible device-wide before the CTA takes its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;  // CTA-uniform
+
+    // ---------------- the last CTA: every row's key is in S, every chunk's maximum in M ----------------
+    __threadfence();
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int m = (int)p.n;
+    FinalizeShared* sh = reinterpret_cast<FinalizeShared*>(smem_raw);
+    u64* surv = reinterpret_cast<u64*>(smem_raw + sizeof(FinalizeShared));  // [POOL_SURV + KP] (or the merge scratch, if larger)
+    double* sc = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) + surv_bytes);
+    long long* id = reinterpret_cast<long long*>(sc + KP);
+    u64* ok = reinterpret_cast<u64*>(id + KP);  // qs follows
+    if (p.cta_clock && t == 0) {
+        unsigned long long* x = p.cta_clock + 2 * gridDim.x;
+        x[0] = globaltimer_ns();  // this (the last) CTA holds its ticket
+        x[2] = t_loop;
+        x[3] = t_loop;
+        x[4] = t_loop;
+    }
+    // one round of loads: the first SMALL_PF keys of every thread and the chunk maxima
+    u64 kreg[SMALL_PF];
+#pragma unroll
+    for (int u = 0; u < SMALL_PF; u++) {
+        const int i = t + 256 * u;  // blockDim.x = 256
+        kreg[u] = i < m ? __ldcg(S + i) : 0ull;
+    }
+    u64* cmax = reinterpret_cast<u64*>(sc);  // 2 KP words: sc | id are free until the re-score
+    if (t < SMALL_CHUNKS) cmax[t] = __ldcg(M + (size_t)t * SMALL_MSTRIDE);
+    if (t == 0) {
+        s_ns = 0;
+        s_cnt = 0;
+        s_tau = 0ull;
+        sh->nsurv = 0;
+        sh->nvalid = 0;
+        sh->maxerr = 0u;
+        sh->ndeep = 0;
+        sh->T0 = 0ull;
+        sh->qnorm2 = 0.0;
+        sh->fail = 0;
+        sh->uncert = 0;
+    }
+    __syncthreads();
+    if (f.err_coef > 0.f && warp == nwarps - 1) {  // |q|^2 for the certification bound (a warp that ranks no chunk maximum)
+        double s2 = 0.0;
+        for (int i = lane; i < f.d; i += 32) s2 = fma(qs[i], qs[i], s2);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        if (lane == 0) sh->qnorm2 = s2;
+    }
+    // T = the KP-th largest chunk maximum (non-empty maxima are unique: exactly one has KP - 1 larger ones; fewer than KP
+    // non-empty chunks -> T stays 0 and every key is kept)
+    if (t < SMALL_CHUNKS) {
+        const u64 v = cmax[t];
+        int r = 0;
+        for (int j = 0; j < SMALL_CHUNKS; j++) r += cmax[j] > v ? 1 : 0;
+        if (v != 0ull && r == KP - 1) s_tau = v;
+    }
+    __syncthreads();
+    const u64 thr = s_tau;
+    // reset the pool header for the next search of this handle (its CTAs touch it only after this kernel has completed)
+    if (t < SMALL_CHUNKS) M[(size_t)t * SMALL_MSTRIDE] = 0ull;
+    if (t == 0) *ticket = 0u;
+    fin_stamp(f, 0);  // chunk maxima ranked
+    // fast path: count the keys >= T batch by batch in registers, append them in one step per batch
+    bool slow = false;
+    for (int b0 = 0; b0 < m; b0 += SMALL_PF * 256) {  // CTA-uniform
+        if (b0 > 0) {
+#pragma unroll
+            for (int u = 0; u < SMALL_PF; u++) {
+                const int i = b0 + t + 256 * u;
+                kreg[u] = i < m ? __ldcg(S + i) : 0ull;
+            }
+        }
+        int c = 0;
+#pragma unroll
+        for (int u = 0; u < SMALL_PF; u++) c += (kreg[u] != 0ull && kreg[u] >= thr) ? 1 : 0;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if (lane == 0 && c) atomicAdd(&s_cnt, c);
+        __syncthreads();
+        if (s_cnt > fast_cap) {  // CTA-uniform: would not fit the survivor buffer
+            slow = true;
+            break;
+        }
+#pragma unroll
+        for (int u = 0; u < SMALL_PF; u++)
+            if (kreg[u] != 0ull && kreg[u] >= thr) surv[atomicAdd(&s_ns, 1)] = kreg[u];
+        __syncthreads();  // every thread has read s_cnt before the next batch adds to it
+    }
+    __syncthreads();
+    if (slow) {
+        // ordered or tied data: the keys once more from global memory in rounds of POOL_SURV / 2; when more than half of the
+        // buffer is taken it is sorted, cut to the best KP and the threshold rises to the KP-th best (no overflow)
+        if (t == 0) s_ns = 0;
+        __syncthreads();
+        u64 th2 = thr;
+        for (int b0 = 0; b0 < m; b0 += POOL_SURV / 2) {
+#pragma unroll
+            for (int u = 0; u < POOL_SURV / 2 / 256; u++) {
+                const int i = b0 + t + 256 * u;
+                const u64 key = i < m ? __ldcg(S + i) : 0ull;
+                if (key != 0ull && key >= th2) surv[atomicAdd(&s_ns, 1)] = key;
+            }
+            __syncthreads();
+            const int ns0 = s_ns;
+            __syncthreads();  // ... read by every thread before the next round adds to it
+            if (ns0 > POOL_SURV / 2 && b0 + POOL_SURV / 2 < m) {  // CTA-uniform
+                for (int i = ns0 + t; i < POOL_SURV; i += nt) surv[i] = 0ull;
+                for (int size = 2; size <= POOL_SURV; size <<= 1)
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        __syncthreads();
+                        for (int e = t; e < (POOL_SURV >> 1); e += nt) {
+                            const int i = bitonic_low(e, stride);
+                            cmpx_desc(surv, i, i + stride, (i & size) == 0);
+                        }
+                    }
+                __syncthreads();
+                if (surv[KP - 1] > th2) th2 = surv[KP - 1];
+                __syncthreads();
+                if (t == 0) s_ns = KP;
+                __syncthreads();
+            }
+        }
+    }
+    const int ns = s_ns;
+    __syncthreads();  // s_ns is reused as a counter below
+    fin_stamp(f, 1);  // survivors in shared memory
+    const u64* A = pool_rank_survivors(f, surv, ns, &s_ns, &s_tau, reinterpret_cast<u64*>(sc));
+    fin_stamp(f, 2);  // the KP best ranked
+    // k <= 16 (the application's default page of results): the canonical re-score takes the best 32 candidates -- one round of
+    // four rows per warp instead of two; every row outside them has a scan key below A[31], which is what the certification
+    // of finalize_rank_emit compares against
+    finalize_rank_emit<4, 16>(f, p.q0, A, sh, sc, id, ok, qs, reinterpret_cast<unsigned char*>(surv), f.k <= KP / 4 ? KP / 2 : KP);
+    if (p.cta_clock && t == 0) p.cta_clock[2 * gridDim.x + 1] = globaltimer_ns();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Variant 2: bulk-async ring.  block = 32 * (consumer warps + 1) <= 288; the LAST warp is the producer.
 // dynamic smem layout (bytes):

@@ -68,6 +68,17 @@ static cudaError_t launch_scan_t(const ScanArgs& a, ScanPlan* plan, cudaStream_t
             const size_t fs = pool_finalize_smem_bytes(64, f.d, f.x.world * f.k);
             smem = (size_t)(plan->threads / 32) * 128 * 8;
             if (fs > smem) smem = fs;
+            if (a.small_fast_cap > 0) {  // small shard: keys by row, threshold from the chunk maxima (no buffers: only the finalise area)
+                auto sk = scan_small_kernel<T, NV>;
+                static size_t optin_s[16] = {};
+                cudaError_t se = ensure_smem_optin(sk, fs, optin_s);
+                if (se != cudaSuccess) return se;
+                const int cap = a.small_fast_cap < POOL_SURV ? a.small_fast_cap : POOL_SURV;
+                se = launch_pdl(sk, dim3((unsigned)plan->grid), dim3((unsigned)plan->threads), fs, st, p, f, reinterpret_cast<u64*>(a.pool), cap);
+                g_kernel_launches.fetch_add(1);
+                if (se != cudaSuccess) return se;
+                return cudaGetLastError();
+            }
             auto pk = scan_pool_kernel<T, NV>;
             static size_t optin_p[16] = {};
             cudaError_t oe = ensure_smem_optin(pk, smem, optin_p);

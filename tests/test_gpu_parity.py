@@ -36,6 +36,8 @@ def _reset_options():
     evs.set_option("pool_select", 1)
     evs.set_option("scan_dynamic", 1)
     evs.set_option("scan_chunk_groups", 4)
+    evs.set_option("small_max_rows", 32768)
+    evs.set_option("small_fast_cap", 2048)
 
 
 def _index(xb, storage="f32", variant=0):
@@ -389,6 +391,63 @@ def test_pool_selection_does_not_depend_on_the_data(storage):
                 assert np.array_equal(I0, Ir[:1]) and np.array_equal(D0, Dr[:1]), (n, name, kk)
             m = idx.last_margins(1)
             assert m[0] >= 0 or n <= 100
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_small_shard_kernel_equals_the_oracle_and_the_pool_kernel(storage):
+    """Shards of up to 32 768 rows -- the application's indexes (BASELINE config 1: 10k rows, oldapp.py:2005) -- take
+    scan_small_kernel: every row's key stored by row, the threshold from 128 chunk maxima, the last CTA's keys in
+    registers.  Its worst cases: more keys above the threshold than the survivor buffer holds (rows in score order, every
+    row the same vector: exact ties; `small_fast_cap` 1 drives the general rounds on ordinary data too), fewer rows than
+    chunks, a row count just past one register batch (10 240) and at the routing limit.  Always one launch, the oracle's
+    bits, the pool kernel's bits, and a pool left clean for the next search whichever kernel runs it."""
+    d = 512
+    q = oracle.synth_fill(3, d, 7)
+    for n in (1, 5, 64, 129, 1000, 10_000, 10_241, 20_000, 32_768, 32_769):
+        xb = oracle.synth_fill(n, d, 21)
+        order = np.argsort(xb @ q[0])
+        cases = {"random": xb}
+        if n in (129, 10_000, 20_000):
+            cases["ascending"] = xb[order]
+            cases["descending"] = xb[order[::-1]]
+            cases["all rows equal"] = np.repeat(xb[:1], n, axis=0)
+            blocks = xb.copy()  # long runs of identical high rows: thousands of exact ties above any chunk threshold
+            blocks[: n // 2] = xb[order[-1]]
+            cases["half the rows tied at the top"] = blocks
+        for name, x in cases.items():
+            x = np.ascontiguousarray(x)
+            idx = evs.IndexFlatIP(d, storage=storage)
+            idx.add(x)
+            for kk in (12, 48, 1):
+                Dr, Ir = oracle.canon_search(q, x, kk)
+                for cap in (2048, 1):
+                    evs.set_option("small_fast_cap", cap)
+                    for rep in range(2):
+                        for qi in range(3):
+                            l0 = evs.kernel_launches()
+                            D, I = idx.search(q[qi:qi + 1], kk)
+                            assert evs.kernel_launches() - l0 == 1
+                            assert np.array_equal(I, Ir[qi:qi + 1]) and np.array_equal(D, Dr[qi:qi + 1]), (n, name, kk, cap, rep, qi)
+                evs.set_option("small_fast_cap", 2048)
+                evs.set_option("small_max_rows", 0)  # the pool kernel on the same handle, then the small kernel again
+                D0, I0 = idx.search(q[:1], kk)
+                evs.set_option("small_max_rows", 32768)
+                D1, I1 = idx.search(q[:1], kk)
+                assert np.array_equal(I0, Ir[:1]) and np.array_equal(D0, Dr[:1]), (n, name, kk)
+                assert np.array_equal(I1, Ir[:1]) and np.array_equal(D1, Dr[:1]), (n, name, kk)
+    # NaN scores never enter (key 0), zero rows tie at 0: the contract of test_zero_and_nan_rows at 3000 rows
+    x = oracle.synth_fill(3000, d, 5)
+    x[7] = np.nan
+    x[100:2000] = 0.0
+    idx = evs.IndexFlatIP(d, storage=storage)
+    idx.add(x)
+    ok = np.ones(3000, bool)
+    ok[7] = False
+    remap = np.nonzero(ok)[0]
+    Dr, Ir = oracle.canon_search(q, x[ok], 48)
+    for qi in range(3):
+        D, I = idx.search(q[qi:qi + 1], 48)
+        assert np.array_equal(I[0], remap[Ir[qi]]) and np.array_equal(D[0], Dr[qi])
 
 
 def test_back_to_back_device_searches_overlap_safely():
