@@ -247,6 +247,9 @@ EVS_API int evs_f32_to_bf16_dev(int device, const float* src_dev, void* dst_dev,
  *                 "tc_inline_pre" (default 1): batches on the one-CTA tensor-core kernel over shards of up to ~2.4M rows take
  *                 their thresholds from one sampled tile per CTA inside the scan launch (two grid barriers) instead of a
  *                 pre-pass launch and a threshold launch;
+ *                 "small_max_rows" (default 32768; 0 = never): single-query searches (k <= 48) of shards up to this many rows take
+ *                 the small-shard kernel (keys stored by row, threshold from 128 chunk maxima: 10k x 512 in 16 us instead of 27);
+ *                 "small_fast_cap" (default 2048, tests lower it): its register fast path up to this many keys above the threshold;
  *                 "io_threads" (default 0 = auto: one per hardware thread, at most 16): threads that pread each 64 MiB chunk of
  *                 index.faiss into the pinned staging buffers (evs_index_read[_rows]; 6.5 GB/s with 1, 35 GB/s with 16);
  *                 "exchange_fail_next" (tests): the next exchange-mode search of this process fails after taking its
