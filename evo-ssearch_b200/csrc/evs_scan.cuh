@@ -836,8 +836,8 @@ __device__ __forceinline__ const u64* pool_rank_survivors(const FinalizeParams& 
 //     CHUNK (warp index mod 128) with one reduction at the end: no buffer, no tau_g read, no reservation;
 //   * the chunks partition the rows, so T = the 64th largest of the 128 chunk maxima has at least 64 keys >= it: it is a
 //     lower bound of the 64th best key, and on unordered data ~90 keys pass it;
-//   * the last CTA has its first 40 keys per thread (10 240 rows) in flight before it knows T, counts the keys >= T in
-//     registers and appends them in one step.  More than 2048 of them (ordered / tied data) -> the general rounds with
+//   * the last CTA has its first 40 keys per thread (10 240 rows) in flight before it knows T and appends the keys >= T
+//     from the registers to the survivor buffer.  More than 2048 of them (ordered / tied data) -> the general rounds with
 //     sort-and-cut, from global memory.
 // The tail (ranking, canonical re-score, certification, output, fused exchange merge) is the pool kernel's.
 // pool layout: chunk maxima M[c] at word 8 c, c < 128 (the pool kernel's 64 slots are the even ones; both kernels leave the
@@ -851,7 +851,7 @@ static_assert(SMALL_CHUNKS * SMALL_MSTRIDE <= POOL_COUNT, "chunk maxima overlap 
 template <typename T, int NV>
 __global__ void __launch_bounds__(256, 2) scan_small_kernel(ScanParams p, FinalizeParams f, u64* pool, int fast_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int s_last, s_ns, s_cnt;
+    __shared__ int s_last, s_ns;
     __shared__ u64 s_tau;
     typedef typename RawVec<T>::type raw_t;
     constexpr int QREGS = NV * Elem<T>::VEC;
@@ -954,7 +954,6 @@ __global__ void __launch_bounds__(256, 2) scan_small_kernel(ScanParams p, Finali
     if (t < SMALL_CHUNKS) cmax[t] = __ldcg(M + (size_t)t * SMALL_MSTRIDE);
     if (t == 0) {
         s_ns = 0;
-        s_cnt = 0;
         s_tau = 0ull;
         sh->nsurv = 0;
         sh->nvalid = 0;
@@ -987,8 +986,8 @@ __global__ void __launch_bounds__(256, 2) scan_small_kernel(ScanParams p, Finali
     if (t < SMALL_CHUNKS) M[(size_t)t * SMALL_MSTRIDE] = 0ull;
     if (t == 0) *ticket = 0u;
     fin_stamp(f, 0);  // chunk maxima ranked
-    // fast path: count the keys >= T batch by batch in registers, append them in one step per batch
-    bool slow = false;
+    // fast path: the keys >= T go from the registers straight into the survivor buffer, batch by batch with no barrier in
+    // between; an append past `fast_cap` is dropped and sends the CTA to the general path afterwards
     for (int b0 = 0; b0 < m; b0 += SMALL_PF * 256) {  // CTA-uniform
         if (b0 > 0) {
 #pragma unroll
@@ -997,23 +996,16 @@ __global__ void __launch_bounds__(256, 2) scan_small_kernel(ScanParams p, Finali
                 kreg[u] = i < m ? __ldcg(S + i) : 0ull;
             }
         }
-        int c = 0;
-#pragma unroll
-        for (int u = 0; u < SMALL_PF; u++) c += (kreg[u] != 0ull && kreg[u] >= thr) ? 1 : 0;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-        if (lane == 0 && c) atomicAdd(&s_cnt, c);
-        __syncthreads();
-        if (s_cnt > fast_cap) {  // CTA-uniform: would not fit the survivor buffer
-            slow = true;
-            break;
-        }
 #pragma unroll
         for (int u = 0; u < SMALL_PF; u++)
-            if (kreg[u] != 0ull && kreg[u] >= thr) surv[atomicAdd(&s_ns, 1)] = kreg[u];
-        __syncthreads();  // every thread has read s_cnt before the next batch adds to it
+            if (kreg[u] != 0ull && kreg[u] >= thr) {
+                const int pos = atomicAdd(&s_ns, 1);
+                if (pos < fast_cap) surv[pos] = kreg[u];
+            }
     }
     __syncthreads();
+    const bool slow = s_ns > fast_cap;  // CTA-uniform: more keys above T than the fast path takes (ordered rows, exact ties)
+    __syncthreads();                    // ... read by every thread before the general path resets the counter
     if (slow) {
         // ordered or tied data: the keys once more from global memory in rounds of POOL_SURV / 2; when more than half of the
         // buffer is taken it is sorted, cut to the best KP and the threshold rises to the KP-th best (no overflow)
