@@ -106,6 +106,9 @@ struct evs_index {
     int64_t* I_pin_dev = nullptr;     // device address of the (mapped) pinned result buffer: the one-launch single-query search
                                       // writes (D, I) straight into host memory -- no device-to-host copy on the latency path
     float* m_pin = nullptr;  size_t m_pin_cap = 0;     // margins of the last host search (tf32 guard)
+    unsigned* done_pin = nullptr;     // host-mapped word the small-shard kernel raises behind its results (polled by evs_index_search)
+    unsigned* done_pin_dev = nullptr;
+    unsigned done_seq = 0;
 };
 
 static int use_device(int device) {
@@ -332,6 +335,7 @@ extern "C" int evs_index_free(evs_index* idx) {
     cudaFreeHost(idx->q_pin);
     cudaFreeHost(idx->I_pin);  // D_pin points into the same allocation
     cudaFreeHost(idx->m_pin);
+    cudaFreeHost(idx->done_pin);
     for (auto& pe : idx->prof_events) {
         cudaEventDestroy(pe.first);
         cudaEventDestroy(pe.second);
@@ -537,6 +541,11 @@ struct SearchOut {
     double* P_scores = nullptr;  // partial mode
     int64_t* P_ids = nullptr;
     const Exchange* x = nullptr;  // exchange mode: the finalise kernel stores the partial into every rank's slot
+    // host single-query search of a small shard (evs_index_search; the caller checked small_shard_applies): the query travels in
+    // the kernel's parameter block and the kernel raises *done_flag = done_seq behind the results
+    const float* q_host = nullptr;
+    unsigned* done_flag = nullptr;
+    unsigned done_seq = 0;
 };
 
 // Which scan serves a batch.  Decided ONCE per search from one snapshot of the tuning options and passed down, so that the
@@ -723,6 +732,12 @@ struct ProfileScope {  // optional CUDA event pair around the scan launches of o
         return EVS_OK;
     }
 };
+
+// one query over a shard of up to small_max_rows rows (k <= 48, fused pool selection): scan_small_kernel (evs_scan.cuh)
+static bool small_shard_applies(const evs_index* idx, const ScanTuning& tune, int kp, const ScanPlan& plan) {
+    return tune.pool_select && kp == 64 && tune.small_max_rows > 0 && idx->ntotal > 0 && idx->ntotal <= tune.small_max_rows &&
+           plan.variant == 1 && plan.threads == 256 && (size_t)idx->ntotal <= scan_pool_key_slots(scan_pool_words(plan));
+}
 
 static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev, int64_t k, const SearchOut& out, cudaStream_t st,
                                  const ScanTuning& tune, const PathInfo& pi, bool scan_only = false, int kp_override = 0);
@@ -1066,10 +1081,17 @@ static int search_enqueue_locked(evs_index* idx, int64_t nq, const float* q_dev,
                     }
                     a.pool = idx->pool;
                     // small shards (the application's 10k-row indexes): one key slot per row instead of the survivor pool
-                    if (tune.small_max_rows > 0 && idx->ntotal <= tune.small_max_rows && plan.threads == 256 &&
-                        (size_t)idx->ntotal <= scan_pool_key_slots(idx->pool_cap))
+                    if (small_shard_applies(idx, tune, kp, plan)) {
                         a.small_fast_cap = tune.small_fast_cap > 0 ? tune.small_fast_cap : 1;
+                        if (out.q_host != nullptr) {
+                            a.q_inline = out.q_host;
+                            f.done_flag = out.done_flag;
+                            f.done_seq = out.done_seq;
+                        }
+                    }
                 }
+                if (out.q_host != nullptr && a.q_inline == nullptr)
+                    return fail(EVS_ECUDA, "internal: the host search expected the small-shard kernel");
                 if (tune.scan_dynamic > 1 || (tune.scan_dynamic == 1 && a.pool != nullptr)) {
                     a.next_chunk = idx->words + W_NEXT_CHUNK;
                     a.chunk_groups = tune.scan_chunk_groups > 0 ? tune.scan_chunk_groups : 2;
@@ -1240,10 +1262,8 @@ extern "C" int evs_index_search(evs_index* idx, int64_t nq, const float* q_host,
     std::lock_guard<std::mutex> lk(idx->mu);
     if ((rc = use_device(idx->device))) return rc;
     if ((rc = host_stage_locked(idx, nq, k))) return rc;
-    memcpy(idx->q_pin, q_host, (size_t)nq * idx->d * sizeof(float));
     cudaStream_t st = idx->stream;
     if ((rc = ws_acquire(idx, st))) return rc;
-    CU(cudaMemcpyAsync(idx->q_dev, idx->q_pin, (size_t)nq * idx->d * sizeof(float), cudaMemcpyHostToDevice, st));
     SearchOut out;
     out.D = idx->D_dev;
     out.I = idx->I_dev;
@@ -1256,8 +1276,62 @@ extern "C" int evs_index_search(evs_index* idx, int64_t nq, const float* q_host,
         out.I = idx->I_pin_dev;
         out.D = reinterpret_cast<float*>(idx->I_pin_dev + (size_t)nq * k);
     }
+    // ... over a small shard (the application's index sizes): the query rides in the kernel's parameter block -- no staging
+    // copy, no host-to-device copy ahead of the launch -- and the kernel raises a host-mapped word behind the results, which is
+    // polled here instead of waiting for the stream to drain
+    bool inline_q = false;
+    if (direct && idx->d <= EVS_SMALL_QUERY_MAX_D) {
+        const bool bf16 = idx->storage == EVS_STORE_BF16_F32;
+        ScanPlan plan;
+        if (plan_scan(idx->ntotal, idx->d, bf16, pi.kp, max_queries_per_pass(idx->d, bf16), idx->sm_count, tune, &plan) == cudaSuccess &&
+            small_shard_applies(idx, tune, pi.kp, plan)) {
+            if (idx->done_pin == nullptr) {
+                void* hp = nullptr;
+                if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped) == cudaSuccess) {
+                    memset(hp, 0, 64);
+                    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&idx->done_pin_dev), hp, 0) == cudaSuccess) {
+                        idx->done_pin = reinterpret_cast<unsigned*>(hp);
+                    } else {
+                        cudaGetLastError();
+                        cudaFreeHost(hp);
+                    }
+                } else {
+                    cudaGetLastError();
+                }
+            }
+            inline_q = idx->done_pin != nullptr;
+        }
+    }
+    if (inline_q) {
+        if (++idx->done_seq == 0u) idx->done_seq = 1u;
+        out.q_host = q_host;
+        out.done_flag = idx->done_pin_dev;
+        out.done_seq = idx->done_seq;
+    } else {
+        memcpy(idx->q_pin, q_host, (size_t)nq * idx->d * sizeof(float));
+        CU(cudaMemcpyAsync(idx->q_dev, idx->q_pin, (size_t)nq * idx->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
     rc = search_dev_common(idx, nq, idx->q_dev, k, out, st, tune, pi);
-    if (!rc && direct) {
+    if (!rc && inline_q) {
+        // the flag arrives behind the results (system-scope fence in the kernel); a failed launch or kernel never raises it, so
+        // the stream is queried from time to time
+        const volatile unsigned* flag = idx->done_pin;
+        const unsigned want = idx->done_seq;
+        unsigned spins = 0;
+        while (*flag != want) {
+            if ((++spins & 1023u) == 0u) {
+                const cudaError_t qe = cudaStreamQuery(st);
+                if (qe == cudaSuccess) break;  // the stream has drained: the results are there (flag or not)
+                if (qe != cudaErrorNotReady) return fail(EVS_ECUDA, "search failed: %s", cudaGetErrorString(qe));
+            }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        memcpy(D_host, idx->D_pin, (size_t)nq * k * sizeof(float));
+        memcpy(I_host, idx->I_pin, (size_t)nq * k * sizeof(int64_t));
+    } else if (!rc && direct) {
         CU(cudaStreamSynchronize(st));
         memcpy(D_host, idx->D_pin, (size_t)nq * k * sizeof(float));
         memcpy(I_host, idx->I_pin, (size_t)nq * k * sizeof(int64_t));

@@ -8,6 +8,8 @@
 
 #include "../../include/evs.h"
 
+#define EVS_SMALL_QUERY_MAX_D 768  // a query of up to this many dimensions fits the 4 KB kernel parameter block beside the rest
+
 namespace evs {
 
 extern std::atomic<long long> g_kernel_launches;
@@ -115,6 +117,8 @@ struct FinalizeParams {
     unsigned long long* uncertified = nullptr;  // device counter: results that stayed uncertified
     unsigned long long* reruns = nullptr;       // device counter: queries finalised again from the exact re-run
     unsigned long long* dbg = nullptr;          // diagnostics (option "scan_clock"): %globaltimer stamps of the finalise's phases
+    unsigned* done_flag = nullptr;              // host-mapped word (scan_small_kernel with the query in its parameters): set to
+    unsigned done_seq = 0;                      //   done_seq behind the results, polled by evs_index_search
 };
 
 struct ScanArgs {
@@ -130,6 +134,7 @@ struct ScanArgs {
     // direct variant only (all optional):
     const FinalizeParams* fuse = nullptr;  // single-query launch: the last CTA finalises the query (needs `ticket` or `pool`)
     unsigned* ticket = nullptr;
+    const float* q_inline = nullptr;       // host pointer (small-shard kernel only): the query travels in the kernel parameters
     int small_fast_cap = 0;                // > 0 (with `pool`): the small-shard kernel (scan_small_kernel), fast path up to this many keys
     unsigned long long* pool = nullptr;    // kp = 64: pool selection (slot maxima, counters, survivor pool of pool_words(grid) words)
     unsigned* next_chunk = nullptr;        // dynamic row dealing (with `ticket` only: the last CTA resets the counter)

@@ -375,6 +375,11 @@ __host__ __device__ inline size_t pool_finalize_smem_bytes(int kp, int d, int wo
     return sizeof(FinalizeShared) + surv + (3 * (size_t)kp + (size_t)d) * 8 + 16;
 }
 
+// byte offset of the fp32 query copy of scan_small_kernel<.., QP = true> (behind the finalise area), 16-byte aligned
+__host__ __device__ inline size_t small_query_smem_offset(int kp, int d, int world_k) {
+    return (pool_finalize_smem_bytes(kp, d, world_k) + 15) & ~(size_t)15;
+}
+
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -848,8 +853,17 @@ constexpr int SMALL_MSTRIDE = 8;        // u64 words between them (64 bytes)
 constexpr int SMALL_PF = 40;            // keys per thread of the last CTA in flight at once (256 threads: 10 240 rows)
 static_assert(SMALL_CHUNKS * SMALL_MSTRIDE <= POOL_COUNT, "chunk maxima overlap the pool counters");
 
-template <typename T, int NV>
-__global__ void __launch_bounds__(256, 2) scan_small_kernel(ScanParams p, FinalizeParams f, u64* pool, int fast_cap) {
+// QP: the query travels in the kernel's parameter block (host searches, evs_index_search: no pinned staging copy, no
+// host-to-device copy ahead of the launch -- the 2-3 KB ride along with the launch itself) and the last CTA raises a
+// host-mapped flag behind the results, which the host polls instead of waiting for the stream to drain.
+struct SmallQuery { float v[EVS_SMALL_QUERY_MAX_D]; };
+struct NoQuery { int unused; };
+template <bool QP> struct SmallQueryArg { typedef NoQuery type; };
+template <> struct SmallQueryArg<true> { typedef SmallQuery type; };
+
+template <typename T, int NV, bool QP>
+__global__ void __launch_bounds__(256, 2) scan_small_kernel(ScanParams p, FinalizeParams f, u64* pool, int fast_cap,
+                                                            const __grid_constant__ typename SmallQueryArg<QP>::type qb) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_last, s_ns;
     __shared__ u64 s_tau;
@@ -875,15 +889,25 @@ __global__ void __launch_bounds__(256, 2) scan_small_kernel(ScanParams p, Finali
     const size_t row_vecs = (size_t)p.d / Elem<T>::VEC;
     const raw_t* base = reinterpret_cast<const raw_t*>(p.xb);
     QueryRegs<T, 1, NV> q;
-    q.load(p.xq, p.q0, p.d, lane);
     // shared memory as in the pool kernel: FinalizeShared | surv | sc | id | ok | qs (the query in fp64, widened by every CTA now)
+    // QP: | the fp32 query (16-byte aligned), copied out of the parameter block
     size_t surv_bytes = (size_t)(POOL_SURV + KP) * 8;
     {
         const size_t merge = (size_t)f.x.world * f.k * 24 + 8;
         if (merge > surv_bytes) surv_bytes = (merge + 7) & ~(size_t)7;
     }
     double* qs = reinterpret_cast<double*>(smem_raw + sizeof(FinalizeShared) + surv_bytes + 3 * (size_t)KP * 8);
-    {
+    if constexpr (QP) {
+        float* qsm = reinterpret_cast<float*>(smem_raw + small_query_smem_offset(KP, p.d, f.x.world * f.k));
+        for (int i = threadIdx.x; i < p.d; i += blockDim.x) {
+            const float v = qb.v[i];
+            qsm[i] = v;
+            qs[i] = (double)v;
+        }
+        __syncthreads();
+        q.load(qsm, 0, p.d, lane);
+    } else {
+        q.load(p.xq, p.q0, p.d, lane);
         const float* qf = p.xq + (size_t)p.q0 * p.d;
         for (int i = threadIdx.x; i < p.d; i += blockDim.x) qs[i] = (double)qf[i];
     }
@@ -1049,6 +1073,16 @@ __global__ void __launch_bounds__(256, 2) scan_small_kernel(ScanParams p, Finali
     // four rows per warp instead of two; every row outside them has a scan key below A[31], which is what the certification
     // of finalize_rank_emit compares against
     finalize_rank_emit<4, 16>(f, p.q0, A, sh, sc, id, ok, qs, reinterpret_cast<unsigned char*>(surv), f.k <= KP / 4 ? KP / 2 : KP);
+    if constexpr (QP) {
+        // the results (host-mapped memory) are complete: tell the host, which polls this word
+        if (f.done_flag != nullptr) {
+            __syncthreads();
+            if (t == 0) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned*>(f.done_flag) = f.done_seq;
+            }
+        }
+    }
     if (p.cta_clock && t == 0) p.cta_clock[2 * gridDim.x + 1] = globaltimer_ns();
 }
 

@@ -2,6 +2,8 @@
 // instantiate them.  The kernels are split over several .cu files by element type and row width only to keep the build
 // short (one file with every instantiation took four minutes of the five-minute clean build).
 #pragma once
+#include <string.h>
+
 #include "evs_internal.h"
 #include "evs_scan.cuh"
 
@@ -69,12 +71,25 @@ static cudaError_t launch_scan_t(const ScanArgs& a, ScanPlan* plan, cudaStream_t
             smem = (size_t)(plan->threads / 32) * 128 * 8;
             if (fs > smem) smem = fs;
             if (a.small_fast_cap > 0) {  // small shard: keys by row, threshold from the chunk maxima (no buffers: only the finalise area)
-                auto sk = scan_small_kernel<T, NV>;
-                static size_t optin_s[16] = {};
-                cudaError_t se = ensure_smem_optin(sk, fs, optin_s);
-                if (se != cudaSuccess) return se;
                 const int cap = a.small_fast_cap < POOL_SURV ? a.small_fast_cap : POOL_SURV;
-                se = launch_pdl(sk, dim3((unsigned)plan->grid), dim3((unsigned)plan->threads), fs, st, p, f, reinterpret_cast<u64*>(a.pool), cap);
+                cudaError_t se;
+                if (a.q_inline != nullptr) {  // host search: the query rides in the parameter block
+                    if (a.d > EVS_SMALL_QUERY_MAX_D) return cudaErrorInvalidValue;
+                    auto sk = scan_small_kernel<T, NV, true>;
+                    static size_t optin_q[16] = {};
+                    const size_t smem_q = small_query_smem_offset(64, f.d, f.x.world * f.k) + (size_t)a.d * 4;
+                    se = ensure_smem_optin(sk, smem_q, optin_q);
+                    if (se != cudaSuccess) return se;
+                    SmallQuery qb;
+                    memcpy(qb.v, a.q_inline, (size_t)a.d * 4);
+                    se = launch_pdl(sk, dim3((unsigned)plan->grid), dim3((unsigned)plan->threads), smem_q, st, p, f, reinterpret_cast<u64*>(a.pool), cap, qb);
+                } else {
+                    auto sk = scan_small_kernel<T, NV, false>;
+                    static size_t optin_s[16] = {};
+                    se = ensure_smem_optin(sk, fs, optin_s);
+                    if (se != cudaSuccess) return se;
+                    se = launch_pdl(sk, dim3((unsigned)plan->grid), dim3((unsigned)plan->threads), fs, st, p, f, reinterpret_cast<u64*>(a.pool), cap, NoQuery{0});
+                }
                 g_kernel_launches.fetch_add(1);
                 if (se != cudaSuccess) return se;
                 return cudaGetLastError();

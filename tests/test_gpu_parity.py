@@ -401,6 +401,7 @@ def test_small_shard_kernel_equals_the_oracle_and_the_pool_kernel(storage):
     row the same vector: exact ties; `small_fast_cap` 1 drives the general rounds on ordinary data too), fewer rows than
     chunks, a row count just past one register batch (10 240) and at the routing limit.  Always one launch, the oracle's
     bits, the pool kernel's bits, and a pool left clean for the next search whichever kernel runs it."""
+    import torch
     d = 512
     q = oracle.synth_fill(3, d, 7)
     for n in (1, 5, 64, 129, 1000, 10_000, 10_241, 20_000, 32_768, 32_769):
@@ -435,6 +436,9 @@ def test_small_shard_kernel_equals_the_oracle_and_the_pool_kernel(storage):
                 D1, I1 = idx.search(q[:1], kk)
                 assert np.array_equal(I0, Ir[:1]) and np.array_equal(D0, Dr[:1]), (n, name, kk)
                 assert np.array_equal(I1, Ir[:1]) and np.array_equal(D1, Dr[:1]), (n, name, kk)
+                # a numpy query travels in the kernel's parameter block; a CUDA tensor is read where it lies
+                Dt, It = idx.search(torch.from_numpy(q[1:2]).cuda(), kk)
+                assert np.array_equal(It.cpu().numpy(), Ir[1:2]) and np.array_equal(Dt.cpu().numpy(), Dr[1:2]), (n, name, kk)
     # NaN scores never enter (key 0), zero rows tie at 0: the contract of test_zero_and_nan_rows at 3000 rows
     x = oracle.synth_fill(3000, d, 5)
     x[7] = np.nan
