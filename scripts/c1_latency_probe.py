@@ -17,6 +17,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rows", default="10000,20000,30000")
 ap.add_argument("--dim", type=int, default=512)
 ap.add_argument("--storage", default="f32")
+ap.add_argument("--small-max", type=int, default=32768, help="routing limit of the small-shard kernel for its leg (sweeps beyond the default)")
+ap.add_argument("--ks", default="12,48")
 a = ap.parse_args()
 qi = evs.IndexFlatIP(a.dim)
 qi.add_synthetic(64, seed=1)
@@ -25,8 +27,8 @@ q = torch.from_numpy(qh).cuda()
 for rows in [int(r) for r in a.rows.split(",")]:
     idx = evs.IndexFlatIP(a.dim, storage=a.storage)
     idx.add_synthetic(rows, seed=0)
-    for k in (12, 48):
-        for name, small in (("pool kernel", 0), ("small-shard kernel", 32768)):
+    for k in [int(x) for x in a.ks.split(",")]:
+        for name, small in (("pool kernel", 0), ("small-shard kernel", a.small_max)):
             evs.set_option("small_max_rows", small)
             D = torch.empty((1, k), dtype=torch.float32, device="cuda")
             I = torch.empty((1, k), dtype=torch.int64, device="cuda")

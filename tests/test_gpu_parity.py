@@ -38,6 +38,7 @@ def _reset_options():
     evs.set_option("scan_chunk_groups", 4)
     evs.set_option("small_max_rows", 32768)
     evs.set_option("small_fast_cap", 2048)
+    evs.set_option("io_threads", 0)
 
 
 def _index(xb, storage="f32", variant=0):
@@ -504,6 +505,20 @@ def test_read_rows_is_the_shard_loader(tmp_path):
             I.append(i)
         D, Ifin = evs.merge_partials(torch.stack(S), torch.stack(I), k)
         assert np.array_equal(Ifin.cpu().numpy(), Is) and np.array_equal(D.cpu().numpy(), Ds), G
+    # every 64 MiB chunk is read by several threads over disjoint slices (option io_threads; 0 = one per hardware thread, at most
+    # 16): whatever the split, the rows are the file's, and a file written again from the loaded index has the same bytes
+    for threads in (1, 5, 16, 0):
+        evs.set_option("io_threads", threads)
+        again = evs.read_index(path)
+        assert again.ntotal == n and np.array_equal(again.reconstruct_n(0, n), xb), threads
+        lo, hi = 12_345, 60_001
+        part, _ = read_index_rows(path, lo, hi)
+        assert np.array_equal(part.reconstruct_n(0, hi - lo), xb[lo:hi]), threads
+    evs.set_option("io_threads", 0)
+    path2 = str(tmp_path / "index2.faiss")
+    evs.write_index(again, path2)
+    with open(path, "rb") as f1, open(path2, "rb") as f2:
+        assert f1.read() == f2.read()
     empty, _ = read_index_rows(path, n, n)
     assert empty.ntotal == 0 and empty.id_base == n
     with pytest.raises(evs.EvsError):
