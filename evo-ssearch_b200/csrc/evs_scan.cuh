@@ -662,8 +662,10 @@ __global__ void __launch_bounds__(256, ScanOcc<T, 1, NV>::value) scan_pool_kerne
             spec[u] = nxt[u];
         }
         __syncthreads();
-        if (s_ns > POOL_SURV / 2 && bend < m) {  // CTA-uniform
-            const int ns = s_ns;
+        const int ns_round = s_ns;
+        __syncthreads();  // ... read by every thread before the next round's appends change it (the branch must be CTA-uniform)
+        if (ns_round > POOL_SURV / 2 && bend < m) {
+            const int ns = ns_round;
             for (int i = ns + t; i < POOL_SURV; i += nt) surv[i] = 0ull;
             for (int size = 2; size <= POOL_SURV; size <<= 1)
                 for (int stride = size >> 1; stride > 0; stride >>= 1) {

@@ -45,6 +45,26 @@ def test_options_roundtrip_and_validation():
         evs.set_option("scan_variant", 7)
     with pytest.raises(evs.EvsError):
         evs.set_option("no_such_option", 1)
+    # the options of the small-shard kernel and of the threaded loader: defaults, round trip, range checks
+    for name, default, good, bad in (("small_max_rows", 32768, 0, -1), ("small_fast_cap", 2048, 1, 0), ("small_fast_cap", 2048, 7, 4096),
+                                     ("io_threads", 0, 5, 65)):
+        assert evs.get_option(name) == default, name
+        evs.set_option(name, good)
+        assert evs.get_option(name) == good, name
+        with pytest.raises(evs.EvsError):
+            evs.set_option(name, bad)
+        assert evs.get_option(name) == good, name
+        evs.set_option(name, default)
+
+
+def test_host_ptr_is_the_array_address():
+    """The search path takes numpy addresses through the buffer protocol (ndarray.ctypes.data_as costs ~5 us per call, three
+    per search); read-only and empty arrays fall back to ndarray.ctypes.data."""
+    for a in (np.zeros((1, 512), np.float32), np.zeros((3, 48), np.int64), np.zeros((5, 8), np.float32)[2:], np.zeros((0, 12), np.float32)):
+        assert _lib.host_ptr(a) == a.ctypes.data
+    ro = np.arange(12, dtype=np.float32).reshape(3, 4)
+    ro.flags.writeable = False
+    assert _lib.host_ptr(ro) == ro.ctypes.data
 
 
 @pytest.mark.skipif(evs.device_count() > 0, reason="checks the no-GPU behaviour")
