@@ -206,3 +206,46 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["config"]["workload"].startswith("20000x512 f32 flat-IP")
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_selection_thresholds_never_drop_a_top_key():
+    """The two threshold rules the single-query kernels rely on (evs_scan.cuh), restated in numpy on unique keys:
+    * small-shard kernel: rows are partitioned into 128 chunks (warp index mod 128); T = the 64th largest chunk maximum.
+      At least 64 keys are >= T, so none of the 64 best keys is below T;
+    * pool kernel: 64 slot maxima, each the maximum of a subset of the keys published to slot (row mod 64); tau = the
+      smallest slot maximum (0 while a slot is empty).  The maxima belong to 64 different rows, so again no top-64 key is
+      below tau -- whatever subset of the keys has been published so far.
+    Ordered, clustered and tiny inputs included: the bound must hold for any data, only the survivor count varies."""
+    rng = np.random.default_rng(5)
+    kp, chunks = 64, 128
+
+    def check(keys, warps, rpg):
+        n = keys.shape[0]
+        top = np.sort(keys)[::-1][:kp]
+        # small-shard rule: group g of rpg rows belongs to warp g mod warps, chunk = warp mod 128
+        rows = np.arange(n)
+        chunk = ((rows // rpg) % warps) % chunks
+        cmax = np.zeros(chunks, dtype=keys.dtype)
+        np.maximum.at(cmax, chunk, keys)
+        nz = np.sort(cmax[cmax > 0])[::-1]
+        T = nz[kp - 1] if nz.shape[0] >= kp else 0
+        assert (top >= T).all()
+        assert (keys >= T).sum() >= min(kp, n)
+        # pool rule: an arbitrary subset of the keys has been published so far
+        for frac in (0.02, 0.5, 1.0):
+            pub = rng.random(n) < frac
+            smax = np.zeros(kp, dtype=keys.dtype)
+            np.maximum.at(smax, rows[pub] % kp, keys[pub])
+            tau = smax.min()  # 0 while any slot is empty
+            assert (top >= tau).all()
+
+    for n in (1, 63, 64, 129, 1000, 10_000, 32_768):
+        base = rng.permutation(n).astype(np.uint64) + 1  # unique, non-zero
+        for keys in (base, np.sort(base), np.sort(base)[::-1].copy()):
+            for warps, rpg in ((2368, 4), (8, 4), (296, 1), (1184, 2)):
+                check(keys, warps, rpg)
+    # all large keys inside a few chunks (rows of one warp)
+    keys = rng.permutation(20_000).astype(np.uint64) + 1
+    hot = ((np.arange(20_000) // 4) % 2368) % 128 < 3
+    keys[hot] += 1_000_000
+    check(keys, 2368, 4)
