@@ -121,24 +121,28 @@ EVS_API int evs_index_get_rows(const evs_index* idx, int64_t row0, int64_t n, fl
  *                           float* distances, idx_t* labels, ...) const).  Host pointers.
  *                          k <= 0 -> EVS_EINVAL (FAISS_THROW_IF_NOT(k > 0)); nq == 0 is a no-op.
  * evs_index_search_dev  same with device pointers for queries and results, enqueued on `stream`.
- *                          Batches of up to 32 queries (k <= 48) never synchronise with the host; larger
- *                          batches synchronise `stream` once, after the results are enqueued, to read the
- *                          overflow flags of the tensor-core scan and the certification flags of the finalise
- *                          (queries whose candidate buffers overflowed -- adversarial data only -- or whose
- *                          result could not be certified are then re-run with the fp32 GEMV scan).
- *                          A single query is ONE kernel launch: the scan's last CTA finalises.
+ *                          Batches of up to 256 queries never synchronise with the host: overflowed candidate buffers
+ *                          (adversarial data only) and uncertified results are repaired by predicated launches on the
+ *                          device.  Larger batches synchronise `stream` once, after the results are enqueued, to read those
+ *                          flags, and the host re-runs the flagged queries with the fp32 GEMV scan.
+ *                          A single query is ONE kernel launch: the scan's last CTA finalises (shards of up to 32 768
+ *                          rows -- the application's index sizes -- take a latency-shaped variant of that launch; from
+ *                          evs_index_search the query then travels in the kernel's parameter block and the host polls a
+ *                          mapped completion word instead of draining the stream).
  *
  * Exactness of fp32-storage indexes (every entry point: host, device, partial, exchange):
  *   1 query        fp32 CUDA-core GEMV scan;
- *   2..32 queries  3xTF32 tensor-core scan (each operand split hi + lo, three MMAs per K step: fp32-class scan error,
- *                  ~1e-6 on unit vectors), on-chip top-k';
- *   more           single-tf32 tensor-core scan (~1e-3 scan error; candidates k' = 64/128 then ranked exactly).
- *   The finalise kernel certifies every result: margin > E, E = (error bound of that scan) * |q| * max|x|
- *   (see evs_index_last_margins).  Uncertified queries are re-run with the fp32 GEMV scan and k' = 128 -- on the
- *   device for batches of up to 32 queries (a queue the finalise fills, a re-run launch that returns at once when it is
- *   empty, a predicated second finalise: no host synchronisation), by the host otherwise.  For the 3xTF32 and GEMV
- *   scans E is an error model of the arithmetic; for the single-tf32 scans it is the statistical
- *   option "tf32_guard_eps_e6".  bf16 storage is the recall mode (north_star: recall@k >= 0.999): not certified.
+ *   2..32 queries  single-tf32 tensor-core scan with the top-k' kept on chip (option "x3": batches of up to 16 queries take
+ *                  the 3xTF32 split scan instead -- fp32-class scan error, ~1e-6 on unit vectors);
+ *   more           single-tf32 tensor-core scan, candidates k' = 64/128 selected through sampled thresholds.
+ *   Every result is then ranked by the canonical fp64 re-score of its candidates, and the finalise step CERTIFIES it: the
+ *   k-th canonical score must clear the worst retained scan score by more than the error bound of the scan that selected
+ *   the candidates, scaled by |q| * max|x| (see evs_index_last_margins).  For the GEMV and 3xTF32 scans that bound is an
+ *   error model of the arithmetic; for single tf32 it is the rigorous truncation bound of DESIGN.md section 2 (both
+ *   operands lose their low 13 mantissa bits towards zero); option "tf32_guard_eps_e6" replaces it by a statistical one
+ *   for experiments.  Uncertified queries are re-run with the fp32 GEMV scan and k' = 128 (on the device up to 256
+ *   queries per batch, by the host beyond).  bf16 storage is the recall mode (north_star: recall@k >= 0.999): not
+ *   certified.
  * evs_index_search_partial_dev
  *                       row-sharded search, stage 1: this shard's k best as (fp64 canonical score,
  *                          int64 global id) pairs, sorted best first, padded with
