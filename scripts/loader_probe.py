@@ -17,6 +17,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=4_000_000)
 ap.add_argument("--dim", type=int, default=512)
 ap.add_argument("--dir", default="/tmp")
+ap.add_argument("--write-threads", default="1,8")
+ap.add_argument("--read-threads", default="1,2,4,8,16,0,0")
 a = ap.parse_args()
 path = os.path.join(a.dir, "evs_loader_probe.faiss")
 src = evs.IndexFlatIP(a.dim)
@@ -27,7 +29,7 @@ probe_rows = [0, 1, a.rows // 3, a.rows - 1]
 want = np.stack([src.reconstruct(i) for i in probe_rows])
 xq = torch.from_numpy(src.reconstruct_n(7, 5)).cuda()
 D0, I0 = src.search(xq, 12)
-for thr in (1, 8):
+for thr in [int(x) for x in a.write_threads.split(",")]:
     evs.set_option("io_threads", thr)
     t0 = time.perf_counter()
     evs.write_index(src, path)
@@ -35,7 +37,7 @@ for thr in (1, 8):
     print(json.dumps({"op": "write_index", "io_threads": thr, "gb": round(gb, 3), "s": round(dt, 3), "gb_per_s": round(gb / dt, 2)}), flush=True)
 del src
 torch.cuda.empty_cache()
-for thr in (1, 2, 4, 8, 16, 0, 0):
+for thr in [int(x) for x in a.read_threads.split(",")]:
     evs.set_option("io_threads", thr)
     t0 = time.perf_counter()
     idx = evs.read_index(path)
